@@ -1,0 +1,151 @@
+/*
+ * jogramop_b200.h -- C-ABI of the B200-native batched collision-query engine.
+ *
+ * The reference (mrudorfer/jogramop-framework) has no FFI of its own: its hot path crosses from Python
+ * into the pybullet C extension.  Each entry point below names the reference call (file:line under the
+ * reference checkout) -- and the pybullet C-API call behind it -- that it replaces.  The Python classes
+ * in jogramop_framework_b200/{simulation,scenario}.py bind these symbols with ctypes (INTEGRATION.md
+ * shows the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / C++ types.  All functions that return int
+ *     return 0 on success and a negative JG_ERR_* code on failure; jg_last_error() gives the
+ *     thread-local message.  No exception crosses the boundary.
+ *   - Handles (jg_robot / jg_scene / jg_engine) are created and destroyed in pairs by the library and
+ *     are immutable after creation: batched calls on one engine are stream-ordered and may be issued
+ *     from several host threads as long as each uses its own stream and output buffers ... EXCEPT that
+ *     an engine owns ONE scratch arena, so concurrent calls on the same engine must be serialised by
+ *     the caller (use one engine per stream).
+ *   - Geometry is passed in double precision host arrays (the engine converts to fp32);
+ *     configurations / results of the `jg_check*` / `jg_fk` entry points are DEVICE pointers (fp32),
+ *     `stream` is a cudaStream_t (NULL = legacy default stream).  The `*_host` variants take HOST
+ *     pointers and run the pipelined H2D -> kernels -> D2H path themselves.
+ *   - Transforms are row-major 3x4 (R | t).
+ *   - Frames: everything is expressed in the ROBOT base frame (scene pieces are
+ *     inv(robot_pose) @ pose @ vertices, create_cpp_export.py:60-61).
+ */
+#ifndef JOGRAMOP_B200_H
+#define JOGRAMOP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JG_ABI_VERSION 1
+
+typedef struct jg_robot jg_robot;
+typedef struct jg_scene jg_scene;
+typedef struct jg_engine jg_engine;
+
+enum {
+    JG_OK = 0,
+    JG_ERR_INVALID = -1,   /* bad argument (NULL, dof mismatch, unsupported topology ...) */
+    JG_ERR_CUDA = -2,      /* a CUDA runtime call failed */
+    JG_ERR_NOMEM = -3,
+    JG_ERR_NODEVICE = -4   /* no usable CUDA device: there is NO CPU fallback */
+};
+
+/* what jg_check tests (scenario.py:109-119 order: limits, self-collision, scene collision) */
+enum {
+    JG_SCENE = 1,   /* robot shapes vs obstacle / object pieces   (simulation.py:97-121 body_in_collision) */
+    JG_PLANE = 2,   /* robot shapes vs ground plane               (burg plane.urdf in _env_bodies)         */
+    JG_SELF = 4,    /* 42 ordered link pairs                      (simulation.py:439-464 in_self_collision) */
+    JG_LIMITS = 8,  /* lo <= q <= hi                              (scenario.py:90-91 in_joint_limits)       */
+    JG_NO_EPA = 16  /* skip the penetration-depth pass: overlapping cores report -(marginA+marginB)         */
+};
+
+enum { JG_JOINT_FIXED = 0, JG_JOINT_REVOLUTE = 1, JG_JOINT_PRISMATIC = 2 };
+enum { JG_POSE_MAT34 = 0, JG_POSE_POS_QUAT_XYZW = 1 };
+
+typedef struct {
+    float threshold;       /* contactDistance below this = collision; default -0.001 (simulation.py:82)     */
+    float query_distance;  /* getClosestPoints distance; default 0.01 (simulation.py:86)                    */
+    float finger_open;     /* finger joint value; default 0.04 (simulation.py:172, reset_gripper 312-316)   */
+    int32_t chunk;         /* configurations per internal pass; 0 = default                                 */
+} jg_params;
+
+void jg_default_params(jg_params* p);
+const char* jg_last_error(void);
+int jg_abi_version(void);
+/* number of CUDA devices visible, or a negative JG_ERR_* */
+int jg_device_count(void);
+
+/* ---- robot: replaces burg SimulatorBase.load_robot -> pybullet.loadURDF (simulation.py:137-144) ----
+ * Link i is the child of joint i (pybullet numbering), parents must precede children.
+ * joint_origin [L,12]; joint_axis [L,3]; joint_qidx [L]: slot of the configuration vector driving the
+ * joint, -1 = fixed at 0, -2 = finger (driven by params.finger_open); q_limits [dof,2].
+ * Shapes (sorted by link; link -1 = base): convex hulls given by their vertices in the LINK frame.
+ * core_verts are the GJK cores (box: shrunk by its margin), plane_verts the vertices used against the
+ * plane and for penetration depth (box: exact corners); shape_margin / shape_plane_margin the margins
+ * subtracted in either case.  self_pairs [K,2] are LINK ids. */
+jg_robot* jg_robot_create(int n_links, const int32_t* joint_type, const int32_t* joint_parent,
+                          const double* joint_origin, const double* joint_axis, const int32_t* joint_qidx,
+                          const double* q_limits, int dof,
+                          int n_shapes, const int32_t* shape_link, const double* shape_margin,
+                          const int32_t* shape_vert_offset, const double* core_verts,
+                          const int32_t* shape_plane_offset, const double* plane_verts,
+                          const double* shape_plane_margin,
+                          int n_self_pairs, const int32_t* self_pairs);
+void jg_robot_free(jg_robot*);
+
+/* ---- scene: replaces burg SimulatorBase.add_scene -> pybullet.loadURDF per object (scenario.py:64) ----
+ * Convex pieces (hull vertices, robot frame) + optional ground plane n.p + d = 0 (plane[4], NULL = none). */
+jg_scene* jg_scene_create(int n_pieces, const int32_t* piece_vert_offset, const double* piece_verts,
+                          const double* piece_margin, const double* plane);
+void jg_scene_free(jg_scene*);
+
+/* ---- engine: uploads hulls / pieces to HBM on `device`, owns the scratch arena ---- */
+jg_engine* jg_engine_create(const jg_robot*, const jg_scene* /* may be NULL: FK / self-collision only */,
+                            int device, const jg_params* /* NULL = defaults */);
+void jg_engine_free(jg_engine*);
+int jg_engine_device(const jg_engine*);
+
+/* ---- forward kinematics: replaces reset_arm_joints + getLinkState (simulation.py:206-212, 223-249) ----
+ * q [n,dof] device fp32; link_ids [L_out] HOST ints; out [n,L_out,12] device fp32: link frames (URDF link
+ * frame = getLinkState items 4-5) pre-multiplied by base_pose (HOST 3x4 doubles, NULL = identity). */
+int jg_fk(jg_engine*, const float* q, int64_t n, int dof, const int32_t* link_ids, int n_link_ids,
+          const double* base_pose, float* out, void* stream);
+
+/* ---- collision check: replaces reset_arm_joints + in_collision / in_self_collision
+ *      (simulation.py:206-212, 439-472 -> getClosestPoints, point[8] < threshold) ----
+ * q [n,dof] device fp32.  bits: ceil(n/32) uint32 words, bit i%32 of word i/32 = configuration i collides
+ * (or violates limits if JG_LIMITS).  min_dist [n] (may be NULL): min contactDistance over everything
+ * checked, clamped to query_distance.  reason [n] uint8 (may be NULL): 0 ok, 1 limits, 2 self, 3 scene. */
+int jg_check(jg_engine*, const float* q, int64_t n, int dof, uint32_t flags, uint32_t* bits, float* min_dist,
+             uint8_t* reason, void* stream);
+
+/* ---- edge validation (new batched API; north_star "planner edge validation") ----
+ * qa,qb [m,dof]; substep k of `substeps` is qa + k/(substeps-1) (qb-qa); edge collides iff any substep does;
+ * min_dist [m] = min over substeps. */
+int jg_check_edges(jg_engine*, const float* qa, const float* qb, int64_t m, int dof, int substeps, uint32_t flags,
+                   uint32_t* bits, float* min_dist, void* stream);
+
+/* ---- free-floating gripper (create_graspset.py:53-60 check_collisions) ----
+ * poses: pose of link `ee_link` in the robot frame, fmt JG_POSE_MAT34 [n,12] or JG_POSE_POS_QUAT_XYZW [n,7];
+ * the shapes of `links` (HOST ints) move rigidly with it (offsets from FK with params.finger_open). */
+int jg_check_poses(jg_engine*, const float* poses, int64_t n, int fmt, int ee_link, const int32_t* links,
+                   int n_links, uint32_t flags, uint32_t* bits, float* min_dist, void* stream);
+
+/* ---- host-buffer convenience (the end-to-end path a drop-in caller uses): pinned staging, chunked
+ *      H2D -> kernels -> D2H overlapped on two streams; blocks until the results are in host memory ---- */
+int jg_check_host(jg_engine*, const float* q_host, int64_t n, int dof, uint32_t flags, uint32_t* bits_host,
+                  float* min_dist_host, uint8_t* reason_host);
+
+/* ---- instrumentation ---- */
+typedef struct {
+    int64_t configs;          /* configurations processed by the last jg_check* call                         */
+    int64_t pairs;            /* (shape, piece) pairs that survived the broad phase                          */
+    int64_t plane_pairs;      /* (shape, plane) candidates                                                   */
+    int64_t self_pairs;       /* self-collision candidates                                                   */
+    int64_t epa_pairs;        /* pairs whose cores overlapped (penetration pass)                             */
+    int64_t kernel_launches;  /* kernels launched by the last call                                           */
+} jg_stats;
+/* synchronises the engine's last stream and reads the device counters */
+int jg_get_stats(jg_engine*, jg_stats*);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

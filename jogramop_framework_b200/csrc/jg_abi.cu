@@ -1,0 +1,752 @@
+// jg_abi.cu -- host side of libjogramop_b200.so: handle management, table upload, pass orchestration.
+// Implements include/jogramop_b200.h.  Plain CUDA runtime, no torch types anywhere in this library.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/jogramop_b200.h"
+#include "jg_kernels.cuh"
+
+using namespace jg;
+
+// ----------------------------------------------------------------------------------------------- errors
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CUDA_TRY(x)                                                                              \
+    do {                                                                                         \
+        cudaError_t e_ = (x);                                                                    \
+        if (e_ != cudaSuccess) return fail(JG_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_));   \
+    } while (0)
+
+extern "C" const char* jg_last_error(void) { return g_err.c_str(); }
+extern "C" int jg_abi_version(void) { return JG_ABI_VERSION; }
+extern "C" void jg_default_params(jg_params* p) {
+    if (!p) return;
+    p->threshold = -0.001f;
+    p->query_distance = 0.01f;
+    p->finger_open = 0.04f;
+    p->chunk = 0;
+}
+extern "C" int jg_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail(JG_ERR_NODEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return n;
+}
+
+// ----------------------------------------------------------------------------------------------- handles
+struct jg_robot {
+    int L = 0, S = 0, dof = 0, K = 0;
+    std::vector<int> joint_type, joint_parent, joint_qidx, shape_link, shape_off, plane_off, self_pairs;
+    std::vector<double> joint_origin, joint_axis, q_limits, shape_margin, core, plane_v, plane_margin;
+};
+
+struct jg_scene {
+    int P = 0;
+    std::vector<int> off;
+    std::vector<double> v, margin;
+    bool has_plane = false;
+    double plane[4] = {0, 0, 1, 0};
+};
+
+extern "C" jg_robot* jg_robot_create(int L, const int32_t* joint_type, const int32_t* joint_parent,
+                                     const double* joint_origin, const double* joint_axis, const int32_t* joint_qidx,
+                                     const double* q_limits, int dof, int S, const int32_t* shape_link,
+                                     const double* shape_margin, const int32_t* shape_off, const double* core,
+                                     const int32_t* plane_off, const double* plane_v, const double* plane_margin,
+                                     int K, const int32_t* self_pairs) {
+    if (L <= 0 || L > MAX_LINKS || S < 0 || S > MAX_SHAPES || dof <= 0 || dof > MAX_DOF || !joint_type ||
+        !joint_parent || !joint_origin || !joint_axis || !joint_qidx || !q_limits || (S && (!shape_link || !shape_off)) ||
+        K < 0 || (K && !self_pairs)) {
+        fail(JG_ERR_INVALID, "jg_robot_create: bad sizes (L=%d<=%d, S=%d<=%d, dof=%d<=%d) or NULL table", L, MAX_LINKS, S,
+             MAX_SHAPES, dof, MAX_DOF);
+        return nullptr;
+    }
+    for (int i = 0; i < L; ++i) {
+        if (joint_parent[i] >= i || joint_parent[i] < -1) {
+            fail(JG_ERR_INVALID, "jg_robot_create: joint %d has parent %d (parents must precede children)", i, joint_parent[i]);
+            return nullptr;
+        }
+        if (joint_qidx[i] >= dof || joint_qidx[i] < -2) {
+            fail(JG_ERR_INVALID, "jg_robot_create: joint %d q index %d out of range", i, joint_qidx[i]);
+            return nullptr;
+        }
+    }
+    for (int s = 0; s < S; ++s) {
+        if (shape_link[s] < -1 || shape_link[s] >= L || (s && shape_link[s] < shape_link[s - 1])) {
+            fail(JG_ERR_INVALID, "jg_robot_create: shapes must be sorted by link id in [-1,%d)", L);
+            return nullptr;
+        }
+        if (shape_off[s + 1] - shape_off[s] <= 0 || shape_off[s + 1] - shape_off[s] >= 65536) {
+            fail(JG_ERR_INVALID, "jg_robot_create: shape %d has an unsupported vertex count", s);
+            return nullptr;
+        }
+    }
+    jg_robot* r = new jg_robot;
+    r->L = L; r->S = S; r->dof = dof; r->K = K;
+    r->joint_type.assign(joint_type, joint_type + L);
+    r->joint_parent.assign(joint_parent, joint_parent + L);
+    r->joint_qidx.assign(joint_qidx, joint_qidx + L);
+    r->joint_origin.assign(joint_origin, joint_origin + 12 * L);
+    r->joint_axis.assign(joint_axis, joint_axis + 3 * L);
+    r->q_limits.assign(q_limits, q_limits + 2 * dof);
+    r->shape_link.assign(shape_link, shape_link + S);
+    r->shape_margin.assign(shape_margin, shape_margin + S);
+    r->shape_off.assign(shape_off, shape_off + S + 1);
+    r->core.assign(core, core + 3 * (S ? shape_off[S] : 0));
+    r->plane_off.assign(plane_off, plane_off + S + 1);
+    r->plane_v.assign(plane_v, plane_v + 3 * (S ? plane_off[S] : 0));
+    r->plane_margin.assign(plane_margin, plane_margin + S);
+    r->self_pairs.assign(self_pairs, self_pairs + 2 * K);
+    return r;
+}
+extern "C" void jg_robot_free(jg_robot* r) { delete r; }
+
+extern "C" jg_scene* jg_scene_create(int P, const int32_t* off, const double* v, const double* margin,
+                                     const double* plane) {
+    if (P < 0 || (P && (!off || !v || !margin))) {
+        fail(JG_ERR_INVALID, "jg_scene_create: bad arguments");
+        return nullptr;
+    }
+    for (int p = 0; p < P; ++p)
+        if (off[p + 1] - off[p] <= 0 || off[p + 1] - off[p] >= 65536) {
+            fail(JG_ERR_INVALID, "jg_scene_create: piece %d has an unsupported vertex count", p);
+            return nullptr;
+        }
+    jg_scene* s = new jg_scene;
+    s->P = P;
+    if (P) {
+        s->off.assign(off, off + P + 1);
+        s->v.assign(v, v + 3 * off[P]);
+        s->margin.assign(margin, margin + P);
+    } else {
+        s->off.assign(1, 0);
+    }
+    s->has_plane = plane != nullptr;
+    if (plane) memcpy(s->plane, plane, sizeof(double) * 4);
+    return s;
+}
+extern "C" void jg_scene_free(jg_scene* s) { delete s; }
+
+// ----------------------------------------------------------------------------------------------- engine
+struct jg_engine {
+    int device = 0;
+    jg_params prm;
+    int L = 0, S = 0, dof = 0, P = 0, K = 0;
+    int n_keys = 0, n_scene_keys = 0, n_verts = 0;
+    bool has_plane = false;
+    float plane[4] = {0, 0, 1, 0};
+    std::vector<int> shape_link;          // host copy, for pose mode
+    std::vector<int> link_first_shape;    // [L+1] first shape of link (index link+1) or -1
+    RobotTab h_robot;
+    // device tables
+    RobotTab* d_robot = nullptr;
+    PieceRec* d_pieces = nullptr;
+    SelfRec* d_selfs = nullptr;
+    KeyRec* d_keys = nullptr;
+    float4* d_verts = nullptr;
+    // scratch arena
+    int cap = 0;                          // configurations per pass
+    float4 *q_r0 = nullptr, *q_r1 = nullptr, *q_r2 = nullptr;
+    int* q_cfg = nullptr;
+    int* counts = nullptr;                // [2*n_keys + 8]
+    int *enc_scene = nullptr, *enc_self = nullptr;
+    uint32_t* viol = nullptr;
+    int* d_link_slot = nullptr;           // FK: [L]
+    Tf* d_rel = nullptr;                  // poses: [MAX_SHAPES]
+    int* d_use_shapes = nullptr;
+    // host staging for jg_check_host
+    cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+    float* stage_q[2] = {nullptr, nullptr};      // device
+    uint32_t* stage_bits[2] = {nullptr, nullptr};
+    float* stage_dist[2] = {nullptr, nullptr};
+    uint8_t* stage_reason[2] = {nullptr, nullptr};
+    float* pin_q[2] = {nullptr, nullptr};        // pinned host
+    uint32_t* pin_bits[2] = {nullptr, nullptr};
+    float* pin_dist[2] = {nullptr, nullptr};
+    uint8_t* pin_reason[2] = {nullptr, nullptr};
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_run[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    bool staging_ready = false;
+    // stats
+    jg_stats stats{};
+    unsigned long long* d_stats = nullptr;       // [8]
+    cudaStream_t last_stream = nullptr;
+    int sm_count = 148;
+    size_t smem_narrow = 0;
+};
+
+static void engine_release(jg_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaFree(e->d_robot); cudaFree(e->d_pieces); cudaFree(e->d_selfs); cudaFree(e->d_keys); cudaFree(e->d_verts);
+    cudaFree(e->q_r0); cudaFree(e->q_r1); cudaFree(e->q_r2); cudaFree(e->q_cfg); cudaFree(e->counts);
+    cudaFree(e->enc_scene); cudaFree(e->enc_self); cudaFree(e->viol); cudaFree(e->d_link_slot); cudaFree(e->d_rel);
+    cudaFree(e->d_use_shapes); cudaFree(e->d_stats);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(e->stage_q[i]); cudaFree(e->stage_bits[i]); cudaFree(e->stage_dist[i]); cudaFree(e->stage_reason[i]);
+        cudaFreeHost(e->pin_q[i]); cudaFreeHost(e->pin_bits[i]); cudaFreeHost(e->pin_dist[i]);
+        cudaFreeHost(e->pin_reason[i]);
+        if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
+        if (e->ev_run[i]) cudaEventDestroy(e->ev_run[i]);
+        if (e->ev_out[i]) cudaEventDestroy(e->ev_out[i]);
+    }
+    if (e->s_in) cudaStreamDestroy(e->s_in);
+    if (e->s_run) cudaStreamDestroy(e->s_run);
+    if (e->s_out) cudaStreamDestroy(e->s_out);
+    delete e;
+}
+
+static int build_tables(jg_engine* e, const jg_robot* r, const jg_scene* sc) {
+    RobotTab& R = e->h_robot;
+    memset(&R, 0, sizeof R);
+    R.L = r->L; R.S = r->S; R.dof = r->dof; R.n_self = r->K;
+    for (int j = 0; j < r->dof; ++j) {
+        R.qlo[j] = (float)r->q_limits[2 * j];
+        R.qhi[j] = (float)r->q_limits[2 * j + 1];
+        // float32 rounding must not reject the float32 image of a limit itself
+        if ((double)R.qlo[j] > r->q_limits[2 * j]) R.qlo[j] = nextafterf(R.qlo[j], -INFINITY);
+        if ((double)R.qhi[j] < r->q_limits[2 * j + 1]) R.qhi[j] = nextafterf(R.qhi[j], INFINITY);
+    }
+    // which links must be kept for later children (one register slot: enough for chains with one branch point)
+    int saved = -2;
+    std::vector<int> need_save(r->L, 0);
+    for (int i = 0; i < r->L; ++i) {
+        const int p = r->joint_parent[i];
+        if (p >= 0 && p != i - 1) need_save[p] = 1;
+    }
+    for (int i = 0; i < r->L; ++i) {
+        JointRec& J = R.joints[i];
+        for (int k = 0; k < 12; ++k) J.o[k] = (float)r->joint_origin[12 * i + k];
+        double ax = r->joint_axis[3 * i], ay = r->joint_axis[3 * i + 1], az = r->joint_axis[3 * i + 2];
+        double nn = std::sqrt(ax * ax + ay * ay + az * az);
+        if (r->joint_type[i] != JG_JOINT_FIXED && !(nn > 0))
+            return fail(JG_ERR_INVALID, "joint %d: zero axis on a movable joint", i);
+        if (nn > 0) { ax /= nn; ay /= nn; az /= nn; }
+        J.axis[0] = (float)ax; J.axis[1] = (float)ay; J.axis[2] = (float)az;
+        J.type = r->joint_type[i];
+        J.qidx = r->joint_qidx[i];
+        const int p = r->joint_parent[i];
+        if (p == -1) J.parent_sel = 2;
+        else if (p == i - 1) J.parent_sel = 0;
+        else if (p == saved) J.parent_sel = 1;
+        else return fail(JG_ERR_INVALID, "joint %d: unsupported tree topology (more than one live branch point)", i);
+        J.save = need_save[i];
+        if (J.save) saved = i;
+        J.shape_first = 0; J.shape_count = 0;
+    }
+    e->link_first_shape.assign(r->L + 1, -1);
+    e->shape_link = r->shape_link;
+    int nv = r->S ? r->shape_off[r->S] : 0;
+    std::vector<float4> verts;
+    verts.reserve(nv + 1024);
+    for (int i = 0; i < nv; ++i)
+        verts.push_back(make_float4((float)r->core[3 * i], (float)r->core[3 * i + 1], (float)r->core[3 * i + 2], 0.f));
+    for (int s = 0; s < r->S; ++s) {
+        ShapeRec& Sh = R.shapes[s];
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        for (int i = r->shape_off[s]; i < r->shape_off[s + 1]; ++i)
+            for (int k = 0; k < 3; ++k) {
+                lo[k] = std::min(lo[k], r->core[3 * i + k]);
+                hi[k] = std::max(hi[k], r->core[3 * i + k]);
+            }
+        for (int k = 0; k < 3; ++k) {
+            Sh.c[k] = (float)(0.5 * (lo[k] + hi[k]));
+            Sh.h[k] = (float)(0.5 * (hi[k] - lo[k]) + 1e-6);
+        }
+        Sh.margin = (float)r->shape_margin[s];
+        Sh.plane_margin = (float)r->plane_margin[s];
+        Sh.voff = r->shape_off[s];
+        Sh.vn = r->shape_off[s + 1] - r->shape_off[s];
+        Sh.link = r->shape_link[s];
+        // plane / EPA vertices: share the core range when identical (hulls), else append (boxes)
+        const int pn = r->plane_off[s + 1] - r->plane_off[s];
+        bool same = pn == Sh.vn;
+        for (int i = 0; same && i < 3 * pn; ++i)
+            same = r->plane_v[3 * r->plane_off[s] + i] == r->core[3 * r->shape_off[s] + i];
+        if (same) { Sh.poff = Sh.voff; Sh.pn = Sh.vn; }
+        else {
+            Sh.poff = (int)verts.size(); Sh.pn = pn;
+            for (int i = r->plane_off[s]; i < r->plane_off[s + 1]; ++i)
+                verts.push_back(make_float4((float)r->plane_v[3 * i], (float)r->plane_v[3 * i + 1],
+                                            (float)r->plane_v[3 * i + 2], 0.f));
+        }
+        const int link = r->shape_link[s];
+        if (e->link_first_shape[link + 1] < 0) e->link_first_shape[link + 1] = s;
+        if (link < 0) {
+            if (R.base_shape_count == 0) R.base_shape_first = s;
+            R.base_shape_count++;
+        } else {
+            if (R.joints[link].shape_count == 0) R.joints[link].shape_first = s;
+            R.joints[link].shape_count++;
+        }
+    }
+    // pieces: centred vertices
+    const int P = sc ? sc->P : 0;
+    e->P = P;
+    std::vector<PieceRec> pieces(P);
+    for (int p = 0; p < P; ++p) {
+        PieceRec& Pc = pieces[p];
+        memset(&Pc, 0, sizeof Pc);
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        for (int i = sc->off[p]; i < sc->off[p + 1]; ++i)
+            for (int k = 0; k < 3; ++k) {
+                lo[k] = std::min(lo[k], sc->v[3 * i + k]);
+                hi[k] = std::max(hi[k], sc->v[3 * i + k]);
+            }
+        for (int k = 0; k < 3; ++k) {
+            Pc.c[k] = (float)(0.5 * (lo[k] + hi[k]));
+            Pc.h[k] = (float)(0.5 * (hi[k] - lo[k]) + 1e-6);
+        }
+        Pc.margin = (float)sc->margin[p];
+        Pc.voff = (int)verts.size();
+        Pc.vn = sc->off[p + 1] - sc->off[p];
+        for (int i = sc->off[p]; i < sc->off[p + 1]; ++i)   // subtract the (float) centre in double, then round
+            verts.push_back(make_float4((float)(sc->v[3 * i] - (double)Pc.c[0]), (float)(sc->v[3 * i + 1] - (double)Pc.c[1]),
+                                        (float)(sc->v[3 * i + 2] - (double)Pc.c[2]), 0.f));
+    }
+    e->has_plane = sc && sc->has_plane;
+    if (e->has_plane)
+        for (int k = 0; k < 4; ++k) e->plane[k] = (float)sc->plane[k];
+    // keys
+    std::vector<KeyRec> keys;
+    for (int s = 0; s < r->S; ++s) {
+        for (int p = 0; p < P; ++p)
+            keys.push_back(KeyRec{R.shapes[s].voff, R.shapes[s].vn, pieces[p].voff, pieces[p].vn,
+                                  R.shapes[s].margin + pieces[p].margin, KEY_HULL});
+        keys.push_back(KeyRec{R.shapes[s].poff, R.shapes[s].pn, 0, 0, R.shapes[s].plane_margin, KEY_PLANE});
+    }
+    e->n_scene_keys = (int)keys.size();
+    std::vector<SelfRec> selfs;
+    for (int k = 0; k < r->K; ++k) {
+        const int la = r->self_pairs[2 * k], lb = r->self_pairs[2 * k + 1];
+        if (la < 0 || lb < 0 || la >= r->L || lb >= r->L)
+            return fail(JG_ERR_INVALID, "self pair %d: link ids (%d,%d) out of range (base link pairs unsupported)", k, la, lb);
+        const int sa = e->link_first_shape[la + 1], sb = e->link_first_shape[lb + 1];
+        if (sa < 0 || sb < 0) return fail(JG_ERR_INVALID, "self pair %d: link without collision shape", k);
+        selfs.push_back(SelfRec{sa, sb, la, lb});
+        keys.push_back(KeyRec{R.shapes[sb].voff, R.shapes[sb].vn, R.shapes[sa].voff, R.shapes[sa].vn,
+                              R.shapes[sa].margin + R.shapes[sb].margin, KEY_SELF});
+    }
+    e->n_keys = (int)keys.size();
+    e->n_verts = (int)verts.size();
+    e->K = r->K;
+
+    CUDA_TRY(cudaMalloc(&e->d_robot, sizeof(RobotTab)));
+    CUDA_TRY(cudaMemcpy(e->d_robot, &R, sizeof(RobotTab), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&e->d_pieces, sizeof(PieceRec) * std::max(P, 1)));
+    if (P) CUDA_TRY(cudaMemcpy(e->d_pieces, pieces.data(), sizeof(PieceRec) * P, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&e->d_selfs, sizeof(SelfRec) * std::max(r->K, 1)));
+    if (r->K) CUDA_TRY(cudaMemcpy(e->d_selfs, selfs.data(), sizeof(SelfRec) * r->K, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&e->d_keys, sizeof(KeyRec) * std::max(e->n_keys, 1)));
+    if (e->n_keys) CUDA_TRY(cudaMemcpy(e->d_keys, keys.data(), sizeof(KeyRec) * e->n_keys, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&e->d_verts, sizeof(float4) * std::max(e->n_verts, 1)));
+    if (e->n_verts) CUDA_TRY(cudaMemcpy(e->d_verts, verts.data(), sizeof(float4) * e->n_verts, cudaMemcpyHostToDevice));
+    return JG_OK;
+}
+
+constexpr int BP_BLOCK = 128;   // broad phase: threads (= configurations) per block
+constexpr int NP_BLOCK = 256;   // narrow phase
+
+static size_t bp_smem(const jg_engine* e, uint32_t flags) {
+    size_t s = sizeof(RobotTab) + sizeof(PieceRec) * e->P + sizeof(float) * BP_BLOCK * e->dof;
+    if (flags & JG_SELF) s += sizeof(float) * 12 * e->L * BP_BLOCK;
+    return s;
+}
+
+extern "C" jg_engine* jg_engine_create(const jg_robot* r, const jg_scene* sc, int device, const jg_params* prm) {
+    if (!r) { fail(JG_ERR_INVALID, "jg_engine_create: robot is NULL"); return nullptr; }
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev <= 0) {
+        fail(JG_ERR_NODEVICE, "no CUDA device available (%s); this engine has no CPU fallback",
+             ce == cudaSuccess ? "device count 0" : cudaGetErrorString(ce));
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) { fail(JG_ERR_INVALID, "device %d out of range [0,%d)", device, ndev); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { fail(JG_ERR_CUDA, "cudaSetDevice(%d) failed", device); return nullptr; }
+    jg_engine* e = new jg_engine;
+    e->device = device;
+    if (prm) e->prm = *prm; else jg_default_params(&e->prm);
+    e->L = r->L; e->S = r->S; e->dof = r->dof;
+    if (build_tables(e, r, sc) != JG_OK) { engine_release(e); return nullptr; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->sm_count = prop.multiProcessorCount;
+    e->smem_narrow = sizeof(float4) * e->n_verts + sizeof(KeyRec) * e->n_keys + sizeof(int) * (e->n_keys + 1) + 64;
+    const size_t smem_max = 227 * 1024;
+    if (e->smem_narrow > smem_max || bp_smem(e, JG_SELF) > smem_max) {
+        fail(JG_ERR_INVALID, "scene too large for the shared-memory resident path (%zu B of vertices/keys)", e->smem_narrow);
+        engine_release(e);
+        return nullptr;
+    }
+    bool ok = cudaFuncSetAttribute(k_narrowphase<NP_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_broadphase<BP_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_broadphase_poses<BP_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
+    if (!ok) {
+        fail(JG_ERR_CUDA, "cudaFuncSetAttribute failed: %s (is this an sm_100 device?)", cudaGetErrorString(cudaGetLastError()));
+        engine_release(e);
+        return nullptr;
+    }
+    // scratch arena
+    int cap = e->prm.chunk > 0 ? e->prm.chunk : (1 << 18);
+    cap = (cap + 1023) / 1024 * 1024;
+    e->cap = cap;
+    const size_t qn = (size_t)std::max(e->n_keys, 1) * cap;
+    bool okm = cudaMalloc(&e->q_r0, sizeof(float4) * qn) == cudaSuccess && cudaMalloc(&e->q_r1, sizeof(float4) * qn) == cudaSuccess &&
+               cudaMalloc(&e->q_r2, sizeof(float4) * qn) == cudaSuccess && cudaMalloc(&e->q_cfg, sizeof(int) * qn) == cudaSuccess &&
+               cudaMalloc(&e->counts, sizeof(int) * (2 * e->n_keys + 8)) == cudaSuccess &&
+               cudaMalloc(&e->enc_scene, sizeof(int) * cap) == cudaSuccess && cudaMalloc(&e->enc_self, sizeof(int) * cap) == cudaSuccess &&
+               cudaMalloc(&e->viol, sizeof(uint32_t) * (cap / 32 + 1)) == cudaSuccess &&
+               cudaMalloc(&e->d_link_slot, sizeof(int) * MAX_LINKS) == cudaSuccess &&
+               cudaMalloc(&e->d_rel, sizeof(Tf) * MAX_SHAPES) == cudaSuccess &&
+               cudaMalloc(&e->d_use_shapes, sizeof(int) * MAX_SHAPES) == cudaSuccess &&
+               cudaMalloc(&e->d_stats, sizeof(unsigned long long) * 8) == cudaSuccess;
+    if (!okm) {
+        fail(JG_ERR_NOMEM, "scratch allocation failed (%zu queue entries): %s", qn, cudaGetErrorString(cudaGetLastError()));
+        engine_release(e);
+        return nullptr;
+    }
+    cudaMemset(e->d_stats, 0, sizeof(unsigned long long) * 8);
+    return e;
+}
+extern "C" void jg_engine_free(jg_engine* e) { engine_release(e); }
+extern "C" int jg_engine_device(const jg_engine* e) { return e ? e->device : JG_ERR_INVALID; }
+
+// ----------------------------------------------------------------------------------------------- passes
+static void fill_args(const jg_engine* e, PassArgs& a, uint32_t flags) {
+    memset(&a, 0, sizeof a);
+    a.dof = e->dof; a.substeps = 1; a.flags = flags;
+    a.finger_open = e->prm.finger_open; a.qd = e->prm.query_distance; a.threshold = e->prm.threshold;
+    for (int k = 0; k < 4; ++k) a.plane[k] = e->plane[k];
+    a.has_plane = e->has_plane ? 1 : 0;
+    a.robot = e->d_robot; a.pieces = e->d_pieces; a.P = e->P; a.selfs = e->d_selfs; a.keys = e->d_keys;
+    a.n_keys = e->n_keys; a.n_scene_keys = e->n_scene_keys; a.verts = e->d_verts; a.n_verts = e->n_verts;
+    a.q_r0 = e->q_r0; a.q_r1 = e->q_r1; a.q_r2 = e->q_r2; a.q_cfg = e->q_cfg; a.cap = e->cap; a.counts = e->counts;
+    a.enc_scene = e->enc_scene; a.enc_self = e->enc_self; a.viol = e->viol;
+}
+
+__global__ void k_accumulate_stats(const int* counts, int n_scene_keys, int n_keys, int P, unsigned long long* stats) {
+    // one warp; stats[0]=hull pairs, [1]=plane, [2]=self
+    unsigned long long h = 0, pl = 0, sf = 0;
+    for (int k = threadIdx.x; k < n_keys; k += 32) {
+        const int c = counts[k];
+        if (k >= n_scene_keys) sf += c;
+        else if (k % (P + 1) == P) pl += c;
+        else h += c;
+    }
+    for (int o = 16; o; o >>= 1) {
+        h += __shfl_xor_sync(0xFFFFFFFFu, h, o);
+        pl += __shfl_xor_sync(0xFFFFFFFFu, pl, o);
+        sf += __shfl_xor_sync(0xFFFFFFFFu, sf, o);
+    }
+    if (threadIdx.x == 0) { stats[0] += h; stats[1] += pl; stats[2] += sf; }
+}
+
+// narrow phase + finalize of the pass described by `a` (queues already filled)
+static int run_narrow_and_finalize(jg_engine* e, const PassArgs& a, int n_out, uint32_t flags, uint32_t* bits, float* dist,
+                                   uint8_t* reason, cudaStream_t st) {
+    if (e->n_keys > 0) {
+        k_accumulate_stats<<<1, 32, 0, st>>>(e->counts, e->n_scene_keys, e->n_keys, e->P, e->d_stats);
+        const int blocks = e->sm_count * 3;
+        k_narrowphase<NP_BLOCK><<<blocks, NP_BLOCK, e->smem_narrow, st>>>(a);
+        e->stats.kernel_launches += 2;
+    }
+    k_finalize<<<(n_out + 255) / 256, 256, 0, st>>>(e->enc_scene, e->enc_self, e->viol, n_out, a.qd, a.threshold, flags, bits,
+                                                    dist, reason);
+    e->stats.kernel_launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return JG_OK;
+}
+
+static int begin_call(jg_engine* e, cudaStream_t st) {
+    CUDA_TRY(cudaSetDevice(e->device));
+    e->stats = jg_stats{};
+    e->last_stream = st;
+    CUDA_TRY(cudaMemsetAsync(e->d_stats, 0, sizeof(unsigned long long) * 8, st));
+    return JG_OK;
+}
+
+extern "C" int jg_check(jg_engine* e, const float* q, int64_t n, int dof, uint32_t flags, uint32_t* bits, float* min_dist,
+                        uint8_t* reason, void* stream) {
+    if (!e) return fail(JG_ERR_INVALID, "jg_check: engine is NULL");
+    if (dof != e->dof) return fail(JG_ERR_INVALID, "jg_check: dof %d does not match the robot's %d", dof, e->dof);
+    if (n < 0 || (n && (!q || !bits))) return fail(JG_ERR_INVALID, "jg_check: NULL q/bits");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = begin_call(e, st);
+    if (rc) return rc;
+    e->stats.configs = n;
+    for (int64_t off = 0; off < n; off += e->cap) {
+        const int m = (int)std::min<int64_t>(e->cap, n - off);
+        PassArgs a;
+        fill_args(e, a, flags);
+        a.q = q + off * dof; a.n = m;
+        CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * (2 * e->n_keys + 8), st));
+        if (flags & JG_LIMITS) CUDA_TRY(cudaMemsetAsync(e->viol, 0, sizeof(uint32_t) * (e->cap / 32 + 1), st));
+        k_broadphase<BP_BLOCK><<<(m + BP_BLOCK - 1) / BP_BLOCK, BP_BLOCK, bp_smem(e, flags), st>>>(a);
+        e->stats.kernel_launches += 1;
+        rc = run_narrow_and_finalize(e, a, m, flags, bits + off / 32, min_dist ? min_dist + off : nullptr,
+                                     reason ? reason + off : nullptr, st);
+        if (rc) return rc;
+    }
+    return JG_OK;
+}
+
+extern "C" int jg_check_edges(jg_engine* e, const float* qa, const float* qb, int64_t m, int dof, int substeps,
+                              uint32_t flags, uint32_t* bits, float* min_dist, void* stream) {
+    if (!e) return fail(JG_ERR_INVALID, "jg_check_edges: engine is NULL");
+    if (dof != e->dof) return fail(JG_ERR_INVALID, "jg_check_edges: dof %d does not match the robot's %d", dof, e->dof);
+    if (substeps < 2 || substeps > e->cap / 32) return fail(JG_ERR_INVALID, "jg_check_edges: substeps %d out of range [2,%d]", substeps, e->cap / 32);
+    if (m < 0 || (m && (!qa || !qb || !bits))) return fail(JG_ERR_INVALID, "jg_check_edges: NULL qa/qb/bits");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = begin_call(e, st);
+    if (rc) return rc;
+    e->stats.configs = m * substeps;
+    const int edges_per_pass = (e->cap / substeps) / 32 * 32;   // keep packed words aligned across passes
+    for (int64_t off = 0; off < m; off += edges_per_pass) {
+        const int me = (int)std::min<int64_t>(edges_per_pass, m - off);
+        PassArgs a;
+        fill_args(e, a, flags);
+        a.q = qa + off * dof; a.qb = qb + off * dof; a.n = me * substeps; a.substeps = substeps;
+        CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * (2 * e->n_keys + 8), st));
+        if (flags & JG_LIMITS) CUDA_TRY(cudaMemsetAsync(e->viol, 0, sizeof(uint32_t) * (e->cap / 32 + 1), st));
+        k_init_scratch<<<(me + 255) / 256, 256, 0, st>>>(e->enc_scene, e->enc_self, me);
+        k_broadphase<BP_BLOCK><<<(a.n + BP_BLOCK - 1) / BP_BLOCK, BP_BLOCK, bp_smem(e, flags), st>>>(a);
+        e->stats.kernel_launches += 2;
+        rc = run_narrow_and_finalize(e, a, me, flags, bits + off / 32, min_dist ? min_dist + off : nullptr, nullptr, st);
+        if (rc) return rc;
+    }
+    return JG_OK;
+}
+
+// host-side double FK (set-up only: rigid offsets of the gripper shapes for pose mode)
+static void host_fk(const RobotTab& R, float finger_open, double out[][12]) {
+    for (int i = 0; i < R.L; ++i) {
+        const JointRec& J = R.joints[i];
+        double O[12], M[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+        for (int k = 0; k < 12; ++k) O[k] = J.o[k];
+        const double val = J.qidx == -2 ? finger_open : 0.0;
+        if (J.type == 1) {
+            const double x = J.axis[0], y = J.axis[1], z = J.axis[2], c = std::cos(val), s = std::sin(val), t = 1 - c;
+            M[0] = t * x * x + c; M[1] = t * x * y - s * z; M[2] = t * x * z + s * y;
+            M[4] = t * x * y + s * z; M[5] = t * y * y + c; M[6] = t * y * z - s * x;
+            M[8] = t * x * z - s * y; M[9] = t * y * z + s * x; M[10] = t * z * z + c;
+        } else if (J.type == 2) {
+            M[3] = J.axis[0] * val; M[7] = J.axis[1] * val; M[11] = J.axis[2] * val;
+        }
+        auto mul = [](const double* A, const double* B, double* C) {
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 4; ++c)
+                    C[4 * r + c] = A[4 * r] * B[c] + A[4 * r + 1] * B[4 + c] + A[4 * r + 2] * B[8 + c] + (c == 3 ? A[4 * r + 3] : 0.0);
+        };
+        double loc[12];
+        mul(O, M, loc);
+        int parent = -1;
+        if (J.parent_sel == 0) parent = i - 1;
+        else if (J.parent_sel == 1) { for (int k = i - 1; k >= 0; --k) if (R.joints[k].save) { parent = k; break; } }
+        if (parent >= 0) mul(out[parent], loc, out[i]);
+        else memcpy(out[i], loc, sizeof loc);
+    }
+}
+
+extern "C" int jg_check_poses(jg_engine* e, const float* poses, int64_t n, int fmt, int ee_link, const int32_t* links,
+                              int n_links, uint32_t flags, uint32_t* bits, float* min_dist, void* stream) {
+    if (!e) return fail(JG_ERR_INVALID, "jg_check_poses: engine is NULL");
+    if (fmt != JG_POSE_MAT34 && fmt != JG_POSE_POS_QUAT_XYZW) return fail(JG_ERR_INVALID, "jg_check_poses: unknown pose format %d", fmt);
+    if (ee_link < 0 || ee_link >= e->L || !links || n_links <= 0) return fail(JG_ERR_INVALID, "jg_check_poses: bad link arguments");
+    if (n < 0 || (n && (!poses || !bits))) return fail(JG_ERR_INVALID, "jg_check_poses: NULL poses/bits");
+    flags &= (JG_SCENE | JG_PLANE | JG_NO_EPA);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = begin_call(e, st);
+    if (rc) return rc;
+    e->stats.configs = n;
+    // rigid offsets rel_s = inv(T_ee) * T_link(s)
+    double fk[MAX_LINKS][12];
+    host_fk(e->h_robot, e->prm.finger_open, fk);
+    std::vector<Tf> rel;
+    std::vector<int> use;
+    for (int k = 0; k < n_links; ++k) {
+        if (links[k] < 0 || links[k] >= e->L) return fail(JG_ERR_INVALID, "jg_check_poses: link id %d out of range", links[k]);
+        for (int s = 0; s < e->S; ++s) {
+            if (e->shape_link[s] != links[k]) continue;
+            const double* A = fk[ee_link];
+            const double* B = fk[links[k]];
+            double C[12];
+            for (int r = 0; r < 3; ++r) {
+                for (int c = 0; c < 3; ++c) C[4 * r + c] = A[r] * B[c] + A[4 + r] * B[4 + c] + A[8 + r] * B[8 + c];
+                C[4 * r + 3] = A[r] * (B[3] - A[3]) + A[4 + r] * (B[7] - A[7]) + A[8 + r] * (B[11] - A[11]);
+            }
+            Tf T;
+            T.r00 = (float)C[0]; T.r01 = (float)C[1]; T.r02 = (float)C[2]; T.tx = (float)C[3];
+            T.r10 = (float)C[4]; T.r11 = (float)C[5]; T.r12 = (float)C[6]; T.ty = (float)C[7];
+            T.r20 = (float)C[8]; T.r21 = (float)C[9]; T.r22 = (float)C[10]; T.tz = (float)C[11];
+            rel.push_back(T);
+            use.push_back(s);
+        }
+    }
+    if (use.empty() || (int)use.size() > MAX_SHAPES) return fail(JG_ERR_INVALID, "jg_check_poses: the listed links carry no collision shapes");
+    CUDA_TRY(cudaMemcpyAsync(e->d_rel, rel.data(), sizeof(Tf) * rel.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(e->d_use_shapes, use.data(), sizeof(int) * use.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));   // rel/use are stack-lifetime host vectors
+    const int stride = fmt == JG_POSE_MAT34 ? 12 : 7;
+    for (int64_t off = 0; off < n; off += e->cap) {
+        const int m = (int)std::min<int64_t>(e->cap, n - off);
+        PassArgs a;
+        fill_args(e, a, flags);
+        a.n = m;
+        CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * (2 * e->n_keys + 8), st));
+        const size_t smem = sizeof(RobotTab) + sizeof(PieceRec) * e->P;
+        k_broadphase_poses<BP_BLOCK><<<(m + BP_BLOCK - 1) / BP_BLOCK, BP_BLOCK, smem, st>>>(a, poses + off * stride, fmt, e->d_rel,
+                                                                                         e->d_use_shapes, (int)use.size());
+        e->stats.kernel_launches += 1;
+        rc = run_narrow_and_finalize(e, a, m, flags, bits + off / 32, min_dist ? min_dist + off : nullptr, nullptr, st);
+        if (rc) return rc;
+    }
+    return JG_OK;
+}
+
+extern "C" int jg_fk(jg_engine* e, const float* q, int64_t n, int dof, const int32_t* link_ids, int n_link_ids,
+                     const double* base_pose, float* out, void* stream) {
+    if (!e) return fail(JG_ERR_INVALID, "jg_fk: engine is NULL");
+    if (dof != e->dof) return fail(JG_ERR_INVALID, "jg_fk: dof %d does not match the robot's %d", dof, e->dof);
+    if (n < 0 || n > 2000000000LL || (n && (!q || !out)) || !link_ids || n_link_ids <= 0 || n_link_ids > MAX_LINKS)
+        return fail(JG_ERR_INVALID, "jg_fk: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(e->device));
+    int slot[MAX_LINKS];
+    for (int i = 0; i < MAX_LINKS; ++i) slot[i] = -1;
+    for (int k = 0; k < n_link_ids; ++k) {
+        if (link_ids[k] < 0 || link_ids[k] >= e->L) return fail(JG_ERR_INVALID, "jg_fk: link id %d out of range", link_ids[k]);
+        if (slot[link_ids[k]] >= 0) return fail(JG_ERR_INVALID, "jg_fk: link id %d listed twice", link_ids[k]);
+        slot[link_ids[k]] = k;
+    }
+    CUDA_TRY(cudaMemcpyAsync(e->d_link_slot, slot, sizeof slot, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    Tf B = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+    if (base_pose) {
+        B.r00 = (float)base_pose[0]; B.r01 = (float)base_pose[1]; B.r02 = (float)base_pose[2]; B.tx = (float)base_pose[3];
+        B.r10 = (float)base_pose[4]; B.r11 = (float)base_pose[5]; B.r12 = (float)base_pose[6]; B.ty = (float)base_pose[7];
+        B.r20 = (float)base_pose[8]; B.r21 = (float)base_pose[9]; B.r22 = (float)base_pose[10]; B.tz = (float)base_pose[11];
+    }
+    if (n == 0) return JG_OK;
+    const size_t smem = sizeof(RobotTab) + sizeof(float) * BP_BLOCK * e->dof;
+    k_fk<BP_BLOCK><<<(int)((n + BP_BLOCK - 1) / BP_BLOCK), BP_BLOCK, smem, st>>>(e->d_robot, q, (int)n, dof, e->prm.finger_open,
+                                                                              e->d_link_slot, n_link_ids, B, out);
+    CUDA_TRY(cudaGetLastError());
+    return JG_OK;
+}
+
+// ----------------------------------------------------------------------------------------------- host path
+static int ensure_staging(jg_engine* e) {
+    if (e->staging_ready) return JG_OK;
+    CUDA_TRY(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&e->s_run, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CUDA_TRY(cudaMalloc(&e->stage_q[i], sizeof(float) * e->cap * e->dof));
+        CUDA_TRY(cudaMalloc(&e->stage_bits[i], sizeof(uint32_t) * (e->cap / 32)));
+        CUDA_TRY(cudaMalloc(&e->stage_dist[i], sizeof(float) * e->cap));
+        CUDA_TRY(cudaMalloc(&e->stage_reason[i], e->cap));
+        CUDA_TRY(cudaMallocHost(&e->pin_q[i], sizeof(float) * e->cap * e->dof));
+        CUDA_TRY(cudaMallocHost(&e->pin_bits[i], sizeof(uint32_t) * (e->cap / 32)));
+        CUDA_TRY(cudaMallocHost(&e->pin_dist[i], sizeof(float) * e->cap));
+        CUDA_TRY(cudaMallocHost(&e->pin_reason[i], e->cap));
+        CUDA_TRY(cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&e->ev_run[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&e->ev_out[i], cudaEventDisableTiming));
+    }
+    e->staging_ready = true;
+    return JG_OK;
+}
+
+static bool is_pinned(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+extern "C" int jg_check_host(jg_engine* e, const float* q, int64_t n, int dof, uint32_t flags, uint32_t* bits, float* dist,
+                             uint8_t* reason) {
+    if (!e) return fail(JG_ERR_INVALID, "jg_check_host: engine is NULL");
+    if (dof != e->dof) return fail(JG_ERR_INVALID, "jg_check_host: dof %d does not match the robot's %d", dof, e->dof);
+    if (n < 0 || (n && (!q || !bits))) return fail(JG_ERR_INVALID, "jg_check_host: NULL q/bits");
+    CUDA_TRY(cudaSetDevice(e->device));
+    int rc = ensure_staging(e);
+    if (rc) return rc;
+    const bool pq = is_pinned(q), pb = is_pinned(bits), pd = dist && is_pinned(dist), pr = reason && is_pinned(reason);
+    jg_stats total{};
+    const int64_t n_pass = (n + e->cap - 1) / e->cap;
+    // software pipeline over passes: copy-in(i+1) || run(i) || copy-out(i-1); buffers alternate
+    for (int64_t i = 0; i < n_pass; ++i) {
+        const int b = (int)(i & 1);
+        const int64_t off = i * e->cap;
+        const int m = (int)std::min<int64_t>(e->cap, n - off);
+        // buffer b was last used by pass i-2: its copy-out must be finished before we overwrite staging
+        if (i >= 2) CUDA_TRY(cudaEventSynchronize(e->ev_out[b]));
+        if (i >= 2) {   // drain pass i-2 results from pinned staging into pageable user memory
+            const int64_t o2 = (i - 2) * e->cap;
+            const int m2 = e->cap;
+            if (!pb) memcpy(bits + o2 / 32, e->pin_bits[b], sizeof(uint32_t) * ((m2 + 31) / 32));
+            if (dist && !pd) memcpy(dist + o2, e->pin_dist[b], sizeof(float) * m2);
+            if (reason && !pr) memcpy(reason + o2, e->pin_reason[b], m2);
+        }
+        const float* src = q + off * dof;
+        if (!pq) { memcpy(e->pin_q[b], src, sizeof(float) * m * dof); src = e->pin_q[b]; }
+        CUDA_TRY(cudaMemcpyAsync(e->stage_q[b], src, sizeof(float) * m * dof, cudaMemcpyHostToDevice, e->s_in));
+        CUDA_TRY(cudaEventRecord(e->ev_in[b], e->s_in));
+        CUDA_TRY(cudaStreamWaitEvent(e->s_run, e->ev_in[b], 0));
+        rc = jg_check(e, e->stage_q[b], m, dof, flags, e->stage_bits[b], dist ? e->stage_dist[b] : nullptr,
+                      reason ? e->stage_reason[b] : nullptr, e->s_run);
+        if (rc) return rc;
+        total.kernel_launches += e->stats.kernel_launches;
+        CUDA_TRY(cudaEventRecord(e->ev_run[b], e->s_run));
+        CUDA_TRY(cudaStreamWaitEvent(e->s_out, e->ev_run[b], 0));
+        CUDA_TRY(cudaMemcpyAsync(pb ? bits + off / 32 : e->pin_bits[b], e->stage_bits[b], sizeof(uint32_t) * ((m + 31) / 32),
+                                 cudaMemcpyDeviceToHost, e->s_out));
+        if (dist) CUDA_TRY(cudaMemcpyAsync(pd ? dist + off : e->pin_dist[b], e->stage_dist[b], sizeof(float) * m, cudaMemcpyDeviceToHost, e->s_out));
+        if (reason) CUDA_TRY(cudaMemcpyAsync(pr ? reason + off : e->pin_reason[b], e->stage_reason[b], m, cudaMemcpyDeviceToHost, e->s_out));
+        CUDA_TRY(cudaEventRecord(e->ev_out[b], e->s_out));
+        // the next pass's jg_check resets d_stats on s_run; the staging input of pass i must not be overwritten
+        // before its H2D finished: guaranteed by the ev_out wait above (copy-out follows run follows copy-in).
+    }
+    CUDA_TRY(cudaStreamSynchronize(e->s_out));
+    for (int64_t i = std::max<int64_t>(0, n_pass - 2); i < n_pass; ++i) {
+        const int b = (int)(i & 1);
+        const int64_t off = i * e->cap;
+        const int m = (int)std::min<int64_t>(e->cap, n - off);
+        if (!pb) memcpy(bits + off / 32, e->pin_bits[b], sizeof(uint32_t) * ((m + 31) / 32));
+        if (dist && !pd) memcpy(dist + off, e->pin_dist[b], sizeof(float) * m);
+        if (reason && !pr) memcpy(reason + off, e->pin_reason[b], m);
+    }
+    e->stats.configs = n;
+    e->stats.kernel_launches = total.kernel_launches;
+    e->last_stream = e->s_run;
+    return JG_OK;
+}
+
+extern "C" int jg_get_stats(jg_engine* e, jg_stats* out) {
+    if (!e || !out) return fail(JG_ERR_INVALID, "jg_get_stats: NULL argument");
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaStreamSynchronize(e->last_stream));
+    unsigned long long h[8];
+    CUDA_TRY(cudaMemcpy(h, e->d_stats, sizeof h, cudaMemcpyDeviceToHost));
+    *out = e->stats;
+    out->pairs = (int64_t)h[0];
+    out->plane_pairs = (int64_t)h[1];
+    out->self_pairs = (int64_t)h[2];
+    out->epa_pairs = (int64_t)h[3];
+    return JG_OK;
+}

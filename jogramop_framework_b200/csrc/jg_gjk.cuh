@@ -1,0 +1,195 @@
+// jg_gjk.cuh -- per-thread GJK distance between two convex vertex sets held in shared memory.
+//
+// Layout contract: every lane of a warp works on the SAME (A, B) vertex ranges (pairs are bucketed by
+// (link shape, obstacle piece) before this runs), so every shared-memory read in the support scans is a
+// warp-wide broadcast: one LDS.128 feeds 32 lanes x 3 FMA.  Only the direction, the rigid transform of A
+// and the simplex differ per lane and live in registers.
+//
+// Semantics follow Bullet's btGjkPairDetector as restated in oracle/oracle.c (gjk()): distance between
+// the *core* shapes; early exit once a separating axis proves the distance exceeds dmax; overlap (origin
+// inside the simplex / closer than 1e-7 m) is reported as JG_GJK_PENETRATING.
+#pragma once
+#include <float.h>
+
+#include "jg_math.cuh"
+
+namespace jg {
+
+enum { JG_GJK_SEPARATED = 0, JG_GJK_FAR = 1, JG_GJK_PENETRATING = 2 };
+
+#ifndef JG_GJK_MAX_ITER
+#define JG_GJK_MAX_ITER 24
+#endif
+// stop when the duality gap |v| - v.w/|v| is below this many metres (fp32 noise floor is ~2e-7)
+#ifndef JG_GJK_TOL
+#define JG_GJK_TOL 1e-6f
+#endif
+
+// argmax_i dot(verts[i], d) over a shared-memory vertex range (warp-uniform range, per-lane direction)
+__device__ __forceinline__ int support_scan(const float4* __restrict__ verts, int n, V3 d) {
+    float best = -FLT_MAX;
+    int bi = 0;
+#pragma unroll 4
+    for (int i = 0; i < n; ++i) {
+        const float4 p = verts[i];
+        const float s = fmaf(p.x, d.x, fmaf(p.y, d.y, p.z * d.z));
+        if (s > best) {
+            best = s;
+            bi = i;
+        }
+    }
+    return bi;
+}
+
+// closest point of triangle (a,b,c) to the origin; mask bit0/1/2 = a/b/c belongs to the supporting feature
+__device__ __forceinline__ V3 tri_closest(V3 a, V3 b, V3 c, int& mask) {
+    const V3 ab = b - a, ac = c - a;
+    const float d1 = -dot(ab, a), d2 = -dot(ac, a);
+    if (d1 <= 0.f && d2 <= 0.f) { mask = 1; return a; }
+    const float d3 = -dot(ab, b), d4 = -dot(ac, b);
+    if (d3 >= 0.f && d4 <= d3) { mask = 2; return b; }
+    const float vc = d1 * d4 - d3 * d2;
+    if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) { mask = 3; return a + ab * (d1 / (d1 - d3)); }
+    const float d5 = -dot(ab, c), d6 = -dot(ac, c);
+    if (d6 >= 0.f && d5 <= d6) { mask = 4; return c; }
+    const float vb = d5 * d2 - d1 * d6;
+    if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) { mask = 5; return a + ac * (d2 / (d2 - d6)); }
+    const float va = d3 * d6 - d5 * d4;
+    if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) {
+        mask = 6;
+        return b + (c - b) * ((d4 - d3) / ((d4 - d3) + (d5 - d6)));
+    }
+    const V3 n = cross(ab, ac);
+    const float nn = norm2(n);
+    if (!(nn > 0.f)) { mask = 3; return a + ab * (d1 / (d1 - d3)); }
+    mask = 7;
+    return n * (dot(n, a) / nn);  // project the origin onto the plane: stable when the origin is close to it
+}
+
+struct Simplex {
+    V3 a, b, c, d;         // a = newest vertex
+    uint32_t ia, ib, ic, id;  // (index in A) << 16 | index in B
+    int n;
+};
+
+// keep the vertices of (p0,p1,p2) selected by mask, in order
+__device__ __forceinline__ void simplex_set3(Simplex& S, V3 p0, V3 p1, V3 p2, uint32_t i0, uint32_t i1, uint32_t i2,
+                                             int mask) {
+    int n = 0;
+    if (mask & 1) { S.a = p0; S.ia = i0; n = 1; }
+    if (mask & 2) {
+        if (n == 0) { S.a = p1; S.ia = i1; } else { S.b = p1; S.ib = i1; }
+        ++n;
+    }
+    if (mask & 4) {
+        if (n == 0) { S.a = p2; S.ia = i2; } else if (n == 1) { S.b = p2; S.ib = i2; } else { S.c = p2; S.ic = i2; }
+        ++n;
+    }
+    S.n = n;
+}
+
+// Distance between conv(A) placed by T and conv(B) (B frame).  v0: initial separating direction guess.
+// Returns JG_GJK_*; dist is valid for JG_GJK_SEPARATED.
+__device__ __forceinline__ int gjk_distance(const float4* __restrict__ A, int nA, const float4* __restrict__ B, int nB,
+                                            const Tf& T, V3 v0, float dmax, float& dist, int& iters) {
+    Simplex S;
+    S.n = 0;
+    S.a = S.b = S.c = S.d = mk(0.f, 0.f, 0.f);
+    S.ia = S.ib = S.ic = S.id = 0xFFFFFFFFu;
+    V3 v = v0;
+    if (!(norm2(v) > 1e-12f)) v = mk(1.f, 0.f, 0.f);
+    float vv = FLT_MAX;
+    int status = JG_GJK_SEPARATED;
+    int it = 0;
+    for (; it < JG_GJK_MAX_ITER; ++it) {
+        // support point of A - B in direction -v
+        const V3 dl = tf_rot_t(T, -v);
+        const int ia = support_scan(A, nA, dl);
+        const int ib = support_scan(B, nB, v);
+        const float4 pa = A[ia];
+        const float4 pb = B[ib];
+        const V3 w = tf_apply(T, mk(pa.x, pa.y, pa.z)) - mk(pb.x, pb.y, pb.z);
+        const uint32_t id = ((uint32_t)ia << 16) | (uint32_t)ib;
+        const float vw = dot(v, w);
+        const float v2 = norm2(v);
+        if (vw > 0.f && vw * vw > dmax * dmax * v2) { status = JG_GJK_FAR; break; }
+        if (S.n > 0) {
+            const bool dupl = (id == S.ia) || (S.n > 1 && id == S.ib) || (S.n > 2 && id == S.ic);
+            if (dupl || vv - vw <= JG_GJK_TOL * sqrtf(vv)) break;
+        }
+        // push w as the newest vertex
+        S.d = S.c; S.id = S.ic;
+        S.c = S.b; S.ic = S.ib;
+        S.b = S.a; S.ib = S.ia;
+        S.a = w;   S.ia = id;
+        S.n += 1;
+        V3 nv;
+        if (S.n == 1) {
+            nv = w;
+        } else if (S.n == 2) {
+            const V3 ab = S.b - S.a;
+            const float t = -dot(S.a, ab), den = norm2(ab);
+            if (t <= 0.f || !(den > 0.f)) { nv = S.a; S.n = 1; }
+            else if (t >= den) { nv = S.b; S.a = S.b; S.ia = S.ib; S.n = 1; }
+            else nv = S.a + ab * (t / den);
+        } else if (S.n == 3) {
+            int mask;
+            nv = tri_closest(S.a, S.b, S.c, mask);
+            if (mask != 7) simplex_set3(S, S.a, S.b, S.c, S.ia, S.ib, S.ic, mask);
+        } else {
+            // tetrahedron (a,b,c,d): the closest feature always contains the newest vertex a, so only the
+            // three faces through a are candidates; the origin is inside iff it is inside all three.
+            const V3 A0 = S.a, B0 = S.b, C0 = S.c, D0 = S.d;
+            const uint32_t ja = S.ia, jb = S.ib, jc = S.ic, jd = S.id;
+            float best = FLT_MAX;
+            bool any_out = false;
+            nv = mk(0.f, 0.f, 0.f);
+#pragma unroll
+            for (int f = 0; f < 3; ++f) {
+                const V3 x = f == 0 ? B0 : (f == 1 ? C0 : D0);
+                const V3 y = f == 0 ? C0 : (f == 1 ? D0 : B0);
+                const V3 z = f == 0 ? D0 : (f == 1 ? B0 : C0);
+                const uint32_t jx = f == 0 ? jb : (f == 1 ? jc : jd);
+                const uint32_t jy = f == 0 ? jc : (f == 1 ? jd : jb);
+                const V3 nrm = cross(x - A0, y - A0);
+                const float sp = -dot(A0, nrm);
+                const float sd = dot(z - A0, nrm);
+                const bool outside = !(sp * sd > 0.f);
+                if (outside) {
+                    any_out = true;
+                    int mask;
+                    const V3 cand = tri_closest(A0, x, y, mask);
+                    const float c2 = norm2(cand);
+                    if (c2 < best) {
+                        best = c2;
+                        nv = cand;
+                        simplex_set3(S, A0, x, y, ja, jx, jy, mask);
+                    }
+                }
+            }
+            if (!any_out) { status = JG_GJK_PENETRATING; vv = 0.f; break; }
+        }
+        const float nvv = norm2(nv);
+        if (!(nvv > 1e-14f)) { status = JG_GJK_PENETRATING; vv = 0.f; break; }  // touching: treat as overlap
+        if (nvv >= vv) break;                                                   // numerical stall
+        v = nv;
+        vv = nvv;
+    }
+    iters = it + 1;
+    dist = sqrtf(vv);
+    return status;
+}
+
+// lowest signed distance of the vertices of A (placed by T) to the plane n.p + d = 0
+__device__ __forceinline__ float plane_distance(const float4* __restrict__ A, int nA, const Tf& T, V3 n, float d) {
+    const V3 nl = tf_rot_t(T, n);
+    float best = FLT_MAX;
+#pragma unroll 4
+    for (int i = 0; i < nA; ++i) {
+        const float4 p = A[i];
+        best = fminf(best, fmaf(p.x, nl.x, fmaf(p.y, nl.y, p.z * nl.z)));
+    }
+    return best + fmaf(n.x, T.tx, fmaf(n.y, T.ty, n.z * T.tz)) + d;
+}
+
+}  // namespace jg

@@ -1,0 +1,482 @@
+// jg_kernels.cuh -- device tables and the three kernels of one collision-check pass.
+//
+//   k_broadphase  one thread per configuration: forward kinematics down the URDF chain (link transform in
+//                 registers), world AABB of every link shape vs obstacle-piece AABBs / plane / self pairs;
+//                 survivors are appended to per-(shape,piece) queues in HBM with warp-aggregated atomics.
+//   k_narrowphase persistent warps pull 32-entry tiles of ONE queue: every lane of the warp therefore runs GJK
+//                 on the same two vertex sets (shared-memory broadcast reads), each on its own configuration.
+//                 Result: atomicMin of the contact distance into the configuration's slot.
+//   k_finalize    per configuration: clamp at the query distance, threshold, ballot-pack the verdict bits.
+//
+// HBM layout of a pass over C configurations and K keys (key = shape*(P+1)+piece, plane = piece P, then the
+// self-collision pairs):   q_r0/q_r1/q_r2 float4[K*C] (rows of R with t in .w), q_cfg int[K*C], counts int[K].
+#pragma once
+#include "jg_gjk.cuh"
+
+namespace jg {
+
+constexpr int MAX_LINKS = 24;
+constexpr int MAX_SHAPES = 24;
+constexpr int MAX_DOF = 16;
+
+struct JointRec {
+    float o[12];      // joint origin (parent link frame -> joint frame), row-major 3x4
+    float axis[3];
+    int type;         // JG_JOINT_*
+    int qidx;         // >=0 slot of q, -1 fixed, -2 finger
+    int parent_sel;   // 0 previous link, 1 saved link, 2 base
+    int save;         // keep this link's transform for later children
+    int shape_first, shape_count;
+    int pad[3];
+};
+
+struct ShapeRec {
+    float c[3], h[3];  // local AABB of the core vertices
+    float margin, plane_margin;
+    int voff, vn;      // core vertices
+    int poff, pn;      // plane / EPA vertices
+    int link;
+    int pad[3];
+};
+
+struct RobotTab {
+    int L, S, dof, base_shape_first, base_shape_count, n_self, pad0, pad1;
+    float qlo[MAX_DOF], qhi[MAX_DOF];
+    JointRec joints[MAX_LINKS];
+    ShapeRec shapes[MAX_SHAPES];
+};
+
+struct PieceRec {
+    float c[3], h[3];  // AABB centre / half extents (robot frame); vertices are stored relative to c
+    float margin;
+    int voff, vn;
+    int pad[3];
+};
+
+struct SelfRec {
+    int sa, sb;        // shape ids (sa = shape of the first link: the static "B" side of the GJK)
+    int la, lb;        // link ids
+};
+
+enum { KEY_HULL = 0, KEY_PLANE = 1, KEY_SELF = 2 };
+struct KeyRec {
+    int a_off, a_n;    // moving vertex set (robot shape)
+    int b_off, b_n;    // static vertex set (piece / first link shape)
+    float msum;        // margins subtracted from the core distance
+    int kind;
+};
+
+struct PassArgs {
+    // inputs
+    const float* q;    // [n,dof] (or qa for edges)
+    const float* qb;   // edges: end configurations, else NULL
+    int n;             // configurations in this pass (substep-expanded for edges)
+    int dof;
+    int substeps;      // 1, or substeps per edge
+    uint32_t flags;
+    float finger_open, qd, threshold;
+    float plane[4];
+    int has_plane;
+    // tables
+    const RobotTab* robot;
+    const PieceRec* pieces;
+    int P;
+    const SelfRec* selfs;
+    const KeyRec* keys;
+    int n_keys, n_scene_keys;
+    const float4* verts;
+    int n_verts;
+    // queues
+    float4 *q_r0, *q_r1, *q_r2;
+    int* q_cfg;
+    int cap;           // queue capacity per key (= max configs per pass)
+    int* counts;       // [n_keys] + [n_keys]: tile counter, then stats
+    // per-configuration scratch
+    int* enc_scene;    // encoded min contact distance vs scene+plane
+    int* enc_self;
+    uint32_t* viol;    // limit violation bits
+};
+
+__device__ __forceinline__ Tf joint_local(const JointRec& J, float val) {
+    Tf O;
+    O.r00 = J.o[0]; O.r01 = J.o[1]; O.r02 = J.o[2];  O.tx = J.o[3];
+    O.r10 = J.o[4]; O.r11 = J.o[5]; O.r12 = J.o[6];  O.ty = J.o[7];
+    O.r20 = J.o[8]; O.r21 = J.o[9]; O.r22 = J.o[10]; O.tz = J.o[11];
+    if (J.type == 1) {  // revolute: Rodrigues about the unit axis
+        float s, c;
+        sincosf(val, &s, &c);
+        const float x = J.axis[0], y = J.axis[1], z = J.axis[2], t = 1.f - c;
+        Tf M;
+        M.r00 = fmaf(t * x, x, c);      M.r01 = fmaf(t * x, y, -s * z); M.r02 = fmaf(t * x, z, s * y);
+        M.r10 = fmaf(t * x, y, s * z);  M.r11 = fmaf(t * y, y, c);      M.r12 = fmaf(t * y, z, -s * x);
+        M.r20 = fmaf(t * x, z, -s * y); M.r21 = fmaf(t * y, z, s * x);  M.r22 = fmaf(t * z, z, c);
+        M.tx = M.ty = M.tz = 0.f;
+        return tf_mul(O, M);
+    }
+    if (J.type == 2) {  // prismatic
+        const float ax = J.axis[0] * val, ay = J.axis[1] * val, az = J.axis[2] * val;
+        O.tx = fmaf(O.r00, ax, fmaf(O.r01, ay, fmaf(O.r02, az, O.tx)));
+        O.ty = fmaf(O.r10, ax, fmaf(O.r11, ay, fmaf(O.r12, az, O.ty)));
+        O.tz = fmaf(O.r20, ax, fmaf(O.r21, ay, fmaf(O.r22, az, O.tz)));
+    }
+    return O;
+}
+
+// warp-aggregated append of the lanes with `survive` to queue `key`
+__device__ __forceinline__ void queue_push(const PassArgs& a, bool survive, int key, const Tf& T, int cfg) {
+    const unsigned mask = __ballot_sync(0xFFFFFFFFu, survive);
+    if (mask == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(a.counts + key, __popc(mask));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    if (survive) {
+        const size_t slot = (size_t)key * a.cap + base + __popc(mask & ((1u << lane) - 1u));
+        a.q_r0[slot] = make_float4(T.r00, T.r01, T.r02, T.tx);
+        a.q_r1[slot] = make_float4(T.r10, T.r11, T.r12, T.ty);
+        a.q_r2[slot] = make_float4(T.r20, T.r21, T.r22, T.tz);
+        a.q_cfg[slot] = cfg;
+    }
+}
+
+// AABB of the shape (local centre c / half h) under T against a box (centre bc, half bh already inflated)
+__device__ __forceinline__ bool aabb_overlap(const Tf& T, const float* c, const float* h, const float* bc,
+                                             const float* bh, float infl) {
+    const float cx = fmaf(T.r00, c[0], fmaf(T.r01, c[1], fmaf(T.r02, c[2], T.tx)));
+    const float cy = fmaf(T.r10, c[0], fmaf(T.r11, c[1], fmaf(T.r12, c[2], T.ty)));
+    const float cz = fmaf(T.r20, c[0], fmaf(T.r21, c[1], fmaf(T.r22, c[2], T.tz)));
+    const float hx = fmaf(fabsf(T.r00), h[0], fmaf(fabsf(T.r01), h[1], fabsf(T.r02) * h[2]));
+    const float hy = fmaf(fabsf(T.r10), h[0], fmaf(fabsf(T.r11), h[1], fabsf(T.r12) * h[2]));
+    const float hz = fmaf(fabsf(T.r20), h[0], fmaf(fabsf(T.r21), h[1], fabsf(T.r22) * h[2]));
+    return fabsf(cx - bc[0]) <= hx + bh[0] + infl && fabsf(cy - bc[1]) <= hy + bh[1] + infl &&
+           fabsf(cz - bc[2]) <= hz + bh[2] + infl;
+}
+
+// scene + plane candidates of one shape placed by T (uniform control flow across the warp)
+__device__ __forceinline__ void shape_vs_scene(const PassArgs& a, const ShapeRec& Sh, int s, const PieceRec* pieces,
+                                               const Tf& T, bool valid, int out_idx) {
+    if (a.flags & 1u) {
+        for (int p = 0; p < a.P; ++p) {
+            const PieceRec& Pc = pieces[p];
+            const bool hit = valid && aabb_overlap(T, Sh.c, Sh.h, Pc.c, Pc.h, a.qd + Sh.margin + Pc.margin);
+            Tf Tc = T;   // vertices of the piece are stored relative to its AABB centre
+            Tc.tx -= Pc.c[0]; Tc.ty -= Pc.c[1]; Tc.tz -= Pc.c[2];
+            queue_push(a, hit, s * (a.P + 1) + p, Tc, out_idx);
+        }
+    }
+    if ((a.flags & 2u) && a.has_plane) {
+        // conservative: lowest point of the shape's bounding box above the plane
+        const float cx = fmaf(T.r00, Sh.c[0], fmaf(T.r01, Sh.c[1], fmaf(T.r02, Sh.c[2], T.tx)));
+        const float cy = fmaf(T.r10, Sh.c[0], fmaf(T.r11, Sh.c[1], fmaf(T.r12, Sh.c[2], T.ty)));
+        const float cz = fmaf(T.r20, Sh.c[0], fmaf(T.r21, Sh.c[1], fmaf(T.r22, Sh.c[2], T.tz)));
+        const V3 nl = tf_rot_t(T, mk(a.plane[0], a.plane[1], a.plane[2]));
+        const float ext = fmaf(fabsf(nl.x), Sh.h[0], fmaf(fabsf(nl.y), Sh.h[1], fabsf(nl.z) * Sh.h[2]));
+        const float low = fmaf(a.plane[0], cx, fmaf(a.plane[1], cy, fmaf(a.plane[2], cz, a.plane[3]))) - ext;
+        // the plane vertices may exceed the core AABB by the embedded box margin: 2 mm slack
+        const bool hit = valid && (low - 0.002f - Sh.plane_margin <= a.qd);
+        queue_push(a, hit, s * (a.P + 1) + a.P, T, out_idx);
+    }
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_broadphase(const PassArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RobotTab* R = reinterpret_cast<RobotTab*>(smem_raw);
+    PieceRec* pieces = reinterpret_cast<PieceRec*>(smem_raw + sizeof(RobotTab));
+    float* qs = reinterpret_cast<float*>(smem_raw + sizeof(RobotTab) + sizeof(PieceRec) * a.P);
+    float* stash = qs + BLOCK * a.dof;   // [L][12][BLOCK], only with JG_SELF
+    const int tid = threadIdx.x;
+    {
+        const int* src = reinterpret_cast<const int*>(a.robot);
+        int* dst = reinterpret_cast<int*>(R);
+        for (int i = tid; i < (int)(sizeof(RobotTab) / 4); i += BLOCK) dst[i] = src[i];
+        const int* ps = reinterpret_cast<const int*>(a.pieces);
+        int* pd = reinterpret_cast<int*>(pieces);
+        for (int i = tid; i < (int)(sizeof(PieceRec) / 4) * a.P; i += BLOCK) pd[i] = ps[i];
+    }
+    const int cfg0 = blockIdx.x * BLOCK;
+    const int cfg = cfg0 + tid;
+    const bool valid = cfg < a.n;
+    const int dof = a.dof;
+    if (a.substeps <= 1) {   // coalesced load of the block's [BLOCK,dof] tile, transposed into shared memory
+        const int total = min(BLOCK, a.n - cfg0) * dof;
+        const float* src = a.q + (size_t)cfg0 * dof;
+        for (int i = tid; i < total; i += BLOCK) {
+            const int c = i / dof, j = i - c * dof;
+            qs[j * BLOCK + c] = src[i];
+        }
+    } else if (valid) {      // edge substep: q = qa + k/(substeps-1) (qb - qa)
+        const int e = cfg / a.substeps, k = cfg - e * a.substeps;
+        const float t = (float)k / (float)(a.substeps - 1);
+        for (int j = 0; j < dof; ++j) {
+            const float qa = a.q[(size_t)e * dof + j], qb = a.qb[(size_t)e * dof + j];
+            qs[j * BLOCK + tid] = fmaf(t, qb - qa, qa);
+        }
+    }
+    __syncthreads();
+    const int out_idx = a.substeps <= 1 ? cfg : cfg / a.substeps;
+
+    if (valid) {
+        if (a.substeps <= 1) {
+            a.enc_scene[out_idx] = JG_ENC_INF;
+            a.enc_self[out_idx] = JG_ENC_INF;
+        }
+        if (a.flags & 8u) {
+            bool bad = false;
+            for (int j = 0; j < dof; ++j) {
+                const float v = qs[j * BLOCK + tid];
+                bad |= !(R->qlo[j] <= v && v <= R->qhi[j]);
+            }
+            if (bad) atomicOr(a.viol + (out_idx >> 5), 1u << (out_idx & 31));
+        }
+    }
+    const bool want_self = (a.flags & 4u) != 0;
+    const bool want_scene = (a.flags & 3u) != 0;
+
+    // base-link shapes (link -1)
+    Tf cur = tf_identity(), saved = tf_identity();
+    if (want_scene)
+        for (int s = R->base_shape_first; s < R->base_shape_first + R->base_shape_count; ++s)
+            shape_vs_scene(a, R->shapes[s], s, pieces, cur, valid, out_idx);
+
+    for (int i = 0; i < R->L; ++i) {
+        const JointRec& J = R->joints[i];
+        float val = 0.f;
+        if (J.qidx >= 0) val = qs[J.qidx * BLOCK + tid];
+        else if (J.qidx == -2) val = a.finger_open;
+        const Tf loc = joint_local(J, val);
+        if (J.parent_sel == 1) cur = tf_mul(saved, loc);
+        else if (J.parent_sel == 2) cur = loc;
+        else cur = tf_mul(cur, loc);
+        if (J.save) saved = cur;
+        if (want_self) {
+            float* st = stash + (size_t)i * 12 * BLOCK + tid;
+            st[0 * BLOCK] = cur.r00; st[1 * BLOCK] = cur.r01; st[2 * BLOCK] = cur.r02;  st[3 * BLOCK] = cur.tx;
+            st[4 * BLOCK] = cur.r10; st[5 * BLOCK] = cur.r11; st[6 * BLOCK] = cur.r12;  st[7 * BLOCK] = cur.ty;
+            st[8 * BLOCK] = cur.r20; st[9 * BLOCK] = cur.r21; st[10 * BLOCK] = cur.r22; st[11 * BLOCK] = cur.tz;
+        }
+        if (want_scene)
+            for (int s = J.shape_first; s < J.shape_first + J.shape_count; ++s)
+                shape_vs_scene(a, R->shapes[s], s, pieces, cur, valid, out_idx);
+    }
+
+    if (want_self) {
+        for (int k = 0; k < R->n_self; ++k) {
+            const SelfRec sr = a.selfs[k];
+            Tf Ta, Tb;
+            {
+                const float* st = stash + (size_t)sr.la * 12 * BLOCK + tid;
+                Ta.r00 = st[0 * BLOCK]; Ta.r01 = st[1 * BLOCK]; Ta.r02 = st[2 * BLOCK];  Ta.tx = st[3 * BLOCK];
+                Ta.r10 = st[4 * BLOCK]; Ta.r11 = st[5 * BLOCK]; Ta.r12 = st[6 * BLOCK];  Ta.ty = st[7 * BLOCK];
+                Ta.r20 = st[8 * BLOCK]; Ta.r21 = st[9 * BLOCK]; Ta.r22 = st[10 * BLOCK]; Ta.tz = st[11 * BLOCK];
+                st = stash + (size_t)sr.lb * 12 * BLOCK + tid;
+                Tb.r00 = st[0 * BLOCK]; Tb.r01 = st[1 * BLOCK]; Tb.r02 = st[2 * BLOCK];  Tb.tx = st[3 * BLOCK];
+                Tb.r10 = st[4 * BLOCK]; Tb.r11 = st[5 * BLOCK]; Tb.r12 = st[6 * BLOCK];  Tb.ty = st[7 * BLOCK];
+                Tb.r20 = st[8 * BLOCK]; Tb.r21 = st[9 * BLOCK]; Tb.r22 = st[10 * BLOCK]; Tb.tz = st[11 * BLOCK];
+            }
+            const Tf rel = tf_inv_mul(Ta, Tb);   // shape of link lb expressed in the frame of link la
+            const ShapeRec& Sa = R->shapes[sr.sa];
+            const ShapeRec& Sb = R->shapes[sr.sb];
+            const bool hit = valid && aabb_overlap(rel, Sb.c, Sb.h, Sa.c, Sa.h, a.qd + Sa.margin + Sb.margin);
+            queue_push(a, hit, a.n_scene_keys + k, rel, out_idx);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ narrow phase
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_narrowphase(const PassArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* verts = reinterpret_cast<float4*>(smem_raw);
+    KeyRec* keys = reinterpret_cast<KeyRec*>(smem_raw + sizeof(float4) * a.n_verts);
+    int* tile_prefix = reinterpret_cast<int*>(keys + a.n_keys);   // [n_keys+1]
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < a.n_verts; i += BLOCK) verts[i] = a.verts[i];
+    {
+        const int* ks = reinterpret_cast<const int*>(a.keys);
+        int* kd = reinterpret_cast<int*>(keys);
+        for (int i = tid; i < (int)(sizeof(KeyRec) / 4) * a.n_keys; i += BLOCK) kd[i] = ks[i];
+    }
+    if (tid < 32) {   // warp 0: exclusive scan of the per-key tile counts
+        int carry = 0;
+        for (int base = 0; base < a.n_keys; base += 32) {
+            const int k = base + lane;
+            int t = k < a.n_keys ? (a.counts[k] + 31) >> 5 : 0;
+            int incl = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            if (k < a.n_keys) tile_prefix[k] = carry + incl - t;
+            carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
+        }
+        if (lane == 0) tile_prefix[a.n_keys] = carry;
+    }
+    __syncthreads();
+    const int total_tiles = tile_prefix[a.n_keys];
+    int* tile_counter = a.counts + a.n_keys;
+
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(tile_counter, 1);
+        t = __shfl_sync(0xFFFFFFFFu, t, 0);
+        if (t >= total_tiles) break;
+        // key of tile t: last key with tile_prefix[key] <= t
+        int lo = 0, hi = a.n_keys - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (tile_prefix[mid] <= t) lo = mid; else hi = mid - 1;
+        }
+        const int key = lo;
+        const KeyRec K = keys[key];
+        const int off = ((t - tile_prefix[key]) << 5) + lane;
+        const bool active = off < a.counts[key];
+        const size_t slot = (size_t)key * a.cap + (active ? off : 0);
+        const float4 r0 = a.q_r0[slot], r1 = a.q_r1[slot], r2 = a.q_r2[slot];
+        const int cfg = a.q_cfg[slot];
+        Tf T;
+        T.r00 = r0.x; T.r01 = r0.y; T.r02 = r0.z; T.tx = r0.w;
+        T.r10 = r1.x; T.r11 = r1.y; T.r12 = r1.z; T.ty = r1.w;
+        T.r20 = r2.x; T.r21 = r2.y; T.r22 = r2.z; T.tz = r2.w;
+        float d = FLT_MAX;
+        if (K.kind == KEY_PLANE) {
+            d = plane_distance(verts + K.a_off, K.a_n, T, mk(a.plane[0], a.plane[1], a.plane[2]), a.plane[3]) - K.msum;
+        } else if (active) {
+            float dist;
+            int iters;
+            const int st = gjk_distance(verts + K.a_off, K.a_n, verts + K.b_off, K.b_n, T, mk(T.tx, T.ty, T.tz),
+                                        a.qd + K.msum, dist, iters);
+            if (st == JG_GJK_SEPARATED) d = dist - K.msum;
+            else if (st == JG_GJK_PENETRATING) d = -K.msum;
+        }
+        if (active && d <= a.qd) atomicMin((K.kind == KEY_SELF ? a.enc_self : a.enc_scene) + cfg, enc_float(d));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ finalize
+__global__ void k_finalize(const int* __restrict__ enc_scene, const int* __restrict__ enc_self,
+                           const uint32_t* __restrict__ viol, int n, float qd, float threshold, uint32_t flags,
+                           uint32_t* __restrict__ bits, float* __restrict__ dist, uint8_t* __restrict__ reason) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < n;
+    float ds = FLT_MAX, dself = FLT_MAX;
+    bool lim = false;
+    if (valid) {
+        ds = dec_float(enc_scene[i]);
+        dself = dec_float(enc_self[i]);
+        lim = (flags & 8u) && ((viol[i >> 5] >> (i & 31)) & 1u);
+    }
+    const bool cself = dself < threshold, cscene = ds < threshold;
+    const bool bit = valid && (lim || cself || cscene);
+    const unsigned w = __ballot_sync(0xFFFFFFFFu, bit);
+    if (valid) {
+        if ((threadIdx.x & 31) == 0) bits[i >> 5] = w;
+        if (dist) dist[i] = fminf(fminf(ds, dself), qd);
+        if (reason) reason[i] = lim ? 1 : (cself ? 2 : (cscene ? 3 : 0));
+    }
+}
+
+__global__ void k_init_scratch(int* enc_scene, int* enc_self, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        enc_scene[i] = JG_ENC_INF;
+        enc_self[i] = JG_ENC_INF;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ gripper poses
+// Free-floating gripper: one thread per pose of the end-effector link; the listed shapes ride on it rigidly.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_broadphase_poses(const PassArgs a, const float* __restrict__ poses, int fmt,
+                                                            const Tf* __restrict__ rel, const int* __restrict__ use_shapes,
+                                                            int n_use) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RobotTab* R = reinterpret_cast<RobotTab*>(smem_raw);
+    PieceRec* pieces = reinterpret_cast<PieceRec*>(smem_raw + sizeof(RobotTab));
+    const int tid = threadIdx.x;
+    {
+        const int* src = reinterpret_cast<const int*>(a.robot);
+        int* dst = reinterpret_cast<int*>(R);
+        for (int i = tid; i < (int)(sizeof(RobotTab) / 4); i += BLOCK) dst[i] = src[i];
+        const int* ps = reinterpret_cast<const int*>(a.pieces);
+        int* pd = reinterpret_cast<int*>(pieces);
+        for (int i = tid; i < (int)(sizeof(PieceRec) / 4) * a.P; i += BLOCK) pd[i] = ps[i];
+    }
+    __syncthreads();
+    const int cfg = blockIdx.x * BLOCK + tid;
+    const bool valid = cfg < a.n;
+    Tf Pz = tf_identity();
+    if (valid) {
+        a.enc_scene[cfg] = JG_ENC_INF;
+        a.enc_self[cfg] = JG_ENC_INF;
+        if (fmt == 0) {
+            const float4* p4 = reinterpret_cast<const float4*>(poses + (size_t)cfg * 12);
+            const float4 r0 = p4[0], r1 = p4[1], r2 = p4[2];
+            Pz.r00 = r0.x; Pz.r01 = r0.y; Pz.r02 = r0.z; Pz.tx = r0.w;
+            Pz.r10 = r1.x; Pz.r11 = r1.y; Pz.r12 = r1.z; Pz.ty = r1.w;
+            Pz.r20 = r2.x; Pz.r21 = r2.y; Pz.r22 = r2.z; Pz.tz = r2.w;
+        } else {
+            const float* p = poses + (size_t)cfg * 7;
+            float x = p[3], y = p[4], z = p[5], w = p[6];
+            const float inv = rsqrtf(fmaf(x, x, fmaf(y, y, fmaf(z, z, w * w))));
+            x *= inv; y *= inv; z *= inv; w *= inv;
+            Pz.r00 = 1.f - 2.f * (y * y + z * z); Pz.r01 = 2.f * (x * y - z * w);       Pz.r02 = 2.f * (x * z + y * w);
+            Pz.r10 = 2.f * (x * y + z * w);       Pz.r11 = 1.f - 2.f * (x * x + z * z); Pz.r12 = 2.f * (y * z - x * w);
+            Pz.r20 = 2.f * (x * z - y * w);       Pz.r21 = 2.f * (y * z + x * w);       Pz.r22 = 1.f - 2.f * (x * x + y * y);
+            Pz.tx = p[0]; Pz.ty = p[1]; Pz.tz = p[2];
+        }
+    }
+    for (int k = 0; k < n_use; ++k) {
+        const int s = use_shapes[k];
+        const Tf T = tf_mul(Pz, rel[k]);
+        shape_vs_scene(a, R->shapes[s], s, pieces, T, valid, cfg);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ FK only
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_fk(const RobotTab* __restrict__ robot, const float* __restrict__ q, int n,
+                                              int dof, float finger_open, const int* __restrict__ link_slot /*[L]*/,
+                                              int n_out, Tf base, float* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RobotTab* R = reinterpret_cast<RobotTab*>(smem_raw);
+    float* qs = reinterpret_cast<float*>(smem_raw + sizeof(RobotTab));
+    const int tid = threadIdx.x;
+    {
+        const int* src = reinterpret_cast<const int*>(robot);
+        int* dst = reinterpret_cast<int*>(R);
+        for (int i = tid; i < (int)(sizeof(RobotTab) / 4); i += BLOCK) dst[i] = src[i];
+    }
+    const int cfg0 = blockIdx.x * BLOCK, cfg = cfg0 + tid;
+    const int total = min(BLOCK, n - cfg0) * dof;
+    for (int i = tid; i < total; i += BLOCK) {
+        const int c = i / dof, j = i - c * dof;
+        qs[j * BLOCK + c] = q[(size_t)cfg0 * dof + i];
+    }
+    __syncthreads();
+    if (cfg >= n) return;
+    Tf cur = tf_identity(), saved = tf_identity();
+    for (int i = 0; i < R->L; ++i) {
+        const JointRec& J = R->joints[i];
+        float val = 0.f;
+        if (J.qidx >= 0) val = qs[J.qidx * BLOCK + tid];
+        else if (J.qidx == -2) val = finger_open;
+        const Tf loc = joint_local(J, val);
+        if (J.parent_sel == 1) cur = tf_mul(saved, loc);
+        else if (J.parent_sel == 2) cur = loc;
+        else cur = tf_mul(cur, loc);
+        if (J.save) saved = cur;
+        const int slot = link_slot[i];
+        if (slot >= 0) {
+            const Tf W = tf_mul(base, cur);
+            float* o = out + ((size_t)cfg * n_out + slot) * 12;
+            o[0] = W.r00; o[1] = W.r01; o[2] = W.r02;  o[3] = W.tx;
+            o[4] = W.r10; o[5] = W.r11; o[6] = W.r12;  o[7] = W.ty;
+            o[8] = W.r20; o[9] = W.r21; o[10] = W.r22; o[11] = W.tz;
+        }
+    }
+}
+
+}  // namespace jg

@@ -1,0 +1,196 @@
+"""CollisionEngine: the batched, device-resident collision query behind the drop-in classes.
+
+Thin Python over the C-ABI (include/jogramop_b200.h); torch is used only for device memory and the
+current CUDA stream.  All batched methods are pure functions of their inputs.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+SCENE, PLANE, SELF, LIMITS, NO_EPA = 1, 2, 4, 8, 16
+POSE_MAT34, POSE_POS_QUAT = 0, 1
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def joint_qidx(robot):
+    """Joint -> configuration-vector slot (arm_joint_ids order, simulation.py:159); fingers -> -2."""
+    qidx = np.full(robot.n_links, -1, np.int32)
+    for k, j in enumerate(robot.arm_joint_ids):
+        qidx[j] = k
+    for j in robot.finger_joint_ids:
+        qidx[j] = -2
+    return qidx
+
+
+def unpack_bits(words, n):
+    """Packed verdict words (bit i%32 of word i//32) -> bool tensor [n] on the same device."""
+    w = words.view(torch.int32)
+    shifts = torch.arange(32, device=w.device, dtype=torch.int32)
+    return ((w[:, None] >> shifts[None, :]) & 1).reshape(-1)[:n].to(torch.bool)
+
+
+class CollisionEngine:
+    def __init__(self, robot, scene=None, device=0, threshold=-0.001, query_distance=0.01, finger_open=0.04,
+                 chunk=0):
+        L = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.JogramopError('no CUDA device: the jogramop_framework_b200 engine has no CPU fallback')
+        self.robot, self.scene = robot, scene
+        self.dof = len(robot.arm_joint_ids)
+        self.device = torch.device('cuda', device if isinstance(device, int) else torch.device(device).index or 0)
+        self._L = L
+        lim = _f64(robot.joint_limits[robot.arm_joint_ids])
+        k = [_i32(robot.joint_type), _i32(robot.joint_parent), _f64(robot.joint_origin[:, :3, :]),
+             _f64(robot.joint_axis), joint_qidx(robot), lim, _i32(robot.shape_link), _f64(robot.shape_margin),
+             _i32(robot.shape_vert_offset), _f64(robot.core_verts), _i32(robot.shape_plane_offset),
+             _f64(robot.plane_verts), _f64(robot.shape_plane_margin), _i32(robot.self_pairs)]
+        self._r = L.jg_robot_create(robot.n_links, _p(k[0]), _p(k[1]), _p(k[2]), _p(k[3]), _p(k[4]), _p(k[5]), self.dof,
+                                    robot.n_shapes, _p(k[6]), _p(k[7]), _p(k[8]), _p(k[9]), _p(k[10]), _p(k[11]),
+                                    _p(k[12]), len(robot.self_pairs), _p(k[13]))
+        if not self._r:
+            raise _lib.JogramopError('jg_robot_create: ' + L.jg_last_error().decode())
+        self._s = None
+        if scene is not None:
+            ks = [_i32(scene.piece_vert_offset), _f64(scene.piece_verts), _f64(scene.piece_margin), _f64(scene.plane)]
+            self._s = L.jg_scene_create(scene.n_pieces, _p(ks[0]), _p(ks[1]), _p(ks[2]),
+                                        _p(ks[3]) if scene.has_plane else None)
+            if not self._s:
+                raise _lib.JogramopError('jg_scene_create: ' + L.jg_last_error().decode())
+        prm = _lib.Params(threshold, query_distance, finger_open, chunk)
+        self._e = L.jg_engine_create(self._r, self._s, self.device.index, C.byref(prm))
+        if not self._e:
+            raise _lib.JogramopError('jg_engine_create: ' + L.jg_last_error().decode())
+        self.threshold, self.query_distance, self.finger_open = threshold, query_distance, finger_open
+
+    def close(self):
+        L = self._L
+        if getattr(self, '_e', None):
+            L.jg_engine_free(self._e)
+            self._e = None
+        if getattr(self, '_s', None):
+            L.jg_scene_free(self._s)
+            self._s = None
+        if getattr(self, '_r', None):
+            L.jg_robot_free(self._r)
+            self._r = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _dev_f32(self, a, cols):
+        if isinstance(a, torch.Tensor):
+            t = a.to(device=self.device, dtype=torch.float32)
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(self.device)
+        t = t.reshape(-1, cols).contiguous()
+        return t
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ queries
+    def fk(self, q, link_ids=None, base_pose=None):
+        """Link frames [n, len(link_ids), 3, 4] (fp32, device).  base_pose: 4x4 or 3x4 pre-multiplied pose."""
+        q = self._dev_f32(q, self.dof)
+        ids = _i32(range(self.robot.n_links) if link_ids is None else link_ids)
+        out = torch.empty((q.shape[0], len(ids), 3, 4), device=self.device, dtype=torch.float32)
+        bp = np.ascontiguousarray(_f64(base_pose)[:3, :]) if base_pose is not None else None
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.jg_fk(self._e, q.data_ptr(), q.shape[0], self.dof, _p(ids), len(ids), _p(bp),
+                                     out.data_ptr(), self._stream()), 'jg_fk')
+        return out
+
+    def check(self, q, flags=SCENE | PLANE, want_dist=True, want_reason=False, packed=False):
+        """-> (collides bool[n] (or packed int32 words), min_dist fp32[n] | None, reason uint8[n] | None)."""
+        q = self._dev_f32(q, self.dof)
+        n = q.shape[0]
+        bits = torch.empty(((n + 31) // 32,), device=self.device, dtype=torch.int32)
+        dist = torch.empty((n,), device=self.device, dtype=torch.float32) if want_dist else None
+        reason = torch.empty((n,), device=self.device, dtype=torch.uint8) if want_reason else None
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.jg_check(self._e, q.data_ptr(), n, self.dof, flags, bits.data_ptr(),
+                                        dist.data_ptr() if want_dist else None,
+                                        reason.data_ptr() if want_reason else None, self._stream()), 'jg_check')
+        return (bits if packed else unpack_bits(bits, n)), dist, reason
+
+    def check_edges(self, qa, qb, substeps=64, flags=SCENE | PLANE, want_dist=True, packed=False):
+        qa, qb = self._dev_f32(qa, self.dof), self._dev_f32(qb, self.dof)
+        m = qa.shape[0]
+        assert qb.shape[0] == m, 'qa and qb must hold the same number of edges'
+        bits = torch.empty(((m + 31) // 32,), device=self.device, dtype=torch.int32)
+        dist = torch.empty((m,), device=self.device, dtype=torch.float32) if want_dist else None
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.jg_check_edges(self._e, qa.data_ptr(), qb.data_ptr(), m, self.dof, substeps, flags,
+                                              bits.data_ptr(), dist.data_ptr() if want_dist else None,
+                                              self._stream()), 'jg_check_edges')
+        return (bits if packed else unpack_bits(bits, m)), dist
+
+    def check_poses(self, poses, links, ee_link=None, flags=SCENE | PLANE, want_dist=True, packed=False):
+        """poses: [n,4,4] / [n,3,4] matrices or [n,7] (pos, quat xyzw) of link `ee_link` in the robot frame."""
+        if isinstance(poses, torch.Tensor):
+            shp = tuple(poses.shape)
+        else:
+            poses = np.asarray(poses)
+            shp = poses.shape
+        if len(shp) == 3 and shp[1:] == (4, 4):
+            poses = poses[:, :3, :]
+            fmt, cols = POSE_MAT34, 12
+        elif len(shp) == 3 and shp[1:] == (3, 4):
+            fmt, cols = POSE_MAT34, 12
+        elif len(shp) == 2 and shp[1] == 7:
+            fmt, cols = POSE_POS_QUAT, 7
+        else:
+            raise ValueError('poses must be [n,4,4], [n,3,4] or [n,7]')
+        p = self._dev_f32(poses, cols)
+        n = p.shape[0]
+        links = _i32(links)
+        ee = self.robot.end_effector_id if ee_link is None else ee_link
+        bits = torch.empty(((n + 31) // 32,), device=self.device, dtype=torch.int32)
+        dist = torch.empty((n,), device=self.device, dtype=torch.float32) if want_dist else None
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.jg_check_poses(self._e, p.data_ptr(), n, fmt, ee, _p(links), len(links), flags,
+                                              bits.data_ptr(), dist.data_ptr() if want_dist else None,
+                                              self._stream()), 'jg_check_poses')
+        return (bits if packed else unpack_bits(bits, n)), dist
+
+    def check_host(self, q, flags=SCENE | PLANE, want_dist=True, want_reason=False, out=None):
+        """End-to-end path with HOST buffers (numpy or CPU torch tensors, ideally pinned): H2D, kernels and D2H are
+        pipelined inside the library.  Returns (bits uint32 words, dist, reason) as numpy views of `out` buffers."""
+        if isinstance(q, torch.Tensor):
+            assert q.device.type == 'cpu' and q.dtype == torch.float32 and q.is_contiguous()
+            qn, qptr = q.shape[0], q.data_ptr()
+        else:
+            q = np.ascontiguousarray(q, dtype=np.float32)
+            qn, qptr = q.shape[0], q.ctypes.data
+        if out is None:
+            out = {'bits': torch.empty(((qn + 31) // 32,), dtype=torch.int32, pin_memory=True),
+                   'dist': torch.empty((qn,), dtype=torch.float32, pin_memory=True) if want_dist else None,
+                   'reason': torch.empty((qn,), dtype=torch.uint8, pin_memory=True) if want_reason else None}
+        _lib.check(self._L.jg_check_host(self._e, qptr, qn, self.dof, flags, out['bits'].data_ptr(),
+                                         out['dist'].data_ptr() if out.get('dist') is not None else None,
+                                         out['reason'].data_ptr() if out.get('reason') is not None else None),
+                   'jg_check_host')
+        return out['bits'], out.get('dist'), out.get('reason')
+
+    def stats(self):
+        st = _lib.Stats()
+        _lib.check(self._L.jg_get_stats(self._e, C.byref(st)), 'jg_get_stats')
+        return {f: getattr(st, f) for f, _ in st._fields_}

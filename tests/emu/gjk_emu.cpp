@@ -1,0 +1,41 @@
+// Host emulation of the per-thread device GJK (jg_gjk.cuh compiled with g++, JG_HOST_EMU).
+// Test infrastructure: lets the CPU suite check the fp32 kernel numerics against the double oracle.
+#define JG_HOST_EMU 1
+#include "../../jogramop_framework_b200/csrc/jg_gjk.cuh"
+
+#include <vector>
+
+using namespace jg;
+
+// va [na,3], vb [nb,3] float; T [n,12] row-major 3x4 (A placed by T, B static); out dist[n], status[n], iters[n]
+extern "C" void emu_gjk_batch(const float* va, int na, const float* vb, int nb, const float* T, int n, float dmax,
+                              float* dist, int* status, int* iters) {
+    std::vector<float4> A(na), B(nb);
+    for (int i = 0; i < na; ++i) A[i] = make_float4(va[3 * i], va[3 * i + 1], va[3 * i + 2], 0.f);
+    for (int i = 0; i < nb; ++i) B[i] = make_float4(vb[3 * i], vb[3 * i + 1], vb[3 * i + 2], 0.f);
+    for (int k = 0; k < n; ++k) {
+        const float* t = T + 12 * k;
+        Tf X;
+        X.r00 = t[0]; X.r01 = t[1]; X.r02 = t[2]; X.tx = t[3];
+        X.r10 = t[4]; X.r11 = t[5]; X.r12 = t[6]; X.ty = t[7];
+        X.r20 = t[8]; X.r21 = t[9]; X.r22 = t[10]; X.tz = t[11];
+        float d = 0.f;
+        int it = 0;
+        status[k] = gjk_distance(A.data(), na, B.data(), nb, X, mk(X.tx, X.ty, X.tz), dmax, d, it);
+        dist[k] = d;
+        iters[k] = it;
+    }
+}
+
+extern "C" void emu_plane_batch(const float* va, int na, const float* T, int n, const float* plane, float* dist) {
+    std::vector<float4> A(na);
+    for (int i = 0; i < na; ++i) A[i] = make_float4(va[3 * i], va[3 * i + 1], va[3 * i + 2], 0.f);
+    for (int k = 0; k < n; ++k) {
+        const float* t = T + 12 * k;
+        Tf X;
+        X.r00 = t[0]; X.r01 = t[1]; X.r02 = t[2]; X.tx = t[3];
+        X.r10 = t[4]; X.r11 = t[5]; X.r12 = t[6]; X.ty = t[7];
+        X.r20 = t[8]; X.r21 = t[9]; X.r22 = t[10]; X.tz = t[11];
+        dist[k] = plane_distance(A.data(), na, X, mk(plane[0], plane[1], plane[2]), plane[3]);
+    }
+}

@@ -1,0 +1,239 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the double-precision CPU oracle on the same seeded
+inputs.  Bars (BASELINE.json north_star): verdicts identical wherever the reference distance is more than 1 mm
+from the decision surface; |d - d_ref| <= 1e-4 m; FK link poses within 1e-5."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import Oracle
+from ref_numpy import SCENARIO_IDS, uniform_configs
+
+pytestmark = pytest.mark.gpu
+
+DIST_TOL = 1e-4     # north_star: distances must match within 1e-4 m
+BAND = 1e-3         # north_star: verdicts must agree outside 1 mm of the decision surface
+FK_TOL = 1e-5       # north_star: FK link poses within 1e-5
+
+
+@pytest.fixture(scope='module')
+def engines(robot, scene_loader):
+    from jogramop_framework_b200.engine import CollisionEngine
+    cache = {}
+
+    def get(sid, **kw):
+        key = (sid, tuple(sorted(kw.items())))
+        if key not in cache:
+            cache[key] = CollisionEngine(robot, scene_loader(sid) if sid is not None else None, **kw)
+        return cache[key]
+    yield get
+    for e in cache.values():
+        e.close()
+
+
+def compare(bits, dist, rbits, rdist, threshold=-0.001):
+    bits, dist = bits.cpu().numpy(), dist.cpu().numpy().astype(np.float64)
+    err = np.abs(dist - rdist)
+    assert err.max() <= DIST_TOL, f'max |d - d_ref| = {err.max()}'
+    outside = np.abs(rdist - threshold) > BAND
+    assert np.array_equal(bits[outside], rbits[outside])
+    return int((bits != rbits).sum()), float(err.max())
+
+
+def test_library_is_loaded_and_no_cpu_fallback():
+    from jogramop_framework_b200 import _lib
+    L = _lib.load()
+    assert L.jg_device_count() >= 1
+    with open('/proc/self/maps') as fh:
+        assert 'libjogramop_b200.so' in fh.read()
+
+
+def test_fk_parity(robot, engines):
+    e = engines(None)
+    o = Oracle(robot)
+    q = uniform_configs(robot, 20000, 7)
+    ref = o.fk(q.astype(np.float64))
+    got = e.fk(q).cpu().numpy()
+    assert np.abs(got - ref).max() <= FK_TOL
+    # world-frame EE pose through base_pose (forward_kinematics returns link 14 in WORLD, simulation.py:223-249)
+    from jogramop_framework_b200.ingest import default_robot_pose
+    pose = default_robot_pose()
+    got = e.fk(q[:100], link_ids=[14], base_pose=pose).cpu().numpy()[:, 0]
+    refw = np.einsum('ij,njk->nik', pose[:3, :3], ref[:100, 14])
+    refw[:, :, 3] += pose[:3, 3]
+    assert np.abs(got - refw).max() <= FK_TOL
+
+
+@pytest.mark.parametrize('sid', [11, 21, 34, 43, 45])
+def test_scene_parity(sid, robot, scene_loader, engines):
+    e = engines(sid)
+    o = Oracle(robot, scene_loader(sid))
+    q = uniform_configs(robot, 30000, sid)
+    rb, rd = o.check(q.astype(np.float64), flags=oracle.SCENE | oracle.PLANE | oracle.NO_EPA)
+    bits, dist, _ = e.check(q, flags=oracle.SCENE | oracle.PLANE | oracle.NO_EPA)
+    nd, me = compare(bits, dist, rb, rd)
+    print(f'scenario {sid}: collision rate {rb.mean():.3f}, disagreements in band {nd}, max |dd| {me:.2e}')
+    assert 0.15 < rb.mean() < 0.6
+
+
+def test_scene_only_and_plane_only(robot, scene_loader, engines):
+    e = engines(11)
+    o = Oracle(robot, scene_loader(11))
+    q = uniform_configs(robot, 8000, 3)
+    for fl in (oracle.SCENE | oracle.NO_EPA, oracle.PLANE):
+        rb, rd = o.check(q.astype(np.float64), flags=fl)
+        bits, dist, _ = e.check(q, flags=fl)
+        compare(bits, dist, rb, rd)
+
+
+def test_self_collision_and_reason_codes(robot, scene_loader, engines):
+    e = engines(34)
+    o = Oracle(robot, scene_loader(34))
+    lim = robot.joint_limits[robot.arm_joint_ids]
+    q = uniform_configs(robot, 12000, 5)
+    q[::7, 3] = lim[3, 1] + 0.2       # limit violations
+    q[5::11, 0] = np.nan              # NaN never passes the limit test
+    fl = oracle.SCENE | oracle.PLANE | oracle.SELF | oracle.LIMITS | oracle.NO_EPA
+    rb, rd, rr = o.check(q.astype(np.float64), flags=fl, want_reason=True)
+    bits, dist, reason = e.check(q, flags=fl, want_reason=True)
+    ok = ~np.isnan(q).any(1)
+    nd, me = compare(bits[torch.from_numpy(ok)], dist[torch.from_numpy(ok)], rb[ok], rd[ok])
+    assert bits.cpu().numpy()[~ok].all()
+    reason = reason.cpu().numpy()
+    assert (reason[~ok] == 1).all()
+    clear = ok & (np.abs(rd + 0.001) > BAND)
+    agree = (reason[clear] == rr[clear]).mean()
+    assert agree > 0.999          # reason may differ only when self and scene are both within the band
+    assert (rr == 2).sum() > 100 and (rr == 1).sum() > 1000
+    # self-collision alone (in_self_collision, simulation.py:439-464)
+    rb, rd = o.check(q[ok].astype(np.float64), flags=oracle.SELF | oracle.NO_EPA)
+    bits, dist, _ = e.check(q[ok], flags=oracle.SELF | oracle.NO_EPA)
+    compare(bits, dist, rb, rd)
+    assert 0.05 < rb.mean() < 0.4
+
+
+def test_golden_ik_rows_are_free_on_gpu(robot, golden, scene_loader, engines):
+    """G4 on the GPU: all 89 accepted IK solutions pass limits + self + scene."""
+    fl = oracle.SCENE | oracle.PLANE | oracle.SELF | oracle.LIMITS
+    total = 0
+    for sid in SCENARIO_IDS:
+        ik = golden[f'ik_{sid:03d}']
+        if not len(ik):
+            continue
+        e = engines(sid)
+        bits, dist, reason = e.check(ik.astype(np.float32), flags=fl, want_reason=True)
+        assert not bits.any().item(), (sid, reason.cpu().numpy())
+        total += len(ik)
+    assert total == 89
+
+
+def test_edges_parity(robot, scene_loader, engines):
+    e = engines(34)
+    o = Oracle(robot, scene_loader(34))
+    lim = robot.joint_limits[robot.arm_joint_ids]
+    qa = uniform_configs(robot, 3000, 34)
+    rng = np.random.default_rng(3400)
+    qb = np.clip(qa + rng.uniform(-0.25, 0.25, qa.shape), lim[:, 0], lim[:, 1]).astype(np.float32)
+    fl = oracle.SCENE | oracle.PLANE | oracle.NO_EPA
+    for sub in (64, 5):
+        # the oracle interpolates in double from the same float32 endpoints; the kernel interpolates in float32
+        rb, rd = o.check_edges(qa.astype(np.float64), qb.astype(np.float64), substeps=sub, flags=fl)
+        bits, dist = e.check_edges(qa, qb, substeps=sub, flags=fl)
+        compare(bits, dist, rb, rd)
+
+
+def test_gripper_poses_parity(robot, scene_loader, engines):
+    sc = scene_loader(11)
+    e = engines(11)
+    o = Oracle(robot, sc)
+    rng = np.random.default_rng(5011)
+    n = 20000
+    tgt = sc.piece(0)        # target object is body 0 / piece 0
+    lo, hi = tgt.min(0) - 0.25, tgt.max(0) + 0.25
+    pos = lo + (hi - lo) * rng.random((n, 3))
+    quat = rng.normal(size=(n, 4))
+    quat /= np.linalg.norm(quat, axis=1, keepdims=True)
+    pq = np.concatenate([pos, quat], 1).astype(np.float32)
+    x, y, z, w = (pq[:, 3 + i].astype(np.float64) for i in range(4))
+    nrm = np.sqrt(x * x + y * y + z * z + w * w)
+    x, y, z, w = x / nrm, y / nrm, z / nrm, w / nrm
+    Rm = np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                   2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                   2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], 1).reshape(n, 3, 3)
+    T = np.concatenate([Rm, pq[:, :3, None].astype(np.float64)], 2)
+    fl = oracle.SCENE | oracle.PLANE | oracle.NO_EPA
+    rb, rd = o.check_poses(T, links=[11, 12, 13], flags=fl)
+    bits, dist = e.check_poses(pq, links=[11, 12, 13], flags=fl)
+    compare(bits, dist, rb, rd)
+    bits2, dist2 = e.check_poses(T.astype(np.float32), links=[11, 12, 13], flags=fl)
+    compare(bits2, dist2, rb, rd)
+    assert 0.02 < rb.mean() < 0.9
+
+
+def test_chunking_tails_and_empty(robot, scene_loader, engines):
+    """Ragged sizes: n not a multiple of 32 / of the pass size, n = 0, n = 1."""
+    e = engines(34, chunk=4096)
+    big = engines(34)
+    q = uniform_configs(robot, 4096 * 2 + 37, 9)
+    b1, d1, _ = e.check(q, flags=3 | 16)
+    b2, d2, _ = big.check(q, flags=3 | 16)
+    assert torch.equal(b1, b2) and torch.equal(d1, d2)
+    b0, d0, _ = e.check(q[:0], flags=3)
+    assert b0.numel() == 0 and d0.numel() == 0
+    b, d, _ = e.check(q[:1], flags=3 | 16)
+    assert b.shape == (1,) and bool(b[0]) == bool(b2[0])
+    packed, _, _ = e.check(q[:33], flags=3 | 16, packed=True)
+    assert packed.numel() == 2
+
+
+def test_host_path_matches_device_path(robot, scene_loader, engines):
+    e = engines(11, chunk=8192)
+    q = uniform_configs(robot, 8192 * 3 + 100, 21)
+    from jogramop_framework_b200.engine import unpack_bits
+    b1, d1, r1 = e.check(q, flags=15 | 16, want_reason=True)
+    qp = torch.from_numpy(q).pin_memory()
+    wb, wd, wr = e.check_host(qp, flags=15 | 16, want_reason=True)
+    assert torch.equal(unpack_bits(wb.cuda(), len(q)), b1)
+    assert torch.equal(wd.cuda(), d1) and torch.equal(wr.cuda(), r1)
+    wb2, wd2, _ = e.check_host(q, flags=15 | 16)       # pageable numpy input
+    assert torch.equal(wb2, wb) and torch.equal(wd2, wd)
+
+
+def test_error_conventions(robot, scene_loader, engines):
+    from jogramop_framework_b200._lib import JogramopError
+    e = engines(34)
+    with pytest.raises(JogramopError):
+        e._L.jg_check(e._e, None, 5, 9, 3, None, None, None, None) and None
+        from jogramop_framework_b200 import _lib
+        _lib.check(e._L.jg_check(e._e, None, 5, 9, 3, None, None, None, None), 'jg_check')
+    from jogramop_framework_b200 import _lib
+    assert e._L.jg_check(e._e, None, 5, 8, 3, None, None, None, None) == -1      # dof mismatch
+    assert b'dof' in e._L.jg_last_error()
+
+
+def test_full_size_properties(robot, scene_loader, engines):
+    """BASELINE config 2 at full size (1M configs, scenario 011): size-independent properties."""
+    e = engines(11)
+    q = uniform_configs(robot, 1_000_000, 11)
+    bits, dist, _ = e.check(q, flags=3 | 16)
+    assert dist.max().item() <= 0.01 + 1e-9
+    assert torch.equal(bits, dist < -0.001)                      # verdict == thresholded distance
+    # idempotence / determinism
+    bits2, dist2, _ = e.check(q, flags=3 | 16)
+    assert torch.equal(bits, bits2) and torch.equal(dist, dist2)
+    # permutation equivariance: results follow their configurations
+    perm = torch.randperm(len(q), generator=torch.Generator().manual_seed(0))
+    bits3, dist3, _ = e.check(q[perm.numpy()], flags=3 | 16)
+    assert torch.equal(bits3.cpu(), bits.cpu()[perm]) and torch.equal(dist3.cpu(), dist.cpu()[perm])
+    # monotone in the threshold: collides(thr=-0.001) implies collides(thr=0)
+    e0 = engines(11, threshold=0.0)
+    bits0, _, _ = e0.check(q, flags=3 | 16)
+    assert (bits0 | ~bits).all().item()
+    # base translation moves nothing but the platform-relative geometry: q and q shifted outside limits still checks
+    rate = bits.float().mean().item()
+    assert 0.25 < rate < 0.45          # ~0.31 obstacles + ~0.08 plane
+    # 1M-prefix check against the oracle on a 20k sample
+    o = Oracle(robot, scene_loader(11))
+    idx = np.arange(0, 1_000_000, 50)
+    rb, rd = o.check(q[idx].astype(np.float64), flags=3 | 16)
+    compare(bits[torch.from_numpy(idx)], dist[torch.from_numpy(idx)], rb, rd)
