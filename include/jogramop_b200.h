@@ -145,6 +145,17 @@ typedef struct {
 /* synchronises the engine's last stream and reads the device counters */
 int jg_get_stats(jg_engine*, jg_stats*);
 
+/* Per-kernel timing: when enabled, every pass brackets its kernels with CUDA events on the launching stream;
+ * jg_get_profile synchronises and returns the accumulated milliseconds and launch counts since the last
+ * jg_profile_enable(e, 1).  ms[0..3] / launches[0..3] = broad phase, narrow phase (GJK), penetration depth (EPA),
+ * finalize. */
+int jg_profile_enable(jg_engine*, int enable);
+int jg_get_profile(jg_engine*, double ms[4], int64_t launches[4]);
+
+/* FP32 FMA micro-benchmark (roofline denominator of the narrow phase): dependent-chain-free FFMA loop on every
+ * SM of `device`; returns the best of `reps` runs in TFLOP/s (2 flops per FMA). */
+int jg_measure_fp32_peak(int device, int reps, double* tflops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -163,6 +163,7 @@ struct jg_engine {
     int cap = 0;                          // configurations per pass
     float4 *q_r0 = nullptr, *q_r1 = nullptr, *q_r2 = nullptr;
     int* q_cfg = nullptr;
+    int* epa_slot = nullptr;              // [n_keys*cap]
     int* counts = nullptr;                // [2*n_keys + 8]
     int *enc_scene = nullptr, *enc_self = nullptr;
     uint32_t* viol = nullptr;
@@ -187,13 +188,44 @@ struct jg_engine {
     cudaStream_t last_stream = nullptr;
     int sm_count = 148;
     size_t smem_narrow = 0;
+    // optional per-kernel timing (jg_profile_enable)
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_ev;    // 5 events per pass: start | broad | narrow | penetration | finalize
+    size_t prof_used = 0;
+    double prof_ms[4] = {0, 0, 0, 0};
+    int64_t prof_n[4] = {0, 0, 0, 0};
 };
+
+static cudaEvent_t prof_event(jg_engine* e) {
+    if (e->prof_used == e->prof_ev.size()) {
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        e->prof_ev.push_back(ev);
+    }
+    return e->prof_ev[e->prof_used++];
+}
+#define PROF_MARK(e, st) do { if ((e)->profiling) cudaEventRecord(prof_event(e), st); } while (0)
+
+static void prof_collect(jg_engine* e) {
+    // events come in groups of 5 per pass
+    for (size_t i = 0; i + 4 < e->prof_used; i += 5) {
+        cudaEventSynchronize(e->prof_ev[i + 4]);
+        for (int k = 0; k < 4; ++k) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, e->prof_ev[i + k], e->prof_ev[i + k + 1]) == cudaSuccess) {
+                e->prof_ms[k] += ms;
+                e->prof_n[k] += 1;
+            }
+        }
+    }
+    e->prof_used = 0;
+}
 
 static void engine_release(jg_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaFree(e->d_robot); cudaFree(e->d_pieces); cudaFree(e->d_selfs); cudaFree(e->d_keys); cudaFree(e->d_verts);
-    cudaFree(e->q_r0); cudaFree(e->q_r1); cudaFree(e->q_r2); cudaFree(e->q_cfg); cudaFree(e->counts);
+    cudaFree(e->q_r0); cudaFree(e->q_r1); cudaFree(e->q_r2); cudaFree(e->q_cfg); cudaFree(e->epa_slot); cudaFree(e->counts);
     cudaFree(e->enc_scene); cudaFree(e->enc_self); cudaFree(e->viol); cudaFree(e->d_link_slot); cudaFree(e->d_rel);
     cudaFree(e->d_use_shapes); cudaFree(e->d_stats);
     for (int i = 0; i < 2; ++i) {
@@ -207,6 +239,7 @@ static void engine_release(jg_engine* e) {
     if (e->s_in) cudaStreamDestroy(e->s_in);
     if (e->s_run) cudaStreamDestroy(e->s_run);
     if (e->s_out) cudaStreamDestroy(e->s_out);
+    for (cudaEvent_t ev : e->prof_ev) cudaEventDestroy(ev);
     delete e;
 }
 
@@ -326,8 +359,9 @@ static int build_tables(jg_engine* e, const jg_robot* r, const jg_scene* sc) {
     for (int s = 0; s < r->S; ++s) {
         for (int p = 0; p < P; ++p)
             keys.push_back(KeyRec{R.shapes[s].voff, R.shapes[s].vn, pieces[p].voff, pieces[p].vn,
-                                  R.shapes[s].margin + pieces[p].margin, KEY_HULL});
-        keys.push_back(KeyRec{R.shapes[s].poff, R.shapes[s].pn, 0, 0, R.shapes[s].plane_margin, KEY_PLANE});
+                                  R.shapes[s].margin + pieces[p].margin, KEY_HULL, R.shapes[s].poff, R.shapes[s].pn,
+                                  pieces[p].voff, pieces[p].vn, R.shapes[s].plane_margin + pieces[p].margin, 0});
+        keys.push_back(KeyRec{R.shapes[s].poff, R.shapes[s].pn, 0, 0, R.shapes[s].plane_margin, KEY_PLANE, 0, 0, 0, 0, 0.f, 0});
     }
     e->n_scene_keys = (int)keys.size();
     std::vector<SelfRec> selfs;
@@ -339,7 +373,8 @@ static int build_tables(jg_engine* e, const jg_robot* r, const jg_scene* sc) {
         if (sa < 0 || sb < 0) return fail(JG_ERR_INVALID, "self pair %d: link without collision shape", k);
         selfs.push_back(SelfRec{sa, sb, la, lb});
         keys.push_back(KeyRec{R.shapes[sb].voff, R.shapes[sb].vn, R.shapes[sa].voff, R.shapes[sa].vn,
-                              R.shapes[sa].margin + R.shapes[sb].margin, KEY_SELF});
+                              R.shapes[sa].margin + R.shapes[sb].margin, KEY_SELF, R.shapes[sb].poff, R.shapes[sb].pn,
+                              R.shapes[sa].poff, R.shapes[sa].pn, R.shapes[sa].plane_margin + R.shapes[sb].plane_margin, 0});
     }
     e->n_keys = (int)keys.size();
     e->n_verts = (int)verts.size();
@@ -360,6 +395,7 @@ static int build_tables(jg_engine* e, const jg_robot* r, const jg_scene* sc) {
 
 constexpr int BP_BLOCK = 128;   // broad phase: threads (= configurations) per block
 constexpr int NP_BLOCK = 256;   // narrow phase
+constexpr int EPA_BLOCK = 128;  // penetration-depth pass
 
 static size_t bp_smem(const jg_engine* e, uint32_t flags) {
     size_t s = sizeof(RobotTab) + sizeof(PieceRec) * e->P + sizeof(float) * BP_BLOCK * e->dof;
@@ -393,6 +429,7 @@ extern "C" jg_engine* jg_engine_create(const jg_robot* r, const jg_scene* sc, in
         return nullptr;
     }
     bool ok = cudaFuncSetAttribute(k_narrowphase<NP_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_penetration<EPA_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_broadphase<BP_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_broadphase_poses<BP_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
     if (!ok) {
@@ -406,7 +443,7 @@ extern "C" jg_engine* jg_engine_create(const jg_robot* r, const jg_scene* sc, in
     e->cap = cap;
     const size_t qn = (size_t)std::max(e->n_keys, 1) * cap;
     bool okm = cudaMalloc(&e->q_r0, sizeof(float4) * qn) == cudaSuccess && cudaMalloc(&e->q_r1, sizeof(float4) * qn) == cudaSuccess &&
-               cudaMalloc(&e->q_r2, sizeof(float4) * qn) == cudaSuccess && cudaMalloc(&e->q_cfg, sizeof(int) * qn) == cudaSuccess &&
+               cudaMalloc(&e->q_r2, sizeof(float4) * qn) == cudaSuccess && cudaMalloc(&e->q_cfg, sizeof(int) * qn) == cudaSuccess && cudaMalloc(&e->epa_slot, sizeof(int) * qn) == cudaSuccess &&
                cudaMalloc(&e->counts, sizeof(int) * (2 * e->n_keys + 8)) == cudaSuccess &&
                cudaMalloc(&e->enc_scene, sizeof(int) * cap) == cudaSuccess && cudaMalloc(&e->enc_self, sizeof(int) * cap) == cudaSuccess &&
                cudaMalloc(&e->viol, sizeof(uint32_t) * (cap / 32 + 1)) == cudaSuccess &&
@@ -434,7 +471,7 @@ static void fill_args(const jg_engine* e, PassArgs& a, uint32_t flags) {
     a.has_plane = e->has_plane ? 1 : 0;
     a.robot = e->d_robot; a.pieces = e->d_pieces; a.P = e->P; a.selfs = e->d_selfs; a.keys = e->d_keys;
     a.n_keys = e->n_keys; a.n_scene_keys = e->n_scene_keys; a.verts = e->d_verts; a.n_verts = e->n_verts;
-    a.q_r0 = e->q_r0; a.q_r1 = e->q_r1; a.q_r2 = e->q_r2; a.q_cfg = e->q_cfg; a.cap = e->cap; a.counts = e->counts;
+    a.q_r0 = e->q_r0; a.q_r1 = e->q_r1; a.q_r2 = e->q_r2; a.q_cfg = e->q_cfg; a.epa_slot = e->epa_slot; a.cap = e->cap; a.counts = e->counts;
     a.enc_scene = e->enc_scene; a.enc_self = e->enc_self; a.viol = e->viol;
 }
 
@@ -452,21 +489,35 @@ __global__ void k_accumulate_stats(const int* counts, int n_scene_keys, int n_ke
         pl += __shfl_xor_sync(0xFFFFFFFFu, pl, o);
         sf += __shfl_xor_sync(0xFFFFFFFFu, sf, o);
     }
-    if (threadIdx.x == 0) { stats[0] += h; stats[1] += pl; stats[2] += sf; }
+    unsigned long long ep = 0;
+    for (int k = threadIdx.x; k < n_keys; k += 32) ep += counts[n_keys + 8 + k];
+    for (int o = 16; o; o >>= 1) ep += __shfl_xor_sync(0xFFFFFFFFu, ep, o);
+    if (threadIdx.x == 0) { stats[0] += h; stats[1] += pl; stats[2] += sf; stats[3] += ep; }
 }
 
 // narrow phase + finalize of the pass described by `a` (queues already filled)
 static int run_narrow_and_finalize(jg_engine* e, const PassArgs& a, int n_out, uint32_t flags, uint32_t* bits, float* dist,
                                    uint8_t* reason, cudaStream_t st) {
+    PROF_MARK(e, st);   // end of broad phase / start of narrow phase
     if (e->n_keys > 0) {
-        k_accumulate_stats<<<1, 32, 0, st>>>(e->counts, e->n_scene_keys, e->n_keys, e->P, e->d_stats);
         const int blocks = e->sm_count * 3;
         k_narrowphase<NP_BLOCK><<<blocks, NP_BLOCK, e->smem_narrow, st>>>(a);
-        e->stats.kernel_launches += 2;
+        e->stats.kernel_launches += 1;
+    }
+    PROF_MARK(e, st);
+    if (e->n_keys > 0 && !(flags & JG_NO_EPA)) {
+        k_penetration<EPA_BLOCK><<<e->sm_count * 4, EPA_BLOCK, e->smem_narrow, st>>>(a);
+        e->stats.kernel_launches += 1;
+    }
+    PROF_MARK(e, st);
+    if (e->n_keys > 0) {
+        k_accumulate_stats<<<1, 32, 0, st>>>(e->counts, e->n_scene_keys, e->n_keys, e->P, e->d_stats);
+        e->stats.kernel_launches += 1;
     }
     k_finalize<<<(n_out + 255) / 256, 256, 0, st>>>(e->enc_scene, e->enc_self, e->viol, n_out, a.qd, a.threshold, flags, bits,
                                                     dist, reason);
     e->stats.kernel_launches += 1;
+    PROF_MARK(e, st);
     CUDA_TRY(cudaGetLastError());
     return JG_OK;
 }
@@ -495,6 +546,7 @@ extern "C" int jg_check(jg_engine* e, const float* q, int64_t n, int dof, uint32
         a.q = q + off * dof; a.n = m;
         CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * (2 * e->n_keys + 8), st));
         if (flags & JG_LIMITS) CUDA_TRY(cudaMemsetAsync(e->viol, 0, sizeof(uint32_t) * (e->cap / 32 + 1), st));
+        PROF_MARK(e, st);
         k_broadphase<BP_BLOCK><<<(m + BP_BLOCK - 1) / BP_BLOCK, BP_BLOCK, bp_smem(e, flags), st>>>(a);
         e->stats.kernel_launches += 1;
         rc = run_narrow_and_finalize(e, a, m, flags, bits + off / 32, min_dist ? min_dist + off : nullptr,
@@ -522,6 +574,7 @@ extern "C" int jg_check_edges(jg_engine* e, const float* qa, const float* qb, in
         a.q = qa + off * dof; a.qb = qb + off * dof; a.n = me * substeps; a.substeps = substeps;
         CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * (2 * e->n_keys + 8), st));
         if (flags & JG_LIMITS) CUDA_TRY(cudaMemsetAsync(e->viol, 0, sizeof(uint32_t) * (e->cap / 32 + 1), st));
+        PROF_MARK(e, st);
         k_init_scratch<<<(me + 255) / 256, 256, 0, st>>>(e->enc_scene, e->enc_self, me);
         k_broadphase<BP_BLOCK><<<(a.n + BP_BLOCK - 1) / BP_BLOCK, BP_BLOCK, bp_smem(e, flags), st>>>(a);
         e->stats.kernel_launches += 2;
@@ -608,6 +661,7 @@ extern "C" int jg_check_poses(jg_engine* e, const float* poses, int64_t n, int f
         a.n = m;
         CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * (2 * e->n_keys + 8), st));
         const size_t smem = sizeof(RobotTab) + sizeof(PieceRec) * e->P;
+        PROF_MARK(e, st);
         k_broadphase_poses<BP_BLOCK><<<(m + BP_BLOCK - 1) / BP_BLOCK, BP_BLOCK, smem, st>>>(a, poses + off * stride, fmt, e->d_rel,
                                                                                          e->d_use_shapes, (int)use.size());
         e->stats.kernel_launches += 1;
@@ -748,5 +802,65 @@ extern "C" int jg_get_stats(jg_engine* e, jg_stats* out) {
     out->plane_pairs = (int64_t)h[1];
     out->self_pairs = (int64_t)h[2];
     out->epa_pairs = (int64_t)h[3];
+    return JG_OK;
+}
+
+extern "C" int jg_profile_enable(jg_engine* e, int enable) {
+    if (!e) return fail(JG_ERR_INVALID, "jg_profile_enable: engine is NULL");
+    CUDA_TRY(cudaSetDevice(e->device));
+    if (e->profiling) prof_collect(e);
+    e->profiling = enable != 0;
+    if (enable) {
+        for (int k = 0; k < 4; ++k) { e->prof_ms[k] = 0; e->prof_n[k] = 0; }
+        e->prof_used = 0;
+    }
+    return JG_OK;
+}
+
+extern "C" int jg_get_profile(jg_engine* e, double ms[4], int64_t launches[4]) {
+    if (!e || !ms || !launches) return fail(JG_ERR_INVALID, "jg_get_profile: NULL argument");
+    CUDA_TRY(cudaSetDevice(e->device));
+    prof_collect(e);
+    for (int k = 0; k < 4; ++k) { ms[k] = e->prof_ms[k]; launches[k] = e->prof_n[k]; }
+    return JG_OK;
+}
+
+// 8 independent FMA chains per thread, 4096 FMAs each
+__global__ void __launch_bounds__(256) k_fma_peak(float* out, float a, float b, int iters) {
+    float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+extern "C" int jg_measure_fp32_peak(int device, int reps, double* tflops) {
+    if (!tflops) return fail(JG_ERR_INVALID, "jg_measure_fp32_peak: NULL output");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 2048;
+    float* out = nullptr;
+    CUDA_TRY(cudaMalloc(&out, sizeof(float) * blocks * threads));
+    cudaEvent_t a, b;
+    CUDA_TRY(cudaEventCreate(&a));
+    CUDA_TRY(cudaEventCreate(&b));
+    double best = 0;
+    for (int r = 0; r < std::max(reps, 1) + 1; ++r) {
+        CUDA_TRY(cudaEventRecord(a));
+        k_fma_peak<<<blocks, threads>>>(out, 0.999f, 0.001f, iters);
+        CUDA_TRY(cudaEventRecord(b));
+        CUDA_TRY(cudaEventSynchronize(b));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+        const double fl = 2.0 * 8 * 16 * (double)iters * blocks * threads;
+        if (r > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
+    *tflops = best;
     return JG_OK;
 }

@@ -91,8 +91,7 @@ __device__ __forceinline__ void simplex_set3(Simplex& S, V3 p0, V3 p1, V3 p2, ui
 // Distance between conv(A) placed by T and conv(B) (B frame).  v0: initial separating direction guess.
 // Returns JG_GJK_*; dist is valid for JG_GJK_SEPARATED.
 __device__ __forceinline__ int gjk_distance(const float4* __restrict__ A, int nA, const float4* __restrict__ B, int nB,
-                                            const Tf& T, V3 v0, float dmax, float& dist, int& iters) {
-    Simplex S;
+                                            const Tf& T, V3 v0, float dmax, float& dist, int& iters, Simplex& S) {
     S.n = 0;
     S.a = S.b = S.c = S.d = mk(0.f, 0.f, 0.f);
     S.ia = S.ib = S.ic = S.id = 0xFFFFFFFFu;

@@ -11,7 +11,7 @@
 // HBM layout of a pass over C configurations and K keys (key = shape*(P+1)+piece, plane = piece P, then the
 // self-collision pairs):   q_r0/q_r1/q_r2 float4[K*C] (rows of R with t in .w), q_cfg int[K*C], counts int[K].
 #pragma once
-#include "jg_gjk.cuh"
+#include "jg_epa.cuh"
 
 namespace jg {
 
@@ -60,10 +60,14 @@ struct SelfRec {
 
 enum { KEY_HULL = 0, KEY_PLANE = 1, KEY_SELF = 2 };
 struct KeyRec {
-    int a_off, a_n;    // moving vertex set (robot shape)
-    int b_off, b_n;    // static vertex set (piece / first link shape)
+    int a_off, a_n;    // moving vertex set (robot shape), GJK core
+    int b_off, b_n;    // static vertex set (piece / first link shape), GJK core
     float msum;        // margins subtracted from the core distance
     int kind;
+    int ea_off, ea_n;  // penetration-depth geometry (box: exact corners instead of the shrunk core)
+    int eb_off, eb_n;
+    float emsum;       // margins added to the penetration depth
+    int pad;
 };
 
 struct PassArgs {
@@ -90,7 +94,9 @@ struct PassArgs {
     float4 *q_r0, *q_r1, *q_r2;
     int* q_cfg;
     int cap;           // queue capacity per key (= max configs per pass)
-    int* counts;       // [n_keys] + [n_keys]: tile counter, then stats
+    int* counts;       // [n_keys] pair counts, [n_keys] GJK tile counter, [n_keys+1] EPA tile counter,
+                       // [n_keys+8 .. 2 n_keys+8) penetration-queue counts
+    int* epa_slot;     // [n_keys*cap] queue slots whose cores overlap (penetration-depth pass)
     // per-configuration scratch
     int* enc_scene;    // encoded min contact distance vs scene+plane
     int* enc_self;
@@ -341,17 +347,103 @@ __global__ void __launch_bounds__(BLOCK) k_narrowphase(const PassArgs a) {
         T.r10 = r1.x; T.r11 = r1.y; T.r12 = r1.z; T.ty = r1.w;
         T.r20 = r2.x; T.r21 = r2.y; T.r22 = r2.z; T.tz = r2.w;
         float d = FLT_MAX;
+        bool deep = false;
         if (K.kind == KEY_PLANE) {
             d = plane_distance(verts + K.a_off, K.a_n, T, mk(a.plane[0], a.plane[1], a.plane[2]), a.plane[3]) - K.msum;
         } else if (active) {
             float dist;
             int iters;
+            Simplex S;
             const int st = gjk_distance(verts + K.a_off, K.a_n, verts + K.b_off, K.b_n, T, mk(T.tx, T.ty, T.tz),
-                                        a.qd + K.msum, dist, iters);
+                                        a.qd + K.msum, dist, iters, S);
             if (st == JG_GJK_SEPARATED) d = dist - K.msum;
-            else if (st == JG_GJK_PENETRATING) d = -K.msum;
+            else if (st == JG_GJK_PENETRATING) { d = -K.msum; deep = !(a.flags & 16u); }
         }
-        if (active && d <= a.qd) atomicMin((K.kind == KEY_SELF ? a.enc_self : a.enc_scene) + cfg, enc_float(d));
+        if (active && !deep && d <= a.qd) atomicMin((K.kind == KEY_SELF ? a.enc_self : a.enc_scene) + cfg, enc_float(d));
+        if (K.kind != KEY_PLANE && !(a.flags & 16u)) {   // cores overlap: hand over to the penetration-depth pass
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, deep);
+            if (m) {
+                const int leader = __ffs(m) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(a.counts + a.n_keys + 8 + key, __popc(m));
+                base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                if (deep) a.epa_slot[(size_t)key * a.cap + base + __popc(m & ((1u << lane) - 1u))] = off;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------- penetration depth
+// Pairs whose cores overlap: GJK on the penetration geometry for a start simplex, then the expanding polytope.
+// Same bucketing as the narrow phase: one 32-entry tile of one key per warp.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_penetration(const PassArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* verts = reinterpret_cast<float4*>(smem_raw);
+    KeyRec* keys = reinterpret_cast<KeyRec*>(smem_raw + sizeof(float4) * a.n_verts);
+    int* tile_prefix = reinterpret_cast<int*>(keys + a.n_keys);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int* ecounts = a.counts + a.n_keys + 8;
+    for (int i = tid; i < a.n_verts; i += BLOCK) verts[i] = a.verts[i];
+    {
+        const int* ks = reinterpret_cast<const int*>(a.keys);
+        int* kd = reinterpret_cast<int*>(keys);
+        for (int i = tid; i < (int)(sizeof(KeyRec) / 4) * a.n_keys; i += BLOCK) kd[i] = ks[i];
+    }
+    if (tid < 32) {
+        int carry = 0;
+        for (int base = 0; base < a.n_keys; base += 32) {
+            const int k = base + lane;
+            int t = k < a.n_keys ? (ecounts[k] + 31) >> 5 : 0;
+            int incl = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            if (k < a.n_keys) tile_prefix[k] = carry + incl - t;
+            carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
+        }
+        if (lane == 0) tile_prefix[a.n_keys] = carry;
+    }
+    __syncthreads();
+    const int total_tiles = tile_prefix[a.n_keys];
+    int* tile_counter = a.counts + a.n_keys + 1;
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(tile_counter, 1);
+        t = __shfl_sync(0xFFFFFFFFu, t, 0);
+        if (t >= total_tiles) break;
+        int lo = 0, hi = a.n_keys - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (tile_prefix[mid] <= t) lo = mid; else hi = mid - 1;
+        }
+        const int key = lo;
+        const KeyRec K = keys[key];
+        const int off = ((t - tile_prefix[key]) << 5) + lane;
+        if (off >= ecounts[key]) continue;
+        const size_t slot = (size_t)key * a.cap + a.epa_slot[(size_t)key * a.cap + off];
+        const float4 r0 = a.q_r0[slot], r1 = a.q_r1[slot], r2 = a.q_r2[slot];
+        const int cfg = a.q_cfg[slot];
+        Tf T;
+        T.r00 = r0.x; T.r01 = r0.y; T.r02 = r0.z; T.tx = r0.w;
+        T.r10 = r1.x; T.r11 = r1.y; T.r12 = r1.z; T.ty = r1.w;
+        T.r20 = r2.x; T.r21 = r2.y; T.r22 = r2.z; T.tz = r2.w;
+        float dist;
+        int iters;
+        Simplex S;
+        const int st = gjk_distance(verts + K.ea_off, K.ea_n, verts + K.eb_off, K.eb_n, T, mk(T.tx, T.ty, T.tz), 1e30f,
+                                    dist, iters, S);
+        float d;
+        if (st == JG_GJK_PENETRATING) {
+            const float depth = epa_depth(verts + K.ea_off, K.ea_n, verts + K.eb_off, K.eb_n, T, S, iters);
+            d = -(depth + K.emsum);
+        } else {
+            d = dist - K.emsum;
+        }
+        d = fminf(d, -K.msum);   // the cores overlap: never report less penetration than the margins
+        atomicMin((K.kind == KEY_SELF ? a.enc_self : a.enc_scene) + cfg, enc_float(d));
     }
 }
 

@@ -9,7 +9,9 @@
 #define __host__
 #define __device__
 #define __forceinline__ inline
+#define __noinline__
 #define __restrict__
+static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 struct float4 { float x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { float4 r = {x, y, z, w}; return r; }
 #else

@@ -194,3 +194,21 @@ class CollisionEngine:
         st = _lib.Stats()
         _lib.check(self._L.jg_get_stats(self._e, C.byref(st)), 'jg_get_stats')
         return {f: getattr(st, f) for f, _ in st._fields_}
+
+    def profile(self, enable=True):
+        """Enable / disable per-kernel CUDA-event timing inside the library (resets the accumulators when enabling)."""
+        _lib.check(self._L.jg_profile_enable(self._e, 1 if enable else 0), 'jg_profile_enable')
+
+    def get_profile(self):
+        """-> {'broadphase': (ms, launches), 'narrowphase': ..., 'penetration': ..., 'finalize': ...} since profile(True)."""
+        ms = (C.c_double * 4)()
+        n = (C.c_int64 * 4)()
+        _lib.check(self._L.jg_get_profile(self._e, ms, n), 'jg_get_profile')
+        return {k: (ms[i], n[i]) for i, k in enumerate(('broadphase', 'narrowphase', 'penetration', 'finalize'))}
+
+
+def measure_fp32_peak(device=0, reps=5):
+    """FP32 FMA micro-benchmark on `device` -> TFLOP/s (roofline denominator of the narrow phase)."""
+    out = C.c_double(0)
+    _lib.check(_lib.load().jg_measure_fp32_peak(device, reps, C.byref(out)), 'jg_measure_fp32_peak')
+    return out.value

@@ -1,7 +1,7 @@
 // Host emulation of the per-thread device GJK (jg_gjk.cuh compiled with g++, JG_HOST_EMU).
 // Test infrastructure: lets the CPU suite check the fp32 kernel numerics against the double oracle.
 #define JG_HOST_EMU 1
-#include "../../jogramop_framework_b200/csrc/jg_gjk.cuh"
+#include "../../jogramop_framework_b200/csrc/jg_epa.cuh"
 
 #include <vector>
 
@@ -9,7 +9,7 @@ using namespace jg;
 
 // va [na,3], vb [nb,3] float; T [n,12] row-major 3x4 (A placed by T, B static); out dist[n], status[n], iters[n]
 extern "C" void emu_gjk_batch(const float* va, int na, const float* vb, int nb, const float* T, int n, float dmax,
-                              float* dist, int* status, int* iters) {
+                              float* dist, int* status, int* iters, float* depth, int* epa_iters) {
     std::vector<float4> A(na), B(nb);
     for (int i = 0; i < na; ++i) A[i] = make_float4(va[3 * i], va[3 * i + 1], va[3 * i + 2], 0.f);
     for (int i = 0; i < nb; ++i) B[i] = make_float4(vb[3 * i], vb[3 * i + 1], vb[3 * i + 2], 0.f);
@@ -21,9 +21,15 @@ extern "C" void emu_gjk_batch(const float* va, int na, const float* vb, int nb, 
         X.r20 = t[8]; X.r21 = t[9]; X.r22 = t[10]; X.tz = t[11];
         float d = 0.f;
         int it = 0;
-        status[k] = gjk_distance(A.data(), na, B.data(), nb, X, mk(X.tx, X.ty, X.tz), dmax, d, it);
+        Simplex S;
+        status[k] = gjk_distance(A.data(), na, B.data(), nb, X, mk(X.tx, X.ty, X.tz), dmax, d, it, S);
         dist[k] = d;
         iters[k] = it;
+        if (status[k] == JG_GJK_PENETRATING && depth) {
+            int eit = 0;
+            depth[k] = epa_depth(A.data(), na, B.data(), nb, X, S, eit);
+            epa_iters[k] = eit;
+        }
     }
 }
 

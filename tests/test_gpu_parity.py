@@ -65,15 +65,19 @@ def test_fk_parity(robot, engines):
 
 
 @pytest.mark.parametrize('sid', [11, 21, 34, 43, 45])
-def test_scene_parity(sid, robot, scene_loader, engines):
+@pytest.mark.parametrize('no_epa', [0, oracle.NO_EPA])
+def test_scene_parity(sid, no_epa, robot, scene_loader, engines):
+    """Full semantics (signed distance incl. penetration depth) and the clamped JG_NO_EPA mode."""
     e = engines(sid)
     o = Oracle(robot, scene_loader(sid))
     q = uniform_configs(robot, 30000, sid)
-    rb, rd = o.check(q.astype(np.float64), flags=oracle.SCENE | oracle.PLANE | oracle.NO_EPA)
-    bits, dist, _ = e.check(q, flags=oracle.SCENE | oracle.PLANE | oracle.NO_EPA)
+    rb, rd = o.check(q.astype(np.float64), flags=oracle.SCENE | oracle.PLANE | no_epa)
+    bits, dist, _ = e.check(q, flags=oracle.SCENE | oracle.PLANE | no_epa)
     nd, me = compare(bits, dist, rb, rd)
     print(f'scenario {sid}: collision rate {rb.mean():.3f}, disagreements in band {nd}, max |dd| {me:.2e}')
     assert 0.15 < rb.mean() < 0.6
+    if not no_epa:
+        assert rd.min() < -0.05 and e.stats()['epa_pairs'] > 1000     # deep penetrations were really measured
 
 
 def test_scene_only_and_plane_only(robot, scene_loader, engines):
@@ -105,10 +109,11 @@ def test_self_collision_and_reason_codes(robot, scene_loader, engines):
     agree = (reason[clear] == rr[clear]).mean()
     assert agree > 0.999          # reason may differ only when self and scene are both within the band
     assert (rr == 2).sum() > 100 and (rr == 1).sum() > 1000
-    # self-collision alone (in_self_collision, simulation.py:439-464)
-    rb, rd = o.check(q[ok].astype(np.float64), flags=oracle.SELF | oracle.NO_EPA)
-    bits, dist, _ = e.check(q[ok], flags=oracle.SELF | oracle.NO_EPA)
-    compare(bits, dist, rb, rd)
+    # self-collision alone (in_self_collision, simulation.py:439-464), with and without penetration depth
+    for extra in (oracle.NO_EPA, 0):
+        rb, rd = o.check(q[ok].astype(np.float64), flags=oracle.SELF | extra)
+        bits, dist, _ = e.check(q[ok], flags=oracle.SELF | extra)
+        compare(bits, dist, rb, rd)
     assert 0.05 < rb.mean() < 0.4
 
 
@@ -134,8 +139,7 @@ def test_edges_parity(robot, scene_loader, engines):
     qa = uniform_configs(robot, 3000, 34)
     rng = np.random.default_rng(3400)
     qb = np.clip(qa + rng.uniform(-0.25, 0.25, qa.shape), lim[:, 0], lim[:, 1]).astype(np.float32)
-    fl = oracle.SCENE | oracle.PLANE | oracle.NO_EPA
-    for sub in (64, 5):
+    for sub, fl in ((64, oracle.SCENE | oracle.PLANE | oracle.NO_EPA), (5, oracle.SCENE | oracle.PLANE)):
         # the oracle interpolates in double from the same float32 endpoints; the kernel interpolates in float32
         rb, rd = o.check_edges(qa.astype(np.float64), qb.astype(np.float64), substeps=sub, flags=fl)
         bits, dist = e.check_edges(qa, qb, substeps=sub, flags=fl)
@@ -161,12 +165,15 @@ def test_gripper_poses_parity(robot, scene_loader, engines):
                    2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
                    2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], 1).reshape(n, 3, 3)
     T = np.concatenate([Rm, pq[:, :3, None].astype(np.float64)], 2)
-    fl = oracle.SCENE | oracle.PLANE | oracle.NO_EPA
+    fl = oracle.SCENE | oracle.PLANE
     rb, rd = o.check_poses(T, links=[11, 12, 13], flags=fl)
     bits, dist = e.check_poses(pq, links=[11, 12, 13], flags=fl)
     compare(bits, dist, rb, rd)
     bits2, dist2 = e.check_poses(T.astype(np.float32), links=[11, 12, 13], flags=fl)
     compare(bits2, dist2, rb, rd)
+    rb, rd = o.check_poses(T, links=[11, 12, 13], flags=fl | oracle.NO_EPA)
+    bits, dist = e.check_poses(pq, links=[11, 12, 13], flags=fl | oracle.NO_EPA)
+    compare(bits, dist, rb, rd)
     assert 0.02 < rb.mean() < 0.9
 
 
@@ -215,15 +222,21 @@ def test_full_size_properties(robot, scene_loader, engines):
     """BASELINE config 2 at full size (1M configs, scenario 011): size-independent properties."""
     e = engines(11)
     q = uniform_configs(robot, 1_000_000, 11)
-    bits, dist, _ = e.check(q, flags=3 | 16)
+    bits, dist, _ = e.check(q, flags=3)
     assert dist.max().item() <= 0.01 + 1e-9
     assert torch.equal(bits, dist < -0.001)                      # verdict == thresholded distance
     # idempotence / determinism
-    bits2, dist2, _ = e.check(q, flags=3 | 16)
+    bits2, dist2, _ = e.check(q, flags=3)
     assert torch.equal(bits, bits2) and torch.equal(dist, dist2)
+    # the clamped mode (JG_NO_EPA) only differs where hull cores overlap: same verdicts, distance clamped at the
+    # margin sum (-0.002).  Checked on SCENE only: plane distances are exact signed values in both modes.
+    bs, ds, _ = e.check(q, flags=1)
+    bs4, ds4, _ = e.check(q, flags=1 | 16)
+    assert torch.equal(bs4, bs)
+    assert (ds4 - torch.clamp(ds, min=-0.002)).abs().max().item() < 1e-6
     # permutation equivariance: results follow their configurations
     perm = torch.randperm(len(q), generator=torch.Generator().manual_seed(0))
-    bits3, dist3, _ = e.check(q[perm.numpy()], flags=3 | 16)
+    bits3, dist3, _ = e.check(q[perm.numpy()], flags=3)
     assert torch.equal(bits3.cpu(), bits.cpu()[perm]) and torch.equal(dist3.cpu(), dist.cpu()[perm])
     # monotone in the threshold: collides(thr=-0.001) implies collides(thr=0)
     e0 = engines(11, threshold=0.0)
@@ -235,5 +248,5 @@ def test_full_size_properties(robot, scene_loader, engines):
     # 1M-prefix check against the oracle on a 20k sample
     o = Oracle(robot, scene_loader(11))
     idx = np.arange(0, 1_000_000, 50)
-    rb, rd = o.check(q[idx].astype(np.float64), flags=3 | 16)
+    rb, rd = o.check(q[idx].astype(np.float64), flags=3)
     compare(bits[torch.from_numpy(idx)], dist[torch.from_numpy(idx)], rb, rd)
