@@ -249,7 +249,7 @@ def run_b200(args):
                        'penetration_depth': 'clamped at -(marginA+marginB) (JG_NO_EPA)' if args.no_epa else 'EPA',
                        'l2': 'flushed between timed iterations (256 MB write)',
                        'collective': 'ncclAllGather of packed verdict bits' if world > 1 else 'none (1 GPU)',
-                       'pass_size': args.chunk or 262144},
+                       'pass_size': args.chunk or 'auto (<= 2^20 configurations per pass)'},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'checks/s', 'h2d_bytes_per_step': int(n * 36),
                     'd2h_bytes_per_step': int(n * 4 + words * 4)},

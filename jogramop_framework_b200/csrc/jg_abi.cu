@@ -164,6 +164,7 @@ struct jg_engine {
     float4 *q_r0 = nullptr, *q_r1 = nullptr, *q_r2 = nullptr;
     int* q_cfg = nullptr;
     int* epa_slot = nullptr;              // [n_keys*cap]
+    uint4* epa_ids = nullptr;             // [n_keys*cap]
     int* counts = nullptr;                // [2*n_keys + 8]
     int *enc_scene = nullptr, *enc_self = nullptr;
     uint32_t* viol = nullptr;
@@ -187,6 +188,7 @@ struct jg_engine {
     unsigned long long* d_stats = nullptr;       // [8]
     cudaStream_t last_stream = nullptr;
     int sm_count = 148;
+    int np_blocks = 0, epa_blocks = 0;
     size_t smem_narrow = 0;
     // optional per-kernel timing (jg_profile_enable)
     bool profiling = false;
@@ -225,7 +227,7 @@ static void engine_release(jg_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaFree(e->d_robot); cudaFree(e->d_pieces); cudaFree(e->d_selfs); cudaFree(e->d_keys); cudaFree(e->d_verts);
-    cudaFree(e->q_r0); cudaFree(e->q_r1); cudaFree(e->q_r2); cudaFree(e->q_cfg); cudaFree(e->epa_slot); cudaFree(e->counts);
+    cudaFree(e->q_r0); cudaFree(e->q_r1); cudaFree(e->q_r2); cudaFree(e->q_cfg); cudaFree(e->epa_slot); cudaFree(e->epa_ids); cudaFree(e->counts);
     cudaFree(e->enc_scene); cudaFree(e->enc_self); cudaFree(e->viol); cudaFree(e->d_link_slot); cudaFree(e->d_rel);
     cudaFree(e->d_use_shapes); cudaFree(e->d_stats);
     for (int i = 0; i < 2; ++i) {
@@ -421,7 +423,7 @@ extern "C" jg_engine* jg_engine_create(const jg_robot* r, const jg_scene* sc, in
     if (build_tables(e, r, sc) != JG_OK) { engine_release(e); return nullptr; }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->sm_count = prop.multiProcessorCount;
-    e->smem_narrow = sizeof(float4) * e->n_verts + sizeof(KeyRec) * e->n_keys + sizeof(int) * (e->n_keys + 1) + 64;
+    e->smem_narrow = sizeof(float4) * e->n_verts + sizeof(KeyRec) * e->n_keys + sizeof(int) * (e->n_keys + 2) + 64;
     const size_t smem_max = 227 * 1024;
     if (e->smem_narrow > smem_max || bp_smem(e, JG_SELF) > smem_max) {
         fail(JG_ERR_INVALID, "scene too large for the shared-memory resident path (%zu B of vertices/keys)", e->smem_narrow);
@@ -437,13 +439,34 @@ extern "C" jg_engine* jg_engine_create(const jg_robot* r, const jg_scene* sc, in
         engine_release(e);
         return nullptr;
     }
-    // scratch arena
-    int cap = e->prm.chunk > 0 ? e->prm.chunk : (1 << 18);
+    // persistent grids: one resident wave of each narrow-phase kernel
+    {
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_narrowphase<NP_BLOCK>, NP_BLOCK, e->smem_narrow) == cudaSuccess && occ > 0)
+            e->np_blocks = e->sm_count * occ;
+        else
+            e->np_blocks = e->sm_count * 2;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_penetration<EPA_BLOCK>, EPA_BLOCK, e->smem_narrow) == cudaSuccess && occ > 0)
+            e->epa_blocks = e->sm_count * occ;
+        else
+            e->epa_blocks = e->sm_count * 4;
+    }
+    // scratch arena: per-key queues of `cap` entries (72 B each).  Default: the largest power of two <= 2^20
+    // configurations per pass whose arena stays within 16 GB and a quarter of the free device memory.
+    int cap = e->prm.chunk;
+    if (cap <= 0) {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const size_t budget = std::min<size_t>((size_t)16 << 30, free_b / 4);
+        const size_t per_cfg = (size_t)std::max(e->n_keys, 1) * 72 + 16;
+        cap = 1 << 20;
+        while (cap > 4096 && (size_t)cap * per_cfg > budget) cap >>= 1;
+    }
     cap = (cap + 1023) / 1024 * 1024;
     e->cap = cap;
     const size_t qn = (size_t)std::max(e->n_keys, 1) * cap;
     bool okm = cudaMalloc(&e->q_r0, sizeof(float4) * qn) == cudaSuccess && cudaMalloc(&e->q_r1, sizeof(float4) * qn) == cudaSuccess &&
-               cudaMalloc(&e->q_r2, sizeof(float4) * qn) == cudaSuccess && cudaMalloc(&e->q_cfg, sizeof(int) * qn) == cudaSuccess && cudaMalloc(&e->epa_slot, sizeof(int) * qn) == cudaSuccess &&
+               cudaMalloc(&e->q_r2, sizeof(float4) * qn) == cudaSuccess && cudaMalloc(&e->q_cfg, sizeof(int) * qn) == cudaSuccess && cudaMalloc(&e->epa_slot, sizeof(int) * qn) == cudaSuccess && cudaMalloc(&e->epa_ids, sizeof(uint4) * qn) == cudaSuccess &&
                cudaMalloc(&e->counts, sizeof(int) * (2 * e->n_keys + 8)) == cudaSuccess &&
                cudaMalloc(&e->enc_scene, sizeof(int) * cap) == cudaSuccess && cudaMalloc(&e->enc_self, sizeof(int) * cap) == cudaSuccess &&
                cudaMalloc(&e->viol, sizeof(uint32_t) * (cap / 32 + 1)) == cudaSuccess &&
@@ -471,7 +494,7 @@ static void fill_args(const jg_engine* e, PassArgs& a, uint32_t flags) {
     a.has_plane = e->has_plane ? 1 : 0;
     a.robot = e->d_robot; a.pieces = e->d_pieces; a.P = e->P; a.selfs = e->d_selfs; a.keys = e->d_keys;
     a.n_keys = e->n_keys; a.n_scene_keys = e->n_scene_keys; a.verts = e->d_verts; a.n_verts = e->n_verts;
-    a.q_r0 = e->q_r0; a.q_r1 = e->q_r1; a.q_r2 = e->q_r2; a.q_cfg = e->q_cfg; a.epa_slot = e->epa_slot; a.cap = e->cap; a.counts = e->counts;
+    a.q_r0 = e->q_r0; a.q_r1 = e->q_r1; a.q_r2 = e->q_r2; a.q_cfg = e->q_cfg; a.epa_slot = e->epa_slot; a.epa_ids = e->epa_ids; a.cap = e->cap; a.counts = e->counts;
     a.enc_scene = e->enc_scene; a.enc_self = e->enc_self; a.viol = e->viol;
 }
 
@@ -500,13 +523,12 @@ static int run_narrow_and_finalize(jg_engine* e, const PassArgs& a, int n_out, u
                                    uint8_t* reason, cudaStream_t st) {
     PROF_MARK(e, st);   // end of broad phase / start of narrow phase
     if (e->n_keys > 0) {
-        const int blocks = e->sm_count * 3;
-        k_narrowphase<NP_BLOCK><<<blocks, NP_BLOCK, e->smem_narrow, st>>>(a);
+        k_narrowphase<NP_BLOCK><<<e->np_blocks, NP_BLOCK, e->smem_narrow, st>>>(a);
         e->stats.kernel_launches += 1;
     }
     PROF_MARK(e, st);
     if (e->n_keys > 0 && !(flags & JG_NO_EPA)) {
-        k_penetration<EPA_BLOCK><<<e->sm_count * 4, EPA_BLOCK, e->smem_narrow, st>>>(a);
+        k_penetration<EPA_BLOCK><<<e->epa_blocks, EPA_BLOCK, e->smem_narrow, st>>>(a);
         e->stats.kernel_launches += 1;
     }
     PROF_MARK(e, st);

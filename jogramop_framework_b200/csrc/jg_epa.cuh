@@ -117,16 +117,27 @@ __device__ __forceinline__ bool epa_blow_up(const float4* __restrict__ A, int nA
     return true;
 }
 
-// Penetration depth of the overlapping sets (origin inside conv(A - B)); S = GJK end simplex.
-// Expanding polytope with edge-adjacency and a flood fill of the faces visible from each new support point
-// (depth-first from the closest face, children in edge order, as in Bullet's btGjkEpa2 expand()): the removed
-// region is edge-connected by construction, so its horizon is one closed loop even when near-coplanar faces
-// are classified inconsistently by fp32 arithmetic.
-__device__ __noinline__ float epa_depth(const float4* __restrict__ A, int nA, const float4* __restrict__ B, int nB,
-                                        const Tf& T, Simplex S, int& iters) {
-    iters = 0;
-    if (S.n < 4 && !epa_blow_up(A, nA, B, nB, T, S)) return 0.f;
+// Penetration depth of overlapping sets (origin inside conv(A - B)) by an expanding polytope with edge adjacency and
+// a flood fill of the faces visible from each new support point (depth-first from the closest face, children in
+// edge order, as in Bullet's btGjkEpa2 expand()): the removed region is edge-connected by construction, so its
+// horizon is one closed loop even when near-coplanar faces are classified inconsistently by fp32 arithmetic.
+//
+// Every closest-face offset is a lower bound of the depth (the polytope lies inside the difference) and every
+// support value h(n) an upper bound; the state keeps the best of both so a late numerical hiccup cannot lose them.
+struct EpaState {
     EpaPoly E;
+    float lb, ub;
+    int it;
+};
+
+// S = GJK end simplex (origin inside or on it).  Returns false when the difference is flat (depth 0, nothing to do).
+__device__ __forceinline__ bool epa_begin(EpaState& X, const float4* __restrict__ A, int nA,
+                                          const float4* __restrict__ B, int nB, const Tf& T, Simplex S) {
+    X.lb = 0.f;
+    X.ub = FLT_MAX;
+    X.it = 0;
+    if (S.n < 4 && !epa_blow_up(A, nA, B, nB, T, S)) { X.ub = 0.f; return false; }
+    EpaPoly& E = X.E;
     E.P[0] = S.a; E.P[1] = S.b; E.P[2] = S.c; E.P[3] = S.d;
     E.pid[0] = S.ia; E.pid[1] = S.ib; E.pid[2] = S.ic; E.pid[3] = S.id;
     // orient so that face (0,1,2) looks away from vertex 3
@@ -142,88 +153,97 @@ __device__ __noinline__ float epa_depth(const float4* __restrict__ A, int nA, co
     epa_make_face(E, 3, 0, 2, 3);
     epa_bind(E, 0, 0, 1, 0); epa_bind(E, 0, 1, 2, 0); epa_bind(E, 0, 2, 3, 0);
     epa_bind(E, 1, 1, 3, 2); epa_bind(E, 1, 2, 2, 1); epa_bind(E, 2, 2, 3, 1);
-    // Every closest-face offset is a lower bound of the depth (the polytope lies inside the difference) and every
-    // support value h(n) an upper bound; keep the best of both so that a late numerical hiccup cannot lose them.
-    float lb = 0.f, ub = FLT_MAX;
-    int it = 0;
-#pragma unroll 1
-    for (; it < JG_EPA_MAX_ITER; ++it) {
-        int best = -1;
-        float bd = FLT_MAX;
-        for (int f = 0; f < E.nf; ++f)
-            if (((E.fv[f] >> 24) & 1u) && E.fd[f] < bd) { bd = E.fd[f]; best = f; }
-        if (best < 0) break;
-        lb = fmaxf(lb, bd);
-        const V3 n = mk(E.fnx[best], E.fny[best], E.fnz[best]);
-        uint32_t id;
-        const V3 w = support_md(A, nA, B, nB, T, n, id);
-        const float hn = dot(n, w);
-        ub = fminf(ub, hn);
-        if (ub - lb <= JG_EPA_TOL) break;
-        bool dupl = false;
-        for (int i = 0; i < E.nv; ++i) dupl |= (E.pid[i] == id);
-        if (dupl || E.nv >= JG_EPA_MAX_V) break;
-        const int vi = E.nv;
-        // ---- flood fill of the visible faces, horizon edges in loop order
-        const uint32_t mark = (uint32_t)(it + 1);
-        uint16_t stack[JG_EPA_MAX_F];      // face | edge << 8
-        uint16_t horizon[JG_EPA_MAX_F];
-        uint8_t removed[JG_EPA_MAX_F];
-        int sp = 0, nh = 0, nr = 0;
-        bool ok = true;
-        E.fv[best] = (E.fv[best] & 0x01FFFFFFu) | (mark << 25);
-        removed[nr++] = (uint8_t)best;
-        {
-            const uint32_t fa = E.fa[best];
-            stack[sp++] = (uint16_t)epa_adj(fa, 2);
-            stack[sp++] = (uint16_t)epa_adj(fa, 1);
-            stack[sp++] = (uint16_t)epa_adj(fa, 0);
-        }
-        while (sp > 0) {
-            const uint32_t fe = stack[--sp];
-            const int f = (int)(fe & 255u), e = (int)(fe >> 8);
-            const uint32_t fv = E.fv[f];
-            if ((fv >> 25) == mark) { ok = false; break; }   // reached twice: inconsistent classification, give up
-            const bool vis = !(E.fd[f] < FLT_MAX) ||
-                             fmaf(E.fnx[f], w.x, fmaf(E.fny[f], w.y, E.fnz[f] * w.z)) - E.fd[f] > JG_EPA_VIS_EPS;
-            if (!vis) {
-                horizon[nh++] = (uint16_t)fe;
-            } else {
-                E.fv[f] = (fv & 0x01FFFFFFu) | (mark << 25);
-                removed[nr++] = (uint8_t)f;
-                const uint32_t fa = E.fa[f];
-                const int e1 = e == 2 ? 0 : e + 1, e2 = e == 0 ? 2 : e - 1;
-                if (sp + 2 > JG_EPA_MAX_F) { ok = false; break; }
-                stack[sp++] = (uint16_t)epa_adj(fa, e2);
-                stack[sp++] = (uint16_t)epa_adj(fa, e1);
-            }
-        }
-        if (!ok || nh < 3 || nh > nr + (JG_EPA_MAX_F - E.nf)) {
-            // undo the marks? not needed: marks are per iteration and we stop here
-            break;
-        }
-        E.P[vi] = w;
-        E.pid[vi] = id;
-        E.nv = vi + 1;
-        int first = -1, prev = -1;
-        for (int j = 0; j < nh; ++j) {
-            const int f = (int)(horizon[j] & 255u), e = (int)(horizon[j] >> 8);
-            const int e1 = e == 2 ? 0 : e + 1;
-            const uint32_t fv = E.fv[f];
-            const int slot = nr > 0 ? (int)removed[--nr] : E.nf++;
-            epa_make_face(E, slot, epa_vert(fv, e1), epa_vert(fv, e), vi);
-            epa_bind(E, slot, 0, f, e);
-            if (prev >= 0) epa_bind(E, prev, 1, slot, 2); else first = slot;
-            prev = slot;
-        }
-        epa_bind(E, prev, 1, first, 2);
-        while (nr > 0) E.fv[removed[--nr]] &= ~(1u << 24);   // the remaining removed faces die
+    return true;
+}
+
+// One expansion (one support evaluation).  Returns true when finished.
+__device__ __forceinline__ bool epa_step(EpaState& X, const float4* __restrict__ A, int nA, const float4* __restrict__ B,
+                                         int nB, const Tf& T) {
+    EpaPoly& E = X.E;
+    int best = -1;
+    float bd = FLT_MAX;
+    for (int f = 0; f < E.nf; ++f)
+        if (((E.fv[f] >> 24) & 1u) && E.fd[f] < bd) { bd = E.fd[f]; best = f; }
+    if (best < 0) return true;
+    X.lb = fmaxf(X.lb, bd);
+    const V3 n = mk(E.fnx[best], E.fny[best], E.fnz[best]);
+    uint32_t id;
+    const V3 w = support_md(A, nA, B, nB, T, n, id);
+    X.ub = fminf(X.ub, dot(n, w));
+    X.it += 1;
+    if (X.ub - X.lb <= JG_EPA_TOL || X.it >= JG_EPA_MAX_ITER) return true;
+    bool dupl = false;
+    for (int i = 0; i < E.nv; ++i) dupl |= (E.pid[i] == id);
+    if (dupl || E.nv >= JG_EPA_MAX_V) return true;
+    const int vi = E.nv;
+    // ---- flood fill of the visible faces, horizon edges in loop order
+    const uint32_t mark = (uint32_t)X.it;
+    uint16_t stack[JG_EPA_MAX_F];      // face | edge << 8
+    uint16_t horizon[JG_EPA_MAX_F];
+    uint8_t removed[JG_EPA_MAX_F];
+    int sp = 0, nh = 0, nr = 0;
+    E.fv[best] = (E.fv[best] & 0x01FFFFFFu) | (mark << 25);
+    removed[nr++] = (uint8_t)best;
+    {
+        const uint32_t fa = E.fa[best];
+        stack[sp++] = (uint16_t)epa_adj(fa, 2);
+        stack[sp++] = (uint16_t)epa_adj(fa, 1);
+        stack[sp++] = (uint16_t)epa_adj(fa, 0);
     }
-    iters = it + 1;
-    // converged: midpoint of the bracket; otherwise (iteration / size caps, inconsistent mesh) the bracket is still
-    // valid: report its midpoint when tight, else the guaranteed lower bound
-    if (ub < FLT_MAX && ub - lb <= 1e-4f) return fmaxf(0.5f * (lb + ub), 0.f);
-    return lb;
+    while (sp > 0) {
+        const uint32_t fe = stack[--sp];
+        const int f = (int)(fe & 255u), e = (int)(fe >> 8);
+        const uint32_t fv = E.fv[f];
+        if ((fv >> 25) == mark) return true;   // reached twice: inconsistent classification, keep the bracket
+        const bool vis = !(E.fd[f] < FLT_MAX) ||
+                         fmaf(E.fnx[f], w.x, fmaf(E.fny[f], w.y, E.fnz[f] * w.z)) - E.fd[f] > JG_EPA_VIS_EPS;
+        if (!vis) {
+            horizon[nh++] = (uint16_t)fe;
+        } else {
+            E.fv[f] = (fv & 0x01FFFFFFu) | (mark << 25);
+            removed[nr++] = (uint8_t)f;
+            const uint32_t fa = E.fa[f];
+            const int e1 = e == 2 ? 0 : e + 1, e2 = e == 0 ? 2 : e - 1;
+            if (sp + 2 > JG_EPA_MAX_F) return true;
+            stack[sp++] = (uint16_t)epa_adj(fa, e2);
+            stack[sp++] = (uint16_t)epa_adj(fa, e1);
+        }
+    }
+    if (nh < 3 || nh > nr + (JG_EPA_MAX_F - E.nf)) return true;
+    E.P[vi] = w;
+    E.pid[vi] = id;
+    E.nv = vi + 1;
+    int first = -1, prev = -1;
+    for (int j = 0; j < nh; ++j) {
+        const int f = (int)(horizon[j] & 255u), e = (int)(horizon[j] >> 8);
+        const int e1 = e == 2 ? 0 : e + 1;
+        const uint32_t fv = E.fv[f];
+        const int slot = nr > 0 ? (int)removed[--nr] : E.nf++;
+        epa_make_face(E, slot, epa_vert(fv, e1), epa_vert(fv, e), vi);
+        epa_bind(E, slot, 0, f, e);
+        if (prev >= 0) epa_bind(E, prev, 1, slot, 2); else first = slot;
+        prev = slot;
+    }
+    epa_bind(E, prev, 1, first, 2);
+    while (nr > 0) E.fv[removed[--nr]] &= ~(1u << 24);   // the remaining removed faces die
+    return false;
+}
+
+// converged: midpoint of the bracket; otherwise (iteration / size caps, inconsistent mesh) the bracket is still valid:
+// its midpoint when tight, else the guaranteed lower bound
+__device__ __forceinline__ float epa_result(const EpaState& X) {
+    if (X.ub < FLT_MAX && X.ub - X.lb <= 1e-4f) return fmaxf(0.5f * (X.lb + X.ub), 0.f);
+    return X.lb;
+}
+
+__device__ __noinline__ float epa_depth(const float4* __restrict__ A, int nA, const float4* __restrict__ B, int nB,
+                                        const Tf& T, Simplex S, int& iters) {
+    EpaState X;
+    iters = 0;
+    if (!epa_begin(X, A, nA, B, nB, T, S)) return 0.f;
+    while (!epa_step(X, A, nA, B, nB, T)) {}
+    iters = X.it;
+    return epa_result(X);
 }
 
 }  // namespace jg

@@ -88,94 +88,120 @@ __device__ __forceinline__ void simplex_set3(Simplex& S, V3 p0, V3 p1, V3 p2, ui
     S.n = n;
 }
 
-// Distance between conv(A) placed by T and conv(B) (B frame).  v0: initial separating direction guess.
-// Returns JG_GJK_*; dist is valid for JG_GJK_SEPARATED.
-__device__ __forceinline__ int gjk_distance(const float4* __restrict__ A, int nA, const float4* __restrict__ B, int nB,
-                                            const Tf& T, V3 v0, float dmax, float& dist, int& iters, Simplex& S) {
-    S.n = 0;
-    S.a = S.b = S.c = S.d = mk(0.f, 0.f, 0.f);
-    S.ia = S.ib = S.ic = S.id = 0xFFFFFFFFu;
-    V3 v = v0;
-    if (!(norm2(v) > 1e-12f)) v = mk(1.f, 0.f, 0.f);
-    float vv = FLT_MAX;
-    int status = JG_GJK_SEPARATED;
-    int it = 0;
-    for (; it < JG_GJK_MAX_ITER; ++it) {
-        // support point of A - B in direction -v
-        const V3 dl = tf_rot_t(T, -v);
-        const int ia = support_scan(A, nA, dl);
-        const int ib = support_scan(B, nB, v);
-        const float4 pa = A[ia];
-        const float4 pb = B[ib];
-        const V3 w = tf_apply(T, mk(pa.x, pa.y, pa.z)) - mk(pb.x, pb.y, pb.z);
-        const uint32_t id = ((uint32_t)ia << 16) | (uint32_t)ib;
-        const float vw = dot(v, w);
-        const float v2 = norm2(v);
-        if (vw > 0.f && vw * vw > dmax * dmax * v2) { status = JG_GJK_FAR; break; }
-        if (S.n > 0) {
-            const bool dupl = (id == S.ia) || (S.n > 1 && id == S.ib) || (S.n > 2 && id == S.ic);
-            if (dupl || vv - vw <= JG_GJK_TOL * sqrtf(vv)) break;
-        }
-        // push w as the newest vertex
-        S.d = S.c; S.id = S.ic;
-        S.c = S.b; S.ic = S.ib;
-        S.b = S.a; S.ib = S.ia;
-        S.a = w;   S.ia = id;
-        S.n += 1;
-        V3 nv;
-        if (S.n == 1) {
-            nv = w;
-        } else if (S.n == 2) {
-            const V3 ab = S.b - S.a;
-            const float t = -dot(S.a, ab), den = norm2(ab);
-            if (t <= 0.f || !(den > 0.f)) { nv = S.a; S.n = 1; }
-            else if (t >= den) { nv = S.b; S.a = S.b; S.ia = S.ib; S.n = 1; }
-            else nv = S.a + ab * (t / den);
-        } else if (S.n == 3) {
-            int mask;
-            nv = tri_closest(S.a, S.b, S.c, mask);
-            if (mask != 7) simplex_set3(S, S.a, S.b, S.c, S.ia, S.ib, S.ic, mask);
-        } else {
-            // tetrahedron (a,b,c,d): the closest feature always contains the newest vertex a, so only the
-            // three faces through a are candidates; the origin is inside iff it is inside all three.
-            const V3 A0 = S.a, B0 = S.b, C0 = S.c, D0 = S.d;
-            const uint32_t ja = S.ia, jb = S.ib, jc = S.ic, jd = S.id;
-            float best = FLT_MAX;
-            bool any_out = false;
-            nv = mk(0.f, 0.f, 0.f);
+enum { JG_GJK_RUNNING = -1 };
+
+struct GjkState {
+    Simplex S;
+    V3 v;        // current closest point of the simplex to the origin (separating direction)
+    float vv;    // |v|^2 (FLT_MAX before the first vertex)
+    int it;
+};
+
+__device__ __forceinline__ void gjk_init(GjkState& G, V3 v0) {
+    G.S.n = 0;
+    G.S.a = G.S.b = G.S.c = G.S.d = mk(0.f, 0.f, 0.f);
+    G.S.ia = G.S.ib = G.S.ic = G.S.id = 0xFFFFFFFFu;
+    G.v = v0;
+    if (!(norm2(G.v) > 1e-12f)) G.v = mk(1.f, 0.f, 0.f);
+    G.vv = FLT_MAX;
+    G.it = 0;
+}
+
+// One GJK iteration: one support evaluation of A - B plus the simplex update.  Returns JG_GJK_RUNNING or the
+// final status; for JG_GJK_SEPARATED the distance is sqrtf(G.vv).
+__device__ __forceinline__ int gjk_step(GjkState& G, const float4* __restrict__ A, int nA, const float4* __restrict__ B,
+                                        int nB, const Tf& T, float dmax) {
+    Simplex& S = G.S;
+    const V3 v = G.v;
+    // support point of A - B in direction -v
+    const V3 dl = tf_rot_t(T, -v);
+    const int ia = support_scan(A, nA, dl);
+    const int ib = support_scan(B, nB, v);
+    const float4 pa = A[ia];
+    const float4 pb = B[ib];
+    const V3 w = tf_apply(T, mk(pa.x, pa.y, pa.z)) - mk(pb.x, pb.y, pb.z);
+    const uint32_t id = ((uint32_t)ia << 16) | (uint32_t)ib;
+    const float vw = dot(v, w);
+    const float v2 = norm2(v);
+    G.it += 1;
+    if (vw > 0.f && vw * vw > dmax * dmax * v2) return JG_GJK_FAR;
+    if (S.n > 0) {
+        const bool dupl = (id == S.ia) || (S.n > 1 && id == S.ib) || (S.n > 2 && id == S.ic);
+        if (dupl || G.vv - vw <= JG_GJK_TOL * sqrtf(G.vv)) return JG_GJK_SEPARATED;
+    }
+    // push w as the newest vertex
+    S.d = S.c; S.id = S.ic;
+    S.c = S.b; S.ic = S.ib;
+    S.b = S.a; S.ib = S.ia;
+    S.a = w;   S.ia = id;
+    S.n += 1;
+    V3 nv;
+    if (S.n == 1) {
+        nv = w;
+    } else if (S.n == 2) {
+        const V3 ab = S.b - S.a;
+        const float t = -dot(S.a, ab), den = norm2(ab);
+        if (t <= 0.f || !(den > 0.f)) { nv = S.a; S.n = 1; }
+        else if (t >= den) { nv = S.b; S.a = S.b; S.ia = S.ib; S.n = 1; }
+        else nv = S.a + ab * (t / den);
+    } else if (S.n == 3) {
+        int mask;
+        nv = tri_closest(S.a, S.b, S.c, mask);
+        if (mask != 7) simplex_set3(S, S.a, S.b, S.c, S.ia, S.ib, S.ic, mask);
+    } else {
+        // tetrahedron (a,b,c,d): the closest feature always contains the newest vertex a, so only the
+        // three faces through a are candidates; the origin is inside iff it is inside all three.
+        const V3 A0 = S.a, B0 = S.b, C0 = S.c, D0 = S.d;
+        const uint32_t ja = S.ia, jb = S.ib, jc = S.ic, jd = S.id;
+        float best = FLT_MAX;
+        bool any_out = false;
+        nv = mk(0.f, 0.f, 0.f);
 #pragma unroll
-            for (int f = 0; f < 3; ++f) {
-                const V3 x = f == 0 ? B0 : (f == 1 ? C0 : D0);
-                const V3 y = f == 0 ? C0 : (f == 1 ? D0 : B0);
-                const V3 z = f == 0 ? D0 : (f == 1 ? B0 : C0);
-                const uint32_t jx = f == 0 ? jb : (f == 1 ? jc : jd);
-                const uint32_t jy = f == 0 ? jc : (f == 1 ? jd : jb);
-                const V3 nrm = cross(x - A0, y - A0);
-                const float sp = -dot(A0, nrm);
-                const float sd = dot(z - A0, nrm);
-                const bool outside = !(sp * sd > 0.f);
-                if (outside) {
-                    any_out = true;
-                    int mask;
-                    const V3 cand = tri_closest(A0, x, y, mask);
-                    const float c2 = norm2(cand);
-                    if (c2 < best) {
-                        best = c2;
-                        nv = cand;
-                        simplex_set3(S, A0, x, y, ja, jx, jy, mask);
-                    }
+        for (int f = 0; f < 3; ++f) {
+            const V3 x = f == 0 ? B0 : (f == 1 ? C0 : D0);
+            const V3 y = f == 0 ? C0 : (f == 1 ? D0 : B0);
+            const V3 z = f == 0 ? D0 : (f == 1 ? B0 : C0);
+            const uint32_t jx = f == 0 ? jb : (f == 1 ? jc : jd);
+            const uint32_t jy = f == 0 ? jc : (f == 1 ? jd : jb);
+            const V3 nrm = cross(x - A0, y - A0);
+            const float sp = -dot(A0, nrm);
+            const float sd = dot(z - A0, nrm);
+            const bool outside = !(sp * sd > 0.f);
+            if (outside) {
+                any_out = true;
+                int mask;
+                const V3 cand = tri_closest(A0, x, y, mask);
+                const float c2 = norm2(cand);
+                if (c2 < best) {
+                    best = c2;
+                    nv = cand;
+                    simplex_set3(S, A0, x, y, ja, jx, jy, mask);
                 }
             }
-            if (!any_out) { status = JG_GJK_PENETRATING; vv = 0.f; break; }
         }
-        const float nvv = norm2(nv);
-        if (!(nvv > 1e-14f)) { status = JG_GJK_PENETRATING; vv = 0.f; break; }  // touching: treat as overlap
-        if (nvv >= vv) break;                                                   // numerical stall
-        v = nv;
-        vv = nvv;
+        if (!any_out) { G.vv = 0.f; return JG_GJK_PENETRATING; }
     }
-    iters = it + 1;
-    dist = sqrtf(vv);
+    const float nvv = norm2(nv);
+    if (!(nvv > 1e-14f)) { G.vv = 0.f; return JG_GJK_PENETRATING; }   // touching: treat as overlap
+    if (nvv >= G.vv) return JG_GJK_SEPARATED;                         // numerical stall
+    G.v = nv;
+    G.vv = nvv;
+    return G.it >= JG_GJK_MAX_ITER ? (int)JG_GJK_SEPARATED : (int)JG_GJK_RUNNING;
+}
+
+// Distance between conv(A) placed by T and conv(B) (B frame).  v0: initial separating direction guess.
+// Returns JG_GJK_*; dist is valid for JG_GJK_SEPARATED; S receives the end simplex.
+__device__ __forceinline__ int gjk_distance(const float4* __restrict__ A, int nA, const float4* __restrict__ B, int nB,
+                                            const Tf& T, V3 v0, float dmax, float& dist, int& iters, Simplex& S) {
+    GjkState G;
+    gjk_init(G, v0);
+    int status;
+    do {
+        status = gjk_step(G, A, nA, B, nB, T, dmax);
+    } while (status == JG_GJK_RUNNING);
+    iters = G.it;
+    dist = sqrtf(G.vv);
+    S = G.S;
     return status;
 }
 

@@ -97,6 +97,7 @@ struct PassArgs {
     int* counts;       // [n_keys] pair counts, [n_keys] GJK tile counter, [n_keys+1] EPA tile counter,
                        // [n_keys+8 .. 2 n_keys+8) penetration-queue counts
     int* epa_slot;     // [n_keys*cap] queue slots whose cores overlap (penetration-depth pass)
+    uint4* epa_ids;    // [n_keys*cap] their GJK end simplices (vertex ids, 0xFFFFFFFF = unused)
     // per-configuration scratch
     int* enc_scene;    // encoded min contact distance vs scene+plane
     int* enc_self;
@@ -291,12 +292,67 @@ __global__ void __launch_bounds__(BLOCK) k_broadphase(const PassArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------ narrow phase
+// Work distribution shared by the GJK and the penetration kernels.  A key's queue is cut into ranges of `G`
+// consecutive entries; warps pull ranges from a global counter (dynamic balance) and process a range with LANE
+// REFILL: whenever a lane finishes its pair it takes the next entry of the range, so every pass over the vertex
+// sets (the expensive, warp-uniform part of an iteration) runs with all lanes busy until the range drains.
+struct RangeSched {
+    int* prefix;   // smem [n_keys+1] exclusive scan of ranges per key
+    int G;         // entries per range (multiple of 32)
+    int total;     // total ranges
+};
+
+// called by warp 0 of the block; counts = per-key entry counts
+__device__ __forceinline__ void sched_build(const int* __restrict__ counts, int n_keys, int n_warps_total, int* prefix,
+                                            int* g_out, int lane) {
+    int tot = 0;
+    for (int k = lane; k < n_keys; k += 32) tot += counts[k];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xFFFFFFFFu, tot, o);
+    // aim at ~4 ranges per warp so that the dynamic scheduler can balance keys of different cost
+    int G = (tot / (n_warps_total * 4) + 31) & ~31;
+    G = max(64, min(G, 2048));
+    int carry = 0;
+    for (int base = 0; base < n_keys; base += 32) {
+        const int k = base + lane;
+        const int t = k < n_keys ? (counts[k] + G - 1) / G : 0;
+        int incl = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        if (k < n_keys) prefix[k] = carry + incl - t;
+        carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+    if (lane == 0) { prefix[n_keys] = carry; *g_out = G; }
+}
+
+__device__ __forceinline__ int sched_find_key(const int* prefix, int n_keys, int r) {
+    int lo = 0, hi = n_keys - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (prefix[mid] <= r) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ Tf load_entry(const PassArgs& a, size_t slot, int& cfg) {
+    const float4 r0 = a.q_r0[slot], r1 = a.q_r1[slot], r2 = a.q_r2[slot];
+    cfg = a.q_cfg[slot];
+    Tf T;
+    T.r00 = r0.x; T.r01 = r0.y; T.r02 = r0.z; T.tx = r0.w;
+    T.r10 = r1.x; T.r11 = r1.y; T.r12 = r1.z; T.ty = r1.w;
+    T.r20 = r2.x; T.r21 = r2.y; T.r22 = r2.z; T.tz = r2.w;
+    return T;
+}
+
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_narrowphase(const PassArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* verts = reinterpret_cast<float4*>(smem_raw);
     KeyRec* keys = reinterpret_cast<KeyRec*>(smem_raw + sizeof(float4) * a.n_verts);
-    int* tile_prefix = reinterpret_cast<int*>(keys + a.n_keys);   // [n_keys+1]
+    int* prefix = reinterpret_cast<int*>(keys + a.n_keys);   // [n_keys+1], then G
     const int tid = threadIdx.x, lane = tid & 31;
     for (int i = tid; i < a.n_verts; i += BLOCK) verts[i] = a.verts[i];
     {
@@ -304,84 +360,108 @@ __global__ void __launch_bounds__(BLOCK) k_narrowphase(const PassArgs a) {
         int* kd = reinterpret_cast<int*>(keys);
         for (int i = tid; i < (int)(sizeof(KeyRec) / 4) * a.n_keys; i += BLOCK) kd[i] = ks[i];
     }
-    if (tid < 32) {   // warp 0: exclusive scan of the per-key tile counts
-        int carry = 0;
-        for (int base = 0; base < a.n_keys; base += 32) {
-            const int k = base + lane;
-            int t = k < a.n_keys ? (a.counts[k] + 31) >> 5 : 0;
-            int incl = t;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                if (lane >= o) incl += up;
-            }
-            if (k < a.n_keys) tile_prefix[k] = carry + incl - t;
-            carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
-        }
-        if (lane == 0) tile_prefix[a.n_keys] = carry;
-    }
+    if (tid < 32) sched_build(a.counts, a.n_keys, gridDim.x * (BLOCK / 32), prefix, prefix + a.n_keys + 1, lane);
     __syncthreads();
-    const int total_tiles = tile_prefix[a.n_keys];
-    int* tile_counter = a.counts + a.n_keys;
+    const int total = prefix[a.n_keys], G = prefix[a.n_keys + 1];
+    int* range_counter = a.counts + a.n_keys;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const bool want_epa = !(a.flags & 16u);
 
     for (;;) {
-        int t = 0;
-        if (lane == 0) t = atomicAdd(tile_counter, 1);
-        t = __shfl_sync(0xFFFFFFFFu, t, 0);
-        if (t >= total_tiles) break;
-        // key of tile t: last key with tile_prefix[key] <= t
-        int lo = 0, hi = a.n_keys - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (tile_prefix[mid] <= t) lo = mid; else hi = mid - 1;
-        }
-        const int key = lo;
+        int r = 0;
+        if (lane == 0) r = atomicAdd(range_counter, 1);
+        r = __shfl_sync(0xFFFFFFFFu, r, 0);
+        if (r >= total) break;
+        const int key = sched_find_key(prefix, a.n_keys, r);
         const KeyRec K = keys[key];
-        const int off = ((t - tile_prefix[key]) << 5) + lane;
-        const bool active = off < a.counts[key];
-        const size_t slot = (size_t)key * a.cap + (active ? off : 0);
-        const float4 r0 = a.q_r0[slot], r1 = a.q_r1[slot], r2 = a.q_r2[slot];
-        const int cfg = a.q_cfg[slot];
-        Tf T;
-        T.r00 = r0.x; T.r01 = r0.y; T.r02 = r0.z; T.tx = r0.w;
-        T.r10 = r1.x; T.r11 = r1.y; T.r12 = r1.z; T.ty = r1.w;
-        T.r20 = r2.x; T.r21 = r2.y; T.r22 = r2.z; T.tz = r2.w;
-        float d = FLT_MAX;
-        bool deep = false;
-        if (K.kind == KEY_PLANE) {
-            d = plane_distance(verts + K.a_off, K.a_n, T, mk(a.plane[0], a.plane[1], a.plane[2]), a.plane[3]) - K.msum;
-        } else if (active) {
-            float dist;
-            int iters;
-            Simplex S;
-            const int st = gjk_distance(verts + K.a_off, K.a_n, verts + K.b_off, K.b_n, T, mk(T.tx, T.ty, T.tz),
-                                        a.qd + K.msum, dist, iters, S);
-            if (st == JG_GJK_SEPARATED) d = dist - K.msum;
-            else if (st == JG_GJK_PENETRATING) { d = -K.msum; deep = !(a.flags & 16u); }
+        const int begin = (r - prefix[key]) * G;
+        const int end = min(begin + G, a.counts[key]);
+        const size_t kbase = (size_t)key * a.cap;
+        int* enc = K.kind == KEY_SELF ? a.enc_self : a.enc_scene;
+
+        if (K.kind == KEY_PLANE) {   // uniform cost per entry: plain strided loop
+            for (int off = begin + lane; off < end; off += 32) {
+                int cfg;
+                const Tf T = load_entry(a, kbase + off, cfg);
+                const float d = plane_distance(verts + K.a_off, K.a_n, T, mk(a.plane[0], a.plane[1], a.plane[2]),
+                                               a.plane[3]) - K.msum;
+                if (d <= a.qd) atomicMin(enc + cfg, enc_float(d));
+            }
+            continue;
         }
-        if (active && !deep && d <= a.qd) atomicMin((K.kind == KEY_SELF ? a.enc_self : a.enc_scene) + cfg, enc_float(d));
-        if (K.kind != KEY_PLANE && !(a.flags & 16u)) {   // cores overlap: hand over to the penetration-depth pass
-            const unsigned m = __ballot_sync(0xFFFFFFFFu, deep);
-            if (m) {
-                const int leader = __ffs(m) - 1;
-                int base = 0;
-                if (lane == leader) base = atomicAdd(a.counts + a.n_keys + 8 + key, __popc(m));
-                base = __shfl_sync(0xFFFFFFFFu, base, leader);
-                if (deep) a.epa_slot[(size_t)key * a.cap + base + __popc(m & ((1u << lane) - 1u))] = off;
+
+        const float4* A = verts + K.a_off;
+        const float4* B = verts + K.b_off;
+        const float dmax = a.qd + K.msum;
+        int next = begin;
+        bool active = false;
+        GjkState S;
+        Tf T = tf_identity();
+        int cfg = 0, off = 0;
+        for (;;) {
+            // ---- refill idle lanes from the range
+            const unsigned need = __ballot_sync(0xFFFFFFFFu, !active);
+            const int avail = end - next;
+            if (need && avail > 0) {
+                const int rank = __popc(need & lt_mask);
+                if (!active && rank < avail) {
+                    off = next + rank;
+                    T = load_entry(a, kbase + off, cfg);
+                    gjk_init(S, mk(T.tx, T.ty, T.tz));
+                    active = true;
+                }
+                next += min(__popc(need), avail);
+            }
+            if (!__any_sync(0xFFFFFFFFu, active)) break;
+            // ---- one GJK iteration on every busy lane
+            bool deep = false;
+            if (active) {
+                const int st = gjk_step(S, A, K.a_n, B, K.b_n, T, dmax);
+                if (st != JG_GJK_RUNNING) {
+                    active = false;
+                    if (st == JG_GJK_SEPARATED) {
+                        const float d = sqrtf(S.vv) - K.msum;
+                        if (d <= a.qd) atomicMin(enc + cfg, enc_float(d));
+                    } else if (st == JG_GJK_PENETRATING) {
+                        if (want_epa) deep = true;
+                        else atomicMin(enc + cfg, enc_float(-K.msum));
+                    }
+                }
+            }
+            if (want_epa) {   // cores overlap: hand the pair (and its end simplex) to the penetration-depth pass
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, deep);
+                if (m) {
+                    const int leader = __ffs(m) - 1;
+                    int base = 0;
+                    if (lane == leader) base = atomicAdd(a.counts + a.n_keys + 8 + key, __popc(m));
+                    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                    if (deep) {
+                        const size_t j = kbase + base + __popc(m & lt_mask);
+                        a.epa_slot[j] = off;
+                        a.epa_ids[j] = make_uint4(S.S.n > 0 ? S.S.ia : 0xFFFFFFFFu, S.S.n > 1 ? S.S.ib : 0xFFFFFFFFu,
+                                                  S.S.n > 2 ? S.S.ic : 0xFFFFFFFFu, S.S.n > 3 ? S.S.id : 0xFFFFFFFFu);
+                    }
+                }
             }
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------- penetration depth
-// Pairs whose cores overlap: GJK on the penetration geometry for a start simplex, then the expanding polytope.
-// Same bucketing as the narrow phase: one 32-entry tile of one key per warp.
+// Pairs whose cores overlap.  Start simplex = the GJK end simplex handed over by the narrow phase (rebuilt from its
+// vertex ids); shapes whose penetration geometry differs from the GJK core (boxes) rerun GJK on that geometry first.
+__device__ __forceinline__ V3 md_point(const float4* __restrict__ A, const float4* __restrict__ B, const Tf& T,
+                                       uint32_t id) {
+    const float4 pa = A[id >> 16], pb = B[id & 0xFFFFu];
+    return tf_apply(T, mk(pa.x, pa.y, pa.z)) - mk(pb.x, pb.y, pb.z);
+}
+
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_penetration(const PassArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* verts = reinterpret_cast<float4*>(smem_raw);
     KeyRec* keys = reinterpret_cast<KeyRec*>(smem_raw + sizeof(float4) * a.n_verts);
-    int* tile_prefix = reinterpret_cast<int*>(keys + a.n_keys);
+    int* prefix = reinterpret_cast<int*>(keys + a.n_keys);
     const int tid = threadIdx.x, lane = tid & 31;
     const int* ecounts = a.counts + a.n_keys + 8;
     for (int i = tid; i < a.n_verts; i += BLOCK) verts[i] = a.verts[i];
@@ -390,60 +470,84 @@ __global__ void __launch_bounds__(BLOCK) k_penetration(const PassArgs a) {
         int* kd = reinterpret_cast<int*>(keys);
         for (int i = tid; i < (int)(sizeof(KeyRec) / 4) * a.n_keys; i += BLOCK) kd[i] = ks[i];
     }
-    if (tid < 32) {
-        int carry = 0;
-        for (int base = 0; base < a.n_keys; base += 32) {
-            const int k = base + lane;
-            int t = k < a.n_keys ? (ecounts[k] + 31) >> 5 : 0;
-            int incl = t;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                if (lane >= o) incl += up;
-            }
-            if (k < a.n_keys) tile_prefix[k] = carry + incl - t;
-            carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
-        }
-        if (lane == 0) tile_prefix[a.n_keys] = carry;
-    }
+    if (tid < 32) sched_build(ecounts, a.n_keys, gridDim.x * (BLOCK / 32), prefix, prefix + a.n_keys + 1, lane);
     __syncthreads();
-    const int total_tiles = tile_prefix[a.n_keys];
-    int* tile_counter = a.counts + a.n_keys + 1;
+    const int total = prefix[a.n_keys], G = prefix[a.n_keys + 1];
+    int* range_counter = a.counts + a.n_keys + 1;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
     for (;;) {
-        int t = 0;
-        if (lane == 0) t = atomicAdd(tile_counter, 1);
-        t = __shfl_sync(0xFFFFFFFFu, t, 0);
-        if (t >= total_tiles) break;
-        int lo = 0, hi = a.n_keys - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (tile_prefix[mid] <= t) lo = mid; else hi = mid - 1;
-        }
-        const int key = lo;
+        int r = 0;
+        if (lane == 0) r = atomicAdd(range_counter, 1);
+        r = __shfl_sync(0xFFFFFFFFu, r, 0);
+        if (r >= total) break;
+        const int key = sched_find_key(prefix, a.n_keys, r);
         const KeyRec K = keys[key];
-        const int off = ((t - tile_prefix[key]) << 5) + lane;
-        if (off >= ecounts[key]) continue;
-        const size_t slot = (size_t)key * a.cap + a.epa_slot[(size_t)key * a.cap + off];
-        const float4 r0 = a.q_r0[slot], r1 = a.q_r1[slot], r2 = a.q_r2[slot];
-        const int cfg = a.q_cfg[slot];
-        Tf T;
-        T.r00 = r0.x; T.r01 = r0.y; T.r02 = r0.z; T.tx = r0.w;
-        T.r10 = r1.x; T.r11 = r1.y; T.r12 = r1.z; T.ty = r1.w;
-        T.r20 = r2.x; T.r21 = r2.y; T.r22 = r2.z; T.tz = r2.w;
-        float dist;
-        int iters;
-        Simplex S;
-        const int st = gjk_distance(verts + K.ea_off, K.ea_n, verts + K.eb_off, K.eb_n, T, mk(T.tx, T.ty, T.tz), 1e30f,
-                                    dist, iters, S);
-        float d;
-        if (st == JG_GJK_PENETRATING) {
-            const float depth = epa_depth(verts + K.ea_off, K.ea_n, verts + K.eb_off, K.eb_n, T, S, iters);
-            d = -(depth + K.emsum);
-        } else {
-            d = dist - K.emsum;
+        const int begin = (r - prefix[key]) * G;
+        const int end = min(begin + G, ecounts[key]);
+        const size_t kbase = (size_t)key * a.cap;
+        int* enc = K.kind == KEY_SELF ? a.enc_self : a.enc_scene;
+        const float4* A = verts + K.ea_off;
+        const float4* B = verts + K.eb_off;
+        const bool regjk = (K.ea_off != K.a_off) || (K.eb_off != K.b_off);   // warp-uniform
+
+        int next = begin;
+        int phase = 0;   // 0 idle, 1 GJK on the penetration geometry, 2 expanding polytope
+        GjkState S;
+        EpaState X;
+        Tf T = tf_identity();
+        int cfg = 0;
+        for (;;) {
+            const unsigned need = __ballot_sync(0xFFFFFFFFu, phase == 0);
+            const int avail = end - next;
+            if (need && avail > 0) {
+                const int rank = __popc(need & lt_mask);
+                if (phase == 0 && rank < avail) {
+                    const size_t j = kbase + next + rank;
+                    T = load_entry(a, kbase + a.epa_slot[j], cfg);
+                    if (regjk) {
+                        gjk_init(S, mk(T.tx, T.ty, T.tz));
+                        phase = 1;
+                    } else {
+                        const uint4 ids = a.epa_ids[j];
+                        Simplex sx;
+                        sx.a = sx.b = sx.c = sx.d = mk(0.f, 0.f, 0.f);
+                        sx.ia = ids.x; sx.ib = ids.y; sx.ic = ids.z; sx.id = ids.w;
+                        sx.n = 0;
+                        if (ids.x != 0xFFFFFFFFu) { sx.a = md_point(A, B, T, ids.x); sx.n = 1; }
+                        if (ids.y != 0xFFFFFFFFu) { sx.b = md_point(A, B, T, ids.y); sx.n = 2; }
+                        if (ids.z != 0xFFFFFFFFu) { sx.c = md_point(A, B, T, ids.z); sx.n = 3; }
+                        if (ids.w != 0xFFFFFFFFu) { sx.d = md_point(A, B, T, ids.w); sx.n = 4; }
+                        phase = 2;
+                        if (!epa_begin(X, A, K.ea_n, B, K.eb_n, T, sx)) {
+                            atomicMin(enc + cfg, enc_float(fminf(-K.emsum, -K.msum)));
+                            phase = 0;
+                        }
+                    }
+                }
+                next += min(__popc(need), avail);
+            }
+            if (!__any_sync(0xFFFFFFFFu, phase != 0)) break;
+            if (phase == 1) {
+                const int st = gjk_step(S, A, K.ea_n, B, K.eb_n, T, 1e30f);
+                if (st == JG_GJK_PENETRATING) {
+                    phase = 2;
+                    if (!epa_begin(X, A, K.ea_n, B, K.eb_n, T, S.S)) {
+                        atomicMin(enc + cfg, enc_float(fminf(-K.emsum, -K.msum)));
+                        phase = 0;
+                    }
+                } else if (st != JG_GJK_RUNNING) {   // the penetration geometry does not overlap after all
+                    atomicMin(enc + cfg, enc_float(fminf(sqrtf(S.vv) - K.emsum, -K.msum)));
+                    phase = 0;
+                }
+            } else if (phase == 2) {
+                if (epa_step(X, A, K.ea_n, B, K.eb_n, T)) {
+                    // the cores overlap: never report less penetration than the margins
+                    atomicMin(enc + cfg, enc_float(fminf(-(epa_result(X) + K.emsum), -K.msum)));
+                    phase = 0;
+                }
+            }
         }
-        d = fminf(d, -K.msum);   // the cores overlap: never report less penetration than the margins
-        atomicMin((K.kind == KEY_SELF ? a.enc_self : a.enc_scene) + cfg, enc_float(d));
     }
 }
 

@@ -1,0 +1,68 @@
+"""Multi-GPU sharding of configuration batches: one process per GPU, scene replicated on every
+GPU, configurations cut into contiguous 32-aligned shards, no data-path collective; the packed verdict bitmasks are
+gathered with ONE all-gather (NCCL over NVLink on GPUs; gloo in the CPU tests)."""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_size(n_total, world):
+    """Configurations per rank: ceil(n/world) rounded up to a multiple of 32 so packed words never straddle ranks."""
+    per = (n_total + world - 1) // world
+    return (per + 31) // 32 * 32
+
+
+def shard_bounds(n_total, world, rank):
+    per = shard_size(n_total, world)
+    lo = min(rank * per, n_total)
+    return lo, min(lo + per, n_total)
+
+
+def gather_bits(local_words, n_total, group=None):
+    """All-gather the packed verdict words of every rank's shard -> (words for all n_total configurations).
+
+    ``local_words``: int32 tensor with the packed bits of this rank's shard (any length <= shard words; padded here).
+    In-place all-gather: the rank's slot of the output buffer is the collective's input."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    slot = shard_size(n_total, world) // 32
+    out = torch.zeros((world * slot,), dtype=torch.int32, device=local_words.device)
+    mine = out[rank * slot:(rank + 1) * slot]
+    mine[:local_words.numel()].copy_(local_words)
+    if world > 1:
+        dist.all_gather_into_tensor(out, mine, group=group)
+    return out[:(n_total + 31) // 32]
+
+
+def gather_distances(local_dist, n_total, group=None, fill=0.0):
+    """Optional second all-gather for the fp32 distances (4 n bytes)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    per = shard_size(n_total, world)
+    out = torch.full((world * per,), fill, dtype=torch.float32, device=local_dist.device)
+    mine = out[rank * per:(rank + 1) * per]
+    mine[:local_dist.numel()].copy_(local_dist)
+    if world > 1:
+        dist.all_gather_into_tensor(out, mine, group=group)
+    return out[:n_total]
+
+
+def check_sharded(engine, q_all, flags, group=None, want_dist=False):
+    """Every rank passes the SAME full batch (or just needs its own rows): checks its shard on its GPU and returns the
+    verdict words (and optionally distances) of the whole batch on every rank."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n = len(q_all)
+    lo, hi = shard_bounds(n, world, rank)
+    bits, d, _ = engine.check(q_all[lo:hi], flags=flags, want_dist=want_dist, packed=True)
+    words = gather_bits(bits, n, group)
+    return (words, gather_distances(d, n, group)) if want_dist else (words, None)
+
+
+def pack_bits_numpy(bits):
+    """bool[n] -> packed int32 words (bit i%32 of word i//32), the layout the kernels write."""
+    b = np.asarray(bits, dtype=np.uint8)
+    pad = (-len(b)) % 32
+    b = np.concatenate([b, np.zeros(pad, np.uint8)]).reshape(-1, 32)
+    w = (b.astype(np.uint64) << np.arange(32, dtype=np.uint64)).sum(1).astype(np.uint32)
+    return w.view(np.int32)

@@ -391,6 +391,32 @@ class SceneModel:
     def piece(self, p):
         return self.piece_verts[self.piece_vert_offset[p]:self.piece_vert_offset[p + 1]]
 
+    def retarget(self, robot_pose):
+        """The same scene expressed in the frame of a robot placed at ``robot_pose`` (4x4, world)."""
+        robot_pose = np.asarray(robot_pose, dtype=np.float64)
+        if np.array_equal(robot_pose, self.robot_pose):
+            return self
+        T = np.linalg.inv(robot_pose) @ self.robot_pose
+        import copy
+        m = copy.copy(self)
+        m.robot_pose = robot_pose
+        m.piece_verts = self.piece_verts @ T[:3, :3].T + T[:3, 3]
+        m.tri_verts = self.tri_verts @ T[:3, :3].T + T[:3, 3]
+        m.plane = np.array([robot_pose[2, 0], robot_pose[2, 1], robot_pose[2, 2], robot_pose[2, 3]])
+        return m
+
+    def subset(self, bodies, with_plane):
+        """Scene restricted to the pieces of the given body indices (and optionally the plane)."""
+        import copy
+        keep = [p for p in range(self.n_pieces) if self.piece_body[p] in set(bodies)]
+        m = copy.copy(self)
+        m.piece_verts = (np.concatenate([self.piece(p) for p in keep]) if keep else np.zeros((0, 3)))
+        m.piece_vert_offset = np.cumsum([0] + [len(self.piece(p)) for p in keep]).astype(np.int32)
+        m.piece_body = self.piece_body[keep]
+        m.piece_margin = self.piece_margin[keep]
+        m.has_plane = bool(with_plane and self.has_plane)
+        return m
+
     def to_dict(self):
         d = {k: getattr(self, k) for k in (
             'robot_pose', 'piece_vert_offset', 'piece_verts', 'piece_body', 'piece_margin',

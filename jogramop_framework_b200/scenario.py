@@ -1,0 +1,157 @@
+"""Drop-in replacement for the reference's ``scenario.py`` (``Scenario``, scenario.py:12-129).
+
+Loads ``scenarios/<id>/scene.yaml`` + ``grasps.npy`` from a jogramop-framework checkout (``JOGRAMOP_ROOT`` or the
+cwd) or, when none is present, the baked copies shipped under ``jogramop_framework_b200/data`` (tools/bake_data.py).
+No burg_toolkit / open3d / pybullet.
+"""
+import os
+
+import numpy as np
+
+from . import ingest, simulation, util
+from .simulation import FrankaRobot, GraspingSimulator
+
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'data')
+
+
+class GraspSet:
+    """Minimal stand-in for ``burg.GraspSet``: ``poses`` [n,4,4], ``len()``, ``from_poses``, ``transform``."""
+
+    def __init__(self, poses):
+        self.poses = np.asarray(poses).reshape(-1, 4, 4)
+
+    @classmethod
+    def from_poses(cls, poses):
+        return cls(poses)
+
+    def __len__(self):
+        return len(self.poses)
+
+    def transform(self, tf):
+        self.poses = np.asarray(tf) @ self.poses
+        return self
+
+
+class Scenario:
+    """
+    Describes a scenario, including:
+    - scene with objects and obstacles
+    - set of grasp candidates
+    - simulator
+    - robot
+    """
+
+    def __init__(self, scenario_id, robot_pose=None, with_platform=True, gate_fix=True, device=0):
+        self.id = scenario_id
+        self.device = device
+        root = simulation.reference_root()
+        self.robot_pose = np.asarray(robot_pose, dtype=np.float64) if robot_pose is not None else self.default_robot_pose()
+        self.with_platform = with_platform
+        if root is not None:
+            self.scene_fn = os.path.join(root, util.SCENARIO_DIR, f'{scenario_id:03d}', 'scene.yaml')
+            self.scene, lib = ingest.load_scene_yaml(self.scene_fn)
+            overrides = None
+            gate = os.path.join(_DATA, 'gate_0_54_pieces.npz')
+            if gate_fix and os.path.exists(gate) and any(o.object_type == 'gate_0_54' for o in self.scene.bg_objects):
+                z = np.load(gate)      # quirk Q1: the shipped gate_0_54_vhacd.obj is stale (one solid block)
+                overrides = {'gate_0_54': [(z[f'v{i}'], z[f'f{i}']) for i in range(int(z['n']))]}
+            self._scene_model = ingest.build_scene_model(self.scene, self.robot_pose, name=f'{scenario_id:03d}',
+                                                         piece_overrides=overrides)
+            grasps = np.load(os.path.join(root, util.SCENARIO_DIR, f'{scenario_id:03d}', 'grasps.npy'),
+                             allow_pickle=True)
+        else:
+            variant = '' if gate_fix else '_singlehull'
+            fn = os.path.join(_DATA, f'scene_{scenario_id:03d}{variant}.npz')
+            if not os.path.exists(fn):
+                fn = os.path.join(_DATA, f'scene_{scenario_id:03d}.npz')
+            if not os.path.exists(fn):
+                raise FileNotFoundError(f'scenario {scenario_id:03d}: neither a jogramop checkout (JOGRAMOP_ROOT) nor {fn}')
+            self.scene_fn = fn
+            with np.load(fn, allow_pickle=False) as z:
+                d = {k: z[k] for k in z.files}
+            self._scene_model = ingest.SceneModel.from_dict(d).retarget(self.robot_pose)
+            grasps = d['grasps_world']
+            self.scene = ingest.SceneDescription(
+                objects=[ingest.SceneObject(str(t), p, None, True) for t, p in zip(d['object_types'], d['object_poses'])],
+                bg_objects=[ingest.SceneObject(str(t), p, None, False)
+                            for t, p in zip(d['bg_object_types'], d['bg_object_poses'])],
+                scene_fn=fn)
+        print(f'loaded scene with {len(self.scene.objects)} objects and {len(self.scene.bg_objects)} obstacles.')
+        # convert from BURG to franka frame (scenario.py:31)
+        grasps = grasps @ FrankaRobot.tf_grasp2ee
+        self.gs = GraspSet.from_poses(grasps)
+        print(f'loaded {len(self.gs)} grasps')
+        self.select_indices = None  # for grasp set sub-selection
+
+    @property
+    def grasp_poses(self):
+        if self.select_indices is None:
+            return self.gs.poses
+        return self.gs.poses[self.select_indices]
+
+    def select_n_grasps(self, n=None, seed=None):
+        # if n is None, will select all grasps again
+        if n is None:
+            print('erasing grasp selection. whole grasp set available again.')
+            self.select_indices = None
+            return
+        if n > len(self.gs):
+            raise ValueError('cannot select more grasps than available. n must be smaller than number of grasps')
+        rng = np.random.default_rng(seed)
+        self.select_indices = rng.choice(len(self.gs), n, replace=False)
+
+    def get_robot_and_sim(self, with_gui=False):
+        """Get the robot and simulator handles (scenario.py:59-67)."""
+        sim = GraspingSimulator(verbose=with_gui, device=self.device)
+        sim.add_scene(self._scene_model)
+        sim.scene = self.scene
+        robot = FrankaRobot(sim, self.robot_pose, with_platform=self.with_platform)
+        return robot, sim
+
+    @staticmethod
+    def default_robot_pose():
+        """scenario.py:69-80."""
+        return ingest.default_robot_pose()
+
+    def filter_configurations(self, candidates, robot=None):
+        """The check half of ``get_ik_solutions`` (scenario.py:105-125) as ONE batched call: joint limits, then
+        self-collision, then scene collision, with the reference's counters.  ``candidates``: [n,dof] (rows may be
+        None-free only).  Returns (accepted [m,dof] float64, reason uint8[n], Timer)."""
+        if robot is None:
+            robot, _ = self.get_robot_and_sim()
+        candidates = np.asarray(candidates, dtype=np.float64).reshape(-1, len(robot.arm_joint_ids))
+        count = util.Timer()
+        count.start('perform checks')
+        _, _, reason = robot.check_batch(candidates.astype(np.float32), want_dist=False)
+        reason = reason.cpu().numpy()
+        count.stop('perform checks')
+        for code, key in ((1, 'IK solution not in joint limits'), (2, 'IK solution in self-collision'),
+                          (3, 'IK solution in collision'), (0, 'IK solution is OK')):
+            k = int((reason == code).sum())
+            if k:
+                count.count(key, k)
+        return candidates[reason == 0], reason, count
+
+    def get_ik_solutions(self):
+        """scenario.py:82-129.  Needs ``FrankaRobot.inverse_kinematics`` (the first "next" row); the
+        collision filter that follows the IK is available as ``filter_configurations``."""
+        robot, sim = self.get_robot_and_sim()
+        ik_solutions = []
+        count = util.Timer()
+        print('calculating IK solutions for all grasps')
+        candidates = []
+        for g in range(len(self.gs)):
+            count.start('calculate IK')
+            pos, orn = util.position_and_quaternion_from_tf(self.gs.poses[g], convention='pybullet')
+            target_conf = robot.inverse_kinematics(pos, orn, null_space_control=True)
+            count.stop('calculate IK')
+            if target_conf is not None:
+                candidates.append(target_conf)
+            else:
+                count.count('IK solution too far away from goal')
+        if candidates:
+            ik_solutions, _, c2 = self.filter_configurations(np.asarray(candidates), robot)
+            count.timers.update(c2.timers)
+            count.counters.update(c2.counters)
+        count.print()
+        return np.array(ik_solutions)

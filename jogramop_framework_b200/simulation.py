@@ -1,0 +1,417 @@
+"""Drop-in replacements for the reference's ``simulation.py`` classes, backed by the CUDA collision engine.
+
+Same class names, method names, argument meaning and error behaviour as the reference
+(``simulation.py:12-121`` GraspingSimulator, ``simulation.py:124-472`` FrankaRobot); the pyBullet calls behind them
+(``resetJointState``, ``getLinkState``, ``getClosestPoints``) are replaced by the C-ABI of include/jogramop_b200.h.
+Single-shot methods keep the reference's *stateful* convention (set the joints, then query); the new ``*_batch``
+methods are pure functions of their inputs and never touch that state.
+
+Not provided (out of the hot path): dynamics / motor control (``move_to``, ``open``, ``close``,
+``execute_joint_trajectory``), GUI helpers (``add_frame``, ``add_sphere``) and ``bullet_client`` / ``_p``
+(there is no Bullet client: the attributes exist and are ``None``).
+"""
+import logging
+import os
+
+import numpy as np
+
+from . import engine as _engine
+from . import ingest, util
+from ._lib import JogramopError
+
+_log = logging.getLogger(__name__)
+
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'data')
+
+
+def reference_root():
+    """Directory of a jogramop-framework checkout (``JOGRAMOP_ROOT`` or the cwd, like the reference's cwd-relative
+    paths, util.py:9 / simulation.py:137-139), or None: then the baked data shipped with this package is used."""
+    for cand in (os.environ.get('JOGRAMOP_ROOT'), os.getcwd()):
+        if cand and os.path.exists(os.path.join(cand, 'robots', 'franka_panda', 'mobile_panda.urdf')) and \
+                os.path.isdir(os.path.join(cand, 'scenarios')):
+            return cand
+    return None
+
+
+def load_robot_model(with_platform):
+    root = reference_root()
+    name = 'mobile_panda' if with_platform else 'panda'
+    if root is not None:
+        return ingest.load_robot_urdf(os.path.join(root, 'robots', 'franka_panda', f'{name}.urdf'),
+                                      with_platform=with_platform)
+    return ingest.RobotModel.load(os.path.join(_DATA, f'robot_{name}.npz'))
+
+
+class GraspingSimulator:
+    """``simulation.py:12-121``.  Holds the scene bodies; collision queries go to the CUDA engine."""
+
+    PLANE_ID = 0
+
+    def __init__(self, verbose=False, device=0):
+        self.verbose = verbose
+        self.device = device
+        self.bullet_client = None     # no Bullet client behind this simulator
+        self._p = None
+        self._env_bodies = {'plane': self.PLANE_ID}      # burg SimulatorBase._reset(plane_and_gravity=True)
+        self._moving_bodies = {}
+        self._body_of_id = {self.PLANE_ID: None}         # body id -> scene body index (None = plane)
+        self._scene_model = None                         # world-frame independent: stored with its robot_pose
+        self._next_id = 1
+        self._robot = None
+        self._engines = {}
+        self.scene = None
+
+    # ------------------------------------------------------------------ scene
+    def add_scene(self, scene):
+        """``burg SimulatorBase.add_scene`` (scenario.py:64): ``scene`` is an ingest.SceneDescription or a prepared
+        ingest.SceneModel.  bg_objects become environment bodies, objects become moving bodies."""
+        self.scene = scene
+        if isinstance(scene, ingest.SceneModel):
+            model = scene
+        else:
+            model = ingest.build_scene_model(scene, ingest.default_robot_pose(), name='scene')
+        self._scene_model = model
+        for b, (name, is_target) in enumerate(zip(model.body_names, model.body_is_target)):
+            bid = self._next_id
+            self._next_id += 1
+            key = f'{name}_{bid}'
+            (self._moving_bodies if is_target else self._env_bodies)[key] = bid
+            self._body_of_id[bid] = b
+        self._engines.clear()
+
+    def add_scene_from_file(self, scene_fn):
+        scene, _ = ingest.load_scene_yaml(scene_fn)
+        self.add_scene(scene)
+
+    def remove(self, body_id):
+        for d in (self._env_bodies, self._moving_bodies):
+            for k in [k for k, v in d.items() if v == body_id]:
+                del d[k]
+        self._body_of_id.pop(body_id, None)
+        self._engines.clear()
+
+    def dismiss(self):
+        for e in self._engines.values():
+            e.close()
+        self._engines.clear()
+
+    # ------------------------------------------------------------------ engines
+    def _register_robot(self, robot):
+        self._robot = robot
+        robot._body_id = self._next_id
+        self._next_id += 1
+        self._engines.clear()
+
+    def _scene_for(self, bodies, with_plane):
+        """SceneModel in the robot frame restricted to the given scene-body indices."""
+        if self._scene_model is None:
+            if not with_plane:
+                return None
+            m = ingest.SceneModel(name='empty', robot_pose=np.eye(4), piece_vert_offset=np.zeros(1, np.int32),
+                                  piece_verts=np.zeros((0, 3)), piece_body=np.zeros(0, np.int32),
+                                  piece_margin=np.zeros(0), body_names=[], body_is_target=np.zeros(0, bool),
+                                  tri_verts=np.zeros((0, 3)), tris=np.zeros((0, 3), np.int32),
+                                  tri_body=np.zeros(0, np.int32), plane=np.array([0, 0, 1.0, 0]), has_plane=True)
+            return m.retarget(self._robot.pose)
+        m = self._scene_model.retarget(self._robot.pose)
+        return m.subset(bodies, with_plane)
+
+    def _engine(self, key, bodies=None, with_plane=True, self_pairs=None, small=False):
+        """Cached CollisionEngine for (body subset, finger opening, self pair list)."""
+        robot = self._robot
+        if robot is None:
+            raise JogramopError('no robot has been loaded into this simulator')
+        full_key = (key, round(float(robot.finger_open_distance * robot._open_scale), 9))
+        if full_key not in self._engines:
+            model = robot.model
+            if self_pairs is not None:
+                import copy
+                model = copy.copy(model)
+                model.self_pairs = np.asarray(self_pairs, dtype=np.int32).reshape(-1, 2)
+            if bodies is None:
+                bodies = [b for b in self._body_of_id.values() if b is not None]
+            scene = self._scene_for(bodies, with_plane)
+            self._engines[full_key] = _engine.CollisionEngine(
+                model, scene, device=self.device, finger_open=full_key[1], chunk=4096 if small else 0)
+        return self._engines[full_key]
+
+    # ------------------------------------------------------------------ reference API
+    def links_in_collision(self, body1, link1, body2, link2, threshold=-0.001):
+        """``simulation.py:82-95``: getClosestPoints(body1, body2, 0.01, link1, link2), any point[8] < threshold.
+        Supported for two links of the robot (the only use in the reference, simulation.py:460)."""
+        robot = self._robot
+        if robot is None or body1 != robot.body_id or body2 != robot.body_id:
+            raise JogramopError('links_in_collision is only available between two links of the robot')
+        eng = self._engine(('links', int(link1), int(link2)), bodies=[], with_plane=False,
+                           self_pairs=[(int(link1), int(link2))], small=True)
+        _, dist, _ = eng.check(np.asarray(robot._q, dtype=np.float32)[None], flags=_engine.SELF)
+        d = float(dist[0])
+        _log.debug(f'closest distance between links {link1} and {link2}: {d}')
+        return bool(d < threshold)
+
+    def are_in_collision(self, body_id_1, body_id_2, threshold=-0.001):
+        """burg ``SimulatorBase.are_in_collision`` (called at simulation.py:107,116): one of the bodies must be the robot."""
+        robot = self._robot
+        if robot is None or robot.body_id not in (body_id_1, body_id_2):
+            raise JogramopError('are_in_collision needs the robot as one of the two bodies')
+        other = body_id_2 if body_id_1 == robot.body_id else body_id_1
+        if other == robot.body_id:
+            return robot.in_self_collision()
+        if other not in self._body_of_id:
+            raise JogramopError(f'unknown body id {other}')
+        b = self._body_of_id[other]
+        eng = self._engine(('body', other), bodies=[] if b is None else [b], with_plane=b is None, small=True)
+        flags = _engine.PLANE if b is None else _engine.SCENE
+        _, dist, _ = eng.check(np.asarray(robot._q, dtype=np.float32)[None], flags=flags)
+        return bool(float(dist[0]) < threshold)
+
+    def body_in_collision(self, query_body):
+        """``simulation.py:97-121``: environment bodies (plane, bg objects) then moving bodies, skipping the body itself."""
+        _log.debug('checking collisions with environment bodies')
+        for body_key, body_id in self._env_bodies.items():
+            if query_body == body_id:
+                continue
+            if self.are_in_collision(query_body, body_id):
+                _log.debug(f'body in collision with {body_key} ({body_id})')
+                return True
+        _log.debug('checking collisions with other bodies')
+        for body_key, body_id in self._moving_bodies.items():
+            if query_body == body_id:
+                continue
+            if self.are_in_collision(query_body, body_id):
+                _log.debug(f'body in collision with {body_key} ({body_id})')
+                return True
+        _log.debug('COLLISION CHECKS PASSED')
+        return False
+
+    # ------------------------------------------------------------------ batched
+    def gripper_in_collision_batch(self, poses, open_scale=None, want_dist=True):
+        """Free-floating gripper (hand + two fingers riding on ``panda_grasptarget``) at each pose, against all scene
+        bodies and the plane (create_graspset.py:53-60).  ``poses``: [n,4,4] in the WORLD frame or [n,7] (pos, quat
+        xyzw, world).  Returns (collides bool[n], min_dist[n]) as torch tensors on the engine's device."""
+        robot = self._robot
+        if robot is None:
+            raise JogramopError('load a FrankaRobot into the simulator first')
+        poses = np.asarray(poses, dtype=np.float64)
+        if poses.ndim == 2 and poses.shape[1] == 7:
+            T = np.stack([util.tf_from_pos_quat(p[:3], p[3:]) for p in poses]) if len(poses) else np.zeros((0, 4, 4))
+        else:
+            T = poses.reshape(-1, 4, 4)
+        T = np.linalg.inv(robot.pose) @ T          # robot frame
+        old = robot._open_scale
+        if open_scale is not None:
+            robot._open_scale = float(open_scale)
+        try:
+            eng = self._engine('full')
+            links = [robot.end_effector_id - 3, *robot.finger_joint_ids]   # hand, left finger, right finger
+            return eng.check_poses(T[:, :3, :].astype(np.float32), links=links, want_dist=want_dist)
+        finally:
+            robot._open_scale = old
+
+
+class FrankaRobot:
+    """``simulation.py:124-472`` (collision, joint-set, FK parts)."""
+
+    tf_grasp2ee = np.asarray([  # transformation from grasp to end-effector frame (simulation.py:125-130)
+        0, 1, 0, 0,
+        1, 0, 0, 0,
+        0, 0, -1, 0,
+        0, 0, 0, 1
+    ]).reshape(4, 4)
+
+    def __init__(self, simulator, pose, with_platform=False):
+        self._simulator = simulator
+        self._bullet_client = None
+        self.pose = np.asarray(pose, dtype=np.float64)
+        self.model = load_robot_model(with_platform)
+        pos, _ = util.position_and_quaternion_from_tf(self.pose)
+        if pos[2] < 0.05:   # simulation.py:146-148
+            print('WARNING: consider a larger z-value for your robot, to avoid false positives during collision '
+                  'detection with the plane. current pos: ', pos)
+        # burg load_robot: joint info keyed by link name (quirk Q4: the key really is 'upper limit')
+        self.robot_joints = {}
+        for i, name in enumerate(self.model.link_names):
+            self.robot_joints[name] = {'id': i, 'link_name': name, 'joint_name': self.model.joint_names[i],
+                                       'type': int(self.model.joint_type[i]),
+                                       'lower_limit': float(self.model.joint_limits[i, 0]),
+                                       'upper limit': float(self.model.joint_limits[i, 1])}
+        if simulator.verbose:
+            for joint, info in self.robot_joints.items():
+                print(joint, info)
+        self.with_platform = with_platform
+        self.end_effector_id = self.model.end_effector_id
+        self.arm_joint_ids = list(self.model.arm_joint_ids)
+        self.finger_joint_ids = list(self.model.finger_joint_ids)
+        self.home_conf = [-0.017792060227770554, -0.7601235411041661, 0.019782607023391807, -2.342050140544315,
+                          0.029840531355804868, 1.5411935298621688, 0.7534486589746342]
+        if with_platform:
+            self.home_conf = [0.0, 0.0] + self.home_conf
+        self.finger_open_distance = 0.04
+        self.finger_force = 100
+        self.grasp_speed = 0.1
+        self._open_scale = 1.0
+        self._q = list(self.home_conf)
+        self._body_id = None
+        simulator._register_robot(self)
+        self.reset_home_pose()
+
+    # ------------------------------------------------------------------ state
+    @property
+    def body_id(self):
+        return self._body_id
+
+    @property
+    def bullet_client(self):
+        return self._bullet_client
+
+    @property
+    def end_effector_link_id(self):
+        return self.end_effector_id
+
+    def reset_home_pose(self):
+        self.reset_arm_joints()
+        self.reset_gripper()
+
+    def get_ee_pose_for_grasp(self, grasp):
+        raise DeprecationWarning('this is being done during loading of scenario. dont use directly anymore')
+
+    def reset_arm_joints(self, joint_config=None):
+        """``simulation.py:206-212``."""
+        if joint_config is None:
+            joint_config = self.home_conf
+        assert len(joint_config) == len(self.arm_joint_ids)
+        self._q = [float(x) for x in joint_config]
+
+    def reset_gripper(self, open_scale=1.0):
+        """``simulation.py:312-316``."""
+        assert 0.0 <= open_scale <= 1.0, 'open_scale is out of range'
+        self._open_scale = float(open_scale)
+
+    def get_arm_joint_conf_from_motor_joint_conf(self, ik_joint_config):
+        return np.asarray(ik_joint_config)[:len(self.arm_joint_ids)]
+
+    def arm_joints_pos(self):
+        return np.asarray(self._q, dtype=np.float64)
+
+    def joint_pos(self):
+        """Movable joints only: arm + both fingers (simulation.py:365-369)."""
+        f = self.finger_open_distance * self._open_scale
+        return np.asarray(list(self._q) + [f, f], dtype=np.float64)
+
+    def arm_joint_limits(self):
+        """``simulation.py:374-386``: [n,2] (min, max) including the platform joints."""
+        joint_limits = np.empty(shape=(len(self.arm_joint_ids), 2))
+        i = 0
+        for key, joint_info in self.robot_joints.items():
+            if joint_info['id'] in self.arm_joint_ids:
+                joint_limits[i, 0] = joint_info['lower_limit']
+                joint_limits[i, 1] = joint_info['upper limit']
+                i += 1
+        assert i == len(self.arm_joint_ids), 'joint limits should be equal to number of joints'
+        return joint_limits
+
+    # ------------------------------------------------------------------ kinematics
+    def _match_joint_conf(self, joint_conf):
+        if len(joint_conf) == len(self.arm_joint_ids):
+            return joint_conf
+        if len(joint_conf) == len(self.arm_joint_ids) + len(self.finger_joint_ids):
+            return self.get_arm_joint_conf_from_motor_joint_conf(joint_conf)
+        if len(joint_conf) == self.end_effector_link_id:
+            return np.asarray(joint_conf)[self.arm_joint_ids]
+        raise ValueError('cannot match joint conf to arm/motor/all joints; unexpected length.')
+
+    def forward_kinematics(self, joint_conf, as_matrix=False):
+        """``simulation.py:223-249``: end-effector (``panda_grasptarget``) pose in the WORLD frame.
+        caution (as in the reference): sets the robot's joints."""
+        arm_joint_conf = self._match_joint_conf(joint_conf)
+        self.reset_arm_joints(arm_joint_conf)
+        T = self.forward_kinematics_batch(np.asarray(arm_joint_conf, dtype=np.float32)[None], as_matrix=True)[0]
+        T = T.cpu().numpy().astype(np.float64)
+        if as_matrix:
+            return T
+        pos, quat = util.position_and_quaternion_from_tf(T)
+        return np.asarray(pos), np.asarray(quat)
+
+    def end_effector_pose(self):
+        return self.forward_kinematics_batch(np.asarray(self._q, dtype=np.float32)[None],
+                                             as_matrix=True)[0].cpu().numpy().astype(np.float64)
+
+    def inverse_kinematics(self, pos, orn=None, combined_threshold=0.015, null_space_control=False):
+        raise NotImplementedError(
+            'inverse kinematics (pybullet.calculateInverseKinematics, simulation.py:251-310) is the first "next" row '
+            'of the scope table (SURVEY.md §8f) and is not part of this build yet')
+
+    # ------------------------------------------------------------------ collision (single shot, stateful)
+    def in_self_collision(self):
+        """``simulation.py:439-464``: any of the ordered link pairs closer than the threshold."""
+        bits, _, _ = self._simulator._engine('full').check(np.asarray(self._q, dtype=np.float32)[None],
+                                                           flags=_engine.SELF, want_dist=False)
+        return bool(bits[0])
+
+    def in_collision(self):
+        """``simulation.py:466-472``: robot against the scene (plane, obstacles, target object); no self collisions."""
+        return self._simulator.body_in_collision(self.body_id)
+
+    # ------------------------------------------------------------------ batched, pure
+    def forward_kinematics_batch(self, q, all_links=False, as_matrix=False):
+        """q [n,dof] -> world-frame poses.  ``all_links``: [n,L,4,4]; else the end effector: (pos[n,3], quat xyzw[n,4])
+        or [n,4,4] with ``as_matrix``.  Returns torch tensors on the engine's device."""
+        import torch
+        eng = self._simulator._engine('full')
+        ids = None if all_links else [self.end_effector_id]
+        T34 = eng.fk(q, link_ids=ids, base_pose=self.pose)
+        n, L = T34.shape[0], T34.shape[1]
+        T = torch.zeros((n, L, 4, 4), device=T34.device, dtype=T34.dtype)
+        T[:, :, :3, :] = T34
+        T[:, :, 3, 3] = 1.0
+        if all_links:
+            return T
+        T = T[:, 0]
+        if as_matrix:
+            return T
+        return T[:, :3, 3], _quat_from_matrix_torch(T[:, :3, :3])
+
+    def in_collision_batch(self, q, want_dist=True):
+        """-> (collides bool[n], min_dist[n]): scene + plane, like ``in_collision`` for every row of q."""
+        bits, dist, _ = self._simulator._engine('full').check(q, flags=_engine.SCENE | _engine.PLANE, want_dist=want_dist)
+        return bits, dist
+
+    def in_self_collision_batch(self, q, want_dist=True):
+        bits, dist, _ = self._simulator._engine('full').check(q, flags=_engine.SELF, want_dist=want_dist)
+        return bits, dist
+
+    def check_batch(self, q, limits=True, self_collision=True, scene=True, want_dist=True):
+        """The filter of ``Scenario.get_ik_solutions`` (scenario.py:109-119) for every row of q.
+        -> (rejected bool[n], min_dist[n], reason uint8[n]): reason 0 ok, 1 joint limits, 2 self-collision, 3 scene."""
+        flags = (_engine.LIMITS if limits else 0) | (_engine.SELF if self_collision else 0) | \
+                ((_engine.SCENE | _engine.PLANE) if scene else 0)
+        return self._simulator._engine('full').check(q, flags=flags, want_dist=want_dist, want_reason=True)
+
+    def edges_in_collision_batch(self, qa, qb, substeps=64, self_collision=False, want_dist=True):
+        """Edge validation: substep k is qa + k/(substeps-1) (qb-qa); an edge collides iff any substep does."""
+        flags = _engine.SCENE | _engine.PLANE | (_engine.SELF if self_collision else 0)
+        return self._simulator._engine('full').check_edges(qa, qb, substeps=substeps, flags=flags, want_dist=want_dist)
+
+    # ------------------------------------------------------------------ out of scope (dynamics)
+    def _dynamics(self, *a, **k):
+        raise NotImplementedError('dynamics / motor control is outside the collision-query hot path (SURVEY.md §2)')
+
+    move_to = open = close = execute_joint_trajectory = set_target_pos_and_vel = gripper_constraints = _dynamics
+    configure_gripper_friction = _dynamics
+
+
+def _quat_from_matrix_torch(R):
+    """Batched rotation matrix -> quaternion xyzw (pybullet convention)."""
+    import torch
+    m00, m01, m02 = R[:, 0, 0], R[:, 0, 1], R[:, 0, 2]
+    m10, m11, m12 = R[:, 1, 0], R[:, 1, 1], R[:, 1, 2]
+    m20, m21, m22 = R[:, 2, 0], R[:, 2, 1], R[:, 2, 2]
+    qw = torch.sqrt(torch.clamp(1 + m00 + m11 + m22, min=0)) / 2
+    qx = torch.sqrt(torch.clamp(1 + m00 - m11 - m22, min=0)) / 2
+    qy = torch.sqrt(torch.clamp(1 - m00 + m11 - m22, min=0)) / 2
+    qz = torch.sqrt(torch.clamp(1 - m00 - m11 + m22, min=0)) / 2
+    qx = torch.copysign(qx, m21 - m12)
+    qy = torch.copysign(qy, m02 - m20)
+    qz = torch.copysign(qz, m10 - m01)
+    return torch.stack([qx, qy, qz, qw], dim=1)
