@@ -53,7 +53,8 @@ enum {
     JG_PLANE = 2,   /* robot shapes vs ground plane               (burg plane.urdf in _env_bodies)         */
     JG_SELF = 4,    /* 42 ordered link pairs                      (simulation.py:439-464 in_self_collision) */
     JG_LIMITS = 8,  /* lo <= q <= hi                              (scenario.py:90-91 in_joint_limits)       */
-    JG_NO_EPA = 16  /* skip the penetration-depth pass: overlapping cores report -(marginA+marginB)         */
+    JG_NO_EPA = 16, /* skip the penetration-depth pass: overlapping cores report -(marginA+marginB)         */
+    JG_DEBUG_FORCE_OVERFLOW = 0x40000000 /* test hook: send every penetrating pair through the overflow kernel */
 };
 
 enum { JG_JOINT_FIXED = 0, JG_JOINT_REVOLUTE = 1, JG_JOINT_PRISMATIC = 2 };

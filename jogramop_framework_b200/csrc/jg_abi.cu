@@ -165,6 +165,7 @@ struct jg_engine {
     int* q_cfg = nullptr;
     int* epa_slot = nullptr;              // [n_keys*cap]
     uint4* epa_ids = nullptr;             // [n_keys*cap]
+    int2* ovf_list = nullptr;             // [cap]
     int* counts = nullptr;                // [2*n_keys + 8]
     int *enc_scene = nullptr, *enc_self = nullptr;
     uint32_t* viol = nullptr;
@@ -188,8 +189,8 @@ struct jg_engine {
     unsigned long long* d_stats = nullptr;       // [8]
     cudaStream_t last_stream = nullptr;
     int sm_count = 148;
-    int np_blocks = 0, epa_blocks = 0;
-    size_t smem_narrow = 0;
+    int np_blocks = 0, epa_blocks = 0, epa_threads = 0;
+    size_t smem_narrow = 0, smem_epa = 0, smem_epa_big = 0;
     // optional per-kernel timing (jg_profile_enable)
     bool profiling = false;
     std::vector<cudaEvent_t> prof_ev;    // 5 events per pass: start | broad | narrow | penetration | finalize
@@ -227,7 +228,7 @@ static void engine_release(jg_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaFree(e->d_robot); cudaFree(e->d_pieces); cudaFree(e->d_selfs); cudaFree(e->d_keys); cudaFree(e->d_verts);
-    cudaFree(e->q_r0); cudaFree(e->q_r1); cudaFree(e->q_r2); cudaFree(e->q_cfg); cudaFree(e->epa_slot); cudaFree(e->epa_ids); cudaFree(e->counts);
+    cudaFree(e->q_r0); cudaFree(e->q_r1); cudaFree(e->q_r2); cudaFree(e->q_cfg); cudaFree(e->epa_slot); cudaFree(e->epa_ids); cudaFree(e->ovf_list); cudaFree(e->counts);
     cudaFree(e->enc_scene); cudaFree(e->enc_self); cudaFree(e->viol); cudaFree(e->d_link_slot); cudaFree(e->d_rel);
     cudaFree(e->d_use_shapes); cudaFree(e->d_stats);
     for (int i = 0; i < 2; ++i) {
@@ -285,11 +286,10 @@ static int build_tables(jg_engine* e, const jg_robot* r, const jg_scene* sc) {
     }
     e->link_first_shape.assign(r->L + 1, -1);
     e->shape_link = r->shape_link;
-    int nv = r->S ? r->shape_off[r->S] : 0;
+    // every vertex set is padded to a multiple of 4 with copies of its last vertex (support_scan works on groups of 4)
     std::vector<float4> verts;
-    verts.reserve(nv + 1024);
-    for (int i = 0; i < nv; ++i)
-        verts.push_back(make_float4((float)r->core[3 * i], (float)r->core[3 * i + 1], (float)r->core[3 * i + 2], 0.f));
+    verts.reserve(4096);
+    auto pad4 = [&verts]() { while (verts.size() % 4) verts.push_back(verts.back()); };
     for (int s = 0; s < r->S; ++s) {
         ShapeRec& Sh = R.shapes[s];
         double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
@@ -304,8 +304,11 @@ static int build_tables(jg_engine* e, const jg_robot* r, const jg_scene* sc) {
         }
         Sh.margin = (float)r->shape_margin[s];
         Sh.plane_margin = (float)r->plane_margin[s];
-        Sh.voff = r->shape_off[s];
+        Sh.voff = (int)verts.size();
         Sh.vn = r->shape_off[s + 1] - r->shape_off[s];
+        for (int i = r->shape_off[s]; i < r->shape_off[s + 1]; ++i)
+            verts.push_back(make_float4((float)r->core[3 * i], (float)r->core[3 * i + 1], (float)r->core[3 * i + 2], 0.f));
+        pad4();
         Sh.link = r->shape_link[s];
         // plane / EPA vertices: share the core range when identical (hulls), else append (boxes)
         const int pn = r->plane_off[s + 1] - r->plane_off[s];
@@ -318,6 +321,7 @@ static int build_tables(jg_engine* e, const jg_robot* r, const jg_scene* sc) {
             for (int i = r->plane_off[s]; i < r->plane_off[s + 1]; ++i)
                 verts.push_back(make_float4((float)r->plane_v[3 * i], (float)r->plane_v[3 * i + 1],
                                             (float)r->plane_v[3 * i + 2], 0.f));
+            pad4();
         }
         const int link = r->shape_link[s];
         if (e->link_first_shape[link + 1] < 0) e->link_first_shape[link + 1] = s;
@@ -352,6 +356,7 @@ static int build_tables(jg_engine* e, const jg_robot* r, const jg_scene* sc) {
         for (int i = sc->off[p]; i < sc->off[p + 1]; ++i)   // subtract the (float) centre in double, then round
             verts.push_back(make_float4((float)(sc->v[3 * i] - (double)Pc.c[0]), (float)(sc->v[3 * i + 1] - (double)Pc.c[1]),
                                         (float)(sc->v[3 * i + 2] - (double)Pc.c[2]), 0.f));
+        pad4();
     }
     e->has_plane = sc && sc->has_plane;
     if (e->has_plane)
@@ -397,7 +402,7 @@ static int build_tables(jg_engine* e, const jg_robot* r, const jg_scene* sc) {
 
 constexpr int BP_BLOCK = 128;   // broad phase: threads (= configurations) per block
 constexpr int NP_BLOCK = 256;   // narrow phase
-constexpr int EPA_BLOCK = 128;  // penetration-depth pass
+constexpr int EPA_BIG_BLOCK = 128;  // overflow pass of the penetration depth
 
 static size_t bp_smem(const jg_engine* e, uint32_t flags) {
     size_t s = sizeof(RobotTab) + sizeof(PieceRec) * e->P + sizeof(float) * BP_BLOCK * e->dof;
@@ -431,7 +436,12 @@ extern "C" jg_engine* jg_engine_create(const jg_robot* r, const jg_scene* sc, in
         return nullptr;
     }
     bool ok = cudaFuncSetAttribute(k_narrowphase<NP_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(k_penetration<EPA_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_penetration<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_penetration<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_penetration<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_penetration<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_penetration<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_penetration_big<EPA_BIG_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_broadphase<BP_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_broadphase_poses<BP_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
     if (!ok) {
@@ -446,10 +456,20 @@ extern "C" jg_engine* jg_engine_create(const jg_robot* r, const jg_scene* sc, in
             e->np_blocks = e->sm_count * occ;
         else
             e->np_blocks = e->sm_count * 2;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_penetration<EPA_BLOCK>, EPA_BLOCK, e->smem_narrow) == cudaSuccess && occ > 0)
-            e->epa_blocks = e->sm_count * occ;
-        else
-            e->epa_blocks = e->sm_count * 4;
+        // penetration pass: one block per SM, as many threads as shared-memory polytopes fit beside the vertex table
+        const size_t tables = sizeof(float4) * e->n_verts + sizeof(int) * ((e->n_keys + 2 + 3) & ~3);
+        const size_t per_thread = sizeof(uint32_t) * EpaPolySmall<32>::WORDS;
+        e->epa_threads = 0;
+        for (int t : {192, 160, 128, 96, 64})
+            if (tables + per_thread * t + 64 <= smem_max) { e->epa_threads = t; break; }
+        if (!e->epa_threads) {
+            fail(JG_ERR_INVALID, "scene too large for the shared-memory penetration pass (%zu B of tables)", tables);
+            engine_release(e);
+            return nullptr;
+        }
+        e->smem_epa = tables + per_thread * e->epa_threads + 64;
+        e->smem_epa_big = sizeof(float4) * e->n_verts + sizeof(uint32_t) * EpaPolyBig::WORDS * (EPA_BIG_BLOCK / 32) + 64;
+        e->epa_blocks = e->sm_count;
     }
     // scratch arena: per-key queues of `cap` entries (72 B each).  Default: the largest power of two <= 2^20
     // configurations per pass whose arena stays within 16 GB and a quarter of the free device memory.
@@ -466,7 +486,7 @@ extern "C" jg_engine* jg_engine_create(const jg_robot* r, const jg_scene* sc, in
     e->cap = cap;
     const size_t qn = (size_t)std::max(e->n_keys, 1) * cap;
     bool okm = cudaMalloc(&e->q_r0, sizeof(float4) * qn) == cudaSuccess && cudaMalloc(&e->q_r1, sizeof(float4) * qn) == cudaSuccess &&
-               cudaMalloc(&e->q_r2, sizeof(float4) * qn) == cudaSuccess && cudaMalloc(&e->q_cfg, sizeof(int) * qn) == cudaSuccess && cudaMalloc(&e->epa_slot, sizeof(int) * qn) == cudaSuccess && cudaMalloc(&e->epa_ids, sizeof(uint4) * qn) == cudaSuccess &&
+               cudaMalloc(&e->q_r2, sizeof(float4) * qn) == cudaSuccess && cudaMalloc(&e->q_cfg, sizeof(int) * qn) == cudaSuccess && cudaMalloc(&e->epa_slot, sizeof(int) * qn) == cudaSuccess && cudaMalloc(&e->epa_ids, sizeof(uint4) * qn) == cudaSuccess && cudaMalloc(&e->ovf_list, sizeof(int2) * cap) == cudaSuccess &&
                cudaMalloc(&e->counts, sizeof(int) * (2 * e->n_keys + 8)) == cudaSuccess &&
                cudaMalloc(&e->enc_scene, sizeof(int) * cap) == cudaSuccess && cudaMalloc(&e->enc_self, sizeof(int) * cap) == cudaSuccess &&
                cudaMalloc(&e->viol, sizeof(uint32_t) * (cap / 32 + 1)) == cudaSuccess &&
@@ -494,7 +514,7 @@ static void fill_args(const jg_engine* e, PassArgs& a, uint32_t flags) {
     a.has_plane = e->has_plane ? 1 : 0;
     a.robot = e->d_robot; a.pieces = e->d_pieces; a.P = e->P; a.selfs = e->d_selfs; a.keys = e->d_keys;
     a.n_keys = e->n_keys; a.n_scene_keys = e->n_scene_keys; a.verts = e->d_verts; a.n_verts = e->n_verts;
-    a.q_r0 = e->q_r0; a.q_r1 = e->q_r1; a.q_r2 = e->q_r2; a.q_cfg = e->q_cfg; a.epa_slot = e->epa_slot; a.epa_ids = e->epa_ids; a.cap = e->cap; a.counts = e->counts;
+    a.q_r0 = e->q_r0; a.q_r1 = e->q_r1; a.q_r2 = e->q_r2; a.q_cfg = e->q_cfg; a.epa_slot = e->epa_slot; a.epa_ids = e->epa_ids; a.ovf_list = e->ovf_list; a.cap = e->cap; a.counts = e->counts;
     a.enc_scene = e->enc_scene; a.enc_self = e->enc_self; a.viol = e->viol;
 }
 
@@ -528,8 +548,15 @@ static int run_narrow_and_finalize(jg_engine* e, const PassArgs& a, int n_out, u
     }
     PROF_MARK(e, st);
     if (e->n_keys > 0 && !(flags & JG_NO_EPA)) {
-        k_penetration<EPA_BLOCK><<<e->epa_blocks, EPA_BLOCK, e->smem_narrow, st>>>(a);
-        e->stats.kernel_launches += 1;
+        switch (e->epa_threads) {
+            case 192: k_penetration<192><<<e->epa_blocks, 192, e->smem_epa, st>>>(a); break;
+            case 160: k_penetration<160><<<e->epa_blocks, 160, e->smem_epa, st>>>(a); break;
+            case 128: k_penetration<128><<<e->epa_blocks, 128, e->smem_epa, st>>>(a); break;
+            case 96: k_penetration<96><<<e->epa_blocks, 96, e->smem_epa, st>>>(a); break;
+            default: k_penetration<64><<<e->epa_blocks, 64, e->smem_epa, st>>>(a); break;
+        }
+        k_penetration_big<EPA_BIG_BLOCK><<<e->sm_count, EPA_BIG_BLOCK, e->smem_epa_big, st>>>(a);
+        e->stats.kernel_launches += 2;
     }
     PROF_MARK(e, st);
     if (e->n_keys > 0) {

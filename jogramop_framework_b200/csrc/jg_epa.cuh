@@ -10,13 +10,13 @@
 namespace jg {
 
 #ifndef JG_EPA_MAX_V
-#define JG_EPA_MAX_V 40
+#define JG_EPA_MAX_V 48
 #endif
 #ifndef JG_EPA_MAX_F
-#define JG_EPA_MAX_F 80
+#define JG_EPA_MAX_F 96
 #endif
 #ifndef JG_EPA_MAX_ITER
-#define JG_EPA_MAX_ITER 36
+#define JG_EPA_MAX_ITER 44
 #endif
 // expansion stops when the support point gains less than TOL over the closest face; a face counts as visible from
 // the new vertex only beyond VIS_EPS (< TOL).  fp32 face normals are good to ~1e-6 rad, i.e. ~1e-6 m of plane-evaluation
@@ -41,49 +41,92 @@ __device__ __forceinline__ V3 support_md(const float4* __restrict__ A, int nA, c
     return tf_apply(T, mk(pa.x, pa.y, pa.z)) - mk(pb.x, pb.y, pb.z);
 }
 
-struct EpaPoly {
-    V3 P[JG_EPA_MAX_V];
-    uint32_t pid[JG_EPA_MAX_V];
-    float fnx[JG_EPA_MAX_F], fny[JG_EPA_MAX_F], fnz[JG_EPA_MAX_F], fd[JG_EPA_MAX_F];
-    uint32_t fv[JG_EPA_MAX_F];   // a | b<<8 | c<<16 | alive<<24 | mark<<25 (iteration that visited the face)
-    uint32_t fa[JG_EPA_MAX_F];   // adjacency, 10 bits per edge k (c[k]->c[k+1]): neighbour face | neighbour edge << 8
+// Support oracle used by the polytope code: one thread scans both vertex sets (thread-per-pair kernels, emulation).
+// The overflow kernel plugs in a warp-cooperative one with the same call signature.
+struct ThreadSupport {
+    const float4* A; int nA;
+    const float4* B; int nB;
+    Tf T;
+    __device__ __forceinline__ V3 operator()(V3 d, uint32_t& id) const { return support_md(A, nA, B, nB, T, d, id); }
+};
+
+// Polytope storage.  All state lives in 32-bit words addressed as w[k * STRIDE]: STRIDE = 1 for a per-thread array
+// (host emulation, overflow kernel: local memory) and STRIDE = threads-per-block for the fast kernel, where the block's
+// polytopes are interleaved in SHARED memory (lanes that touch the same logical word hit consecutive banks).
+// Face normals are not stored: they are recomputed from the three vertices when needed (closest face once per
+// expansion, a handful of flood-fill visits), which halves the footprint.
+//   V vertices: P (3 words) + id (1);  F faces: offset d, fv (a | b<<8 | c<<16 | alive<<24 | mark<<25),
+//   fa (10 bits per edge k = c[k]->c[k+1]: neighbour face | neighbour edge << 8);  then flood-fill scratch.
+template <int V_, int F_, int S_, int H_, int R_, int STRIDE>
+struct EpaPolyT {
+    static constexpr int V = V_, F = F_, S = S_, H = H_, R = R_;
+    static constexpr int oP = 0, oId = 3 * V, oFd = 4 * V, oFv = 4 * V + F, oFa = 4 * V + 2 * F, oSt = 4 * V + 3 * F,
+                         oHz = oSt + S, oRm = oHz + H, WORDS = oRm + R;
+    uint32_t* w;
     int nv, nf;
+    __device__ __forceinline__ uint32_t& at(int k) const { return w[(size_t)k * STRIDE]; }
+    __device__ __forceinline__ V3 P(int i) const {
+        return mk(__uint_as_float(at(oP + 3 * i)), __uint_as_float(at(oP + 3 * i + 1)), __uint_as_float(at(oP + 3 * i + 2)));
+    }
+    __device__ __forceinline__ void setP(int i, V3 p, uint32_t id) const {
+        at(oP + 3 * i) = __float_as_uint(p.x); at(oP + 3 * i + 1) = __float_as_uint(p.y); at(oP + 3 * i + 2) = __float_as_uint(p.z);
+        at(oId + i) = id;
+    }
+    __device__ __forceinline__ uint32_t pid(int i) const { return at(oId + i); }
+    __device__ __forceinline__ float fd(int f) const { return __uint_as_float(at(oFd + f)); }
+    __device__ __forceinline__ void set_fd(int f, float d) const { at(oFd + f) = __float_as_uint(d); }
+    __device__ __forceinline__ uint32_t& fv(int f) const { return at(oFv + f); }
+    __device__ __forceinline__ uint32_t& fa(int f) const { return at(oFa + f); }
+    __device__ __forceinline__ uint32_t& st(int i) const { return at(oSt + i); }
+    __device__ __forceinline__ uint32_t& hz(int i) const { return at(oHz + i); }
+    __device__ __forceinline__ uint32_t& rm(int i) const { return at(oRm + i); }
 };
 
 __device__ __forceinline__ int epa_vert(uint32_t fv, int k) { return (int)((fv >> (8 * k)) & 255u); }
 __device__ __forceinline__ uint32_t epa_adj(uint32_t fa, int k) { return (fa >> (10 * k)) & 1023u; }
-__device__ __forceinline__ void epa_bind(EpaPoly& E, int f0, int e0, int f1, int e1) {
-    E.fa[f0] = (E.fa[f0] & ~(1023u << (10 * e0))) | (((uint32_t)f1 | ((uint32_t)e1 << 8)) << (10 * e0));
-    E.fa[f1] = (E.fa[f1] & ~(1023u << (10 * e1))) | (((uint32_t)f0 | ((uint32_t)e0 << 8)) << (10 * e1));
+
+template <class E>
+__device__ __forceinline__ void epa_bind(const E& X, int f0, int e0, int f1, int e1) {
+    X.fa(f0) = (X.fa(f0) & ~(1023u << (10 * e0))) | (((uint32_t)f1 | ((uint32_t)e1 << 8)) << (10 * e0));
+    X.fa(f1) = (X.fa(f1) & ~(1023u << (10 * e1))) | (((uint32_t)f0 | ((uint32_t)e0 << 8)) << (10 * e1));
 }
 
-__device__ __forceinline__ void epa_make_face(EpaPoly& E, int f, int a, int b, int c) {
-    const V3 n = cross(E.P[b] - E.P[a], E.P[c] - E.P[a]);
+// unit outward normal of face f (zero vector for a degenerate sliver)
+template <class E>
+__device__ __forceinline__ V3 epa_normal(const E& X, uint32_t fv) {
+    const V3 a = X.P(epa_vert(fv, 0));
+    const V3 n = cross(X.P(epa_vert(fv, 1)) - a, X.P(epa_vert(fv, 2)) - a);
     const float l2 = norm2(n);
-    E.fv[f] = (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16) | (1u << 24);
-    E.fa[f] = 0u;
-    float inv = 0.f, d = FLT_MAX;
+    return l2 > 1e-30f ? n * rsqrtf(l2) : mk(0.f, 0.f, 0.f);
+}
+
+template <class E>
+__device__ __forceinline__ void epa_make_face(const E& X, int f, int a, int b, int c) {
+    const V3 pa = X.P(a);
+    const V3 n = cross(X.P(b) - pa, X.P(c) - pa);
+    const float l2 = norm2(n);
+    X.fv(f) = (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16) | (1u << 24);
+    X.fa(f) = 0u;
+    float d = FLT_MAX;
     if (l2 > 1e-30f) {
-        inv = rsqrtf(l2);
-        d = (n.x * E.P[a].x + n.y * E.P[a].y + n.z * E.P[a].z) * inv;
+        d = dot(n, pa) * rsqrtf(l2);
         // a face that looks at the origin from the wrong side is a numerical fold-over of near-coplanar faces:
         // keep it in the mesh (topology) but never select it as the closest face
         if (d < -1e-5f) d = FLT_MAX;
     }
-    E.fnx[f] = n.x * inv; E.fny[f] = n.y * inv; E.fnz[f] = n.z * inv;
-    E.fd[f] = d;
+    X.set_fd(f, d);
 }
 
 // Grow a lower-dimensional GJK end simplex (origin on it) to a tetrahedron; false if the difference is flat.
-__device__ __forceinline__ bool epa_blow_up(const float4* __restrict__ A, int nA, const float4* __restrict__ B, int nB,
-                                            const Tf& T, Simplex& S) {
+template <class Sup>
+__device__ __forceinline__ bool epa_blow_up(const Sup& sup, Simplex& S) {
     if (S.n == 1) {
 #pragma unroll 1
         for (int k = 0; k < 6 && S.n == 1; ++k) {
             const V3 ax = mk(k == 0 ? 1.f : (k == 1 ? -1.f : 0.f), k == 2 ? 1.f : (k == 3 ? -1.f : 0.f),
                              k == 4 ? 1.f : (k == 5 ? -1.f : 0.f));
             uint32_t id;
-            const V3 w = support_md(A, nA, B, nB, T, ax, id);
+            const V3 w = sup(ax, id);
             if (norm2(w - S.a) > 1e-12f) { S.b = w; S.ib = id; S.n = 2; }
         }
         if (S.n == 1) return false;
@@ -97,7 +140,7 @@ __device__ __forceinline__ bool epa_blow_up(const float4* __restrict__ A, int nA
 #pragma unroll 1
         for (int k = 0; k < 6 && S.n == 2; ++k) {
             uint32_t id;
-            const V3 w = support_md(A, nA, B, nB, T, d, id);
+            const V3 w = sup(d, id);
             if (norm2(cross(ab, w - S.a)) > 1e-14f * norm2(ab)) { S.c = w; S.ic = id; S.n = 3; break; }
             d = d * 0.5f + cross(u, d) * 0.8660254f;   // rotate 60 degrees about the segment
         }
@@ -107,9 +150,9 @@ __device__ __forceinline__ bool epa_blow_up(const float4* __restrict__ A, int nA
         const V3 n = cross(S.b - S.a, S.c - S.a);
         const float tol = 1e-6f * sqrtf(norm2(n));
         uint32_t id;
-        V3 w = support_md(A, nA, B, nB, T, n, id);
+        V3 w = sup(n, id);
         if (fabsf(dot(w - S.a, n)) <= tol) {
-            w = support_md(A, nA, B, nB, T, -n, id);
+            w = sup(-n, id);
             if (fabsf(dot(w - S.a, n)) <= tol) return false;
         }
         S.d = w; S.id = id; S.n = 4;
@@ -124,124 +167,147 @@ __device__ __forceinline__ bool epa_blow_up(const float4* __restrict__ A, int nA
 //
 // Every closest-face offset is a lower bound of the depth (the polytope lies inside the difference) and every
 // support value h(n) an upper bound; the state keeps the best of both so a late numerical hiccup cannot lose them.
-struct EpaState {
-    EpaPoly E;
+enum { JG_EPA_RUNNING = 0, JG_EPA_DONE = 1, JG_EPA_OVERFLOW = 2 };
+
+template <class E>
+struct EpaStateT {
+    E poly;
     float lb, ub;
     int it;
 };
 
 // S = GJK end simplex (origin inside or on it).  Returns false when the difference is flat (depth 0, nothing to do).
-__device__ __forceinline__ bool epa_begin(EpaState& X, const float4* __restrict__ A, int nA,
-                                          const float4* __restrict__ B, int nB, const Tf& T, Simplex S) {
+template <class E, class Sup>
+__device__ __forceinline__ bool epa_begin(EpaStateT<E>& X, const Sup& sup, Simplex S) {
     X.lb = 0.f;
     X.ub = FLT_MAX;
     X.it = 0;
-    if (S.n < 4 && !epa_blow_up(A, nA, B, nB, T, S)) { X.ub = 0.f; return false; }
-    EpaPoly& E = X.E;
-    E.P[0] = S.a; E.P[1] = S.b; E.P[2] = S.c; E.P[3] = S.d;
-    E.pid[0] = S.ia; E.pid[1] = S.ib; E.pid[2] = S.ic; E.pid[3] = S.id;
+    if (S.n < 4 && !epa_blow_up(sup, S)) { X.ub = 0.f; return false; }
+    E& P = X.poly;
     // orient so that face (0,1,2) looks away from vertex 3
-    if (dot(cross(E.P[1] - E.P[0], E.P[2] - E.P[0]), E.P[3] - E.P[0]) > 0.f) {
-        const V3 tp = E.P[0]; E.P[0] = E.P[1]; E.P[1] = tp;
-        const uint32_t ti = E.pid[0]; E.pid[0] = E.pid[1]; E.pid[1] = ti;
+    if (dot(cross(S.b - S.a, S.c - S.a), S.d - S.a) > 0.f) {
+        const V3 tp = S.a; S.a = S.b; S.b = tp;
+        const uint32_t ti = S.ia; S.ia = S.ib; S.ib = ti;
     }
-    E.nv = 4;
-    E.nf = 4;
-    epa_make_face(E, 0, 0, 1, 2);
-    epa_make_face(E, 1, 1, 0, 3);
-    epa_make_face(E, 2, 2, 1, 3);
-    epa_make_face(E, 3, 0, 2, 3);
-    epa_bind(E, 0, 0, 1, 0); epa_bind(E, 0, 1, 2, 0); epa_bind(E, 0, 2, 3, 0);
-    epa_bind(E, 1, 1, 3, 2); epa_bind(E, 1, 2, 2, 1); epa_bind(E, 2, 2, 3, 1);
+    P.setP(0, S.a, S.ia); P.setP(1, S.b, S.ib); P.setP(2, S.c, S.ic); P.setP(3, S.d, S.id);
+    P.nv = 4;
+    P.nf = 4;
+    epa_make_face(P, 0, 0, 1, 2);
+    epa_make_face(P, 1, 1, 0, 3);
+    epa_make_face(P, 2, 2, 1, 3);
+    epa_make_face(P, 3, 0, 2, 3);
+    epa_bind(P, 0, 0, 1, 0); epa_bind(P, 0, 1, 2, 0); epa_bind(P, 0, 2, 3, 0);
+    epa_bind(P, 1, 1, 3, 2); epa_bind(P, 1, 2, 2, 1); epa_bind(P, 2, 2, 3, 1);
     return true;
 }
 
-// One expansion (one support evaluation).  Returns true when finished.
-__device__ __forceinline__ bool epa_step(EpaState& X, const float4* __restrict__ A, int nA, const float4* __restrict__ B,
-                                         int nB, const Tf& T) {
-    EpaPoly& E = X.E;
+// One expansion (one support evaluation).  JG_EPA_OVERFLOW: the polytope or the flood-fill scratch outgrew this
+// storage class (nothing was modified in that step): the pair must be redone with a larger one.
+template <class E, class Sup>
+__device__ __forceinline__ int epa_step(EpaStateT<E>& X, const Sup& sup) {
+    E& P = X.poly;
     int best = -1;
     float bd = FLT_MAX;
-    for (int f = 0; f < E.nf; ++f)
-        if (((E.fv[f] >> 24) & 1u) && E.fd[f] < bd) { bd = E.fd[f]; best = f; }
-    if (best < 0) return true;
+    for (int f = 0; f < P.nf; ++f) {
+        const float d = P.fd(f);     // dead faces carry FLT_MAX
+        if (d < bd) { bd = d; best = f; }
+    }
+    if (best < 0) return JG_EPA_DONE;
     X.lb = fmaxf(X.lb, bd);
-    const V3 n = mk(E.fnx[best], E.fny[best], E.fnz[best]);
+    const V3 n = epa_normal(P, P.fv(best));
     uint32_t id;
-    const V3 w = support_md(A, nA, B, nB, T, n, id);
+    const V3 w = sup(n, id);
     X.ub = fminf(X.ub, dot(n, w));
     X.it += 1;
-    if (X.ub - X.lb <= JG_EPA_TOL || X.it >= JG_EPA_MAX_ITER) return true;
+    if (X.ub - X.lb <= JG_EPA_TOL || X.it >= JG_EPA_MAX_ITER) return JG_EPA_DONE;
     bool dupl = false;
-    for (int i = 0; i < E.nv; ++i) dupl |= (E.pid[i] == id);
-    if (dupl || E.nv >= JG_EPA_MAX_V) return true;
-    const int vi = E.nv;
+    for (int i = 0; i < P.nv; ++i) dupl |= (P.pid(i) == id);
+    if (dupl) return JG_EPA_DONE;
+    if (P.nv >= E::V) return JG_EPA_OVERFLOW;
+    const int vi = P.nv;
     // ---- flood fill of the visible faces, horizon edges in loop order
     const uint32_t mark = (uint32_t)X.it;
-    uint16_t stack[JG_EPA_MAX_F];      // face | edge << 8
-    uint16_t horizon[JG_EPA_MAX_F];
-    uint8_t removed[JG_EPA_MAX_F];
     int sp = 0, nh = 0, nr = 0;
-    E.fv[best] = (E.fv[best] & 0x01FFFFFFu) | (mark << 25);
-    removed[nr++] = (uint8_t)best;
+    bool ok = true, over = false;
+    P.fv(best) = (P.fv(best) & 0x01FFFFFFu) | (mark << 25);
+    P.rm(nr++) = (uint32_t)best;
     {
-        const uint32_t fa = E.fa[best];
-        stack[sp++] = (uint16_t)epa_adj(fa, 2);
-        stack[sp++] = (uint16_t)epa_adj(fa, 1);
-        stack[sp++] = (uint16_t)epa_adj(fa, 0);
+        const uint32_t fa = P.fa(best);
+        P.st(sp++) = epa_adj(fa, 2);
+        P.st(sp++) = epa_adj(fa, 1);
+        P.st(sp++) = epa_adj(fa, 0);
     }
     while (sp > 0) {
-        const uint32_t fe = stack[--sp];
+        const uint32_t fe = P.st(--sp);
         const int f = (int)(fe & 255u), e = (int)(fe >> 8);
-        const uint32_t fv = E.fv[f];
-        if ((fv >> 25) == mark) return true;   // reached twice: inconsistent classification, keep the bracket
-        const bool vis = !(E.fd[f] < FLT_MAX) ||
-                         fmaf(E.fnx[f], w.x, fmaf(E.fny[f], w.y, E.fnz[f] * w.z)) - E.fd[f] > JG_EPA_VIS_EPS;
+        const uint32_t fv = P.fv(f);
+        if ((fv >> 25) == mark) { ok = false; break; }   // reached twice: inconsistent classification
+        const float d = P.fd(f);
+        bool vis = !(d < FLT_MAX);
+        if (!vis) vis = dot(epa_normal(P, fv), w) - d > JG_EPA_VIS_EPS;
         if (!vis) {
-            horizon[nh++] = (uint16_t)fe;
+            if (nh >= E::H) { over = true; break; }
+            P.hz(nh++) = fe;
         } else {
-            E.fv[f] = (fv & 0x01FFFFFFu) | (mark << 25);
-            removed[nr++] = (uint8_t)f;
-            const uint32_t fa = E.fa[f];
+            if (nr >= E::R || sp + 2 > E::S) { over = true; break; }
+            P.fv(f) = (fv & 0x01FFFFFFu) | (mark << 25);
+            P.rm(nr++) = (uint32_t)f;
+            const uint32_t fa = P.fa(f);
             const int e1 = e == 2 ? 0 : e + 1, e2 = e == 0 ? 2 : e - 1;
-            if (sp + 2 > JG_EPA_MAX_F) return true;
-            stack[sp++] = (uint16_t)epa_adj(fa, e2);
-            stack[sp++] = (uint16_t)epa_adj(fa, e1);
+            P.st(sp++) = epa_adj(fa, e2);
+            P.st(sp++) = epa_adj(fa, e1);
         }
     }
-    if (nh < 3 || nh > nr + (JG_EPA_MAX_F - E.nf)) return true;
-    E.P[vi] = w;
-    E.pid[vi] = id;
-    E.nv = vi + 1;
+    if (!over && ok && nh >= 3 && nh > nr + (E::F - P.nf)) over = true;
+    if (over) {   // undo the marks of this step so that a restart / larger storage sees a clean polytope
+        for (int i = 0; i < nr; ++i) P.fv((int)P.rm(i)) &= 0x01FFFFFFu;
+        return JG_EPA_OVERFLOW;
+    }
+    if (!ok || nh < 3) return JG_EPA_DONE;   // keep the bracket
+    P.setP(vi, w, id);
+    P.nv = vi + 1;
     int first = -1, prev = -1;
     for (int j = 0; j < nh; ++j) {
-        const int f = (int)(horizon[j] & 255u), e = (int)(horizon[j] >> 8);
+        const uint32_t he = P.hz(j);
+        const int f = (int)(he & 255u), e = (int)(he >> 8);
         const int e1 = e == 2 ? 0 : e + 1;
-        const uint32_t fv = E.fv[f];
-        const int slot = nr > 0 ? (int)removed[--nr] : E.nf++;
-        epa_make_face(E, slot, epa_vert(fv, e1), epa_vert(fv, e), vi);
-        epa_bind(E, slot, 0, f, e);
-        if (prev >= 0) epa_bind(E, prev, 1, slot, 2); else first = slot;
+        const uint32_t fv = P.fv(f);
+        const int slot = nr > 0 ? (int)P.rm(--nr) : P.nf++;
+        epa_make_face(P, slot, epa_vert(fv, e1), epa_vert(fv, e), vi);
+        epa_bind(P, slot, 0, f, e);
+        if (prev >= 0) epa_bind(P, prev, 1, slot, 2); else first = slot;
         prev = slot;
     }
-    epa_bind(E, prev, 1, first, 2);
-    while (nr > 0) E.fv[removed[--nr]] &= ~(1u << 24);   // the remaining removed faces die
-    return false;
+    epa_bind(P, prev, 1, first, 2);
+    while (nr > 0) {   // the remaining removed faces die
+        const int f = (int)P.rm(--nr);
+        P.fv(f) &= ~(1u << 24);
+        P.set_fd(f, FLT_MAX);
+    }
+    return JG_EPA_RUNNING;
 }
 
-// converged: midpoint of the bracket; otherwise (iteration / size caps, inconsistent mesh) the bracket is still valid:
+// converged: midpoint of the bracket; otherwise (iteration caps, inconsistent mesh) the bracket is still valid:
 // its midpoint when tight, else the guaranteed lower bound
-__device__ __forceinline__ float epa_result(const EpaState& X) {
+template <class E>
+__device__ __forceinline__ float epa_result(const EpaStateT<E>& X) {
     if (X.ub < FLT_MAX && X.ub - X.lb <= 1e-4f) return fmaxf(0.5f * (X.lb + X.ub), 0.f);
     return X.lb;
 }
 
+// storage classes: small = the fast kernel's shared-memory polytope; big = per-thread array (overflow kernel, tests)
+typedef EpaPolyT<JG_EPA_MAX_V, JG_EPA_MAX_F, JG_EPA_MAX_F, JG_EPA_MAX_F, JG_EPA_MAX_F, 1> EpaPolyBig;
+
+// whole query in one call on a per-thread array (overflow kernel, host emulation)
 __device__ __noinline__ float epa_depth(const float4* __restrict__ A, int nA, const float4* __restrict__ B, int nB,
                                         const Tf& T, Simplex S, int& iters) {
-    EpaState X;
+    uint32_t words[EpaPolyBig::WORDS];
+    EpaStateT<EpaPolyBig> X;
+    X.poly.w = words;
     iters = 0;
-    if (!epa_begin(X, A, nA, B, nB, T, S)) return 0.f;
-    while (!epa_step(X, A, nA, B, nB, T)) {}
+    const ThreadSupport sup = {A, nA, B, nB, T};
+    if (!epa_begin(X, sup, S)) return 0.f;
+    while (epa_step(X, sup) == JG_EPA_RUNNING) {}
     iters = X.it;
     return epa_result(X);
 }

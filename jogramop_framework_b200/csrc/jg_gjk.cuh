@@ -25,20 +25,33 @@ enum { JG_GJK_SEPARATED = 0, JG_GJK_FAR = 1, JG_GJK_PENETRATING = 2 };
 #define JG_GJK_TOL 1e-6f
 #endif
 
-// argmax_i dot(verts[i], d) over a shared-memory vertex range (warp-uniform range, per-lane direction)
+// argmax_i dot(verts[i], d) over a shared-memory vertex range (warp-uniform range, per-lane direction).
+// Vertex sets are padded to a multiple of 4 with copies of their last vertex (host side).  Four dot products per
+// step are reduced with a max tree and only the group index is tracked: 5.5 issue slots per vertex instead of 7 and a
+// loop-carried dependency once per 4 vertices.  The winner inside the winning group is located afterwards by
+// repeating the same arithmetic (bitwise identical values); ties resolve to the lowest index, like a sequential scan.
+__device__ __forceinline__ float dot4(const float4 p, V3 d) { return fmaf(p.x, d.x, fmaf(p.y, d.y, p.z * d.z)); }
+
 __device__ __forceinline__ int support_scan(const float4* __restrict__ verts, int n, V3 d) {
+    const int ng = (n + 3) >> 2;
     float best = -FLT_MAX;
-    int bi = 0;
-#pragma unroll 4
-    for (int i = 0; i < n; ++i) {
-        const float4 p = verts[i];
-        const float s = fmaf(p.x, d.x, fmaf(p.y, d.y, p.z * d.z));
-        if (s > best) {
-            best = s;
-            bi = i;
+    int bg = 0;
+#pragma unroll 2
+    for (int g = 0; g < ng; ++g) {
+        const float s0 = dot4(verts[4 * g], d), s1 = dot4(verts[4 * g + 1], d);
+        const float s2 = dot4(verts[4 * g + 2], d), s3 = dot4(verts[4 * g + 3], d);
+        const float m = fmaxf(fmaxf(s0, s1), fmaxf(s2, s3));
+        if (m > best) {
+            best = m;
+            bg = g;
         }
     }
-    return bi;
+    const float s0 = dot4(verts[4 * bg], d), s1 = dot4(verts[4 * bg + 1], d), s2 = dot4(verts[4 * bg + 2], d);
+    int k = 3;
+    if (s2 == best) k = 2;
+    if (s1 == best) k = 1;
+    if (s0 == best) k = 0;
+    return 4 * bg + k;
 }
 
 // closest point of triangle (a,b,c) to the origin; mask bit0/1/2 = a/b/c belongs to the supporting feature

@@ -95,9 +95,10 @@ struct PassArgs {
     int* q_cfg;
     int cap;           // queue capacity per key (= max configs per pass)
     int* counts;       // [n_keys] pair counts, [n_keys] GJK tile counter, [n_keys+1] EPA tile counter,
-                       // [n_keys+8 .. 2 n_keys+8) penetration-queue counts
+                       // [n_keys+2] overflow-list length, [n_keys+8 .. 2 n_keys+8) penetration-queue counts
     int* epa_slot;     // [n_keys*cap] queue slots whose cores overlap (penetration-depth pass)
     uint4* epa_ids;    // [n_keys*cap] their GJK end simplices (vertex ids, 0xFFFFFFFF = unused)
+    int2* ovf_list;    // [cap] (key, index in the penetration queue) of polytopes that outgrew shared memory
     // per-configuration scratch
     int* enc_scene;    // encoded min contact distance vs scene+plane
     int* enc_self;
@@ -456,25 +457,44 @@ __device__ __forceinline__ V3 md_point(const float4* __restrict__ A, const float
     return tf_apply(T, mk(pa.x, pa.y, pa.z)) - mk(pb.x, pb.y, pb.z);
 }
 
+// Fast storage class: polytopes of the block interleaved in shared memory (18 expansions; larger ones overflow to
+// k_penetration_big).  Footprint: (4*22 + 3*40 + 12 + 20 + 12) words = 1008 B per thread.
+template <int BLOCK>
+using EpaPolySmall = EpaPolyT<22, 40, 12, 20, 12, BLOCK>;
+
+__device__ __forceinline__ Simplex simplex_from_ids(const float4* __restrict__ A, const float4* __restrict__ B,
+                                                    const Tf& T, uint4 ids) {
+    Simplex sx;
+    sx.a = sx.b = sx.c = sx.d = mk(0.f, 0.f, 0.f);
+    sx.ia = ids.x; sx.ib = ids.y; sx.ic = ids.z; sx.id = ids.w;
+    sx.n = 0;
+    if (ids.x != 0xFFFFFFFFu) { sx.a = md_point(A, B, T, ids.x); sx.n = 1; }
+    if (ids.y != 0xFFFFFFFFu) { sx.b = md_point(A, B, T, ids.y); sx.n = 2; }
+    if (ids.z != 0xFFFFFFFFu) { sx.c = md_point(A, B, T, ids.z); sx.n = 3; }
+    if (ids.w != 0xFFFFFFFFu) { sx.d = md_point(A, B, T, ids.w); sx.n = 4; }
+    return sx;
+}
+
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_penetration(const PassArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* verts = reinterpret_cast<float4*>(smem_raw);
-    KeyRec* keys = reinterpret_cast<KeyRec*>(smem_raw + sizeof(float4) * a.n_verts);
-    int* prefix = reinterpret_cast<int*>(keys + a.n_keys);
+    int* prefix = reinterpret_cast<int*>(smem_raw + sizeof(float4) * a.n_verts);   // [n_keys + 2]
+    uint32_t* poly_words = reinterpret_cast<uint32_t*>(prefix + ((a.n_keys + 2 + 3) & ~3));
     const int tid = threadIdx.x, lane = tid & 31;
     const int* ecounts = a.counts + a.n_keys + 8;
     for (int i = tid; i < a.n_verts; i += BLOCK) verts[i] = a.verts[i];
-    {
-        const int* ks = reinterpret_cast<const int*>(a.keys);
-        int* kd = reinterpret_cast<int*>(keys);
-        for (int i = tid; i < (int)(sizeof(KeyRec) / 4) * a.n_keys; i += BLOCK) kd[i] = ks[i];
-    }
     if (tid < 32) sched_build(ecounts, a.n_keys, gridDim.x * (BLOCK / 32), prefix, prefix + a.n_keys + 1, lane);
     __syncthreads();
     const int total = prefix[a.n_keys], G = prefix[a.n_keys + 1];
     int* range_counter = a.counts + a.n_keys + 1;
+    int* ovf_counter = a.counts + a.n_keys + 2;
     const unsigned lt_mask = (1u << lane) - 1u;
+
+    EpaStateT<EpaPolySmall<BLOCK>> X;
+    X.poly.w = poly_words + tid;
+    X.poly.nv = X.poly.nf = 0;
+    X.lb = 0.f; X.ub = FLT_MAX; X.it = 0;
 
     for (;;) {
         int r = 0;
@@ -482,7 +502,7 @@ __global__ void __launch_bounds__(BLOCK) k_penetration(const PassArgs a) {
         r = __shfl_sync(0xFFFFFFFFu, r, 0);
         if (r >= total) break;
         const int key = sched_find_key(prefix, a.n_keys, r);
-        const KeyRec K = keys[key];
+        const KeyRec K = a.keys[key];
         const int begin = (r - prefix[key]) * G;
         const int end = min(begin + G, ecounts[key]);
         const size_t kbase = (size_t)key * a.cap;
@@ -494,32 +514,24 @@ __global__ void __launch_bounds__(BLOCK) k_penetration(const PassArgs a) {
         int next = begin;
         int phase = 0;   // 0 idle, 1 GJK on the penetration geometry, 2 expanding polytope
         GjkState S;
-        EpaState X;
         Tf T = tf_identity();
-        int cfg = 0;
+        int cfg = 0, myj = 0;
         for (;;) {
             const unsigned need = __ballot_sync(0xFFFFFFFFu, phase == 0);
             const int avail = end - next;
             if (need && avail > 0) {
                 const int rank = __popc(need & lt_mask);
                 if (phase == 0 && rank < avail) {
-                    const size_t j = kbase + next + rank;
+                    myj = next + rank;
+                    const size_t j = kbase + myj;
                     T = load_entry(a, kbase + a.epa_slot[j], cfg);
                     if (regjk) {
                         gjk_init(S, mk(T.tx, T.ty, T.tz));
                         phase = 1;
                     } else {
-                        const uint4 ids = a.epa_ids[j];
-                        Simplex sx;
-                        sx.a = sx.b = sx.c = sx.d = mk(0.f, 0.f, 0.f);
-                        sx.ia = ids.x; sx.ib = ids.y; sx.ic = ids.z; sx.id = ids.w;
-                        sx.n = 0;
-                        if (ids.x != 0xFFFFFFFFu) { sx.a = md_point(A, B, T, ids.x); sx.n = 1; }
-                        if (ids.y != 0xFFFFFFFFu) { sx.b = md_point(A, B, T, ids.y); sx.n = 2; }
-                        if (ids.z != 0xFFFFFFFFu) { sx.c = md_point(A, B, T, ids.z); sx.n = 3; }
-                        if (ids.w != 0xFFFFFFFFu) { sx.d = md_point(A, B, T, ids.w); sx.n = 4; }
                         phase = 2;
-                        if (!epa_begin(X, A, K.ea_n, B, K.eb_n, T, sx)) {
+                        const ThreadSupport sup = {A, K.ea_n, B, K.eb_n, T};
+                        if (!epa_begin(X, sup, simplex_from_ids(A, B, T, a.epa_ids[j]))) {
                             atomicMin(enc + cfg, enc_float(fminf(-K.emsum, -K.msum)));
                             phase = 0;
                         }
@@ -532,7 +544,8 @@ __global__ void __launch_bounds__(BLOCK) k_penetration(const PassArgs a) {
                 const int st = gjk_step(S, A, K.ea_n, B, K.eb_n, T, 1e30f);
                 if (st == JG_GJK_PENETRATING) {
                     phase = 2;
-                    if (!epa_begin(X, A, K.ea_n, B, K.eb_n, T, S.S)) {
+                    const ThreadSupport sup = {A, K.ea_n, B, K.eb_n, T};
+                    if (!epa_begin(X, sup, S.S)) {
                         atomicMin(enc + cfg, enc_float(fminf(-K.emsum, -K.msum)));
                         phase = 0;
                     }
@@ -541,13 +554,98 @@ __global__ void __launch_bounds__(BLOCK) k_penetration(const PassArgs a) {
                     phase = 0;
                 }
             } else if (phase == 2) {
-                if (epa_step(X, A, K.ea_n, B, K.eb_n, T)) {
+                const ThreadSupport sup = {A, K.ea_n, B, K.eb_n, T};
+                const int st = (a.flags & 0x40000000u) ? (int)JG_EPA_OVERFLOW : epa_step(X, sup);   // test hook
+                if (st == JG_EPA_DONE) {
                     // the cores overlap: never report less penetration than the margins
                     atomicMin(enc + cfg, enc_float(fminf(-(epa_result(X) + K.emsum), -K.msum)));
+                    phase = 0;
+                } else if (st == JG_EPA_OVERFLOW) {   // rare large polytope: redo with per-thread storage
+                    const int o = atomicAdd(ovf_counter, 1);
+                    if (o < a.cap) a.ovf_list[o] = make_int2(key, myj);
+                    else atomicMin(enc + cfg, enc_float(fminf(-(epa_result(X) + K.emsum), -K.msum)));
                     phase = 0;
                 }
             }
         }
+    }
+}
+
+// Overflow pass: the few pairs whose polytope outgrew the fast storage class.  ONE PAIR PER WARP: the lanes split
+// the vertex scans (lane-strided + shuffle arg-max, identical result on every lane) and then all execute the same
+// polytope update on a large polytope held in shared memory (identical values written by every lane).  This keeps
+// the latency of a 40-expansion query in the microseconds instead of a single thread walking 260 vertices serially.
+struct WarpSupport {
+    const float4* A; int nA;
+    const float4* B; int nB;
+    Tf T;
+    int lane;
+    __device__ __forceinline__ int scan(const float4* __restrict__ v, int n, V3 d) const {
+        float best = -FLT_MAX;
+        int bi = 0x7FFFFFFF;
+        for (int i = lane; i < n; i += 32) {
+            const float s = dot4(v[i], d);
+            if (s > best) { best = s; bi = i; }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+            const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        return bi;
+    }
+    __device__ __forceinline__ V3 operator()(V3 d, uint32_t& id) const {
+        const int ia = scan(A, nA, tf_rot_t(T, d));
+        const int ib = scan(B, nB, -d);
+        const float4 pa = A[ia], pb = B[ib];
+        id = ((uint32_t)ia << 16) | (uint32_t)ib;
+        return tf_apply(T, mk(pa.x, pa.y, pa.z)) - mk(pb.x, pb.y, pb.z);
+    }
+};
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_penetration_big(const PassArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* verts = reinterpret_cast<float4*>(smem_raw);
+    uint32_t* poly_words = reinterpret_cast<uint32_t*>(smem_raw + sizeof(float4) * a.n_verts);
+    const int n = min(a.counts[a.n_keys + 2], a.cap);
+    if (n == 0) return;
+    for (int i = threadIdx.x; i < a.n_verts; i += BLOCK) verts[i] = a.verts[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    EpaStateT<EpaPolyBig> X;
+    X.poly.w = poly_words + (size_t)warp * EpaPolyBig::WORDS;
+    for (int i = blockIdx.x * (BLOCK / 32) + warp; i < n; i += gridDim.x * (BLOCK / 32)) {
+        const int2 e = a.ovf_list[i];
+        const KeyRec K = a.keys[e.x];
+        const size_t kbase = (size_t)e.x * a.cap;
+        const size_t j = kbase + e.y;
+        int cfg;
+        const Tf T = load_entry(a, kbase + a.epa_slot[j], cfg);
+        const WarpSupport sup = {verts + K.ea_off, K.ea_n, verts + K.eb_off, K.eb_n, T, lane};
+        Simplex sx;
+        bool pen = true;
+        float d = 0.f;
+        if ((K.ea_off != K.a_off) || (K.eb_off != K.b_off)) {   // box: every lane reruns the (identical) GJK
+            float dist;
+            int it;
+            pen = gjk_distance(sup.A, sup.nA, sup.B, sup.nB, T, mk(T.tx, T.ty, T.tz), 1e30f, dist, it, sx) == JG_GJK_PENETRATING;
+            d = dist - K.emsum;
+        } else {
+            sx = simplex_from_ids(sup.A, sup.B, T, a.epa_ids[j]);
+        }
+        if (pen) {
+            d = -K.emsum;
+            __syncwarp();
+            if (epa_begin(X, sup, sx)) {
+                __syncwarp();
+                while (epa_step(X, sup) == JG_EPA_RUNNING) { __syncwarp(); }
+                d = -(epa_result(X) + K.emsum);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) atomicMin((K.kind == KEY_SELF ? a.enc_self : a.enc_scene) + cfg, enc_float(fminf(d, -K.msum)));
     }
 }
 

@@ -12,6 +12,8 @@
 #define __noinline__
 #define __restrict__
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+static inline float __uint_as_float(uint32_t u) { union { uint32_t u; float f; } c; c.u = u; return c.f; }
+static inline uint32_t __float_as_uint(float f) { union { uint32_t u; float f; } c; c.f = f; return c.u; }
 struct float4 { float x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { float4 r = {x, y, z, w}; return r; }
 #else

@@ -3,16 +3,23 @@
 #define JG_HOST_EMU 1
 #include "../../jogramop_framework_b200/csrc/jg_epa.cuh"
 
+#include <algorithm>
 #include <vector>
 
 using namespace jg;
 
+static int g_small_storage = 0;
+static long g_overflows = 0;
+extern "C" void emu_set_small_storage(int on) { g_small_storage = on; g_overflows = 0; }
+extern "C" long emu_overflows() { return g_overflows; }
+
 // va [na,3], vb [nb,3] float; T [n,12] row-major 3x4 (A placed by T, B static); out dist[n], status[n], iters[n]
 extern "C" void emu_gjk_batch(const float* va, int na, const float* vb, int nb, const float* T, int n, float dmax,
                               float* dist, int* status, int* iters, float* depth, int* epa_iters) {
-    std::vector<float4> A(na), B(nb);
-    for (int i = 0; i < na; ++i) A[i] = make_float4(va[3 * i], va[3 * i + 1], va[3 * i + 2], 0.f);
-    for (int i = 0; i < nb; ++i) B[i] = make_float4(vb[3 * i], vb[3 * i + 1], vb[3 * i + 2], 0.f);
+    // device layout: vertex sets padded to a multiple of 4 with copies of their last vertex
+    std::vector<float4> A((na + 3) / 4 * 4), B((nb + 3) / 4 * 4);
+    for (size_t i = 0; i < A.size(); ++i) { const int k = std::min<int>((int)i, na - 1); A[i] = make_float4(va[3 * k], va[3 * k + 1], va[3 * k + 2], 0.f); }
+    for (size_t i = 0; i < B.size(); ++i) { const int k = std::min<int>((int)i, nb - 1); B[i] = make_float4(vb[3 * k], vb[3 * k + 1], vb[3 * k + 2], 0.f); }
     for (int k = 0; k < n; ++k) {
         const float* t = T + 12 * k;
         Tf X;
@@ -27,7 +34,28 @@ extern "C" void emu_gjk_batch(const float* va, int na, const float* vb, int nb, 
         iters[k] = it;
         if (status[k] == JG_GJK_PENETRATING && depth) {
             int eit = 0;
-            depth[k] = epa_depth(A.data(), na, B.data(), nb, X, S, eit);
+            if (g_small_storage) {
+                // the fast kernel's storage class (18 expansions, small flood-fill scratch) with the overflow fallback
+                typedef EpaPolyT<22, 40, 12, 20, 12, 1> Small;
+                uint32_t words[Small::WORDS];
+                EpaStateT<Small> E;
+                E.poly.w = words;
+                int st = JG_EPA_DONE;
+                const ThreadSupport sup = {A.data(), na, B.data(), nb, X};
+                if (epa_begin(E, sup, S)) {
+                    do { st = epa_step(E, sup); } while (st == JG_EPA_RUNNING);
+                    depth[k] = epa_result(E);
+                    eit = E.it;
+                } else {
+                    depth[k] = 0.f;
+                }
+                if (st == JG_EPA_OVERFLOW) {
+                    g_overflows++;
+                    depth[k] = epa_depth(A.data(), na, B.data(), nb, X, S, eit);
+                }
+            } else {
+                depth[k] = epa_depth(A.data(), na, B.data(), nb, X, S, eit);
+            }
             epa_iters[k] = eit;
         }
     }

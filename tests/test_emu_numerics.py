@@ -30,8 +30,11 @@ def vp(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-@pytest.mark.parametrize('sid', [11, 34, 45])
-def test_fp32_gjk_and_epa_match_oracle(sid, emu, robot, scene_loader):
+@pytest.mark.parametrize('sid,small', [(11, 0), (34, 0), (45, 0), (11, 1), (21, 1)])
+def test_fp32_gjk_and_epa_match_oracle(sid, small, emu, robot, scene_loader):
+    """small=1: the shared-memory storage class of the fast kernel (22 vertices / 40 faces) + overflow fallback."""
+    emu.emu_set_small_storage(small)
+    emu.emu_overflows.restype = C.c_long
     sc = scene_loader(sid)
     o = Oracle(robot, sc)
     n = 700
@@ -73,6 +76,9 @@ def test_fp32_gjk_and_epa_match_oracle(sid, emu, robot, scene_loader):
                 assert np.abs(-(out[3][pen] + em) - ref[pen]).max() < 2e-5
                 n_pen += int(pen.sum())
     assert n_sep > 50 and n_pen > 300
+    if small:
+        assert emu.emu_overflows() < 0.02 * n_pen      # the overflow path is rare
+    emu.emu_set_small_storage(0)
 
 
 def test_fp32_plane_distance(emu, robot, scene_loader):

@@ -80,6 +80,18 @@ def test_scene_parity(sid, no_epa, robot, scene_loader, engines):
         assert rd.min() < -0.05 and e.stats()['epa_pairs'] > 1000     # deep penetrations were really measured
 
 
+def test_overflow_kernel_parity(robot, scene_loader, engines):
+    """The warp-cooperative overflow pass (large polytopes) on EVERY penetrating pair (JG_DEBUG_FORCE_OVERFLOW)."""
+    e = engines(11)
+    o = Oracle(robot, scene_loader(11))
+    q = uniform_configs(robot, 20000, 17)
+    rb, rd = o.check(q.astype(np.float64), flags=oracle.SCENE | oracle.PLANE | oracle.SELF)
+    bits, dist, _ = e.check(q, flags=oracle.SCENE | oracle.PLANE | oracle.SELF | 0x40000000)
+    compare(bits, dist, rb, rd)
+    bits2, dist2, _ = e.check(q, flags=oracle.SCENE | oracle.PLANE | oracle.SELF)
+    assert (dist - dist2).abs().max().item() < 2e-5
+
+
 def test_scene_only_and_plane_only(robot, scene_loader, engines):
     e = engines(11)
     o = Oracle(robot, scene_loader(11))
