@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -436,10 +437,11 @@ extern "C" jg_engine* jg_engine_create(const jg_robot* r, const jg_scene* sc, in
         return nullptr;
     }
     bool ok = cudaFuncSetAttribute(k_narrowphase<NP_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_penetration<352>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_penetration<320>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_penetration<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_penetration<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(k_penetration<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_penetration<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(k_penetration<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_penetration<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_penetration_big<EPA_BIG_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_broadphase<BP_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
@@ -458,10 +460,12 @@ extern "C" jg_engine* jg_engine_create(const jg_robot* r, const jg_scene* sc, in
             e->np_blocks = e->sm_count * 2;
         // penetration pass: one block per SM, as many threads as shared-memory polytopes fit beside the vertex table
         const size_t tables = sizeof(float4) * e->n_verts + sizeof(int) * ((e->n_keys + 2 + 3) & ~3);
-        const size_t per_thread = sizeof(uint32_t) * EpaPolySmall<32>::WORDS;
+        const size_t per_thread = sizeof(uint32_t) * EpaCompact<1>::WORDS;
         e->epa_threads = 0;
-        for (int t : {192, 160, 128, 96, 64})
-            if (tables + per_thread * t + 64 <= smem_max) { e->epa_threads = t; break; }
+        int want = 352;
+        if (const char* ev = getenv("JG_EPA_THREADS")) want = atoi(ev);   // tuning knob (experiments only)
+        for (int t : {352, 320, 256, 192, 128, 64})
+            if (t <= want && tables + per_thread * t + 64 <= smem_max) { e->epa_threads = t; break; }
         if (!e->epa_threads) {
             fail(JG_ERR_INVALID, "scene too large for the shared-memory penetration pass (%zu B of tables)", tables);
             engine_release(e);
@@ -549,10 +553,11 @@ static int run_narrow_and_finalize(jg_engine* e, const PassArgs& a, int n_out, u
     PROF_MARK(e, st);
     if (e->n_keys > 0 && !(flags & JG_NO_EPA)) {
         switch (e->epa_threads) {
+            case 352: k_penetration<352><<<e->epa_blocks, 352, e->smem_epa, st>>>(a); break;
+            case 320: k_penetration<320><<<e->epa_blocks, 320, e->smem_epa, st>>>(a); break;
+            case 256: k_penetration<256><<<e->epa_blocks, 256, e->smem_epa, st>>>(a); break;
             case 192: k_penetration<192><<<e->epa_blocks, 192, e->smem_epa, st>>>(a); break;
-            case 160: k_penetration<160><<<e->epa_blocks, 160, e->smem_epa, st>>>(a); break;
             case 128: k_penetration<128><<<e->epa_blocks, 128, e->smem_epa, st>>>(a); break;
-            case 96: k_penetration<96><<<e->epa_blocks, 96, e->smem_epa, st>>>(a); break;
             default: k_penetration<64><<<e->epa_blocks, 64, e->smem_epa, st>>>(a); break;
         }
         k_penetration_big<EPA_BIG_BLOCK><<<e->sm_count, EPA_BIG_BLOCK, e->smem_epa_big, st>>>(a);

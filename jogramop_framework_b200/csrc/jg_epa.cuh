@@ -242,9 +242,13 @@ __device__ __forceinline__ int epa_step(EpaStateT<E>& X, const Sup& sup) {
         const int f = (int)(fe & 255u), e = (int)(fe >> 8);
         const uint32_t fv = P.fv(f);
         if ((fv >> 25) == mark) { ok = false; break; }   // reached twice: inconsistent classification
-        const float d = P.fd(f);
-        bool vis = !(d < FLT_MAX);
-        if (!vis) vis = dot(epa_normal(P, fv), w) - d > JG_EPA_VIS_EPS;
+        bool vis = !(P.fd(f) < FLT_MAX);
+        if (!vis) {   // w above the face plane by more than VIS_EPS (no normalisation: compare squares)
+            const V3 pa = P.P(epa_vert(fv, 0));
+            const V3 nu = cross(P.P(epa_vert(fv, 1)) - pa, P.P(epa_vert(fv, 2)) - pa);
+            const float t = dot(nu, w - pa);
+            vis = t > 0.f && t * t > (JG_EPA_VIS_EPS * JG_EPA_VIS_EPS) * norm2(nu);
+        }
         if (!vis) {
             if (nh >= E::H) { over = true; break; }
             P.hz(nh++) = fe;
@@ -266,23 +270,52 @@ __device__ __forceinline__ int epa_step(EpaStateT<E>& X, const Sup& sup) {
     if (!ok || nh < 3) return JG_EPA_DONE;   // keep the bracket
     P.setP(vi, w, id);
     P.nv = vi + 1;
-    int first = -1, prev = -1;
-    for (int j = 0; j < nh; ++j) {
-        const uint32_t he = P.hz(j);
-        const int f = (int)(he & 255u), e = (int)(he >> 8);
-        const int e1 = e == 2 ? 0 : e + 1;
-        const uint32_t fv = P.fv(f);
-        const int slot = nr > 0 ? (int)P.rm(--nr) : P.nf++;
-        epa_make_face(P, slot, epa_vert(fv, e1), epa_vert(fv, e), vi);
-        epa_bind(P, slot, 0, f, e);
-        if (prev >= 0) epa_bind(P, prev, 1, slot, 2); else first = slot;
-        prev = slot;
+    // slots of the new faces: recycle the removed ones, then grow.  hz(j) |= slot << 16
+    {
+        int nfree = nr;
+        for (int j = 0; j < nh; ++j) {
+            const int slot = nfree > 0 ? (int)P.rm(--nfree) : P.nf++;
+            P.hz(j) |= (uint32_t)slot << 16;
+        }
+        while (nfree > 0) {   // the remaining removed faces die
+            const int f = (int)P.rm(--nfree);
+            P.fv(f) &= ~(1u << 24);
+            P.set_fd(f, FLT_MAX);
+        }
     }
-    epa_bind(P, prev, 1, first, 2);
-    while (nr > 0) {   // the remaining removed faces die
-        const int f = (int)P.rm(--nr);
-        P.fv(f) &= ~(1u << 24);
-        P.set_fd(f, FLT_MAX);
+    // new face j = (a_j, b_j, w): edge 0 <-> outside face, edge 1 <-> face j+1 (its edge 2), edge 2 <-> face j-1
+    // (its edge 1).  Consecutive horizon faces share a vertex (b_j == a_{j+1}), so each face loads one vertex.
+    {
+        const uint32_t h0 = P.hz(0);
+        uint32_t prev_slot = P.hz(nh - 1) >> 16;
+        uint32_t hcur = h0;
+        int f = (int)(hcur & 255u), e = (int)((hcur >> 8) & 3u);
+        uint32_t fvo = P.fv(f);
+        int ia = epa_vert(fvo, e == 2 ? 0 : e + 1);
+        V3 pa = P.P(ia);
+        for (int j = 0; j < nh; ++j) {
+            const uint32_t hnext = j + 1 < nh ? P.hz(j + 1) : h0;
+            const uint32_t slot = hcur >> 16, next_slot = hnext >> 16;
+            const int ib = epa_vert(fvo, e);
+            const V3 pb = P.P(ib);
+            const V3 n = cross(pb - pa, w - pa);
+            const float l2 = norm2(n);
+            float d = FLT_MAX;
+            if (l2 > 1e-30f) {
+                d = dot(n, pa) * rsqrtf(l2);
+                if (d < -1e-5f) d = FLT_MAX;   // folded face (see epa_make_face)
+            }
+            P.set_fd((int)slot, d);
+            P.fv((int)slot) = (uint32_t)ia | ((uint32_t)ib << 8) | ((uint32_t)vi << 16) | (1u << 24);
+            P.fa((int)slot) = ((uint32_t)f | ((uint32_t)e << 8)) | ((next_slot | (2u << 8)) << 10) | ((prev_slot | (1u << 8)) << 20);
+            P.fa(f) = (P.fa(f) & ~(1023u << (10 * e))) | (slot << (10 * e));   // outside face now borders (slot, edge 0)
+            prev_slot = slot;
+            hcur = hnext;
+            f = (int)(hcur & 255u); e = (int)((hcur >> 8) & 3u);
+            fvo = P.fv(f);
+            ia = ib;
+            pa = pb;
+        }
     }
     return JG_EPA_RUNNING;
 }
@@ -291,6 +324,203 @@ __device__ __forceinline__ int epa_step(EpaStateT<E>& X, const Sup& sup) {
 // its midpoint when tight, else the guaranteed lower bound
 template <class E>
 __device__ __forceinline__ float epa_result(const EpaStateT<E>& X) {
+    if (X.ub < FLT_MAX && X.ub - X.lb <= 1e-4f) return fmaxf(0.5f * (X.lb + X.ub), 0.f);
+    return X.lb;
+}
+
+// ---------------------------------------------------------------------------------------------- compact polytope
+// The fast kernel is bound by how many pairs fit in shared memory at once (its time scales 1/threads), so its
+// polytope is packed to 548 bytes: 18 vertices (3 words each), 32 faces (2 words each: offset d and one word with
+// three 5-bit vertex ids, three 5-bit neighbour faces and an alive bit), 16-bit flood-fill stack / horizon entries,
+// 8-bit removed list.  The neighbour's edge index is not stored: it is found from the shared vertex when the
+// neighbour is visited.  Visited marks are a 32-bit register.  14 expansions fit; larger polytopes overflow.
+template <int STRIDE>
+struct EpaCompact {
+    static constexpr int V = 18, F = 32, S = 12, H = 20, R = 12;
+    static constexpr int oP = 0, oFd = 3 * V, oFx = oFd + F, oSt = oFx + F, oHz = oSt + S / 2, oRm = oHz + H / 2,
+                         WORDS = oRm + R / 4;
+    uint32_t* w;
+    int nv, nf;
+    __device__ __forceinline__ uint32_t& at(int k) const { return w[(size_t)k * STRIDE]; }
+    __device__ __forceinline__ V3 P(int i) const {
+        return mk(__uint_as_float(at(oP + 3 * i)), __uint_as_float(at(oP + 3 * i + 1)), __uint_as_float(at(oP + 3 * i + 2)));
+    }
+    __device__ __forceinline__ void setP(int i, V3 p) const {
+        at(oP + 3 * i) = __float_as_uint(p.x); at(oP + 3 * i + 1) = __float_as_uint(p.y); at(oP + 3 * i + 2) = __float_as_uint(p.z);
+    }
+    __device__ __forceinline__ float fd(int f) const { return __uint_as_float(at(oFd + f)); }
+    __device__ __forceinline__ void set_fd(int f, float d) const { at(oFd + f) = __float_as_uint(d); }
+    __device__ __forceinline__ uint32_t& fx(int f) const { return at(oFx + f); }
+    // 16-bit / 8-bit packed scratch
+    __device__ __forceinline__ uint32_t get16(int base, int i) const { return (at(base + (i >> 1)) >> ((i & 1) * 16)) & 0xFFFFu; }
+    __device__ __forceinline__ void set16(int base, int i, uint32_t v) const {
+        uint32_t& x = at(base + (i >> 1));
+        const int sh = (i & 1) * 16;
+        x = (x & ~(0xFFFFu << sh)) | (v << sh);
+    }
+    __device__ __forceinline__ uint32_t get8(int base, int i) const { return (at(base + (i >> 2)) >> ((i & 3) * 8)) & 0xFFu; }
+    __device__ __forceinline__ void set8(int base, int i, uint32_t v) const {
+        uint32_t& x = at(base + (i >> 2));
+        const int sh = (i & 3) * 8;
+        x = (x & ~(0xFFu << sh)) | (v << sh);
+    }
+};
+// fx word: vertex k at bits 5k (k = 0..2), neighbour across edge k (c[k]->c[k+1]) at bits 15 + 5k, alive = bit 30
+__device__ __forceinline__ int cx_vert(uint32_t fx, int k) { return (int)((fx >> (5 * k)) & 31u); }
+__device__ __forceinline__ int cx_nbr(uint32_t fx, int k) { return (int)((fx >> (15 + 5 * k)) & 31u); }
+
+template <int STRIDE>
+struct EpaStateC {
+    EpaCompact<STRIDE> poly;
+    float lb, ub;
+    int it;
+};
+
+template <int STRIDE, class Sup>
+__device__ __forceinline__ bool epa_begin(EpaStateC<STRIDE>& X, const Sup& sup, Simplex S) {
+    X.lb = 0.f;
+    X.ub = FLT_MAX;
+    X.it = 0;
+    if (S.n < 4 && !epa_blow_up(sup, S)) { X.ub = 0.f; return false; }
+    EpaCompact<STRIDE>& P = X.poly;
+    if (dot(cross(S.b - S.a, S.c - S.a), S.d - S.a) > 0.f) { const V3 tp = S.a; S.a = S.b; S.b = tp; }
+    P.setP(0, S.a); P.setP(1, S.b); P.setP(2, S.c); P.setP(3, S.d);
+    P.nv = 4;
+    P.nf = 4;
+    // faces (0,1,2) (1,0,3) (2,1,3) (0,2,3); neighbours across edges 0,1,2 (see the generic epa_begin binds)
+    const int fv[4][3] = {{0, 1, 2}, {1, 0, 3}, {2, 1, 3}, {0, 2, 3}};
+    const int fn[4][3] = {{1, 2, 3}, {0, 3, 2}, {0, 1, 3}, {0, 2, 1}};
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+        const V3 pa = P.P(fv[f][0]);
+        const V3 n = cross(P.P(fv[f][1]) - pa, P.P(fv[f][2]) - pa);
+        const float l2 = norm2(n);
+        float d = FLT_MAX;
+        if (l2 > 1e-30f) {
+            d = dot(n, pa) * rsqrtf(l2);
+            if (d < -1e-5f) d = FLT_MAX;
+        }
+        P.set_fd(f, d);
+        P.fx(f) = (uint32_t)fv[f][0] | ((uint32_t)fv[f][1] << 5) | ((uint32_t)fv[f][2] << 10) | ((uint32_t)fn[f][0] << 15) |
+                  ((uint32_t)fn[f][1] << 20) | ((uint32_t)fn[f][2] << 25) | (1u << 30);
+    }
+    return true;
+}
+
+template <int STRIDE, class Sup>
+__device__ __forceinline__ int epa_step(EpaStateC<STRIDE>& X, const Sup& sup) {
+    typedef EpaCompact<STRIDE> E;
+    E& P = X.poly;
+    int best = -1;
+    float bd = FLT_MAX;
+    for (int f = 0; f < P.nf; ++f) {
+        const float d = P.fd(f);     // dead faces carry FLT_MAX
+        if (d < bd) { bd = d; best = f; }
+    }
+    if (best < 0) return JG_EPA_DONE;
+    X.lb = fmaxf(X.lb, bd);
+    const uint32_t fxb = P.fx(best);
+    V3 n;
+    {
+        const V3 pa = P.P(cx_vert(fxb, 0));
+        n = cross(P.P(cx_vert(fxb, 1)) - pa, P.P(cx_vert(fxb, 2)) - pa);
+        n = n * rsqrtf(norm2(n));
+    }
+    uint32_t id;
+    const V3 w = sup(n, id);
+    X.ub = fminf(X.ub, dot(n, w));
+    X.it += 1;
+    // (a support point that is already a polytope vertex cannot gain over the closest face: the bracket test ends it)
+    if (X.ub - X.lb <= JG_EPA_TOL || X.it >= JG_EPA_MAX_ITER) return JG_EPA_DONE;
+    if (P.nv >= E::V) return JG_EPA_OVERFLOW;
+    const int vi = P.nv;
+    // ---- flood fill of the visible faces, horizon edges in loop order.  stack entry: face | start vertex << 5
+    uint32_t visited = 1u << best;
+    int sp = 0, nh = 0, nr = 0;
+    bool ok = true, over = false;
+    P.set8(E::oRm, nr++, (uint32_t)best);
+    P.set16(E::oSt, sp++, (uint32_t)cx_nbr(fxb, 2) | ((uint32_t)cx_vert(fxb, 0) << 5));
+    P.set16(E::oSt, sp++, (uint32_t)cx_nbr(fxb, 1) | ((uint32_t)cx_vert(fxb, 2) << 5));
+    P.set16(E::oSt, sp++, (uint32_t)cx_nbr(fxb, 0) | ((uint32_t)cx_vert(fxb, 1) << 5));
+    while (sp > 0) {
+        const uint32_t se = P.get16(E::oSt, --sp);
+        const int f = (int)(se & 31u), v0 = (int)(se >> 5);
+        if ((visited >> f) & 1u) { ok = false; break; }   // reached twice: inconsistent classification
+        const uint32_t fx = P.fx(f);
+        const int e = cx_vert(fx, 0) == v0 ? 0 : (cx_vert(fx, 1) == v0 ? 1 : 2);   // the edge we came through
+        bool vis = !(P.fd(f) < FLT_MAX);
+        if (!vis) {
+            const V3 pa = P.P(cx_vert(fx, 0));
+            const V3 nu = cross(P.P(cx_vert(fx, 1)) - pa, P.P(cx_vert(fx, 2)) - pa);
+            const float t = dot(nu, w - pa);
+            vis = t > 0.f && t * t > (JG_EPA_VIS_EPS * JG_EPA_VIS_EPS) * norm2(nu);
+        }
+        if (!vis) {
+            if (nh >= E::H) { over = true; break; }
+            P.set16(E::oHz, nh++, (uint32_t)f | ((uint32_t)e << 5));
+        } else {
+            if (nr >= E::R || sp + 2 > E::S) { over = true; break; }
+            visited |= 1u << f;
+            P.set8(E::oRm, nr++, (uint32_t)f);
+            const int e1 = e == 2 ? 0 : e + 1, e2 = e == 0 ? 2 : e - 1;
+            // neighbour across edge k starts that edge (in its own orientation) at our vertex k+1
+            P.set16(E::oSt, sp++, (uint32_t)cx_nbr(fx, e2) | ((uint32_t)cx_vert(fx, e2 == 2 ? 0 : e2 + 1) << 5));
+            P.set16(E::oSt, sp++, (uint32_t)cx_nbr(fx, e1) | ((uint32_t)cx_vert(fx, e1 == 2 ? 0 : e1 + 1) << 5));
+        }
+    }
+    if (!over && ok && nh >= 3 && nh > nr + (E::F - P.nf)) over = true;
+    if (over) return JG_EPA_OVERFLOW;       // nothing was modified
+    if (!ok || nh < 3) return JG_EPA_DONE;   // keep the bracket
+    P.setP(vi, w);
+    P.nv = vi + 1;
+    // slots of the new faces: recycle removed ones (last removed first), then grow; the rest of the removed die
+    const int nr0 = nr, nf0 = P.nf;
+    auto slot_of = [&](int j) -> int { return j < nr0 ? (int)P.get8(E::oRm, nr0 - 1 - j) : nf0 + (j - nr0); };
+    if (nh > nr0) P.nf = nf0 + (nh - nr0);
+    for (int i = 0; i < nr0 - nh; ++i) {
+        const int f = (int)P.get8(E::oRm, i);
+        P.fx(f) = 0u;
+        P.set_fd(f, FLT_MAX);
+    }
+    {
+        uint32_t hcur = P.get16(E::oHz, 0);
+        const uint32_t h0 = hcur;
+        int prev_slot = slot_of(nh - 1), slot = slot_of(0);
+        int f = (int)(hcur & 31u), e = (int)(hcur >> 5);
+        uint32_t fxo = P.fx(f);
+        int ia = cx_vert(fxo, e == 2 ? 0 : e + 1);
+        V3 pa = P.P(ia);
+        for (int j = 0; j < nh; ++j) {
+            const uint32_t hnext = j + 1 < nh ? P.get16(E::oHz, j + 1) : h0;
+            const int next_slot = j + 1 < nh ? slot_of(j + 1) : slot_of(0);
+            const int ib = cx_vert(fxo, e);
+            const V3 pb = P.P(ib);
+            const V3 nn = cross(pb - pa, w - pa);
+            const float l2 = norm2(nn);
+            float d = FLT_MAX;
+            if (l2 > 1e-30f) {
+                d = dot(nn, pa) * rsqrtf(l2);
+                if (d < -1e-5f) d = FLT_MAX;   // folded face: stays in the mesh, never selected
+            }
+            P.set_fd(slot, d);
+            P.fx(slot) = (uint32_t)ia | ((uint32_t)ib << 5) | ((uint32_t)vi << 10) | ((uint32_t)f << 15) |
+                         ((uint32_t)next_slot << 20) | ((uint32_t)prev_slot << 25) | (1u << 30);
+            // outside face: its edge e now borders the new face (re-read: two horizon edges may share it)
+            P.fx(f) = (P.fx(f) & ~(31u << (15 + 5 * e))) | ((uint32_t)slot << (15 + 5 * e));
+            prev_slot = slot;
+            slot = next_slot;
+            hcur = hnext;
+            f = (int)(hcur & 31u); e = (int)(hcur >> 5);
+            fxo = P.fx(f);
+            ia = ib;
+            pa = pb;
+        }
+    }
+    return JG_EPA_RUNNING;
+}
+
+template <int STRIDE>
+__device__ __forceinline__ float epa_result(const EpaStateC<STRIDE>& X) {
     if (X.ub < FLT_MAX && X.ub - X.lb <= 1e-4f) return fmaxf(0.5f * (X.lb + X.ub), 0.f);
     return X.lb;
 }

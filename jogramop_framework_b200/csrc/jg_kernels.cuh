@@ -457,11 +457,6 @@ __device__ __forceinline__ V3 md_point(const float4* __restrict__ A, const float
     return tf_apply(T, mk(pa.x, pa.y, pa.z)) - mk(pb.x, pb.y, pb.z);
 }
 
-// Fast storage class: polytopes of the block interleaved in shared memory (18 expansions; larger ones overflow to
-// k_penetration_big).  Footprint: (4*22 + 3*40 + 12 + 20 + 12) words = 1008 B per thread.
-template <int BLOCK>
-using EpaPolySmall = EpaPolyT<22, 40, 12, 20, 12, BLOCK>;
-
 __device__ __forceinline__ Simplex simplex_from_ids(const float4* __restrict__ A, const float4* __restrict__ B,
                                                     const Tf& T, uint4 ids) {
     Simplex sx;
@@ -491,7 +486,7 @@ __global__ void __launch_bounds__(BLOCK) k_penetration(const PassArgs a) {
     int* ovf_counter = a.counts + a.n_keys + 2;
     const unsigned lt_mask = (1u << lane) - 1u;
 
-    EpaStateT<EpaPolySmall<BLOCK>> X;
+    EpaStateC<BLOCK> X;   // compact polytope, interleaved across the block in shared memory (jg_epa.cuh)
     X.poly.w = poly_words + tid;
     X.poly.nv = X.poly.nf = 0;
     X.lb = 0.f; X.ub = FLT_MAX; X.it = 0;

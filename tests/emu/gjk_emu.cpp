@@ -35,10 +35,9 @@ extern "C" void emu_gjk_batch(const float* va, int na, const float* vb, int nb, 
         if (status[k] == JG_GJK_PENETRATING && depth) {
             int eit = 0;
             if (g_small_storage) {
-                // the fast kernel's storage class (18 expansions, small flood-fill scratch) with the overflow fallback
-                typedef EpaPolyT<22, 40, 12, 20, 12, 1> Small;
-                uint32_t words[Small::WORDS];
-                EpaStateT<Small> E;
+                // the fast kernel's compact shared-memory storage class (14 expansions) with the overflow fallback
+                uint32_t words[EpaCompact<1>::WORDS];
+                EpaStateC<1> E;
                 E.poly.w = words;
                 int st = JG_EPA_DONE;
                 const ThreadSupport sup = {A.data(), na, B.data(), nb, X};
