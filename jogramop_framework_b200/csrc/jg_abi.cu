@@ -403,7 +403,7 @@ static int build_tables(jg_engine* e, const jg_robot* r, const jg_scene* sc) {
 
 constexpr int BP_BLOCK = 128;   // broad phase: threads (= configurations) per block
 constexpr int NP_BLOCK = 256;   // narrow phase
-constexpr int EPA_BIG_BLOCK = 128;  // overflow pass of the penetration depth
+constexpr int EPA_BIG_BLOCK = 512;  // overflow pass of the penetration depth: one pair per warp, 16 warps per block
 
 static size_t bp_smem(const jg_engine* e, uint32_t flags) {
     size_t s = sizeof(RobotTab) + sizeof(PieceRec) * e->P + sizeof(float) * BP_BLOCK * e->dof;
@@ -560,7 +560,7 @@ static int run_narrow_and_finalize(jg_engine* e, const PassArgs& a, int n_out, u
             case 128: k_penetration<128><<<e->epa_blocks, 128, e->smem_epa, st>>>(a); break;
             default: k_penetration<64><<<e->epa_blocks, 64, e->smem_epa, st>>>(a); break;
         }
-        k_penetration_big<EPA_BIG_BLOCK><<<e->sm_count, EPA_BIG_BLOCK, e->smem_epa_big, st>>>(a);
+        k_penetration_big<EPA_BIG_BLOCK><<<e->sm_count * 2, EPA_BIG_BLOCK, e->smem_epa_big, st>>>(a);
         e->stats.kernel_launches += 2;
     }
     PROF_MARK(e, st);
