@@ -167,7 +167,10 @@ struct jg_engine {
     int* epa_slot = nullptr;              // [n_keys*cap]
     uint4* epa_ids = nullptr;             // [n_keys*cap]
     int2* ovf_list = nullptr;             // [cap]
-    int* counts = nullptr;                // [2*n_keys + 8]
+    float* epa_prio = nullptr;            // [n_keys*cap]
+    int* act_list = nullptr;              // [n_keys*cap]
+    unsigned long long *champ_scene = nullptr, *champ_self = nullptr;   // [cap]
+    int* counts = nullptr;                // [3*n_keys + 16], layout in jg_kernels.cuh PassArgs
     int *enc_scene = nullptr, *enc_self = nullptr;
     uint32_t* viol = nullptr;
     int* d_link_slot = nullptr;           // FK: [L]
@@ -229,7 +232,7 @@ static void engine_release(jg_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaFree(e->d_robot); cudaFree(e->d_pieces); cudaFree(e->d_selfs); cudaFree(e->d_keys); cudaFree(e->d_verts);
-    cudaFree(e->q_r0); cudaFree(e->q_r1); cudaFree(e->q_r2); cudaFree(e->q_cfg); cudaFree(e->epa_slot); cudaFree(e->epa_ids); cudaFree(e->ovf_list); cudaFree(e->counts);
+    cudaFree(e->q_r0); cudaFree(e->q_r1); cudaFree(e->q_r2); cudaFree(e->q_cfg); cudaFree(e->epa_slot); cudaFree(e->epa_ids); cudaFree(e->ovf_list); cudaFree(e->epa_prio); cudaFree(e->act_list); cudaFree(e->champ_scene); cudaFree(e->champ_self); cudaFree(e->counts);
     cudaFree(e->enc_scene); cudaFree(e->enc_self); cudaFree(e->viol); cudaFree(e->d_link_slot); cudaFree(e->d_rel);
     cudaFree(e->d_use_shapes); cudaFree(e->d_stats);
     for (int i = 0; i < 2; ++i) {
@@ -291,6 +294,7 @@ static int build_tables(jg_engine* e, const jg_robot* r, const jg_scene* sc) {
     std::vector<float4> verts;
     verts.reserve(4096);
     auto pad4 = [&verts]() { while (verts.size() % 4) verts.push_back(verts.back()); };
+    float epa_box_c[MAX_SHAPES][3], epa_box_h[MAX_SHAPES][3];
     for (int s = 0; s < r->S; ++s) {
         ShapeRec& Sh = R.shapes[s];
         double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
@@ -323,6 +327,18 @@ static int build_tables(jg_engine* e, const jg_robot* r, const jg_scene* sc) {
                 verts.push_back(make_float4((float)r->plane_v[3 * i], (float)r->plane_v[3 * i + 1],
                                             (float)r->plane_v[3 * i + 2], 0.f));
             pad4();
+        }
+        {   // AABB of the penetration geometry (box: exact corners), used for the penetration upper bound
+            double plo[3] = {1e300, 1e300, 1e300}, phi[3] = {-1e300, -1e300, -1e300};
+            for (int i = r->plane_off[s]; i < r->plane_off[s + 1]; ++i)
+                for (int k = 0; k < 3; ++k) {
+                    plo[k] = std::min(plo[k], r->plane_v[3 * i + k]);
+                    phi[k] = std::max(phi[k], r->plane_v[3 * i + k]);
+                }
+            for (int k = 0; k < 3; ++k) {
+                epa_box_c[s][k] = (float)(0.5 * (plo[k] + phi[k]));
+                epa_box_h[s][k] = (float)(0.5 * (phi[k] - plo[k]) + 1e-6);
+            }
         }
         const int link = r->shape_link[s];
         if (e->link_first_shape[link + 1] < 0) e->link_first_shape[link + 1] = s;
@@ -366,10 +382,18 @@ static int build_tables(jg_engine* e, const jg_robot* r, const jg_scene* sc) {
     std::vector<KeyRec> keys;
     for (int s = 0; s < r->S; ++s) {
         for (int p = 0; p < P; ++p)
-            keys.push_back(KeyRec{R.shapes[s].voff, R.shapes[s].vn, pieces[p].voff, pieces[p].vn,
-                                  R.shapes[s].margin + pieces[p].margin, KEY_HULL, R.shapes[s].poff, R.shapes[s].pn,
-                                  pieces[p].voff, pieces[p].vn, R.shapes[s].plane_margin + pieces[p].margin, 0});
-        keys.push_back(KeyRec{R.shapes[s].poff, R.shapes[s].pn, 0, 0, R.shapes[s].plane_margin, KEY_PLANE, 0, 0, 0, 0, 0.f, 0});
+        {
+            KeyRec k{R.shapes[s].voff, R.shapes[s].vn, pieces[p].voff, pieces[p].vn,
+                     R.shapes[s].margin + pieces[p].margin, KEY_HULL, R.shapes[s].poff, R.shapes[s].pn,
+                     pieces[p].voff, pieces[p].vn, R.shapes[s].plane_margin + pieces[p].margin, 0, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+            for (int c = 0; c < 3; ++c) {
+                k.a_c[c] = epa_box_c[s][c]; k.a_h[c] = epa_box_h[s][c];
+                k.b_c[c] = 0.f; k.b_h[c] = pieces[p].h[c];     // piece vertices are centred on their AABB centre
+            }
+            keys.push_back(k);
+        }
+        keys.push_back(KeyRec{R.shapes[s].poff, R.shapes[s].pn, 0, 0, R.shapes[s].plane_margin, KEY_PLANE, 0, 0, 0, 0, 0.f, 0,
+                              {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}});
     }
     e->n_scene_keys = (int)keys.size();
     std::vector<SelfRec> selfs;
@@ -380,9 +404,15 @@ static int build_tables(jg_engine* e, const jg_robot* r, const jg_scene* sc) {
         const int sa = e->link_first_shape[la + 1], sb = e->link_first_shape[lb + 1];
         if (sa < 0 || sb < 0) return fail(JG_ERR_INVALID, "self pair %d: link without collision shape", k);
         selfs.push_back(SelfRec{sa, sb, la, lb});
-        keys.push_back(KeyRec{R.shapes[sb].voff, R.shapes[sb].vn, R.shapes[sa].voff, R.shapes[sa].vn,
-                              R.shapes[sa].margin + R.shapes[sb].margin, KEY_SELF, R.shapes[sb].poff, R.shapes[sb].pn,
-                              R.shapes[sa].poff, R.shapes[sa].pn, R.shapes[sa].plane_margin + R.shapes[sb].plane_margin, 0});
+        KeyRec kr{R.shapes[sb].voff, R.shapes[sb].vn, R.shapes[sa].voff, R.shapes[sa].vn,
+                 R.shapes[sa].margin + R.shapes[sb].margin, KEY_SELF, R.shapes[sb].poff, R.shapes[sb].pn,
+                 R.shapes[sa].poff, R.shapes[sa].pn, R.shapes[sa].plane_margin + R.shapes[sb].plane_margin, 0,
+                 {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+        for (int c = 0; c < 3; ++c) {
+            kr.a_c[c] = epa_box_c[sb][c]; kr.a_h[c] = epa_box_h[sb][c];
+            kr.b_c[c] = epa_box_c[sa][c]; kr.b_h[c] = epa_box_h[sa][c];
+        }
+        keys.push_back(kr);
     }
     e->n_keys = (int)keys.size();
     e->n_verts = (int)verts.size();
@@ -482,7 +512,7 @@ extern "C" jg_engine* jg_engine_create(const jg_robot* r, const jg_scene* sc, in
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
         const size_t budget = std::min<size_t>((size_t)16 << 30, free_b / 4);
-        const size_t per_cfg = (size_t)std::max(e->n_keys, 1) * 72 + 16;
+        const size_t per_cfg = (size_t)std::max(e->n_keys, 1) * 80 + 48;
         cap = 1 << 20;
         while (cap > 4096 && (size_t)cap * per_cfg > budget) cap >>= 1;
     }
@@ -490,8 +520,10 @@ extern "C" jg_engine* jg_engine_create(const jg_robot* r, const jg_scene* sc, in
     e->cap = cap;
     const size_t qn = (size_t)std::max(e->n_keys, 1) * cap;
     bool okm = cudaMalloc(&e->q_r0, sizeof(float4) * qn) == cudaSuccess && cudaMalloc(&e->q_r1, sizeof(float4) * qn) == cudaSuccess &&
-               cudaMalloc(&e->q_r2, sizeof(float4) * qn) == cudaSuccess && cudaMalloc(&e->q_cfg, sizeof(int) * qn) == cudaSuccess && cudaMalloc(&e->epa_slot, sizeof(int) * qn) == cudaSuccess && cudaMalloc(&e->epa_ids, sizeof(uint4) * qn) == cudaSuccess && cudaMalloc(&e->ovf_list, sizeof(int2) * cap) == cudaSuccess &&
-               cudaMalloc(&e->counts, sizeof(int) * (2 * e->n_keys + 8)) == cudaSuccess &&
+               cudaMalloc(&e->q_r2, sizeof(float4) * qn) == cudaSuccess && cudaMalloc(&e->q_cfg, sizeof(int) * qn) == cudaSuccess && cudaMalloc(&e->epa_slot, sizeof(int) * qn) == cudaSuccess && cudaMalloc(&e->epa_ids, sizeof(uint4) * qn) == cudaSuccess && cudaMalloc(&e->ovf_list, sizeof(int2) * cap) == cudaSuccess && cudaMalloc(&e->epa_prio, sizeof(float) * qn) == cudaSuccess &&
+               cudaMalloc(&e->act_list, sizeof(int) * qn) == cudaSuccess && cudaMalloc(&e->champ_scene, sizeof(unsigned long long) * cap) == cudaSuccess &&
+               cudaMalloc(&e->champ_self, sizeof(unsigned long long) * cap) == cudaSuccess &&
+               cudaMalloc(&e->counts, sizeof(int) * (3 * e->n_keys + 16)) == cudaSuccess &&
                cudaMalloc(&e->enc_scene, sizeof(int) * cap) == cudaSuccess && cudaMalloc(&e->enc_self, sizeof(int) * cap) == cudaSuccess &&
                cudaMalloc(&e->viol, sizeof(uint32_t) * (cap / 32 + 1)) == cudaSuccess &&
                cudaMalloc(&e->d_link_slot, sizeof(int) * MAX_LINKS) == cudaSuccess &&
@@ -518,7 +550,7 @@ static void fill_args(const jg_engine* e, PassArgs& a, uint32_t flags) {
     a.has_plane = e->has_plane ? 1 : 0;
     a.robot = e->d_robot; a.pieces = e->d_pieces; a.P = e->P; a.selfs = e->d_selfs; a.keys = e->d_keys;
     a.n_keys = e->n_keys; a.n_scene_keys = e->n_scene_keys; a.verts = e->d_verts; a.n_verts = e->n_verts;
-    a.q_r0 = e->q_r0; a.q_r1 = e->q_r1; a.q_r2 = e->q_r2; a.q_cfg = e->q_cfg; a.epa_slot = e->epa_slot; a.epa_ids = e->epa_ids; a.ovf_list = e->ovf_list; a.cap = e->cap; a.counts = e->counts;
+    a.q_r0 = e->q_r0; a.q_r1 = e->q_r1; a.q_r2 = e->q_r2; a.q_cfg = e->q_cfg; a.epa_slot = e->epa_slot; a.epa_ids = e->epa_ids; a.ovf_list = e->ovf_list; a.epa_prio = e->epa_prio; a.act_list = e->act_list; a.champ_scene = e->champ_scene; a.champ_self = e->champ_self; a.cap = e->cap; a.counts = e->counts;
     a.enc_scene = e->enc_scene; a.enc_self = e->enc_self; a.viol = e->viol;
 }
 
@@ -552,16 +584,29 @@ static int run_narrow_and_finalize(jg_engine* e, const PassArgs& a, int n_out, u
     }
     PROF_MARK(e, st);
     if (e->n_keys > 0 && !(flags & JG_NO_EPA)) {
-        switch (e->epa_threads) {
-            case 352: k_penetration<352><<<e->epa_blocks, 352, e->smem_epa, st>>>(a); break;
-            case 320: k_penetration<320><<<e->epa_blocks, 320, e->smem_epa, st>>>(a); break;
-            case 256: k_penetration<256><<<e->epa_blocks, 256, e->smem_epa, st>>>(a); break;
-            case 192: k_penetration<192><<<e->epa_blocks, 192, e->smem_epa, st>>>(a); break;
-            case 128: k_penetration<128><<<e->epa_blocks, 128, e->smem_epa, st>>>(a); break;
-            default: k_penetration<64><<<e->epa_blocks, 64, e->smem_epa, st>>>(a); break;
+        // round 1: the pair with the largest penetration bound of every configuration; round 2: the pairs whose
+        // bound can still beat what round 1 proved; then the rare large polytopes of both rounds
+        int* round_state = e->counts + e->n_keys + 1;               // EPA range counter, (overflow), filter counter
+        int* round_counts = e->counts + 2 * e->n_keys + 8;
+        for (int round = 1; round <= 2; ++round) {
+            if (round == 2) {
+                CUDA_TRY(cudaMemsetAsync(round_state, 0, sizeof(int), st));
+                CUDA_TRY(cudaMemsetAsync(round_state + 2, 0, sizeof(int), st));
+                CUDA_TRY(cudaMemsetAsync(round_counts, 0, sizeof(int) * e->n_keys, st));
+            }
+            k_penetration_select<256><<<e->sm_count * 4, 256, sizeof(int) * (e->n_keys + 2), st>>>(a, round);
+            switch (e->epa_threads) {
+                case 352: k_penetration<352><<<e->epa_blocks, 352, e->smem_epa, st>>>(a); break;
+                case 320: k_penetration<320><<<e->epa_blocks, 320, e->smem_epa, st>>>(a); break;
+                case 256: k_penetration<256><<<e->epa_blocks, 256, e->smem_epa, st>>>(a); break;
+                case 192: k_penetration<192><<<e->epa_blocks, 192, e->smem_epa, st>>>(a); break;
+                case 128: k_penetration<128><<<e->epa_blocks, 128, e->smem_epa, st>>>(a); break;
+                default: k_penetration<64><<<e->epa_blocks, 64, e->smem_epa, st>>>(a); break;
+            }
+            e->stats.kernel_launches += 2;
         }
         k_penetration_big<EPA_BIG_BLOCK><<<e->sm_count * 2, EPA_BIG_BLOCK, e->smem_epa_big, st>>>(a);
-        e->stats.kernel_launches += 2;
+        e->stats.kernel_launches += 1;
     }
     PROF_MARK(e, st);
     if (e->n_keys > 0) {
@@ -598,7 +643,7 @@ extern "C" int jg_check(jg_engine* e, const float* q, int64_t n, int dof, uint32
         PassArgs a;
         fill_args(e, a, flags);
         a.q = q + off * dof; a.n = m;
-        CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * (2 * e->n_keys + 8), st));
+        CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * (3 * e->n_keys + 16), st));
         if (flags & JG_LIMITS) CUDA_TRY(cudaMemsetAsync(e->viol, 0, sizeof(uint32_t) * (e->cap / 32 + 1), st));
         PROF_MARK(e, st);
         k_broadphase<BP_BLOCK><<<(m + BP_BLOCK - 1) / BP_BLOCK, BP_BLOCK, bp_smem(e, flags), st>>>(a);
@@ -626,10 +671,10 @@ extern "C" int jg_check_edges(jg_engine* e, const float* qa, const float* qb, in
         PassArgs a;
         fill_args(e, a, flags);
         a.q = qa + off * dof; a.qb = qb + off * dof; a.n = me * substeps; a.substeps = substeps;
-        CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * (2 * e->n_keys + 8), st));
+        CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * (3 * e->n_keys + 16), st));
         if (flags & JG_LIMITS) CUDA_TRY(cudaMemsetAsync(e->viol, 0, sizeof(uint32_t) * (e->cap / 32 + 1), st));
         PROF_MARK(e, st);
-        k_init_scratch<<<(me + 255) / 256, 256, 0, st>>>(e->enc_scene, e->enc_self, me);
+        k_init_scratch<<<(me + 255) / 256, 256, 0, st>>>(e->enc_scene, e->enc_self, e->champ_scene, e->champ_self, me);
         k_broadphase<BP_BLOCK><<<(a.n + BP_BLOCK - 1) / BP_BLOCK, BP_BLOCK, bp_smem(e, flags), st>>>(a);
         e->stats.kernel_launches += 2;
         rc = run_narrow_and_finalize(e, a, me, flags, bits + off / 32, min_dist ? min_dist + off : nullptr, nullptr, st);
@@ -713,7 +758,7 @@ extern "C" int jg_check_poses(jg_engine* e, const float* poses, int64_t n, int f
         PassArgs a;
         fill_args(e, a, flags);
         a.n = m;
-        CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * (2 * e->n_keys + 8), st));
+        CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * (3 * e->n_keys + 16), st));
         const size_t smem = sizeof(RobotTab) + sizeof(PieceRec) * e->P;
         PROF_MARK(e, st);
         k_broadphase_poses<BP_BLOCK><<<(m + BP_BLOCK - 1) / BP_BLOCK, BP_BLOCK, smem, st>>>(a, poses + off * stride, fmt, e->d_rel,

@@ -68,6 +68,8 @@ struct KeyRec {
     int eb_off, eb_n;
     float emsum;       // margins added to the penetration depth
     int pad;
+    float a_c[3], a_h[3];   // AABB (own frame) of the moving penetration geometry
+    float b_c[3], b_h[3];   // AABB (own frame) of the static penetration geometry
 };
 
 struct PassArgs {
@@ -95,10 +97,15 @@ struct PassArgs {
     int* q_cfg;
     int cap;           // queue capacity per key (= max configs per pass)
     int* counts;       // [n_keys] pair counts, [n_keys] GJK tile counter, [n_keys+1] EPA tile counter,
-                       // [n_keys+2] overflow-list length, [n_keys+8 .. 2 n_keys+8) penetration-queue counts
+                       // [n_keys+2] overflow-list length, [n_keys+3] filter range counter,
+                       // [n_keys+8 .. 2 n_keys+8) penetration-queue counts, [2 n_keys+8 .. 3 n_keys+8) round counts
     int* epa_slot;     // [n_keys*cap] queue slots whose cores overlap (penetration-depth pass)
     uint4* epa_ids;    // [n_keys*cap] their GJK end simplices (vertex ids, 0xFFFFFFFF = unused)
     int2* ovf_list;    // [cap] (key, index in the penetration queue) of polytopes that outgrew shared memory
+    float* epa_prio;   // [n_keys*cap] upper bound of each queued pair's total penetration (AABB overlap + margins)
+    int* act_list;     // [n_keys*cap] per key: penetration-queue indices selected for the current round
+    unsigned long long *champ_scene, *champ_self;   // [cap] per configuration: (prio bits << 32 | pair code) of the
+                                                    // queued pair with the largest upper bound
     // per-configuration scratch
     int* enc_scene;    // encoded min contact distance vs scene+plane
     int* enc_self;
@@ -229,6 +236,8 @@ __global__ void __launch_bounds__(BLOCK) k_broadphase(const PassArgs a) {
         if (a.substeps <= 1) {
             a.enc_scene[out_idx] = JG_ENC_INF;
             a.enc_self[out_idx] = JG_ENC_INF;
+            a.champ_scene[out_idx] = 0ull;
+            a.champ_self[out_idx] = 0ull;
         }
         if (a.flags & 8u) {
             bool bad = false;
@@ -437,7 +446,22 @@ __global__ void __launch_bounds__(BLOCK) k_narrowphase(const PassArgs a) {
                     if (lane == leader) base = atomicAdd(a.counts + a.n_keys + 8 + key, __popc(m));
                     base = __shfl_sync(0xFFFFFFFFu, base, leader);
                     if (deep) {
-                        const size_t j = kbase + base + __popc(m & lt_mask);
+                        const int jj = base + __popc(m & lt_mask);
+                        const size_t j = kbase + jj;
+                        // upper bound of this pair's total penetration: smallest axis overlap of the two boxes
+                        // (A's box rotated into B's frame) + margins; the pair with the largest bound of a
+                        // configuration is expanded first, the others only if their bound can still beat it
+                        const float cx = fmaf(T.r00, K.a_c[0], fmaf(T.r01, K.a_c[1], fmaf(T.r02, K.a_c[2], T.tx))) - K.b_c[0];
+                        const float cy = fmaf(T.r10, K.a_c[0], fmaf(T.r11, K.a_c[1], fmaf(T.r12, K.a_c[2], T.ty))) - K.b_c[1];
+                        const float cz = fmaf(T.r20, K.a_c[0], fmaf(T.r21, K.a_c[1], fmaf(T.r22, K.a_c[2], T.tz))) - K.b_c[2];
+                        const float hx = fmaf(fabsf(T.r00), K.a_h[0], fmaf(fabsf(T.r01), K.a_h[1], fabsf(T.r02) * K.a_h[2]));
+                        const float hy = fmaf(fabsf(T.r10), K.a_h[0], fmaf(fabsf(T.r11), K.a_h[1], fabsf(T.r12) * K.a_h[2]));
+                        const float hz = fmaf(fabsf(T.r20), K.a_h[0], fmaf(fabsf(T.r21), K.a_h[1], fabsf(T.r22) * K.a_h[2]));
+                        const float ov = fminf(fminf(hx + K.b_h[0] - fabsf(cx), hy + K.b_h[1] - fabsf(cy)), hz + K.b_h[2] - fabsf(cz));
+                        const float prio = fmaxf(ov, 0.f) + fmaxf(K.emsum, K.msum) + 2e-5f;
+                        a.epa_prio[j] = prio;
+                        atomicMax((K.kind == KEY_SELF ? a.champ_self : a.champ_scene) + cfg,
+                                  ((unsigned long long)__float_as_uint(prio) << 32) | (unsigned)((key << 20) | jj));
                         a.epa_slot[j] = off;
                         a.epa_ids[j] = make_uint4(S.S.n > 0 ? S.S.ia : 0xFFFFFFFFu, S.S.n > 1 ? S.S.ib : 0xFFFFFFFFu,
                                                   S.S.n > 2 ? S.S.ic : 0xFFFFFFFFu, S.S.n > 3 ? S.S.id : 0xFFFFFFFFu);
@@ -470,6 +494,56 @@ __device__ __forceinline__ Simplex simplex_from_ids(const float4* __restrict__ A
     return sx;
 }
 
+// Selects the penetration-queue entries of one round into per-key lists.  round 1: the champion of every
+// configuration (largest upper bound); round 2: every other pair whose bound still exceeds the configuration's best
+// proven penetration.  Exact: a skipped pair provably cannot be the deepest one of its configuration.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_penetration_select(const PassArgs a, int round) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int* prefix = reinterpret_cast<int*>(smem_raw);   // [n_keys + 2]
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int* ecounts = a.counts + a.n_keys + 8;
+    int* acounts = a.counts + 2 * a.n_keys + 8;
+    if (tid < 32) sched_build(ecounts, a.n_keys, gridDim.x * (BLOCK / 32), prefix, prefix + a.n_keys + 1, lane);
+    __syncthreads();
+    const int total = prefix[a.n_keys], G = prefix[a.n_keys + 1];
+    int* range_counter = a.counts + a.n_keys + 3;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (;;) {
+        int r = 0;
+        if (lane == 0) r = atomicAdd(range_counter, 1);
+        r = __shfl_sync(0xFFFFFFFFu, r, 0);
+        if (r >= total) break;
+        const int key = sched_find_key(prefix, a.n_keys, r);
+        const int kind = a.keys[key].kind;
+        const int begin = (r - prefix[key]) * G;
+        const int end = min(begin + G, ecounts[key]);
+        const size_t kbase = (size_t)key * a.cap;
+        for (int j0 = begin; j0 < end; j0 += 32) {
+            const int j = j0 + lane;
+            bool sel = false;
+            if (j < end) {
+                const int cfg = a.q_cfg[kbase + a.epa_slot[kbase + j]];
+                const unsigned long long ch = (kind == KEY_SELF ? a.champ_self : a.champ_scene)[cfg];
+                const bool is_champ = (unsigned)(ch & 0xFFFFFFFFull) == (unsigned)((key << 20) | j);
+                if (round == 1) sel = is_champ;
+                else if (!is_champ) {
+                    const float best = -dec_float((kind == KEY_SELF ? a.enc_self : a.enc_scene)[cfg]);   // proven total
+                    sel = a.epa_prio[kbase + j] > best;
+                }
+            }
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, sel);
+            if (m) {
+                const int leader = __ffs(m) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(acounts + key, __popc(m));
+                base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                if (sel) a.act_list[kbase + base + __popc(m & lt_mask)] = j;
+            }
+        }
+    }
+}
+
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_penetration(const PassArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -477,7 +551,7 @@ __global__ void __launch_bounds__(BLOCK) k_penetration(const PassArgs a) {
     int* prefix = reinterpret_cast<int*>(smem_raw + sizeof(float4) * a.n_verts);   // [n_keys + 2]
     uint32_t* poly_words = reinterpret_cast<uint32_t*>(prefix + ((a.n_keys + 2 + 3) & ~3));
     const int tid = threadIdx.x, lane = tid & 31;
-    const int* ecounts = a.counts + a.n_keys + 8;
+    const int* ecounts = a.counts + 2 * a.n_keys + 8;   // entries selected for this round (k_penetration_select)
     for (int i = tid; i < a.n_verts; i += BLOCK) verts[i] = a.verts[i];
     if (tid < 32) sched_build(ecounts, a.n_keys, gridDim.x * (BLOCK / 32), prefix, prefix + a.n_keys + 1, lane);
     __syncthreads();
@@ -517,7 +591,7 @@ __global__ void __launch_bounds__(BLOCK) k_penetration(const PassArgs a) {
             if (need && avail > 0) {
                 const int rank = __popc(need & lt_mask);
                 if (phase == 0 && rank < avail) {
-                    myj = next + rank;
+                    myj = a.act_list[kbase + next + rank];
                     const size_t j = kbase + myj;
                     T = load_entry(a, kbase + a.epa_slot[j], cfg);
                     if (regjk) {
@@ -667,11 +741,14 @@ __global__ void k_finalize(const int* __restrict__ enc_scene, const int* __restr
     }
 }
 
-__global__ void k_init_scratch(int* enc_scene, int* enc_self, int n) {
+__global__ void k_init_scratch(int* enc_scene, int* enc_self, unsigned long long* champ_scene,
+                               unsigned long long* champ_self, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         enc_scene[i] = JG_ENC_INF;
         enc_self[i] = JG_ENC_INF;
+        champ_scene[i] = 0ull;
+        champ_self[i] = 0ull;
     }
 }
 
@@ -700,6 +777,8 @@ __global__ void __launch_bounds__(BLOCK) k_broadphase_poses(const PassArgs a, co
     if (valid) {
         a.enc_scene[cfg] = JG_ENC_INF;
         a.enc_self[cfg] = JG_ENC_INF;
+        a.champ_scene[cfg] = 0ull;
+        a.champ_self[cfg] = 0ull;
         if (fmt == 0) {
             const float4* p4 = reinterpret_cast<const float4*>(poses + (size_t)cfg * 12);
             const float4 r0 = p4[0], r1 = p4[1], r2 = p4[2];
