@@ -168,6 +168,8 @@ struct jg_engine {
     uint4* epa_ids = nullptr;             // [n_keys*cap]
     int2* ovf_list = nullptr;             // [cap]
     float* epa_prio = nullptr;            // [n_keys*cap]
+    float* q_prio = nullptr;              // [n_keys*cap]
+    float max_msum = 0.f;
     int* act_list = nullptr;              // [n_keys*cap]
     unsigned long long *champ_scene = nullptr, *champ_self = nullptr;   // [cap]
     int* counts = nullptr;                // [3*n_keys + 16], layout in jg_kernels.cuh PassArgs
@@ -197,7 +199,9 @@ struct jg_engine {
     size_t smem_narrow = 0, smem_epa = 0, smem_epa_big = 0;
     // optional per-kernel timing (jg_profile_enable)
     bool profiling = false;
-    std::vector<cudaEvent_t> prof_ev;    // 5 events per pass: start | broad | narrow | penetration | finalize
+    std::vector<cudaEvent_t> prof_ev;    // event pool
+    struct ProfSection { int cat; cudaEvent_t a, b; };
+    std::vector<ProfSection> prof_sections;
     size_t prof_used = 0;
     double prof_ms[4] = {0, 0, 0, 0};
     int64_t prof_n[4] = {0, 0, 0, 0};
@@ -211,20 +215,35 @@ static cudaEvent_t prof_event(jg_engine* e) {
     }
     return e->prof_ev[e->prof_used++];
 }
-#define PROF_MARK(e, st) do { if ((e)->profiling) cudaEventRecord(prof_event(e), st); } while (0)
+// timed section of category `cat` (0 broad phase, 1 GJK stages, 2 penetration stages, 3 finalize): events on the
+// launching stream; sections are (cat, start, end) triples resolved in prof_collect
+static void prof_begin(jg_engine* e, int cat, cudaStream_t st) {
+    if (!e->profiling) return;
+    cudaEvent_t ev = prof_event(e);
+    cudaEventRecord(ev, st);
+    e->prof_sections.push_back({cat, ev, nullptr});
+}
+static void prof_end(jg_engine* e, cudaStream_t st) {
+    if (!e->profiling || e->prof_sections.empty()) return;
+    cudaEvent_t ev = prof_event(e);
+    cudaEventRecord(ev, st);
+    e->prof_sections.back().b = ev;
+}
 
 static void prof_collect(jg_engine* e) {
-    // events come in groups of 5 per pass
-    for (size_t i = 0; i + 4 < e->prof_used; i += 5) {
-        cudaEventSynchronize(e->prof_ev[i + 4]);
-        for (int k = 0; k < 4; ++k) {
-            float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, e->prof_ev[i + k], e->prof_ev[i + k + 1]) == cudaSuccess) {
-                e->prof_ms[k] += ms;
-                e->prof_n[k] += 1;
-            }
-        }
+    bool counted[4] = {false, false, false, false};
+    int last_pass_cat = -1;
+    for (const auto& sec : e->prof_sections) {
+        if (!sec.b) continue;
+        cudaEventSynchronize(sec.b);
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sec.a, sec.b) == cudaSuccess) e->prof_ms[sec.cat] += ms;
+        // launches = number of passes in which the category ran (a new pass starts with category 0)
+        if (sec.cat == 0 || last_pass_cat < 0) { for (bool& c : counted) c = false; }
+        if (!counted[sec.cat]) { e->prof_n[sec.cat] += 1; counted[sec.cat] = true; }
+        last_pass_cat = sec.cat;
     }
+    e->prof_sections.clear();
     e->prof_used = 0;
 }
 
@@ -232,7 +251,7 @@ static void engine_release(jg_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaFree(e->d_robot); cudaFree(e->d_pieces); cudaFree(e->d_selfs); cudaFree(e->d_keys); cudaFree(e->d_verts);
-    cudaFree(e->q_r0); cudaFree(e->q_r1); cudaFree(e->q_r2); cudaFree(e->q_cfg); cudaFree(e->epa_slot); cudaFree(e->epa_ids); cudaFree(e->ovf_list); cudaFree(e->epa_prio); cudaFree(e->act_list); cudaFree(e->champ_scene); cudaFree(e->champ_self); cudaFree(e->counts);
+    cudaFree(e->q_r0); cudaFree(e->q_r1); cudaFree(e->q_r2); cudaFree(e->q_cfg); cudaFree(e->epa_slot); cudaFree(e->epa_ids); cudaFree(e->ovf_list); cudaFree(e->epa_prio); cudaFree(e->q_prio); cudaFree(e->act_list); cudaFree(e->champ_scene); cudaFree(e->champ_self); cudaFree(e->counts);
     cudaFree(e->enc_scene); cudaFree(e->enc_self); cudaFree(e->viol); cudaFree(e->d_link_slot); cudaFree(e->d_rel);
     cudaFree(e->d_use_shapes); cudaFree(e->d_stats);
     for (int i = 0; i < 2; ++i) {
@@ -416,6 +435,8 @@ static int build_tables(jg_engine* e, const jg_robot* r, const jg_scene* sc) {
     }
     e->n_keys = (int)keys.size();
     e->n_verts = (int)verts.size();
+    for (const KeyRec& k : keys) e->max_msum = std::max(e->max_msum, k.msum);
+    if (e->n_keys >= 2048) return fail(JG_ERR_INVALID, "too many (shape, piece) keys (%d >= 2048)", e->n_keys);
     e->K = r->K;
 
     CUDA_TRY(cudaMalloc(&e->d_robot, sizeof(RobotTab)));
@@ -512,7 +533,7 @@ extern "C" jg_engine* jg_engine_create(const jg_robot* r, const jg_scene* sc, in
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
         const size_t budget = std::min<size_t>((size_t)16 << 30, free_b / 4);
-        const size_t per_cfg = (size_t)std::max(e->n_keys, 1) * 80 + 48;
+        const size_t per_cfg = (size_t)std::max(e->n_keys, 1) * 84 + 48;
         cap = 1 << 20;
         while (cap > 4096 && (size_t)cap * per_cfg > budget) cap >>= 1;
     }
@@ -520,10 +541,10 @@ extern "C" jg_engine* jg_engine_create(const jg_robot* r, const jg_scene* sc, in
     e->cap = cap;
     const size_t qn = (size_t)std::max(e->n_keys, 1) * cap;
     bool okm = cudaMalloc(&e->q_r0, sizeof(float4) * qn) == cudaSuccess && cudaMalloc(&e->q_r1, sizeof(float4) * qn) == cudaSuccess &&
-               cudaMalloc(&e->q_r2, sizeof(float4) * qn) == cudaSuccess && cudaMalloc(&e->q_cfg, sizeof(int) * qn) == cudaSuccess && cudaMalloc(&e->epa_slot, sizeof(int) * qn) == cudaSuccess && cudaMalloc(&e->epa_ids, sizeof(uint4) * qn) == cudaSuccess && cudaMalloc(&e->ovf_list, sizeof(int2) * cap) == cudaSuccess && cudaMalloc(&e->epa_prio, sizeof(float) * qn) == cudaSuccess &&
+               cudaMalloc(&e->q_r2, sizeof(float4) * qn) == cudaSuccess && cudaMalloc(&e->q_cfg, sizeof(int) * qn) == cudaSuccess && cudaMalloc(&e->epa_slot, sizeof(int) * qn) == cudaSuccess && cudaMalloc(&e->epa_ids, sizeof(uint4) * qn) == cudaSuccess && cudaMalloc(&e->ovf_list, sizeof(int2) * cap) == cudaSuccess && cudaMalloc(&e->epa_prio, sizeof(float) * qn) == cudaSuccess && cudaMalloc(&e->q_prio, sizeof(float) * qn) == cudaSuccess &&
                cudaMalloc(&e->act_list, sizeof(int) * qn) == cudaSuccess && cudaMalloc(&e->champ_scene, sizeof(unsigned long long) * cap) == cudaSuccess &&
                cudaMalloc(&e->champ_self, sizeof(unsigned long long) * cap) == cudaSuccess &&
-               cudaMalloc(&e->counts, sizeof(int) * (3 * e->n_keys + 16)) == cudaSuccess &&
+               cudaMalloc(&e->counts, sizeof(int) * (4 * e->n_keys + 8)) == cudaSuccess &&
                cudaMalloc(&e->enc_scene, sizeof(int) * cap) == cudaSuccess && cudaMalloc(&e->enc_self, sizeof(int) * cap) == cudaSuccess &&
                cudaMalloc(&e->viol, sizeof(uint32_t) * (cap / 32 + 1)) == cudaSuccess &&
                cudaMalloc(&e->d_link_slot, sizeof(int) * MAX_LINKS) == cudaSuccess &&
@@ -550,7 +571,7 @@ static void fill_args(const jg_engine* e, PassArgs& a, uint32_t flags) {
     a.has_plane = e->has_plane ? 1 : 0;
     a.robot = e->d_robot; a.pieces = e->d_pieces; a.P = e->P; a.selfs = e->d_selfs; a.keys = e->d_keys;
     a.n_keys = e->n_keys; a.n_scene_keys = e->n_scene_keys; a.verts = e->d_verts; a.n_verts = e->n_verts;
-    a.q_r0 = e->q_r0; a.q_r1 = e->q_r1; a.q_r2 = e->q_r2; a.q_cfg = e->q_cfg; a.epa_slot = e->epa_slot; a.epa_ids = e->epa_ids; a.ovf_list = e->ovf_list; a.epa_prio = e->epa_prio; a.act_list = e->act_list; a.champ_scene = e->champ_scene; a.champ_self = e->champ_self; a.cap = e->cap; a.counts = e->counts;
+    a.q_r0 = e->q_r0; a.q_r1 = e->q_r1; a.q_r2 = e->q_r2; a.q_cfg = e->q_cfg; a.epa_slot = e->epa_slot; a.epa_ids = e->epa_ids; a.ovf_list = e->ovf_list; a.epa_prio = e->epa_prio; a.q_prio = e->q_prio; a.max_msum = e->max_msum; a.act_list = e->act_list; a.champ_scene = e->champ_scene; a.champ_self = e->champ_self; a.cap = e->cap; a.counts = e->counts;
     a.enc_scene = e->enc_scene; a.enc_self = e->enc_self; a.viol = e->viol;
 }
 
@@ -569,7 +590,7 @@ __global__ void k_accumulate_stats(const int* counts, int n_scene_keys, int n_ke
         sf += __shfl_xor_sync(0xFFFFFFFFu, sf, o);
     }
     unsigned long long ep = 0;
-    for (int k = threadIdx.x; k < n_keys; k += 32) ep += counts[n_keys + 8 + k];
+    for (int k = threadIdx.x; k < n_keys; k += 32) ep += counts[n_keys + k];
     for (int o = 16; o; o >>= 1) ep += __shfl_xor_sync(0xFFFFFFFFu, ep, o);
     if (threadIdx.x == 0) { stats[0] += h; stats[1] += pl; stats[2] += sf; stats[3] += ep; }
 }
@@ -577,38 +598,48 @@ __global__ void k_accumulate_stats(const int* counts, int n_scene_keys, int n_ke
 // narrow phase + finalize of the pass described by `a` (queues already filled)
 static int run_narrow_and_finalize(jg_engine* e, const PassArgs& a, int n_out, uint32_t flags, uint32_t* bits, float* dist,
                                    uint8_t* reason, cudaStream_t st) {
-    PROF_MARK(e, st);   // end of broad phase / start of narrow phase
-    if (e->n_keys > 0) {
-        k_narrowphase<NP_BLOCK><<<e->np_blocks, NP_BLOCK, e->smem_narrow, st>>>(a);
-        e->stats.kernel_launches += 1;
-    }
-    PROF_MARK(e, st);
-    if (e->n_keys > 0 && !(flags & JG_NO_EPA)) {
-        // round 1: the pair with the largest penetration bound of every configuration; round 2: the pairs whose
-        // bound can still beat what round 1 proved; then the rare large polytopes of both rounds
-        int* round_state = e->counts + e->n_keys + 1;               // EPA range counter, (overflow), filter counter
-        int* round_counts = e->counts + 2 * e->n_keys + 8;
-        for (int round = 1; round <= 2; ++round) {
-            if (round == 2) {
-                CUDA_TRY(cudaMemsetAsync(round_state, 0, sizeof(int), st));
-                CUDA_TRY(cudaMemsetAsync(round_state + 2, 0, sizeof(int), st));
-                CUDA_TRY(cudaMemsetAsync(round_counts, 0, sizeof(int) * e->n_keys, st));
-            }
-            k_penetration_select<256><<<e->sm_count * 4, 256, sizeof(int) * (e->n_keys + 2), st>>>(a, round);
-            switch (e->epa_threads) {
-                case 352: k_penetration<352><<<e->epa_blocks, 352, e->smem_epa, st>>>(a); break;
-                case 320: k_penetration<320><<<e->epa_blocks, 320, e->smem_epa, st>>>(a); break;
-                case 256: k_penetration<256><<<e->epa_blocks, 256, e->smem_epa, st>>>(a); break;
-                case 192: k_penetration<192><<<e->epa_blocks, 192, e->smem_epa, st>>>(a); break;
-                case 128: k_penetration<128><<<e->epa_blocks, 128, e->smem_epa, st>>>(a); break;
-                default: k_penetration<64><<<e->epa_blocks, 64, e->smem_epa, st>>>(a); break;
-            }
-            e->stats.kernel_launches += 2;
+    prof_end(e, st);   // broad phase
+    // Stages (each works on lists built by k_select):  GJK on every configuration's champion pair (+ plane entries),
+    // penetration depth of the champions that overlap, GJK on the pairs that can still matter, their penetration
+    // depth, then the rare large polytopes of both penetration stages.
+    const bool epa = !(flags & JG_NO_EPA);
+    const size_t sel_smem = sizeof(int) * (2 * e->n_keys + 2);
+    auto launch_penetration = [&]() {
+        switch (e->epa_threads) {
+            case 352: k_penetration<352><<<e->epa_blocks, 352, e->smem_epa, st>>>(a); break;
+            case 320: k_penetration<320><<<e->epa_blocks, 320, e->smem_epa, st>>>(a); break;
+            case 256: k_penetration<256><<<e->epa_blocks, 256, e->smem_epa, st>>>(a); break;
+            case 192: k_penetration<192><<<e->epa_blocks, 192, e->smem_epa, st>>>(a); break;
+            case 128: k_penetration<128><<<e->epa_blocks, 128, e->smem_epa, st>>>(a); break;
+            default: k_penetration<64><<<e->epa_blocks, 64, e->smem_epa, st>>>(a); break;
         }
-        k_penetration_big<EPA_BIG_BLOCK><<<e->sm_count * 2, EPA_BIG_BLOCK, e->smem_epa_big, st>>>(a);
-        e->stats.kernel_launches += 1;
+    };
+    if (e->n_keys > 0) {
+        for (int round = 0; round < 2; ++round) {
+            if (round == 1) { k_stage_reset<<<1, 256, 0, st>>>(a, 0); e->stats.kernel_launches += 1; }
+            prof_begin(e, 1, st);
+            k_select<256><<<e->sm_count * 4, 256, sel_smem, st>>>(a, round == 0 ? SEL_GJK_CHAMP : SEL_GJK_REST);
+            k_narrowphase<NP_BLOCK><<<e->np_blocks, NP_BLOCK, e->smem_narrow, st>>>(a);
+            prof_end(e, st);
+            e->stats.kernel_launches += 2;
+            if (epa) {
+                prof_begin(e, 2, st);
+                k_stage_reset<<<1, 256, 0, st>>>(a, 0);
+                k_select<256><<<e->sm_count * 4, 256, sel_smem, st>>>(a, SEL_EPA_NEW);
+                launch_penetration();
+                k_stage_reset<<<1, 256, 0, st>>>(a, 1);     // remember what has been expanded
+                prof_end(e, st);
+                e->stats.kernel_launches += 4;
+            }
+        }
+        if (epa) {
+            prof_begin(e, 2, st);
+            k_penetration_big<EPA_BIG_BLOCK><<<e->sm_count * 2, EPA_BIG_BLOCK, e->smem_epa_big, st>>>(a);
+            prof_end(e, st);
+            e->stats.kernel_launches += 1;
+        }
     }
-    PROF_MARK(e, st);
+    prof_begin(e, 3, st);
     if (e->n_keys > 0) {
         k_accumulate_stats<<<1, 32, 0, st>>>(e->counts, e->n_scene_keys, e->n_keys, e->P, e->d_stats);
         e->stats.kernel_launches += 1;
@@ -616,7 +647,7 @@ static int run_narrow_and_finalize(jg_engine* e, const PassArgs& a, int n_out, u
     k_finalize<<<(n_out + 255) / 256, 256, 0, st>>>(e->enc_scene, e->enc_self, e->viol, n_out, a.qd, a.threshold, flags, bits,
                                                     dist, reason);
     e->stats.kernel_launches += 1;
-    PROF_MARK(e, st);
+    prof_end(e, st);
     CUDA_TRY(cudaGetLastError());
     return JG_OK;
 }
@@ -643,9 +674,9 @@ extern "C" int jg_check(jg_engine* e, const float* q, int64_t n, int dof, uint32
         PassArgs a;
         fill_args(e, a, flags);
         a.q = q + off * dof; a.n = m;
-        CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * (3 * e->n_keys + 16), st));
+        CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * (4 * e->n_keys + 8), st));
         if (flags & JG_LIMITS) CUDA_TRY(cudaMemsetAsync(e->viol, 0, sizeof(uint32_t) * (e->cap / 32 + 1), st));
-        PROF_MARK(e, st);
+        prof_begin(e, 0, st);
         k_broadphase<BP_BLOCK><<<(m + BP_BLOCK - 1) / BP_BLOCK, BP_BLOCK, bp_smem(e, flags), st>>>(a);
         e->stats.kernel_launches += 1;
         rc = run_narrow_and_finalize(e, a, m, flags, bits + off / 32, min_dist ? min_dist + off : nullptr,
@@ -671,9 +702,9 @@ extern "C" int jg_check_edges(jg_engine* e, const float* qa, const float* qb, in
         PassArgs a;
         fill_args(e, a, flags);
         a.q = qa + off * dof; a.qb = qb + off * dof; a.n = me * substeps; a.substeps = substeps;
-        CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * (3 * e->n_keys + 16), st));
+        CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * (4 * e->n_keys + 8), st));
         if (flags & JG_LIMITS) CUDA_TRY(cudaMemsetAsync(e->viol, 0, sizeof(uint32_t) * (e->cap / 32 + 1), st));
-        PROF_MARK(e, st);
+        prof_begin(e, 0, st);
         k_init_scratch<<<(me + 255) / 256, 256, 0, st>>>(e->enc_scene, e->enc_self, e->champ_scene, e->champ_self, me);
         k_broadphase<BP_BLOCK><<<(a.n + BP_BLOCK - 1) / BP_BLOCK, BP_BLOCK, bp_smem(e, flags), st>>>(a);
         e->stats.kernel_launches += 2;
@@ -758,9 +789,9 @@ extern "C" int jg_check_poses(jg_engine* e, const float* poses, int64_t n, int f
         PassArgs a;
         fill_args(e, a, flags);
         a.n = m;
-        CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * (3 * e->n_keys + 16), st));
+        CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * (4 * e->n_keys + 8), st));
         const size_t smem = sizeof(RobotTab) + sizeof(PieceRec) * e->P;
-        PROF_MARK(e, st);
+        prof_begin(e, 0, st);
         k_broadphase_poses<BP_BLOCK><<<(m + BP_BLOCK - 1) / BP_BLOCK, BP_BLOCK, smem, st>>>(a, poses + off * stride, fmt, e->d_rel,
                                                                                          e->d_use_shapes, (int)use.size());
         e->stats.kernel_launches += 1;

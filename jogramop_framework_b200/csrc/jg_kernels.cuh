@@ -96,21 +96,30 @@ struct PassArgs {
     float4 *q_r0, *q_r1, *q_r2;
     int* q_cfg;
     int cap;           // queue capacity per key (= max configs per pass)
-    int* counts;       // [n_keys] pair counts, [n_keys] GJK tile counter, [n_keys+1] EPA tile counter,
-                       // [n_keys+2] overflow-list length, [n_keys+3] filter range counter,
-                       // [n_keys+8 .. 2 n_keys+8) penetration-queue counts, [2 n_keys+8 .. 3 n_keys+8) round counts
+    int* counts;       // 4*n_keys + 8 ints: pair-queue counts | penetration-queue counts | entries selected for the
+                       // current stage | penetration entries already expanded | gjk range ctr, penetration range ctr,
+                       // overflow-list length, select range ctr
+    float* q_prio;     // [n_keys*cap] upper bound of the pair's total penetration (AABB overlap + margins)
     int* epa_slot;     // [n_keys*cap] queue slots whose cores overlap (penetration-depth pass)
     uint4* epa_ids;    // [n_keys*cap] their GJK end simplices (vertex ids, 0xFFFFFFFF = unused)
     int2* ovf_list;    // [cap] (key, index in the penetration queue) of polytopes that outgrew shared memory
-    float* epa_prio;   // [n_keys*cap] upper bound of each queued pair's total penetration (AABB overlap + margins)
-    int* act_list;     // [n_keys*cap] per key: penetration-queue indices selected for the current round
-    unsigned long long *champ_scene, *champ_self;   // [cap] per configuration: (prio bits << 32 | pair code) of the
-                                                    // queued pair with the largest upper bound
+    float* epa_prio;   // [n_keys*cap] the same bound for the entries of the penetration queue
+    int* act_list;     // [n_keys*cap] per key: queue indices selected for the current stage (k_select)
+    unsigned long long *champ_scene, *champ_self;   // [cap] per configuration: (prio bits << 32 | key << 20 | slot) of the
+                                                    // queued pair with the largest upper bound ("champion")
+    float max_msum;    // largest margin sum over the keys (JG_NO_EPA pruning)
     // per-configuration scratch
     int* enc_scene;    // encoded min contact distance vs scene+plane
     int* enc_self;
     uint32_t* viol;    // limit violation bits
 };
+
+__device__ __forceinline__ int* cnt_pair(const PassArgs& a) { return a.counts; }
+__device__ __forceinline__ int* cnt_epa(const PassArgs& a) { return a.counts + a.n_keys; }
+__device__ __forceinline__ int* cnt_act(const PassArgs& a) { return a.counts + 2 * a.n_keys; }
+__device__ __forceinline__ int* cnt_done(const PassArgs& a) { return a.counts + 3 * a.n_keys; }
+enum { CTR_GJK = 0, CTR_EPA = 1, CTR_OVF = 2, CTR_SEL = 3 };
+__device__ __forceinline__ int* cnt_misc(const PassArgs& a) { return a.counts + 4 * a.n_keys; }
 
 __device__ __forceinline__ Tf joint_local(const JointRec& J, float val) {
     Tf O;
@@ -137,8 +146,10 @@ __device__ __forceinline__ Tf joint_local(const JointRec& J, float val) {
     return O;
 }
 
-// warp-aggregated append of the lanes with `survive` to queue `key`
-__device__ __forceinline__ void queue_push(const PassArgs& a, bool survive, int key, const Tf& T, int cfg) {
+// warp-aggregated append of the lanes with `survive` to queue `key`.  prio = upper bound of the pair's total
+// penetration (0 for plane entries); the pair with the largest bound becomes the configuration's champion.
+__device__ __forceinline__ void queue_push(const PassArgs& a, bool survive, int key, const Tf& T, int cfg, float prio,
+                                           unsigned long long* champ) {
     const unsigned mask = __ballot_sync(0xFFFFFFFFu, survive);
     if (mask == 0) return;
     const int lane = threadIdx.x & 31;
@@ -147,26 +158,32 @@ __device__ __forceinline__ void queue_push(const PassArgs& a, bool survive, int 
     if (lane == leader) base = atomicAdd(a.counts + key, __popc(mask));
     base = __shfl_sync(0xFFFFFFFFu, base, leader);
     if (survive) {
-        const size_t slot = (size_t)key * a.cap + base + __popc(mask & ((1u << lane) - 1u));
+        const int idx = base + __popc(mask & ((1u << lane) - 1u));
+        const size_t slot = (size_t)key * a.cap + idx;
         a.q_r0[slot] = make_float4(T.r00, T.r01, T.r02, T.tx);
         a.q_r1[slot] = make_float4(T.r10, T.r11, T.r12, T.ty);
         a.q_r2[slot] = make_float4(T.r20, T.r21, T.r22, T.tz);
         a.q_cfg[slot] = cfg;
+        a.q_prio[slot] = prio;
+        if (champ) atomicMax(champ + cfg, ((unsigned long long)__float_as_uint(prio) << 32) | (unsigned)((key << 20) | idx));
     }
 }
 
-// AABB of the shape (local centre c / half h) under T against a box (centre bc, half bh already inflated)
-__device__ __forceinline__ bool aabb_overlap(const Tf& T, const float* c, const float* h, const float* bc,
-                                             const float* bh, float infl) {
+// AABB of the shape (local centre c / half h) under T against a box (centre bc, half bh): smallest signed overlap over
+// the three axes (negative = separated along that axis by that much)
+__device__ __forceinline__ float aabb_overlap(const Tf& T, const float* c, const float* h, const float* bc,
+                                              const float* bh) {
     const float cx = fmaf(T.r00, c[0], fmaf(T.r01, c[1], fmaf(T.r02, c[2], T.tx)));
     const float cy = fmaf(T.r10, c[0], fmaf(T.r11, c[1], fmaf(T.r12, c[2], T.ty)));
     const float cz = fmaf(T.r20, c[0], fmaf(T.r21, c[1], fmaf(T.r22, c[2], T.tz)));
     const float hx = fmaf(fabsf(T.r00), h[0], fmaf(fabsf(T.r01), h[1], fabsf(T.r02) * h[2]));
     const float hy = fmaf(fabsf(T.r10), h[0], fmaf(fabsf(T.r11), h[1], fabsf(T.r12) * h[2]));
     const float hz = fmaf(fabsf(T.r20), h[0], fmaf(fabsf(T.r21), h[1], fabsf(T.r22) * h[2]));
-    return fabsf(cx - bc[0]) <= hx + bh[0] + infl && fabsf(cy - bc[1]) <= hy + bh[1] + infl &&
-           fabsf(cz - bc[2]) <= hz + bh[2] + infl;
+    return fminf(fminf(hx + bh[0] - fabsf(cx - bc[0]), hy + bh[1] - fabsf(cy - bc[1])), hz + bh[2] - fabsf(cz - bc[2]));
 }
+// bound of the total penetration from the box overlap: the core boxes may be up to 1 mm (embedded box margin)
+// smaller than the penetration geometry on each side
+__device__ __forceinline__ float prio_of(float ov, float msum) { return fmaxf(ov, 0.f) + msum + 0.0021f; }
 
 // scene + plane candidates of one shape placed by T (uniform control flow across the warp)
 __device__ __forceinline__ void shape_vs_scene(const PassArgs& a, const ShapeRec& Sh, int s, const PieceRec* pieces,
@@ -174,10 +191,12 @@ __device__ __forceinline__ void shape_vs_scene(const PassArgs& a, const ShapeRec
     if (a.flags & 1u) {
         for (int p = 0; p < a.P; ++p) {
             const PieceRec& Pc = pieces[p];
-            const bool hit = valid && aabb_overlap(T, Sh.c, Sh.h, Pc.c, Pc.h, a.qd + Sh.margin + Pc.margin);
+            const float msum = Sh.margin + Pc.margin;
+            const float ov = aabb_overlap(T, Sh.c, Sh.h, Pc.c, Pc.h);
+            const bool hit = valid && ov + a.qd + msum >= 0.f;
             Tf Tc = T;   // vertices of the piece are stored relative to its AABB centre
             Tc.tx -= Pc.c[0]; Tc.ty -= Pc.c[1]; Tc.tz -= Pc.c[2];
-            queue_push(a, hit, s * (a.P + 1) + p, Tc, out_idx);
+            queue_push(a, hit, s * (a.P + 1) + p, Tc, out_idx, prio_of(ov, msum), a.champ_scene);
         }
     }
     if ((a.flags & 2u) && a.has_plane) {
@@ -190,7 +209,7 @@ __device__ __forceinline__ void shape_vs_scene(const PassArgs& a, const ShapeRec
         const float low = fmaf(a.plane[0], cx, fmaf(a.plane[1], cy, fmaf(a.plane[2], cz, a.plane[3]))) - ext;
         // the plane vertices may exceed the core AABB by the embedded box margin: 2 mm slack
         const bool hit = valid && (low - 0.002f - Sh.plane_margin <= a.qd);
-        queue_push(a, hit, s * (a.P + 1) + a.P, T, out_idx);
+        queue_push(a, hit, s * (a.P + 1) + a.P, T, out_idx, 0.f, nullptr);
     }
 }
 
@@ -295,8 +314,10 @@ __global__ void __launch_bounds__(BLOCK) k_broadphase(const PassArgs a) {
             const Tf rel = tf_inv_mul(Ta, Tb);   // shape of link lb expressed in the frame of link la
             const ShapeRec& Sa = R->shapes[sr.sa];
             const ShapeRec& Sb = R->shapes[sr.sb];
-            const bool hit = valid && aabb_overlap(rel, Sb.c, Sb.h, Sa.c, Sa.h, a.qd + Sa.margin + Sb.margin);
-            queue_push(a, hit, a.n_scene_keys + k, rel, out_idx);
+            const float msum = Sa.margin + Sb.margin;
+            const float ov = aabb_overlap(rel, Sb.c, Sb.h, Sa.c, Sa.h);
+            const bool hit = valid && ov + a.qd + msum >= 0.f;
+            queue_push(a, hit, a.n_scene_keys + k, rel, out_idx, prio_of(ov, msum), a.champ_self);
         }
     }
 }
@@ -370,10 +391,11 @@ __global__ void __launch_bounds__(BLOCK) k_narrowphase(const PassArgs a) {
         int* kd = reinterpret_cast<int*>(keys);
         for (int i = tid; i < (int)(sizeof(KeyRec) / 4) * a.n_keys; i += BLOCK) kd[i] = ks[i];
     }
-    if (tid < 32) sched_build(a.counts, a.n_keys, gridDim.x * (BLOCK / 32), prefix, prefix + a.n_keys + 1, lane);
+    const int* acounts = cnt_act(a);   // entries selected for this stage (k_select)
+    if (tid < 32) sched_build(acounts, a.n_keys, gridDim.x * (BLOCK / 32), prefix, prefix + a.n_keys + 1, lane);
     __syncthreads();
     const int total = prefix[a.n_keys], G = prefix[a.n_keys + 1];
-    int* range_counter = a.counts + a.n_keys;
+    int* range_counter = cnt_misc(a) + CTR_GJK;
     const unsigned lt_mask = (1u << lane) - 1u;
     const bool want_epa = !(a.flags & 16u);
 
@@ -385,14 +407,14 @@ __global__ void __launch_bounds__(BLOCK) k_narrowphase(const PassArgs a) {
         const int key = sched_find_key(prefix, a.n_keys, r);
         const KeyRec K = keys[key];
         const int begin = (r - prefix[key]) * G;
-        const int end = min(begin + G, a.counts[key]);
+        const int end = min(begin + G, acounts[key]);
         const size_t kbase = (size_t)key * a.cap;
         int* enc = K.kind == KEY_SELF ? a.enc_self : a.enc_scene;
 
         if (K.kind == KEY_PLANE) {   // uniform cost per entry: plain strided loop
-            for (int off = begin + lane; off < end; off += 32) {
+            for (int i = begin + lane; i < end; i += 32) {
                 int cfg;
-                const Tf T = load_entry(a, kbase + off, cfg);
+                const Tf T = load_entry(a, kbase + a.act_list[kbase + i], cfg);
                 const float d = plane_distance(verts + K.a_off, K.a_n, T, mk(a.plane[0], a.plane[1], a.plane[2]),
                                                a.plane[3]) - K.msum;
                 if (d <= a.qd) atomicMin(enc + cfg, enc_float(d));
@@ -415,7 +437,7 @@ __global__ void __launch_bounds__(BLOCK) k_narrowphase(const PassArgs a) {
             if (need && avail > 0) {
                 const int rank = __popc(need & lt_mask);
                 if (!active && rank < avail) {
-                    off = next + rank;
+                    off = a.act_list[kbase + next + rank];
                     T = load_entry(a, kbase + off, cfg);
                     gjk_init(S, mk(T.tx, T.ty, T.tz));
                     active = true;
@@ -443,25 +465,12 @@ __global__ void __launch_bounds__(BLOCK) k_narrowphase(const PassArgs a) {
                 if (m) {
                     const int leader = __ffs(m) - 1;
                     int base = 0;
-                    if (lane == leader) base = atomicAdd(a.counts + a.n_keys + 8 + key, __popc(m));
+                    if (lane == leader) base = atomicAdd(cnt_epa(a) + key, __popc(m));
                     base = __shfl_sync(0xFFFFFFFFu, base, leader);
                     if (deep) {
                         const int jj = base + __popc(m & lt_mask);
                         const size_t j = kbase + jj;
-                        // upper bound of this pair's total penetration: smallest axis overlap of the two boxes
-                        // (A's box rotated into B's frame) + margins; the pair with the largest bound of a
-                        // configuration is expanded first, the others only if their bound can still beat it
-                        const float cx = fmaf(T.r00, K.a_c[0], fmaf(T.r01, K.a_c[1], fmaf(T.r02, K.a_c[2], T.tx))) - K.b_c[0];
-                        const float cy = fmaf(T.r10, K.a_c[0], fmaf(T.r11, K.a_c[1], fmaf(T.r12, K.a_c[2], T.ty))) - K.b_c[1];
-                        const float cz = fmaf(T.r20, K.a_c[0], fmaf(T.r21, K.a_c[1], fmaf(T.r22, K.a_c[2], T.tz))) - K.b_c[2];
-                        const float hx = fmaf(fabsf(T.r00), K.a_h[0], fmaf(fabsf(T.r01), K.a_h[1], fabsf(T.r02) * K.a_h[2]));
-                        const float hy = fmaf(fabsf(T.r10), K.a_h[0], fmaf(fabsf(T.r11), K.a_h[1], fabsf(T.r12) * K.a_h[2]));
-                        const float hz = fmaf(fabsf(T.r20), K.a_h[0], fmaf(fabsf(T.r21), K.a_h[1], fabsf(T.r22) * K.a_h[2]));
-                        const float ov = fminf(fminf(hx + K.b_h[0] - fabsf(cx), hy + K.b_h[1] - fabsf(cy)), hz + K.b_h[2] - fabsf(cz));
-                        const float prio = fmaxf(ov, 0.f) + fmaxf(K.emsum, K.msum) + 2e-5f;
-                        a.epa_prio[j] = prio;
-                        atomicMax((K.kind == KEY_SELF ? a.champ_self : a.champ_scene) + cfg,
-                                  ((unsigned long long)__float_as_uint(prio) << 32) | (unsigned)((key << 20) | jj));
+                        a.epa_prio[j] = a.q_prio[kbase + off];
                         a.epa_slot[j] = off;
                         a.epa_ids[j] = make_uint4(S.S.n > 0 ? S.S.ia : 0xFFFFFFFFu, S.S.n > 1 ? S.S.ib : 0xFFFFFFFFu,
                                                   S.S.n > 2 ? S.S.ic : 0xFFFFFFFFu, S.S.n > 3 ? S.S.id : 0xFFFFFFFFu);
@@ -494,21 +503,33 @@ __device__ __forceinline__ Simplex simplex_from_ids(const float4* __restrict__ A
     return sx;
 }
 
-// Selects the penetration-queue entries of one round into per-key lists.  round 1: the champion of every
-// configuration (largest upper bound); round 2: every other pair whose bound still exceeds the configuration's best
-// proven penetration.  Exact: a skipped pair provably cannot be the deepest one of its configuration.
+// Stage selection.  Every stage of a pass (GJK on the champions, penetration depth of the champions, GJK on the
+// rest, penetration depth of the rest) works on per-key lists of queue indices built here:
+//   SEL_GJK_CHAMP  pair queue: the champion of every configuration (largest penetration bound) + all plane entries
+//   SEL_GJK_REST   pair queue: every other pair whose bound still exceeds the configuration's proven penetration
+//                  (all of them while no penetration is proven: then the minimum distance needs every pair)
+//   SEL_EPA_NEW    penetration queue: entries appended since the last penetration stage, same bound test
+// Exact: a skipped pair provably cannot change the configuration's minimum.
+enum { SEL_GJK_CHAMP = 0, SEL_GJK_REST = 1, SEL_EPA_NEW = 2 };
+
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_penetration_select(const PassArgs a, int round) {
+__global__ void __launch_bounds__(BLOCK) k_select(const PassArgs a, int mode) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int* prefix = reinterpret_cast<int*>(smem_raw);   // [n_keys + 2]
+    int* span = prefix + a.n_keys + 2;                // [n_keys] entries to look at per key
     const int tid = threadIdx.x, lane = tid & 31;
-    const int* ecounts = a.counts + a.n_keys + 8;
-    int* acounts = a.counts + 2 * a.n_keys + 8;
-    if (tid < 32) sched_build(ecounts, a.n_keys, gridDim.x * (BLOCK / 32), prefix, prefix + a.n_keys + 1, lane);
+    const bool epa = mode == SEL_EPA_NEW;
+    const int* qcount = epa ? cnt_epa(a) : cnt_pair(a);
+    const int* qstart = cnt_done(a);
+    for (int k = tid; k < a.n_keys; k += BLOCK) span[k] = qcount[k] - (epa ? qstart[k] : 0);
+    __syncthreads();
+    if (tid < 32) sched_build(span, a.n_keys, gridDim.x * (BLOCK / 32), prefix, prefix + a.n_keys + 1, lane);
     __syncthreads();
     const int total = prefix[a.n_keys], G = prefix[a.n_keys + 1];
-    int* range_counter = a.counts + a.n_keys + 3;
+    int* range_counter = cnt_misc(a) + CTR_SEL;
+    int* acounts = cnt_act(a);
     const unsigned lt_mask = (1u << lane) - 1u;
+    const bool no_epa = (a.flags & 16u) != 0;
     for (;;) {
         int r = 0;
         if (lane == 0) r = atomicAdd(range_counter, 1);
@@ -516,20 +537,30 @@ __global__ void __launch_bounds__(BLOCK) k_penetration_select(const PassArgs a, 
         if (r >= total) break;
         const int key = sched_find_key(prefix, a.n_keys, r);
         const int kind = a.keys[key].kind;
-        const int begin = (r - prefix[key]) * G;
-        const int end = min(begin + G, ecounts[key]);
+        const int start = epa ? qstart[key] : 0;
+        const int begin = start + (r - prefix[key]) * G;
+        const int end = min(begin + G, qcount[key]);
         const size_t kbase = (size_t)key * a.cap;
+        const unsigned long long* champ = kind == KEY_SELF ? a.champ_self : a.champ_scene;
+        const int* enc = kind == KEY_SELF ? a.enc_self : a.enc_scene;
         for (int j0 = begin; j0 < end; j0 += 32) {
             const int j = j0 + lane;
             bool sel = false;
             if (j < end) {
-                const int cfg = a.q_cfg[kbase + a.epa_slot[kbase + j]];
-                const unsigned long long ch = (kind == KEY_SELF ? a.champ_self : a.champ_scene)[cfg];
-                const bool is_champ = (unsigned)(ch & 0xFFFFFFFFull) == (unsigned)((key << 20) | j);
-                if (round == 1) sel = is_champ;
-                else if (!is_champ) {
-                    const float best = -dec_float((kind == KEY_SELF ? a.enc_self : a.enc_scene)[cfg]);   // proven total
-                    sel = a.epa_prio[kbase + j] > best;
+                if (kind == KEY_PLANE) {
+                    sel = mode == SEL_GJK_CHAMP;
+                } else {
+                    const int slot = epa ? a.epa_slot[kbase + j] : j;
+                    const int cfg = a.q_cfg[kbase + slot];
+                    if (mode == SEL_GJK_CHAMP) {
+                        sel = (unsigned)(champ[cfg] & 0xFFFFFFFFull) == (unsigned)((key << 20) | slot);
+                    } else {
+                        float best = -dec_float(enc[cfg]);          // proven total penetration (negative: none yet)
+                        if (no_epa && best >= a.max_msum - 1e-6f) best = FLT_MAX;   // clamped mode: any overlap settles it
+                        sel = a.q_prio[kbase + slot] > best;
+                        if (mode == SEL_GJK_REST)
+                            sel = sel && (unsigned)(champ[cfg] & 0xFFFFFFFFull) != (unsigned)((key << 20) | slot);
+                    }
                 }
             }
             const unsigned m = __ballot_sync(0xFFFFFFFFu, sel);
@@ -544,6 +575,20 @@ __global__ void __launch_bounds__(BLOCK) k_penetration_select(const PassArgs a, 
     }
 }
 
+// between stages: clear the selection counts and the range counters; `mark_done`: remember how much of the
+// penetration queue has been expanded
+__global__ void k_stage_reset(const PassArgs a, int mark_done) {
+    for (int k = threadIdx.x; k < a.n_keys; k += blockDim.x) {
+        cnt_act(a)[k] = 0;
+        if (mark_done) cnt_done(a)[k] = cnt_epa(a)[k];
+    }
+    if (threadIdx.x == 0) {
+        cnt_misc(a)[CTR_GJK] = 0;
+        cnt_misc(a)[CTR_EPA] = 0;
+        cnt_misc(a)[CTR_SEL] = 0;
+    }
+}
+
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_penetration(const PassArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -551,13 +596,13 @@ __global__ void __launch_bounds__(BLOCK) k_penetration(const PassArgs a) {
     int* prefix = reinterpret_cast<int*>(smem_raw + sizeof(float4) * a.n_verts);   // [n_keys + 2]
     uint32_t* poly_words = reinterpret_cast<uint32_t*>(prefix + ((a.n_keys + 2 + 3) & ~3));
     const int tid = threadIdx.x, lane = tid & 31;
-    const int* ecounts = a.counts + 2 * a.n_keys + 8;   // entries selected for this round (k_penetration_select)
+    const int* ecounts = cnt_act(a);   // entries selected for this stage (k_select)
     for (int i = tid; i < a.n_verts; i += BLOCK) verts[i] = a.verts[i];
     if (tid < 32) sched_build(ecounts, a.n_keys, gridDim.x * (BLOCK / 32), prefix, prefix + a.n_keys + 1, lane);
     __syncthreads();
     const int total = prefix[a.n_keys], G = prefix[a.n_keys + 1];
-    int* range_counter = a.counts + a.n_keys + 1;
-    int* ovf_counter = a.counts + a.n_keys + 2;
+    int* range_counter = cnt_misc(a) + CTR_EPA;
+    int* ovf_counter = cnt_misc(a) + CTR_OVF;
     const unsigned lt_mask = (1u << lane) - 1u;
 
     EpaStateC<BLOCK> X;   // compact polytope, interleaved across the block in shared memory (jg_epa.cuh)
@@ -678,7 +723,7 @@ __global__ void __launch_bounds__(BLOCK) k_penetration_big(const PassArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* verts = reinterpret_cast<float4*>(smem_raw);
     uint32_t* poly_words = reinterpret_cast<uint32_t*>(smem_raw + sizeof(float4) * a.n_verts);
-    const int n = min(a.counts[a.n_keys + 2], a.cap);
+    const int n = min(cnt_misc(a)[CTR_OVF], a.cap);
     if (n == 0) return;
     for (int i = threadIdx.x; i < a.n_verts; i += BLOCK) verts[i] = a.verts[i];
     __syncthreads();
