@@ -107,6 +107,8 @@ struct GjkState {
     Simplex S;
     V3 v;        // current closest point of the simplex to the origin (separating direction)
     float vv;    // |v|^2 (FLT_MAX before the first vertex)
+    float hmin;  // smallest support value h(d) = max_x d.x over the unit directions tried: if the sets overlap, an upper
+                 // bound of their penetration depth (free by-product of the iterations)
     int it;
 };
 
@@ -117,6 +119,7 @@ __device__ __forceinline__ void gjk_init(GjkState& G, V3 v0) {
     G.v = v0;
     if (!(norm2(G.v) > 1e-12f)) G.v = mk(1.f, 0.f, 0.f);
     G.vv = FLT_MAX;
+    G.hmin = FLT_MAX;
     G.it = 0;
 }
 
@@ -137,6 +140,7 @@ __device__ __forceinline__ int gjk_step(GjkState& G, const float4* __restrict__ 
     const float vw = dot(v, w);
     const float v2 = norm2(v);
     G.it += 1;
+    G.hmin = fminf(G.hmin, -vw * rsqrtf(v2));
     if (vw > 0.f && vw * vw > dmax * dmax * v2) return JG_GJK_FAR;
     if (S.n > 0) {
         const bool dupl = (id == S.ia) || (S.n > 1 && id == S.ib) || (S.n > 2 && id == S.ic);

@@ -470,7 +470,9 @@ __global__ void __launch_bounds__(BLOCK) k_narrowphase(const PassArgs a) {
                     if (deep) {
                         const int jj = base + __popc(m & lt_mask);
                         const size_t j = kbase + jj;
-                        a.epa_prio[j] = a.q_prio[kbase + off];
+                        // bound of the total penetration: box overlap from the broad phase, tightened by the smallest
+                        // support value seen during GJK (+4 mm: margins of the penetration geometry vs the cores)
+                        a.epa_prio[j] = fminf(a.q_prio[kbase + off], fmaxf(S.hmin, 0.f) + fmaxf(K.emsum, K.msum) + 0.004f);
                         a.epa_slot[j] = off;
                         a.epa_ids[j] = make_uint4(S.S.n > 0 ? S.S.ia : 0xFFFFFFFFu, S.S.n > 1 ? S.S.ib : 0xFFFFFFFFu,
                                                   S.S.n > 2 ? S.S.ic : 0xFFFFFFFFu, S.S.n > 3 ? S.S.id : 0xFFFFFFFFu);
@@ -557,7 +559,7 @@ __global__ void __launch_bounds__(BLOCK) k_select(const PassArgs a, int mode) {
                     } else {
                         float best = -dec_float(enc[cfg]);          // proven total penetration (negative: none yet)
                         if (no_epa && best >= a.max_msum - 1e-6f) best = FLT_MAX;   // clamped mode: any overlap settles it
-                        sel = a.q_prio[kbase + slot] > best;
+                        sel = (epa ? a.epa_prio[kbase + j] : a.q_prio[kbase + slot]) > best;
                         if (mode == SEL_GJK_REST)
                             sel = sel && (unsigned)(champ[cfg] & 0xFFFFFFFFull) != (unsigned)((key << 20) | slot);
                     }
