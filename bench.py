@@ -272,7 +272,9 @@ def run_b200(args):
                                    'penetration': epa_ms / args.steps, 'finalize': fin_ms / args.steps},
             'work': {'pairs_per_check': stats['pairs'] / max(stats['configs'], 1),
                      'plane_pairs_per_check': stats['plane_pairs'] / max(stats['configs'], 1),
-                     'epa_pairs_per_check': stats['epa_pairs'] / max(stats['configs'], 1)},
+                     'overlapping_pairs_per_check': stats['epa_pairs'] / max(stats['configs'], 1),
+                     'gjk_run_per_check': stats['gjk_run'] / max(stats['configs'], 1),
+                     'polytopes_expanded_per_check': stats['epa_run'] / max(stats['configs'], 1)},
             'wall_s_timed_region': wall,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -95,6 +95,12 @@ void jg_robot_free(jg_robot*);
  * Convex pieces (hull vertices, robot frame) + optional ground plane n.p + d = 0 (plane[4], NULL = none). */
 jg_scene* jg_scene_create(int n_pieces, const int32_t* piece_vert_offset, const double* piece_verts,
                           const double* piece_margin, const double* plane);
+/* ---- scene as ONE triangle mesh ("mesh mode"): the merged export/obstacles.obj of create_cpp_export.py:40-69 ----
+ * verts [n_verts,3] (robot frame), tris [n_tris,3] vertex indices.  The engine builds an LBVH over the triangles on
+ * the GPU and reports the distance link hull <-> triangle (triangle margin `margin`, default 0.001); overlapping
+ * pairs report -(margins) (no penetration depth on a surface).  Verdict / query-distance semantics as for pieces. */
+jg_scene* jg_scene_create_mesh(int n_verts, const double* verts, int n_tris, const int32_t* tris, double margin,
+                               const double* plane);
 void jg_scene_free(jg_scene*);
 
 /* ---- engine: uploads hulls / pieces to HBM on `device`, owns the scratch arena ---- */
@@ -140,7 +146,9 @@ typedef struct {
     int64_t pairs;            /* (shape, piece) pairs that survived the broad phase                          */
     int64_t plane_pairs;      /* (shape, plane) candidates                                                   */
     int64_t self_pairs;       /* self-collision candidates                                                   */
-    int64_t epa_pairs;        /* pairs whose cores overlapped (penetration pass)                             */
+    int64_t epa_pairs;        /* pairs whose cores overlapped (queued for the penetration pass)              */
+    int64_t gjk_run;          /* pair-queue entries the GJK stages really processed (incl. plane entries)    */
+    int64_t epa_run;          /* polytopes the penetration stages really expanded (after bound pruning)      */
     int64_t kernel_launches;  /* kernels launched by the last call                                           */
 } jg_stats;
 /* synchronises the engine's last stream and reads the device counters */

@@ -34,6 +34,8 @@ def load():
     L.jg_robot_free.argtypes = [vp]
     L.jg_scene_create.restype = vp
     L.jg_scene_create.argtypes = [i32, vp, vp, vp, vp]
+    L.jg_scene_create_mesh.restype = vp
+    L.jg_scene_create_mesh.argtypes = [i32, vp, i32, vp, f64, vp]
     L.jg_scene_free.argtypes = [vp]
     L.jg_engine_create.restype = vp
     L.jg_engine_create.argtypes = [vp, vp, i32, vp]
@@ -59,7 +61,7 @@ class Params(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [('configs', C.c_int64), ('pairs', C.c_int64), ('plane_pairs', C.c_int64), ('self_pairs', C.c_int64),
-                ('epa_pairs', C.c_int64), ('kernel_launches', C.c_int64)]
+                ('epa_pairs', C.c_int64), ('gjk_run', C.c_int64), ('epa_run', C.c_int64), ('kernel_launches', C.c_int64)]
 
 
 def check(rc, what=''):
@@ -70,6 +72,6 @@ def check(rc, what=''):
 
 EXPORTED_SYMBOLS = [
     'jg_default_params', 'jg_last_error', 'jg_abi_version', 'jg_device_count', 'jg_robot_create', 'jg_robot_free',
-    'jg_scene_create', 'jg_scene_free', 'jg_engine_create', 'jg_engine_free', 'jg_engine_device', 'jg_fk', 'jg_check',
+    'jg_scene_create', 'jg_scene_create_mesh', 'jg_scene_free', 'jg_engine_create', 'jg_engine_free', 'jg_engine_device', 'jg_fk', 'jg_check',
     'jg_check_edges', 'jg_check_poses', 'jg_check_host', 'jg_get_stats', 'jg_profile_enable', 'jg_get_profile',
     'jg_measure_fp32_peak']

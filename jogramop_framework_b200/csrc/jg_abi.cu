@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cfloat>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -60,6 +61,10 @@ struct jg_scene {
     int P = 0;
     std::vector<int> off;
     std::vector<double> v, margin;
+    bool is_mesh = false;              // triangle soup behind an LBVH instead of convex pieces
+    std::vector<float> mesh_v;         // [n,3]
+    std::vector<int> mesh_t;           // [m,3]
+    double mesh_margin = 0.001;
     bool has_plane = false;
     double plane[4] = {0, 0, 1, 0};
 };
@@ -141,6 +146,28 @@ extern "C" jg_scene* jg_scene_create(int P, const int32_t* off, const double* v,
     if (plane) memcpy(s->plane, plane, sizeof(double) * 4);
     return s;
 }
+extern "C" jg_scene* jg_scene_create_mesh(int n_verts, const double* verts, int n_tris, const int32_t* tris, double margin,
+                                          const double* plane) {
+    if (n_verts <= 0 || n_tris <= 0 || !verts || !tris || !(margin >= 0)) {
+        fail(JG_ERR_INVALID, "jg_scene_create_mesh: bad arguments");
+        return nullptr;
+    }
+    for (int i = 0; i < 3 * n_tris; ++i)
+        if (tris[i] < 0 || tris[i] >= n_verts) {
+            fail(JG_ERR_INVALID, "jg_scene_create_mesh: triangle %d references vertex %d of %d", i / 3, tris[i], n_verts);
+            return nullptr;
+        }
+    jg_scene* s = new jg_scene;
+    s->is_mesh = true;
+    s->off.assign(1, 0);
+    s->mesh_v.resize(3 * (size_t)n_verts);
+    for (size_t i = 0; i < s->mesh_v.size(); ++i) s->mesh_v[i] = (float)verts[i];
+    s->mesh_t.assign(tris, tris + 3 * (size_t)n_tris);
+    s->mesh_margin = margin;
+    s->has_plane = plane != nullptr;
+    if (plane) memcpy(s->plane, plane, sizeof(double) * 4);
+    return s;
+}
 extern "C" void jg_scene_free(jg_scene* s) { delete s; }
 
 // ----------------------------------------------------------------------------------------------- engine
@@ -170,6 +197,10 @@ struct jg_engine {
     float* epa_prio = nullptr;            // [n_keys*cap]
     float* q_prio = nullptr;              // [n_keys*cap]
     float max_msum = 0.f;
+    bool mesh = false;
+    float mesh_margin = 0.f;
+    Lbvh bvh;
+    int* d_err = nullptr;
     int* act_list = nullptr;              // [n_keys*cap]
     unsigned long long *champ_scene = nullptr, *champ_self = nullptr;   // [cap]
     int* counts = nullptr;                // [3*n_keys + 16], layout in jg_kernels.cuh PassArgs
@@ -251,7 +282,7 @@ static void engine_release(jg_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaFree(e->d_robot); cudaFree(e->d_pieces); cudaFree(e->d_selfs); cudaFree(e->d_keys); cudaFree(e->d_verts);
-    cudaFree(e->q_r0); cudaFree(e->q_r1); cudaFree(e->q_r2); cudaFree(e->q_cfg); cudaFree(e->epa_slot); cudaFree(e->epa_ids); cudaFree(e->ovf_list); cudaFree(e->epa_prio); cudaFree(e->q_prio); cudaFree(e->act_list); cudaFree(e->champ_scene); cudaFree(e->champ_self); cudaFree(e->counts);
+    cudaFree(e->q_r0); cudaFree(e->q_r1); cudaFree(e->q_r2); cudaFree(e->q_cfg); cudaFree(e->epa_slot); cudaFree(e->epa_ids); cudaFree(e->ovf_list); cudaFree(e->epa_prio); cudaFree(e->q_prio); cudaFree(e->bvh.nodes); cudaFree(e->bvh.tri_v); cudaFree(e->bvh.tri_id); cudaFree(e->d_err); cudaFree(e->act_list); cudaFree(e->champ_scene); cudaFree(e->champ_self); cudaFree(e->counts);
     cudaFree(e->enc_scene); cudaFree(e->enc_self); cudaFree(e->viol); cudaFree(e->d_link_slot); cudaFree(e->d_rel);
     cudaFree(e->d_use_shapes); cudaFree(e->d_stats);
     for (int i = 0; i < 2; ++i) {
@@ -369,9 +400,11 @@ static int build_tables(jg_engine* e, const jg_robot* r, const jg_scene* sc) {
             R.joints[link].shape_count++;
         }
     }
-    // pieces: centred vertices
-    const int P = sc ? sc->P : 0;
-    e->P = P;
+    // pieces: centred vertices (mesh mode: the whole triangle soup is "piece 0" of the key numbering)
+    e->mesh = sc && sc->is_mesh;
+    e->mesh_margin = e->mesh ? (float)sc->mesh_margin : 0.f;
+    const int P = e->mesh ? 0 : (sc ? sc->P : 0);
+    e->P = e->mesh ? 1 : P;
     std::vector<PieceRec> pieces(P);
     for (int p = 0; p < P; ++p) {
         PieceRec& Pc = pieces[p];
@@ -400,6 +433,9 @@ static int build_tables(jg_engine* e, const jg_robot* r, const jg_scene* sc) {
     // keys
     std::vector<KeyRec> keys;
     for (int s = 0; s < r->S; ++s) {
+        if (e->mesh)
+            keys.push_back(KeyRec{R.shapes[s].voff, R.shapes[s].vn, 0, 0, R.shapes[s].margin + e->mesh_margin, KEY_MESH, 0, 0, 0, 0,
+                                  0.f, 0, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}});
         for (int p = 0; p < P; ++p)
         {
             KeyRec k{R.shapes[s].voff, R.shapes[s].vn, pieces[p].voff, pieces[p].vn,
@@ -452,6 +488,57 @@ static int build_tables(jg_engine* e, const jg_robot* r, const jg_scene* sc) {
     return JG_OK;
 }
 
+
+// GPU build of the LBVH (set-up time, once per scene)
+static int build_lbvh(jg_engine* e, const jg_scene* sc) {
+    const int nv = (int)sc->mesh_v.size() / 3, n = (int)sc->mesh_t.size() / 3;
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int i = 0; i < nv; ++i)
+        for (int k = 0; k < 3; ++k) {
+            lo[k] = std::min(lo[k], sc->mesh_v[3 * i + k]);
+            hi[k] = std::max(hi[k], sc->mesh_v[3 * i + k]);
+        }
+    float *d_v = nullptr;
+    int *d_t = nullptr, *d_vals = nullptr, *d_vals2 = nullptr, *d_parent = nullptr, *d_visits = nullptr;
+    unsigned long long *d_keys = nullptr, *d_keys2 = nullptr;
+    void* d_tmp = nullptr;
+    size_t tmp_bytes = 0;
+    Lbvh& B = e->bvh;
+    B.n_tris = n;
+    CUDA_TRY(cudaMalloc(&d_v, sizeof(float) * 3 * nv));
+    CUDA_TRY(cudaMalloc(&d_t, sizeof(int) * 3 * n));
+    CUDA_TRY(cudaMemcpy(d_v, sc->mesh_v.data(), sizeof(float) * 3 * nv, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_t, sc->mesh_t.data(), sizeof(int) * 3 * n, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&d_keys, sizeof(unsigned long long) * n));
+    CUDA_TRY(cudaMalloc(&d_keys2, sizeof(unsigned long long) * n));
+    CUDA_TRY(cudaMalloc(&d_vals, sizeof(int) * n));
+    CUDA_TRY(cudaMalloc(&d_vals2, sizeof(int) * n));
+    CUDA_TRY(cudaMalloc(&d_parent, sizeof(int) * (2 * n)));
+    CUDA_TRY(cudaMalloc(&d_visits, sizeof(int) * std::max(n, 1)));
+    CUDA_TRY(cudaMemset(d_visits, 0, sizeof(int) * std::max(n, 1)));
+    CUDA_TRY(cudaMalloc(&B.nodes, sizeof(BvhNode) * std::max(n - 1, 1)));
+    CUDA_TRY(cudaMalloc(&B.tri_v, sizeof(float4) * 3 * n));
+    CUDA_TRY(cudaMalloc(&B.tri_id, sizeof(int) * n));
+    const float3 flo = make_float3(lo[0], lo[1], lo[2]);
+    const float3 inv = make_float3(1.f / std::max(hi[0] - lo[0], 1e-9f), 1.f / std::max(hi[1] - lo[1], 1e-9f),
+                                   1.f / std::max(hi[2] - lo[2], 1e-9f));
+    const int blocks = (n + 127) / 128;
+    k_lbvh_morton<<<blocks, 128>>>(d_v, d_t, n, flo, inv, d_keys, d_vals);
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, n));
+    CUDA_TRY(cudaMalloc(&d_tmp, std::max<size_t>(tmp_bytes, 16)));
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, n));
+    k_lbvh_gather<<<blocks, 128>>>(d_v, d_t, d_vals2, n, B.tri_v, B.tri_id);
+    if (n > 1) {
+        k_lbvh_hierarchy<<<blocks, 128>>>(d_keys2, n, B.nodes, d_parent);
+        k_lbvh_refit<<<blocks, 128>>>(B.tri_v, n, B.nodes, d_parent, d_visits);
+    }
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaGetLastError());
+    cudaFree(d_v); cudaFree(d_t); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_vals); cudaFree(d_vals2);
+    cudaFree(d_parent); cudaFree(d_visits); cudaFree(d_tmp);
+    return JG_OK;
+}
+
 constexpr int BP_BLOCK = 128;   // broad phase: threads (= configurations) per block
 constexpr int NP_BLOCK = 256;   // narrow phase
 constexpr int EPA_BIG_BLOCK = 512;  // overflow pass of the penetration depth: one pair per warp, 16 warps per block
@@ -478,6 +565,7 @@ extern "C" jg_engine* jg_engine_create(const jg_robot* r, const jg_scene* sc, in
     if (prm) e->prm = *prm; else jg_default_params(&e->prm);
     e->L = r->L; e->S = r->S; e->dof = r->dof;
     if (build_tables(e, r, sc) != JG_OK) { engine_release(e); return nullptr; }
+    if (e->mesh && build_lbvh(e, sc) != JG_OK) { engine_release(e); return nullptr; }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->sm_count = prop.multiProcessorCount;
     e->smem_narrow = sizeof(float4) * e->n_verts + sizeof(KeyRec) * e->n_keys + sizeof(int) * (e->n_keys + 2) + 64;
@@ -550,13 +638,14 @@ extern "C" jg_engine* jg_engine_create(const jg_robot* r, const jg_scene* sc, in
                cudaMalloc(&e->d_link_slot, sizeof(int) * MAX_LINKS) == cudaSuccess &&
                cudaMalloc(&e->d_rel, sizeof(Tf) * MAX_SHAPES) == cudaSuccess &&
                cudaMalloc(&e->d_use_shapes, sizeof(int) * MAX_SHAPES) == cudaSuccess &&
-               cudaMalloc(&e->d_stats, sizeof(unsigned long long) * 8) == cudaSuccess;
+               cudaMalloc(&e->d_stats, sizeof(unsigned long long) * 8) == cudaSuccess && cudaMalloc(&e->d_err, sizeof(int)) == cudaSuccess;
     if (!okm) {
         fail(JG_ERR_NOMEM, "scratch allocation failed (%zu queue entries): %s", qn, cudaGetErrorString(cudaGetLastError()));
         engine_release(e);
         return nullptr;
     }
     cudaMemset(e->d_stats, 0, sizeof(unsigned long long) * 8);
+    cudaMemset(e->d_err, 0, sizeof(int));
     return e;
 }
 extern "C" void jg_engine_free(jg_engine* e) { engine_release(e); }
@@ -571,7 +660,9 @@ static void fill_args(const jg_engine* e, PassArgs& a, uint32_t flags) {
     a.has_plane = e->has_plane ? 1 : 0;
     a.robot = e->d_robot; a.pieces = e->d_pieces; a.P = e->P; a.selfs = e->d_selfs; a.keys = e->d_keys;
     a.n_keys = e->n_keys; a.n_scene_keys = e->n_scene_keys; a.verts = e->d_verts; a.n_verts = e->n_verts;
-    a.q_r0 = e->q_r0; a.q_r1 = e->q_r1; a.q_r2 = e->q_r2; a.q_cfg = e->q_cfg; a.epa_slot = e->epa_slot; a.epa_ids = e->epa_ids; a.ovf_list = e->ovf_list; a.epa_prio = e->epa_prio; a.q_prio = e->q_prio; a.max_msum = e->max_msum; a.act_list = e->act_list; a.champ_scene = e->champ_scene; a.champ_self = e->champ_self; a.cap = e->cap; a.counts = e->counts;
+    a.q_r0 = e->q_r0; a.q_r1 = e->q_r1; a.q_r2 = e->q_r2; a.q_cfg = e->q_cfg; a.epa_slot = e->epa_slot; a.epa_ids = e->epa_ids; a.ovf_list = e->ovf_list; a.epa_prio = e->epa_prio; a.q_prio = e->q_prio; a.max_msum = e->max_msum; a.stats = e->d_stats;
+    a.mesh = e->mesh ? 1 : 0; a.bvh_nodes = e->bvh.nodes; a.bvh_tri = e->bvh.tri_v; a.bvh_n = e->bvh.n_tris;
+    a.mesh_margin = e->mesh_margin; a.q_tri = e->epa_slot; a.err_flag = e->d_err; a.act_list = e->act_list; a.champ_scene = e->champ_scene; a.champ_self = e->champ_self; a.cap = e->cap; a.counts = e->counts;
     a.enc_scene = e->enc_scene; a.enc_self = e->enc_self; a.viol = e->viol;
 }
 
@@ -616,20 +707,19 @@ static int run_narrow_and_finalize(jg_engine* e, const PassArgs& a, int n_out, u
     };
     if (e->n_keys > 0) {
         for (int round = 0; round < 2; ++round) {
-            if (round == 1) { k_stage_reset<<<1, 256, 0, st>>>(a, 0); e->stats.kernel_launches += 1; }
             prof_begin(e, 1, st);
             k_select<256><<<e->sm_count * 4, 256, sel_smem, st>>>(a, round == 0 ? SEL_GJK_CHAMP : SEL_GJK_REST);
             k_narrowphase<NP_BLOCK><<<e->np_blocks, NP_BLOCK, e->smem_narrow, st>>>(a);
+            k_stage_reset<<<1, 256, 0, st>>>(a, 0, 4);      // stats[4] += GJK pairs run
             prof_end(e, st);
-            e->stats.kernel_launches += 2;
+            e->stats.kernel_launches += 3;
             if (epa) {
                 prof_begin(e, 2, st);
-                k_stage_reset<<<1, 256, 0, st>>>(a, 0);
                 k_select<256><<<e->sm_count * 4, 256, sel_smem, st>>>(a, SEL_EPA_NEW);
                 launch_penetration();
-                k_stage_reset<<<1, 256, 0, st>>>(a, 1);     // remember what has been expanded
+                k_stage_reset<<<1, 256, 0, st>>>(a, 1, 5);  // stats[5] += polytopes expanded; remember how far
                 prof_end(e, st);
-                e->stats.kernel_launches += 4;
+                e->stats.kernel_launches += 3;
             }
         }
         if (epa) {
@@ -669,8 +759,10 @@ extern "C" int jg_check(jg_engine* e, const float* q, int64_t n, int dof, uint32
     int rc = begin_call(e, st);
     if (rc) return rc;
     e->stats.configs = n;
-    for (int64_t off = 0; off < n; off += e->cap) {
-        const int m = (int)std::min<int64_t>(e->cap, n - off);
+    // mesh mode: a configuration may queue many triangles per link, so a pass takes fewer configurations
+    const int64_t pass = e->mesh ? std::max(1024, e->cap / 32 / 1024 * 1024) : e->cap;
+    for (int64_t off = 0; off < n; off += pass) {
+        const int m = (int)std::min<int64_t>(pass, n - off);
         PassArgs a;
         fill_args(e, a, flags);
         a.q = q + off * dof; a.n = m;
@@ -683,6 +775,16 @@ extern "C" int jg_check(jg_engine* e, const float* q, int64_t n, int dof, uint32
                                      reason ? reason + off : nullptr, st);
         if (rc) return rc;
     }
+    if (e->mesh) {   // secondary path: check the queue-overflow flag synchronously
+        int err = 0;
+        CUDA_TRY(cudaMemcpyAsync(&err, e->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (err) {
+            cudaMemset(e->d_err, 0, sizeof(int));
+            return fail(JG_ERR_NOMEM, "mesh mode: a triangle candidate queue overflowed (more than %d candidates per link and pass); "
+                        "create the engine with a larger `chunk`", e->cap);
+        }
+    }
     return JG_OK;
 }
 
@@ -691,6 +793,7 @@ extern "C" int jg_check_edges(jg_engine* e, const float* qa, const float* qb, in
     if (!e) return fail(JG_ERR_INVALID, "jg_check_edges: engine is NULL");
     if (dof != e->dof) return fail(JG_ERR_INVALID, "jg_check_edges: dof %d does not match the robot's %d", dof, e->dof);
     if (substeps < 2 || substeps > e->cap / 32) return fail(JG_ERR_INVALID, "jg_check_edges: substeps %d out of range [2,%d]", substeps, e->cap / 32);
+    if (e->mesh) return fail(JG_ERR_INVALID, "jg_check_edges: not available in mesh mode");
     if (m < 0 || (m && (!qa || !qb || !bits))) return fail(JG_ERR_INVALID, "jg_check_edges: NULL qa/qb/bits");
     cudaStream_t st = (cudaStream_t)stream;
     int rc = begin_call(e, st);
@@ -751,6 +854,7 @@ extern "C" int jg_check_poses(jg_engine* e, const float* poses, int64_t n, int f
     if (ee_link < 0 || ee_link >= e->L || !links || n_links <= 0) return fail(JG_ERR_INVALID, "jg_check_poses: bad link arguments");
     if (n < 0 || (n && (!poses || !bits))) return fail(JG_ERR_INVALID, "jg_check_poses: NULL poses/bits");
     flags &= (JG_SCENE | JG_PLANE | JG_NO_EPA);
+    if (e->mesh) return fail(JG_ERR_INVALID, "jg_check_poses: not available in mesh mode");
     cudaStream_t st = (cudaStream_t)stream;
     int rc = begin_call(e, st);
     if (rc) return rc;
@@ -932,6 +1036,8 @@ extern "C" int jg_get_stats(jg_engine* e, jg_stats* out) {
     out->plane_pairs = (int64_t)h[1];
     out->self_pairs = (int64_t)h[2];
     out->epa_pairs = (int64_t)h[3];
+    out->gjk_run = (int64_t)h[4];
+    out->epa_run = (int64_t)h[5];
     return JG_OK;
 }
 

@@ -125,17 +125,36 @@ __device__ __forceinline__ void gjk_init(GjkState& G, V3 v0) {
 
 // One GJK iteration: one support evaluation of A - B plus the simplex update.  Returns JG_GJK_RUNNING or the
 // final status; for JG_GJK_SEPARATED the distance is sqrtf(G.vv).
-__device__ __forceinline__ int gjk_step(GjkState& G, const float4* __restrict__ A, int nA, const float4* __restrict__ B,
-                                        int nB, const Tf& T, float dmax) {
+// support oracle of the static set B: a shared-memory vertex range (SetSupport) or a triangle held in registers
+struct SetSupport {
+    const float4* B; int nB;
+    __device__ __forceinline__ V3 operator()(V3 d, int& idx) const {
+        idx = support_scan(B, nB, d);
+        const float4 p = B[idx];
+        return mk(p.x, p.y, p.z);
+    }
+};
+struct TriSupport {
+    V3 p0, p1, p2;
+    __device__ __forceinline__ V3 operator()(V3 d, int& idx) const {
+        const float s0 = dot(p0, d), s1 = dot(p1, d), s2 = dot(p2, d);
+        idx = (s1 > s0) ? (s2 > s1 ? 2 : 1) : (s2 > s0 ? 2 : 0);
+        return idx == 0 ? p0 : (idx == 1 ? p1 : p2);
+    }
+};
+
+template <class SupB>
+__device__ __forceinline__ int gjk_step(GjkState& G, const float4* __restrict__ A, int nA, const SupB& supB, const Tf& T,
+                                        float dmax) {
     Simplex& S = G.S;
     const V3 v = G.v;
     // support point of A - B in direction -v
     const V3 dl = tf_rot_t(T, -v);
     const int ia = support_scan(A, nA, dl);
-    const int ib = support_scan(B, nB, v);
+    int ib;
+    const V3 pb = supB(v, ib);
     const float4 pa = A[ia];
-    const float4 pb = B[ib];
-    const V3 w = tf_apply(T, mk(pa.x, pa.y, pa.z)) - mk(pb.x, pb.y, pb.z);
+    const V3 w = tf_apply(T, mk(pa.x, pa.y, pa.z)) - pb;
     const uint32_t id = ((uint32_t)ia << 16) | (uint32_t)ib;
     const float vw = dot(v, w);
     const float v2 = norm2(v);
@@ -214,7 +233,7 @@ __device__ __forceinline__ int gjk_distance(const float4* __restrict__ A, int nA
     gjk_init(G, v0);
     int status;
     do {
-        status = gjk_step(G, A, nA, B, nB, T, dmax);
+        status = gjk_step(G, A, nA, SetSupport{B, nB}, T, dmax);
     } while (status == JG_GJK_RUNNING);
     iters = G.it;
     dist = sqrtf(G.vv);

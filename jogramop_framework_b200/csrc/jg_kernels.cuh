@@ -12,6 +12,7 @@
 // self-collision pairs):   q_r0/q_r1/q_r2 float4[K*C] (rows of R with t in .w), q_cfg int[K*C], counts int[K].
 #pragma once
 #include "jg_epa.cuh"
+#include "jg_lbvh.cuh"
 
 namespace jg {
 
@@ -58,7 +59,7 @@ struct SelfRec {
     int la, lb;        // link ids
 };
 
-enum { KEY_HULL = 0, KEY_PLANE = 1, KEY_SELF = 2 };
+enum { KEY_HULL = 0, KEY_PLANE = 1, KEY_SELF = 2, KEY_MESH = 3 };
 struct KeyRec {
     int a_off, a_n;    // moving vertex set (robot shape), GJK core
     int b_off, b_n;    // static vertex set (piece / first link shape), GJK core
@@ -108,6 +109,15 @@ struct PassArgs {
     unsigned long long *champ_scene, *champ_self;   // [cap] per configuration: (prio bits << 32 | key << 20 | slot) of the
                                                     // queued pair with the largest upper bound ("champion")
     float max_msum;    // largest margin sum over the keys (JG_NO_EPA pruning)
+    unsigned long long* stats;   // [8] device counters (jg_get_stats)
+    // mesh mode: obstacle triangle soup behind an LBVH instead of convex pieces
+    int mesh;
+    const BvhNode* bvh_nodes;
+    const float4* bvh_tri;     // [3 * bvh_n] triangle vertices, Morton order
+    int bvh_n;
+    float mesh_margin;
+    int* q_tri;                // [n_keys*cap] triangle slot of a mesh queue entry (aliases epa_slot: no EPA on triangles)
+    int* err_flag;             // set when a mesh queue overflowed
     // per-configuration scratch
     int* enc_scene;    // encoded min contact distance vs scene+plane
     int* enc_self;
@@ -188,7 +198,39 @@ __device__ __forceinline__ float prio_of(float ov, float msum) { return fmaxf(ov
 // scene + plane candidates of one shape placed by T (uniform control flow across the warp)
 __device__ __forceinline__ void shape_vs_scene(const PassArgs& a, const ShapeRec& Sh, int s, const PieceRec* pieces,
                                                const Tf& T, bool valid, int out_idx) {
-    if (a.flags & 1u) {
+    if ((a.flags & 1u) && a.mesh) {
+        // world box of the shape, inflated by everything a reported distance may span; every triangle whose box
+        // overlaps it is a candidate (per-lane LBVH traversal; lanes that emit together share one atomicAdd)
+        const float infl = a.qd + Sh.margin + a.mesh_margin + 1e-5f;
+        const float cx = fmaf(T.r00, Sh.c[0], fmaf(T.r01, Sh.c[1], fmaf(T.r02, Sh.c[2], T.tx)));
+        const float cy = fmaf(T.r10, Sh.c[0], fmaf(T.r11, Sh.c[1], fmaf(T.r12, Sh.c[2], T.ty)));
+        const float cz = fmaf(T.r20, Sh.c[0], fmaf(T.r21, Sh.c[1], fmaf(T.r22, Sh.c[2], T.tz)));
+        const float hx = fmaf(fabsf(T.r00), Sh.h[0], fmaf(fabsf(T.r01), Sh.h[1], fabsf(T.r02) * Sh.h[2])) + infl;
+        const float hy = fmaf(fabsf(T.r10), Sh.h[0], fmaf(fabsf(T.r11), Sh.h[1], fabsf(T.r12) * Sh.h[2])) + infl;
+        const float hz = fmaf(fabsf(T.r20), Sh.h[0], fmaf(fabsf(T.r21), Sh.h[1], fabsf(T.r22) * Sh.h[2])) + infl;
+        const float qlo[3] = {cx - hx, cy - hy, cz - hz}, qhi[3] = {cx + hx, cy + hy, cz + hz};
+        const int key = s * (a.P + 1);
+        const int lane = threadIdx.x & 31;
+        if (valid)
+            lbvh_traverse(a.bvh_nodes, a.bvh_tri, a.bvh_n, qlo, qhi, [&](int tri) {
+                const unsigned m = __activemask();
+                const int leader = __ffs(m) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(a.counts + key, __popc(m));
+                base = __shfl_sync(m, base, leader);
+                const int idx = base + __popc(m & ((1u << lane) - 1u));
+                if (idx < a.cap) {
+                    const size_t slot = (size_t)key * a.cap + idx;
+                    a.q_r0[slot] = make_float4(T.r00, T.r01, T.r02, T.tx);
+                    a.q_r1[slot] = make_float4(T.r10, T.r11, T.r12, T.ty);
+                    a.q_r2[slot] = make_float4(T.r20, T.r21, T.r22, T.tz);
+                    a.q_cfg[slot] = out_idx;
+                    a.q_tri[slot] = tri;
+                } else {
+                    *a.err_flag = 1;
+                }
+            });
+    } else if (a.flags & 1u) {
         for (int p = 0; p < a.P; ++p) {
             const PieceRec& Pc = pieces[p];
             const float msum = Sh.margin + Pc.margin;
@@ -430,6 +472,45 @@ __global__ void __launch_bounds__(BLOCK) k_narrowphase(const PassArgs a) {
         GjkState S;
         Tf T = tf_identity();
         int cfg = 0, off = 0;
+        if (K.kind == KEY_MESH) {   // link hull vs one triangle per lane (registers); same lane refill, no penetration pass
+            TriSupport tri;
+            tri.p0 = tri.p1 = tri.p2 = mk(0.f, 0.f, 0.f);
+            for (;;) {
+                const unsigned need = __ballot_sync(0xFFFFFFFFu, !active);
+                const int avail = end - next;
+                if (need && avail > 0) {
+                    const int rank = __popc(need & lt_mask);
+                    if (!active && rank < avail) {
+                        off = a.act_list[kbase + next + rank];
+                        T = load_entry(a, kbase + off, cfg);
+                        const int t3 = 3 * a.q_tri[kbase + off];
+                        const float4 v0 = a.bvh_tri[t3], v1 = a.bvh_tri[t3 + 1], v2 = a.bvh_tri[t3 + 2];
+                        // work in a frame centred on the triangle (fp32 precision, like the centred pieces)
+                        const V3 c = mk((v0.x + v1.x + v2.x) * (1.f / 3.f), (v0.y + v1.y + v2.y) * (1.f / 3.f),
+                                        (v0.z + v1.z + v2.z) * (1.f / 3.f));
+                        tri.p0 = mk(v0.x, v0.y, v0.z) - c; tri.p1 = mk(v1.x, v1.y, v1.z) - c; tri.p2 = mk(v2.x, v2.y, v2.z) - c;
+                        T.tx -= c.x; T.ty -= c.y; T.tz -= c.z;
+                        gjk_init(S, mk(T.tx, T.ty, T.tz));
+                        active = true;
+                    }
+                    next += min(__popc(need), avail);
+                }
+                if (!__any_sync(0xFFFFFFFFu, active)) break;
+                if (active) {
+                    const int st = gjk_step(S, A, K.a_n, tri, T, dmax);
+                    if (st != JG_GJK_RUNNING) {
+                        active = false;
+                        if (st == JG_GJK_SEPARATED) {
+                            const float d = sqrtf(S.vv) - K.msum;
+                            if (d <= a.qd) atomicMin(enc + cfg, enc_float(d));
+                        } else if (st == JG_GJK_PENETRATING) {
+                            atomicMin(enc + cfg, enc_float(-K.msum));
+                        }
+                    }
+                }
+            }
+            continue;
+        }
         for (;;) {
             // ---- refill idle lanes from the range
             const unsigned need = __ballot_sync(0xFFFFFFFFu, !active);
@@ -448,7 +529,7 @@ __global__ void __launch_bounds__(BLOCK) k_narrowphase(const PassArgs a) {
             // ---- one GJK iteration on every busy lane
             bool deep = false;
             if (active) {
-                const int st = gjk_step(S, A, K.a_n, B, K.b_n, T, dmax);
+                const int st = gjk_step(S, A, K.a_n, SetSupport{B, K.b_n}, T, dmax);
                 if (st != JG_GJK_RUNNING) {
                     active = false;
                     if (st == JG_GJK_SEPARATED) {
@@ -523,7 +604,7 @@ __global__ void __launch_bounds__(BLOCK) k_select(const PassArgs a, int mode) {
     const bool epa = mode == SEL_EPA_NEW;
     const int* qcount = epa ? cnt_epa(a) : cnt_pair(a);
     const int* qstart = cnt_done(a);
-    for (int k = tid; k < a.n_keys; k += BLOCK) span[k] = qcount[k] - (epa ? qstart[k] : 0);
+    for (int k = tid; k < a.n_keys; k += BLOCK) span[k] = min(qcount[k], a.cap) - (epa ? qstart[k] : 0);
     __syncthreads();
     if (tid < 32) sched_build(span, a.n_keys, gridDim.x * (BLOCK / 32), prefix, prefix + a.n_keys + 1, lane);
     __syncthreads();
@@ -541,7 +622,7 @@ __global__ void __launch_bounds__(BLOCK) k_select(const PassArgs a, int mode) {
         const int kind = a.keys[key].kind;
         const int start = epa ? qstart[key] : 0;
         const int begin = start + (r - prefix[key]) * G;
-        const int end = min(begin + G, qcount[key]);
+        const int end = min(begin + G, min(qcount[key], a.cap));
         const size_t kbase = (size_t)key * a.cap;
         const unsigned long long* champ = kind == KEY_SELF ? a.champ_self : a.champ_scene;
         const int* enc = kind == KEY_SELF ? a.enc_self : a.enc_scene;
@@ -549,7 +630,7 @@ __global__ void __launch_bounds__(BLOCK) k_select(const PassArgs a, int mode) {
             const int j = j0 + lane;
             bool sel = false;
             if (j < end) {
-                if (kind == KEY_PLANE) {
+                if (kind == KEY_PLANE || kind == KEY_MESH) {
                     sel = mode == SEL_GJK_CHAMP;
                 } else {
                     const int slot = epa ? a.epa_slot[kbase + j] : j;
@@ -579,12 +660,20 @@ __global__ void __launch_bounds__(BLOCK) k_select(const PassArgs a, int mode) {
 
 // between stages: clear the selection counts and the range counters; `mark_done`: remember how much of the
 // penetration queue has been expanded
-__global__ void k_stage_reset(const PassArgs a, int mark_done) {
+__global__ void k_stage_reset(const PassArgs a, int mark_done, int stat_slot) {
+    __shared__ int sum;
+    if (threadIdx.x == 0) sum = 0;
+    __syncthreads();
+    int mine = 0;
     for (int k = threadIdx.x; k < a.n_keys; k += blockDim.x) {
+        mine += cnt_act(a)[k];
         cnt_act(a)[k] = 0;
         if (mark_done) cnt_done(a)[k] = cnt_epa(a)[k];
     }
+    if (stat_slot >= 0 && mine) atomicAdd(&sum, mine);
+    __syncthreads();
     if (threadIdx.x == 0) {
+        if (stat_slot >= 0) a.stats[stat_slot] += (unsigned long long)sum;   // entries the finished stage really ran
         cnt_misc(a)[CTR_GJK] = 0;
         cnt_misc(a)[CTR_EPA] = 0;
         cnt_misc(a)[CTR_SEL] = 0;
@@ -657,7 +746,7 @@ __global__ void __launch_bounds__(BLOCK) k_penetration(const PassArgs a) {
             }
             if (!__any_sync(0xFFFFFFFFu, phase != 0)) break;
             if (phase == 1) {
-                const int st = gjk_step(S, A, K.ea_n, B, K.eb_n, T, 1e30f);
+                const int st = gjk_step(S, A, K.ea_n, SetSupport{B, K.eb_n}, T, 1e30f);
                 if (st == JG_GJK_PENETRATING) {
                     phase = 2;
                     const ThreadSupport sup = {A, K.ea_n, B, K.eb_n, T};

@@ -1,0 +1,159 @@
+// jg_lbvh.cuh -- linear BVH over the triangles of the merged obstacle mesh, built on the GPU at scene load
+// (Morton codes -> radix sort -> Karras 2012 hierarchy -> bottom-up box refit), and its per-thread traversal.
+//
+// The reference exports every scenario's obstacles as ONE triangle mesh (create_cpp_export.py:40-69,
+// scenarios/<id>/export/obstacles.obj) for the sister planners; "mesh mode" answers the same query against that mesh
+// (distance link hull <-> triangle soup) instead of against the convex pieces.
+#pragma once
+#include <cub/device/device_radix_sort.cuh>
+
+#include "jg_math.cuh"
+
+namespace jg {
+
+struct BvhNode {
+    float lo[3], hi[3];
+    int left, right;    // >= 0: internal node index; < 0: leaf, triangle slot = ~child (slot in Morton order)
+};
+
+struct Lbvh {
+    int n_tris = 0;
+    BvhNode* nodes = nullptr;     // [max(n-1, 1)] internal nodes, root = 0
+    float4* tri_v = nullptr;      // [3n] triangle vertices in Morton order (w unused)
+    int* tri_id = nullptr;        // [n] original triangle index of slot i
+};
+
+__device__ __forceinline__ unsigned expand_bits(unsigned v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+
+__global__ void k_lbvh_morton(const float* __restrict__ verts, const int* __restrict__ tris, int n, float3 lo, float3 inv,
+                              unsigned long long* __restrict__ keys, int* __restrict__ vals) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float c[3] = {0.f, 0.f, 0.f};
+    for (int k = 0; k < 3; ++k)
+        for (int a = 0; a < 3; ++a) c[a] += verts[3 * tris[3 * i + k] + a] * (1.f / 3.f);
+    const unsigned x = (unsigned)fminf(fmaxf((c[0] - lo.x) * inv.x * 1024.f, 0.f), 1023.f);
+    const unsigned y = (unsigned)fminf(fmaxf((c[1] - lo.y) * inv.y * 1024.f, 0.f), 1023.f);
+    const unsigned z = (unsigned)fminf(fmaxf((c[2] - lo.z) * inv.z * 1024.f, 0.f), 1023.f);
+    const unsigned code = (expand_bits(x) << 2) | (expand_bits(y) << 1) | expand_bits(z);
+    keys[i] = ((unsigned long long)code << 32) | (unsigned)i;   // index appended: keys are unique
+    vals[i] = i;
+}
+
+__device__ __forceinline__ int lbvh_delta(const unsigned long long* keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    return __clzll(keys[i] ^ keys[j]);
+}
+
+// one thread per internal node (Karras 2012, fig. 4)
+__global__ void k_lbvh_hierarchy(const unsigned long long* __restrict__ keys, int n, BvhNode* __restrict__ nodes,
+                                 int* __restrict__ parent /* [2n-1]: internal 0..n-2, leaves n-1.. */) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int d = lbvh_delta(keys, n, i, i + 1) - lbvh_delta(keys, n, i, i - 1) >= 0 ? 1 : -1;
+    const int dmin = lbvh_delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (lbvh_delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (lbvh_delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = lbvh_delta(keys, n, i, j);
+    int s = 0;
+    for (int t = (l + 1) >> 1;; t = (t + 1) >> 1) {
+        if (lbvh_delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+        if (t <= 1) break;
+    }
+    const int gamma = i + s * d + min(d, 0);
+    const int lo = min(i, j), hi = max(i, j);
+    const int left = lo == gamma ? ~gamma : gamma;            // leaf slots are encoded as ~slot
+    const int right = hi == gamma + 1 ? ~(gamma + 1) : gamma + 1;
+    nodes[i].left = left;
+    nodes[i].right = right;
+    parent[left < 0 ? (n - 1) + ~left : left] = i;
+    parent[right < 0 ? (n - 1) + ~right : right] = i;
+    if (i == 0) parent[0] = -1;
+}
+
+// gather triangles into Morton order; then one thread per leaf climbs to the root, the second arrival at a node
+// merges the child boxes
+__global__ void k_lbvh_gather(const float* __restrict__ verts, const int* __restrict__ tris, const int* __restrict__ order,
+                              int n, float4* __restrict__ tri_v, int* __restrict__ tri_id) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int t = order[i];
+    tri_id[i] = t;
+    for (int k = 0; k < 3; ++k) {
+        const int v = tris[3 * t + k];
+        tri_v[3 * i + k] = make_float4(verts[3 * v], verts[3 * v + 1], verts[3 * v + 2], 0.f);
+    }
+}
+
+__global__ void k_lbvh_refit(const float4* __restrict__ tri_v, int n, BvhNode* __restrict__ nodes,
+                             const int* __restrict__ parent, int* __restrict__ visits) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int node = parent[(n - 1) + i];
+    while (node >= 0) {
+        if (atomicAdd(visits + node, 1) == 0) return;   // first arrival: the sibling subtree is not ready yet
+        __threadfence();
+        BvhNode& N = nodes[node];
+        float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        for (int c = 0; c < 2; ++c) {
+            const int ch = c == 0 ? N.left : N.right;
+            if (ch < 0) {
+                for (int k = 0; k < 3; ++k) {
+                    const float4 p = tri_v[3 * (~ch) + k];
+                    lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
+                    hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
+                }
+            } else {
+                const volatile BvhNode& C = nodes[ch];
+                for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], C.lo[a]); hi[a] = fmaxf(hi[a], C.hi[a]); }
+            }
+        }
+        for (int a = 0; a < 3; ++a) { N.lo[a] = lo[a]; N.hi[a] = hi[a]; }
+        __threadfence();
+        node = parent[node];
+    }
+}
+
+// Calls f(slot) for every triangle whose box overlaps [qlo, qhi].  Per-thread stack; depth of a 30-bit Morton tree
+// with index tie-break is bounded by 64.
+template <class F>
+__device__ __forceinline__ void lbvh_traverse(const BvhNode* __restrict__ nodes, const float4* __restrict__ tri_v, int n,
+                                              const float* qlo, const float* qhi, F f) {
+    if (n <= 0) return;
+    auto tri_hits = [&](int slot) {
+        float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        for (int k = 0; k < 3; ++k) {
+            const float4 p = tri_v[3 * slot + k];
+            lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
+            hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
+        }
+        return lo[0] <= qhi[0] && hi[0] >= qlo[0] && lo[1] <= qhi[1] && hi[1] >= qlo[1] && lo[2] <= qhi[2] && hi[2] >= qlo[2];
+    };
+    if (n == 1) {
+        if (tri_hits(0)) f(0);
+        return;
+    }
+    int stack[64];
+    int sp = 0;
+    stack[sp++] = 0;
+    while (sp > 0) {
+        const BvhNode N = nodes[stack[--sp]];
+        if (!(N.lo[0] <= qhi[0] && N.hi[0] >= qlo[0] && N.lo[1] <= qhi[1] && N.hi[1] >= qlo[1] && N.lo[2] <= qhi[2] &&
+              N.hi[2] >= qlo[2]))
+            continue;
+        if (N.left < 0) { if (tri_hits(~N.left)) f(~N.left); } else if (sp < 64) stack[sp++] = N.left;
+        if (N.right < 0) { if (tri_hits(~N.right)) f(~N.right); } else if (sp < 64) stack[sp++] = N.right;
+    }
+}
+
+}  // namespace jg

@@ -45,7 +45,9 @@ def unpack_bits(words, n):
 
 class CollisionEngine:
     def __init__(self, robot, scene=None, device=0, threshold=-0.001, query_distance=0.01, finger_open=0.04,
-                 chunk=0):
+                 chunk=0, mesh_mode=False, mesh_margin=0.001):
+        """mesh_mode: check against the scene's merged triangle mesh (``scene.tri_verts`` / ``scene.tris`` = the
+        reference's export/obstacles.obj) through a GPU-built LBVH instead of against the convex pieces."""
         L = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.JogramopError('no CUDA device: the jogramop_framework_b200 engine has no CPU fallback')
@@ -64,7 +66,14 @@ class CollisionEngine:
         if not self._r:
             raise _lib.JogramopError('jg_robot_create: ' + L.jg_last_error().decode())
         self._s = None
-        if scene is not None:
+        self.mesh_mode = bool(mesh_mode)
+        if scene is not None and mesh_mode:
+            ks = [_f64(scene.tri_verts), _i32(scene.tris), _f64(scene.plane)]
+            self._s = L.jg_scene_create_mesh(len(ks[0]), _p(ks[0]), len(ks[1]), _p(ks[1]), float(mesh_margin),
+                                             _p(ks[2]) if scene.has_plane else None)
+            if not self._s:
+                raise _lib.JogramopError('jg_scene_create_mesh: ' + L.jg_last_error().decode())
+        elif scene is not None:
             ks = [_i32(scene.piece_vert_offset), _f64(scene.piece_verts), _f64(scene.piece_margin), _f64(scene.plane)]
             self._s = L.jg_scene_create(scene.n_pieces, _p(ks[0]), _p(ks[1]), _p(ks[2]),
                                         _p(ks[3]) if scene.has_plane else None)

@@ -92,6 +92,32 @@ def test_overflow_kernel_parity(robot, scene_loader, engines):
     assert (dist - dist2).abs().max().item() < 2e-5
 
 
+@pytest.mark.parametrize('sid', [11, 34])
+def test_mesh_mode_lbvh_parity(sid, robot, scene_loader):
+    """Mesh mode: link hulls vs the merged triangle mesh (export/obstacles.obj) through the GPU-built LBVH ==
+    the oracle run on a scene whose convex pieces are the individual triangles."""
+    import copy
+    from jogramop_framework_b200.engine import CollisionEngine
+    sc = scene_loader(sid)
+    tri_scene = copy.copy(sc)
+    tri_scene.piece_verts = sc.tri_verts[sc.tris].reshape(-1, 3)
+    tri_scene.piece_vert_offset = (np.arange(len(sc.tris) + 1) * 3).astype(np.int32)
+    tri_scene.piece_body = sc.tri_body
+    tri_scene.piece_margin = np.full(len(sc.tris), 0.001)
+    o = Oracle(robot, tri_scene)
+    e = CollisionEngine(robot, sc, mesh_mode=True)
+    q = uniform_configs(robot, 20000, 100 + sid)
+    fl = oracle.SCENE | oracle.PLANE | oracle.NO_EPA
+    rb, rd = o.check(q.astype(np.float64), flags=fl)
+    bits, dist, _ = e.check(q, flags=fl)
+    compare(bits, dist, rb, rd)
+    # the surface of the mesh is what collides: a mesh-mode hit implies a hit of the solid convex pieces
+    eb, ed, _ = Oracle(robot, sc).check(q.astype(np.float64), flags=fl), None, None
+    assert (eb[0] | ~rb).mean() > 0.999
+    assert 0.1 < rb.mean() < 0.6
+    e.close()
+
+
 def test_scene_only_and_plane_only(robot, scene_loader, engines):
     e = engines(11)
     o = Oracle(robot, scene_loader(11))
