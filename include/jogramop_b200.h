@@ -135,6 +135,15 @@ int jg_check_edges(jg_engine*, const float* qa, const float* qb, int64_t m, int 
 int jg_check_poses(jg_engine*, const float* poses, int64_t n, int fmt, int ee_link, const int32_t* links,
                    int n_links, uint32_t flags, uint32_t* bits, float* min_dist, void* stream);
 
+/* ---- inverse kinematics ("next" row: replaces pybullet.calculateInverseKinematics, simulation.py:251-310) ----
+ * targets [n,12]: pose of link `ee_link` in the robot frame (device fp32); q_init [n,dof] or NULL (start from
+ * q_rest); q_rest [dof] HOST doubles = null-space rest pose (the reference passes home_conf).  Damped least squares
+ * with null-space pull and joint-limit clamping, at most `iters` iterations (reference 100), residual `tol`
+ * (reference 1e-3).  q_out [n,dof]; err_out [n] = position error [m] + orientation error [deg]/1000, the quantity the
+ * reference thresholds at 0.015 (simulation.py:299-306). */
+int jg_ik(jg_engine*, const float* targets, int64_t n, int ee_link, const float* q_init, const double* q_rest, int iters,
+          float tol, float damping, float null_gain, int position_only, float* q_out, float* err_out, void* stream);
+
 /* ---- host-buffer convenience (the end-to-end path a drop-in caller uses): pinned staging, chunked
  *      H2D -> kernels -> D2H overlapped on two streams; blocks until the results are in host memory ---- */
 int jg_check_host(jg_engine*, const float* q_host, int64_t n, int dof, uint32_t flags, uint32_t* bits_host,

@@ -201,6 +201,7 @@ struct jg_engine {
     float mesh_margin = 0.f;
     Lbvh bvh;
     int* d_err = nullptr;
+    float* d_qrest = nullptr;
     int* act_list = nullptr;              // [n_keys*cap]
     unsigned long long *champ_scene = nullptr, *champ_self = nullptr;   // [cap]
     int* counts = nullptr;                // [3*n_keys + 16], layout in jg_kernels.cuh PassArgs
@@ -282,7 +283,7 @@ static void engine_release(jg_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaFree(e->d_robot); cudaFree(e->d_pieces); cudaFree(e->d_selfs); cudaFree(e->d_keys); cudaFree(e->d_verts);
-    cudaFree(e->q_r0); cudaFree(e->q_r1); cudaFree(e->q_r2); cudaFree(e->q_cfg); cudaFree(e->epa_slot); cudaFree(e->epa_ids); cudaFree(e->ovf_list); cudaFree(e->epa_prio); cudaFree(e->q_prio); cudaFree(e->bvh.nodes); cudaFree(e->bvh.tri_v); cudaFree(e->bvh.tri_id); cudaFree(e->d_err); cudaFree(e->act_list); cudaFree(e->champ_scene); cudaFree(e->champ_self); cudaFree(e->counts);
+    cudaFree(e->q_r0); cudaFree(e->q_r1); cudaFree(e->q_r2); cudaFree(e->q_cfg); cudaFree(e->epa_slot); cudaFree(e->epa_ids); cudaFree(e->ovf_list); cudaFree(e->epa_prio); cudaFree(e->q_prio); cudaFree(e->bvh.nodes); cudaFree(e->bvh.tri_v); cudaFree(e->bvh.tri_id); cudaFree(e->d_err); cudaFree(e->d_qrest); cudaFree(e->act_list); cudaFree(e->champ_scene); cudaFree(e->champ_self); cudaFree(e->counts);
     cudaFree(e->enc_scene); cudaFree(e->enc_self); cudaFree(e->viol); cudaFree(e->d_link_slot); cudaFree(e->d_rel);
     cudaFree(e->d_use_shapes); cudaFree(e->d_stats);
     for (int i = 0; i < 2; ++i) {
@@ -638,7 +639,7 @@ extern "C" jg_engine* jg_engine_create(const jg_robot* r, const jg_scene* sc, in
                cudaMalloc(&e->d_link_slot, sizeof(int) * MAX_LINKS) == cudaSuccess &&
                cudaMalloc(&e->d_rel, sizeof(Tf) * MAX_SHAPES) == cudaSuccess &&
                cudaMalloc(&e->d_use_shapes, sizeof(int) * MAX_SHAPES) == cudaSuccess &&
-               cudaMalloc(&e->d_stats, sizeof(unsigned long long) * 8) == cudaSuccess && cudaMalloc(&e->d_err, sizeof(int)) == cudaSuccess;
+               cudaMalloc(&e->d_stats, sizeof(unsigned long long) * 8) == cudaSuccess && cudaMalloc(&e->d_err, sizeof(int)) == cudaSuccess && cudaMalloc(&e->d_qrest, sizeof(float) * MAX_DOF) == cudaSuccess;
     if (!okm) {
         fail(JG_ERR_NOMEM, "scratch allocation failed (%zu queue entries): %s", qn, cudaGetErrorString(cudaGetLastError()));
         engine_release(e);
@@ -1098,5 +1099,29 @@ extern "C" int jg_measure_fp32_peak(int device, int reps, double* tflops) {
     }
     cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
     *tflops = best;
+    return JG_OK;
+}
+
+extern "C" int jg_ik(jg_engine* e, const float* targets, int64_t n, int ee_link, const float* q_init, const double* q_rest,
+                     int iters, float tol, float damping, float null_gain, int position_only, float* q_out, float* err_out,
+                     void* stream) {
+    if (!e) return fail(JG_ERR_INVALID, "jg_ik: engine is NULL");
+    if (n < 0 || n > 2000000000LL || (n && (!targets || !q_out || !err_out)) || !q_rest)
+        return fail(JG_ERR_INVALID, "jg_ik: NULL argument");
+    if (ee_link < 0 || ee_link >= e->L) return fail(JG_ERR_INVALID, "jg_ik: end-effector link %d out of range", ee_link);
+    if (iters < 0 || !(tol > 0.f) || !(damping > 0.f)) return fail(JG_ERR_INVALID, "jg_ik: bad iteration parameters");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(e->device));
+    float rest[MAX_DOF] = {0};
+    for (int j = 0; j < e->dof; ++j) rest[j] = (float)q_rest[j];
+    CUDA_TRY(cudaMemcpyAsync(e->d_qrest, rest, sizeof rest, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (n == 0) return JG_OK;
+    IkArgs a;
+    a.robot = e->d_robot; a.targets = targets; a.q_init = q_init; a.q_rest = e->d_qrest; a.n = (int)n; a.dof = e->dof;
+    a.ee_link = ee_link; a.iters = iters; a.pos_only = position_only ? 1 : 0; a.tol = tol; a.damping = damping; a.null_gain = null_gain;
+    a.finger_open = e->prm.finger_open; a.q_out = q_out; a.err_out = err_out;
+    k_ik<128><<<(int)((n + 127) / 128), 128, sizeof(RobotTab), st>>>(a);
+    CUDA_TRY(cudaGetLastError());
     return JG_OK;
 }

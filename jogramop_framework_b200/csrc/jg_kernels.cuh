@@ -984,3 +984,187 @@ __global__ void __launch_bounds__(BLOCK) k_fk(const RobotTab* __restrict__ robot
 }
 
 }  // namespace jg
+
+// ================================================================================================ inverse kinematics
+// "Next" row (f1): replaces pybullet.calculateInverseKinematics (simulation.py:251-310).  One thread per target pose of
+// the end-effector link: damped least squares on the geometric Jacobian with a null-space pull towards the rest
+// configuration (the reference passes lowerLimits / upperLimits / jointRanges / restPoses = home_conf), joint-limit
+// clamping, up to `iters` iterations (reference: 100) or until the residual drops below `tol` (reference: 1e-3).
+namespace jg {
+
+struct IkArgs {
+    const RobotTab* robot;
+    const float* targets;   // [n,12] pose of the end-effector link, robot base frame
+    const float* q_init;    // [n,dof] or NULL (rest pose)
+    const float* q_rest;    // [dof] device
+    int n, dof, ee_link, iters, pos_only;
+    float tol, damping, null_gain, finger_open;
+    float* q_out;           // [n,dof]
+    float* err_out;         // [n] position error [m] + orientation error [deg]/1000 (simulation.py:299-306)
+};
+
+// solve (M) y = b for a symmetric positive definite 6x6 (Cholesky, in place)
+__device__ __forceinline__ void spd6_factor(float (&M)[6][6]) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        float d = M[j][j];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) if (k < j) d -= M[j][k] * M[j][k];
+        d = sqrtf(fmaxf(d, 1e-20f));
+        M[j][j] = d;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) if (i > j) {
+            float v = M[i][j];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) if (k < j) v -= M[i][k] * M[j][k];
+            M[i][j] = v / d;
+        }
+    }
+}
+__device__ __forceinline__ void spd6_solve(const float (&L)[6][6], float (&b)[6]) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        float v = b[i];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) if (k < i) v -= L[i][k] * b[k];
+        b[i] = v / L[i][i];
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+        float v = b[i];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) if (k > i) v -= L[k][i] * b[k];
+        b[i] = v / L[i][i];
+    }
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_ik(const IkArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RobotTab* R = reinterpret_cast<RobotTab*>(smem_raw);
+    {
+        const int* src = reinterpret_cast<const int*>(a.robot);
+        int* dst = reinterpret_cast<int*>(R);
+        for (int i = threadIdx.x; i < (int)(sizeof(RobotTab) / 4); i += BLOCK) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int idx = blockIdx.x * BLOCK + threadIdx.x;
+    if (idx >= a.n) return;
+    const int dof = a.dof;
+    float q[MAX_DOF];
+    for (int j = 0; j < MAX_DOF; ++j) q[j] = j < dof ? (a.q_init ? a.q_init[(size_t)idx * dof + j] : a.q_rest[j]) : 0.f;
+    Tf Tt;
+    {
+        const float* t = a.targets + (size_t)idx * 12;
+        Tt.r00 = t[0]; Tt.r01 = t[1]; Tt.r02 = t[2]; Tt.tx = t[3];
+        Tt.r10 = t[4]; Tt.r11 = t[5]; Tt.r12 = t[6]; Tt.ty = t[7];
+        Tt.r20 = t[8]; Tt.r21 = t[9]; Tt.r22 = t[10]; Tt.tz = t[11];
+    }
+    float err = FLT_MAX;
+    for (int it = 0; it <= a.iters; ++it) {
+        // ---- FK with the world axis / origin of every driven joint
+        V3 jax[MAX_DOF], jor[MAX_DOF];
+        int jtype[MAX_DOF];
+        for (int j = 0; j < MAX_DOF; ++j) { jax[j] = mk(0.f, 0.f, 0.f); jor[j] = mk(0.f, 0.f, 0.f); jtype[j] = 0; }
+        Tf cur = tf_identity(), saved = tf_identity(), ee = tf_identity();
+        // which joints lie on the path to the end effector: all driven joints of the Panda do (serial arm)
+        for (int i = 0; i < R->L; ++i) {
+            const JointRec& J = R->joints[i];
+            float val = 0.f;
+            if (J.qidx >= 0) val = q[J.qidx];
+            else if (J.qidx == -2) val = a.finger_open;
+            const Tf par = J.parent_sel == 1 ? saved : (J.parent_sel == 2 ? tf_identity() : cur);
+            if (J.qidx >= 0) {
+                JointRec J0 = J;
+                J0.type = 0;
+                const Tf frame = tf_mul(par, joint_local(J0, 0.f));   // joint frame before its own motion
+                jax[J.qidx] = mk(fmaf(frame.r00, J.axis[0], fmaf(frame.r01, J.axis[1], frame.r02 * J.axis[2])),
+                                 fmaf(frame.r10, J.axis[0], fmaf(frame.r11, J.axis[1], frame.r12 * J.axis[2])),
+                                 fmaf(frame.r20, J.axis[0], fmaf(frame.r21, J.axis[1], frame.r22 * J.axis[2])));
+                jor[J.qidx] = mk(frame.tx, frame.ty, frame.tz);
+                jtype[J.qidx] = J.type;
+            }
+            cur = tf_mul(par, joint_local(J, val));
+            if (J.save) saved = cur;
+            if (i == a.ee_link) ee = cur;
+        }
+        // ---- task-space error: position + rotation vector of R_target * R_ee^T
+        float e6[6];
+        e6[0] = Tt.tx - ee.tx; e6[1] = Tt.ty - ee.ty; e6[2] = Tt.tz - ee.tz;
+        {
+            const float r00 = Tt.r00 * ee.r00 + Tt.r01 * ee.r01 + Tt.r02 * ee.r02, r01 = Tt.r00 * ee.r10 + Tt.r01 * ee.r11 + Tt.r02 * ee.r12,
+                        r02 = Tt.r00 * ee.r20 + Tt.r01 * ee.r21 + Tt.r02 * ee.r22;
+            const float r10 = Tt.r10 * ee.r00 + Tt.r11 * ee.r01 + Tt.r12 * ee.r02, r11 = Tt.r10 * ee.r10 + Tt.r11 * ee.r11 + Tt.r12 * ee.r12,
+                        r12 = Tt.r10 * ee.r20 + Tt.r11 * ee.r21 + Tt.r12 * ee.r22;
+            const float r20 = Tt.r20 * ee.r00 + Tt.r21 * ee.r01 + Tt.r22 * ee.r02, r21 = Tt.r20 * ee.r10 + Tt.r21 * ee.r11 + Tt.r22 * ee.r12,
+                        r22 = Tt.r20 * ee.r20 + Tt.r21 * ee.r21 + Tt.r22 * ee.r22;
+            const V3 sk = mk(0.5f * (r21 - r12), 0.5f * (r02 - r20), 0.5f * (r10 - r01));   // sin(angle) * axis
+            const float sn = sqrtf(norm2(sk)), cs = 0.5f * (r00 + r11 + r22 - 1.f);
+            const float ang = atan2f(sn, cs);
+            V3 w;
+            if (sn > 1e-6f) w = sk * (ang / sn);
+            else if (cs > 0.f) w = sk;                       // ~identity
+            else {                                           // ~pi: axis from the diagonal
+                const V3 ax = mk(sqrtf(fmaxf(0.5f * (r00 + 1.f), 0.f)), sqrtf(fmaxf(0.5f * (r11 + 1.f), 0.f)),
+                                 sqrtf(fmaxf(0.5f * (r22 + 1.f), 0.f)));
+                w = ax * ang;
+            }
+            e6[3] = w.x; e6[4] = w.y; e6[5] = w.z;
+            if (a.pos_only) { e6[3] = 0.f; e6[4] = 0.f; e6[5] = 0.f; }
+        }
+        const float perr = sqrtf(e6[0] * e6[0] + e6[1] * e6[1] + e6[2] * e6[2]);
+        const float aerr = sqrtf(e6[3] * e6[3] + e6[4] * e6[4] + e6[5] * e6[5]);
+        err = perr + aerr * (57.29577951f / 1000.f);
+        if (it == a.iters || (perr < a.tol && aerr < a.tol)) break;
+        // ---- Jacobian columns, (J J^T + lambda^2 I)
+        float Jc[MAX_DOF][6];
+        for (int j = 0; j < MAX_DOF; ++j) {
+            if (j < dof && jtype[j] == 1) {
+                const V3 lin = cross(jax[j], mk(ee.tx, ee.ty, ee.tz) - jor[j]);
+                Jc[j][0] = lin.x; Jc[j][1] = lin.y; Jc[j][2] = lin.z;
+                Jc[j][3] = a.pos_only ? 0.f : jax[j].x; Jc[j][4] = a.pos_only ? 0.f : jax[j].y; Jc[j][5] = a.pos_only ? 0.f : jax[j].z;
+            } else if (j < dof && jtype[j] == 2) {
+                Jc[j][0] = jax[j].x; Jc[j][1] = jax[j].y; Jc[j][2] = jax[j].z; Jc[j][3] = 0.f; Jc[j][4] = 0.f; Jc[j][5] = 0.f;
+            } else {
+                for (int r = 0; r < 6; ++r) Jc[j][r] = 0.f;
+            }
+        }
+        float M[6][6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                float v = r == c ? a.damping * a.damping : 0.f;
+                for (int j = 0; j < dof; ++j) v = fmaf(Jc[j][r], Jc[j][c], v);
+                M[r][c] = v;
+            }
+        spd6_factor(M);
+        // primary task
+        float y[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) y[r] = e6[r];
+        spd6_solve(M, y);
+        // null-space pull towards the rest configuration: z - J^T (J J^T + l^2 I)^-1 J z
+        float z[MAX_DOF], jz[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int j = 0; j < dof; ++j) {
+            z[j] = a.null_gain * (a.q_rest[j] - q[j]);
+#pragma unroll
+            for (int r = 0; r < 6; ++r) jz[r] = fmaf(Jc[j][r], z[j], jz[r]);
+        }
+        spd6_solve(M, jz);
+        float dq[MAX_DOF], big = 0.f;
+        for (int j = 0; j < dof; ++j) {
+            float v = z[j];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) v += Jc[j][r] * (y[r] - jz[r]);
+            dq[j] = v;
+            big = fmaxf(big, fabsf(v));
+        }
+        const float scale = big > 0.3f ? 0.3f / big : 1.f;   // trust region: at most 0.3 rad / 0.3 m per iteration
+        for (int j = 0; j < dof; ++j) q[j] = fminf(fmaxf(fmaf(scale, dq[j], q[j]), R->qlo[j]), R->qhi[j]);
+    }
+    for (int j = 0; j < dof; ++j) a.q_out[(size_t)idx * dof + j] = q[j];
+    a.err_out[idx] = err;
+}
+
+}  // namespace jg

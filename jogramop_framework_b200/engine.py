@@ -199,6 +199,30 @@ class CollisionEngine:
                    'jg_check_host')
         return out['bits'], out.get('dist'), out.get('reason')
 
+    def ik(self, targets, q_rest, q_init=None, ee_link=None, iters=100, tol=1e-3, damping=0.05, null_gain=0.05,
+           position_only=False):
+        """Batched damped-least-squares IK.  targets: [n,4,4] / [n,3,4] poses of `ee_link` in the robot frame.
+        -> (q [n,dof], err [n] = position error + deg/1000) as device tensors."""
+        if isinstance(targets, torch.Tensor):
+            t = targets
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(targets, dtype=np.float32))
+        t = t.to(device=self.device, dtype=torch.float32).reshape(-1, t.shape[-2], 4)[:, :3, :].contiguous()
+        n = t.shape[0]
+        qi = self._dev_f32(q_init, self.dof) if q_init is not None else None
+        if qi is not None:
+            assert qi.shape[0] == n, 'q_init must hold one start configuration per target'
+        rest = _f64(q_rest)
+        assert len(rest) == self.dof
+        q = torch.empty((n, self.dof), device=self.device, dtype=torch.float32)
+        err = torch.empty((n,), device=self.device, dtype=torch.float32)
+        ee = self.robot.end_effector_id if ee_link is None else ee_link
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.jg_ik(self._e, t.data_ptr(), n, ee, qi.data_ptr() if qi is not None else None, _p(rest),
+                                     int(iters), float(tol), float(damping), float(null_gain), 1 if position_only else 0,
+                                     q.data_ptr(), err.data_ptr(), self._stream()), 'jg_ik')
+        return q, err
+
     def stats(self):
         st = _lib.Stats()
         _lib.check(self._L.jg_get_stats(self._e, C.byref(st)), 'jg_get_stats')

@@ -133,25 +133,60 @@ class Scenario:
         return candidates[reason == 0], reason, count
 
     def get_ik_solutions(self):
-        """scenario.py:82-129.  Needs ``FrankaRobot.inverse_kinematics`` (the first "next" row); the
-        collision filter that follows the IK is available as ``filter_configurations``."""
+        """scenario.py:82-129: IK for every grasp (null-space control, accepted when position error + deg/1000 <=
+        0.015), then joint limits, self-collision and scene collision.  Same loop structure, state handling (the IK of
+        grasp g starts from the configuration the previous grasp left the robot in) and counters as the reference."""
         robot, sim = self.get_robot_and_sim()
+        joint_limits = robot.arm_joint_limits()
+
+        def in_joint_limits(joint_conf):
+            return np.all(joint_limits[:, 0] <= joint_conf) and np.all(joint_conf <= joint_limits[:, 1])
+
         ik_solutions = []
         count = util.Timer()
         print('calculating IK solutions for all grasps')
-        candidates = []
         for g in range(len(self.gs)):
             count.start('calculate IK')
             pos, orn = util.position_and_quaternion_from_tf(self.gs.poses[g], convention='pybullet')
             target_conf = robot.inverse_kinematics(pos, orn, null_space_control=True)
             count.stop('calculate IK')
+            count.start('perform checks')
             if target_conf is not None:
-                candidates.append(target_conf)
+                robot.reset_arm_joints(target_conf)
+                if not in_joint_limits(target_conf):
+                    target_conf = None
+                    count.count('IK solution not in joint limits')
+                elif robot.in_self_collision():
+                    target_conf = None
+                    count.count('IK solution in self-collision')
+                elif robot.in_collision():
+                    target_conf = None
+                    count.count('IK solution in collision')
+                else:
+                    count.count('IK solution is OK')
             else:
                 count.count('IK solution too far away from goal')
-        if candidates:
-            ik_solutions, _, c2 = self.filter_configurations(np.asarray(candidates), robot)
-            count.timers.update(c2.timers)
-            count.counters.update(c2.counters)
+            count.stop('perform checks')
+            if target_conf is not None:
+                ik_solutions.append(target_conf)
         count.print()
         return np.array(ik_solutions)
+
+    def get_ik_solutions_batch(self, restarts=8, seed=0):
+        """Batched variant: all grasps (x ``restarts`` start configurations: home + uniform samples) go through ONE IK
+        launch and ONE filter launch.  Returns (accepted [m,dof], grasp index of each accepted row)."""
+        robot, sim = self.get_robot_and_sim()
+        n = len(self.gs)
+        lim = robot.arm_joint_limits()
+        rng = np.random.default_rng(seed)
+        starts = [np.tile(np.asarray(robot.home_conf), (n, 1))]
+        for _ in range(restarts - 1):
+            starts.append(lim[:, 0] + (lim[:, 1] - lim[:, 0]) * rng.random((n, len(lim))))
+        q0 = np.concatenate(starts).astype(np.float32)
+        poses = np.tile(self.gs.poses, (restarts, 1, 1))
+        q, err = robot.inverse_kinematics_batch(poses, q_init=q0)
+        q, err = q.cpu().numpy().astype(np.float64), err.cpu().numpy()
+        _, _, reason = robot.check_batch(q.astype(np.float32), want_dist=False)
+        ok = (err <= 0.015) & (reason.cpu().numpy() == 0)
+        idx = np.nonzero(ok)[0]
+        return q[idx], idx % n

@@ -338,9 +338,32 @@ class FrankaRobot:
                                              as_matrix=True)[0].cpu().numpy().astype(np.float64)
 
     def inverse_kinematics(self, pos, orn=None, combined_threshold=0.015, null_space_control=False):
-        raise NotImplementedError(
-            'inverse kinematics (pybullet.calculateInverseKinematics, simulation.py:251-310) is the first "next" row '
-            'of the scope table (SURVEY.md §8f) and is not part of this build yet')
+        """``simulation.py:251-310``: IK for the end effector at world position ``pos`` (and orientation ``orn``,
+        quaternion xyzw); returns the arm configuration or None when the reached pose is farther than
+        ``combined_threshold`` (position [m] + angle [deg]/1000) from the request.
+
+        Replaces pybullet.calculateInverseKinematics (100 iterations, residual 1e-3; with ``null_space_control`` the
+        limits / ranges / rest pose = home_conf) by the engine's batched damped-least-squares kernel, started -- like
+        pyBullet -- from the robot's current joint state.  pyBullet's IK is not bit-reproducible; only the acceptance
+        criterion is the same.  Like the reference, the call leaves the robot at the returned configuration."""
+        q, err = self.inverse_kinematics_batch(
+            util.tf_from_pos_quat(pos, orn)[None], q_init=np.asarray(self._q, dtype=np.float32)[None],
+            null_space_control=null_space_control, position_only=orn is None)
+        q = q[0].cpu().numpy().astype(np.float64)
+        self.reset_arm_joints(q)
+        if float(err[0]) <= combined_threshold:
+            return q
+        return None
+
+    def inverse_kinematics_batch(self, poses, q_init=None, null_space_control=True, position_only=False, iters=100,
+                                 tol=1e-3):
+        """Batched IK: ``poses`` [n,4,4] end-effector targets in the WORLD frame; ``q_init`` [n,dof] start
+        configurations (default: home_conf).  -> (q [n,dof], err [n]) device tensors; a solution is acceptable in the
+        reference's sense when err <= 0.015."""
+        T = np.linalg.inv(self.pose) @ np.asarray(poses, dtype=np.float64).reshape(-1, 4, 4)
+        return self._simulator._engine('full').ik(T.astype(np.float32), q_rest=self.home_conf, q_init=q_init, iters=iters,
+                                                  tol=tol, null_gain=0.05 if null_space_control else 0.0,
+                                                  position_only=position_only)
 
     # ------------------------------------------------------------------ collision (single shot, stateful)
     def in_self_collision(self):
