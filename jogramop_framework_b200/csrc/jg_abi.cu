@@ -201,6 +201,7 @@ struct jg_engine {
     float mesh_margin = 0.f;
     Lbvh bvh;
     int* d_err = nullptr;
+    int mesh_pass = 0;                   // configurations per pass in mesh mode (adaptive)
     float* d_qrest = nullptr;
     int* act_list = nullptr;              // [n_keys*cap]
     unsigned long long *champ_scene = nullptr, *champ_self = nullptr;   // [cap]
@@ -760,9 +761,11 @@ extern "C" int jg_check(jg_engine* e, const float* q, int64_t n, int dof, uint32
     int rc = begin_call(e, st);
     if (rc) return rc;
     e->stats.configs = n;
-    // mesh mode: a configuration may queue many triangles per link, so a pass takes fewer configurations
-    const int64_t pass = e->mesh ? std::max(1024, e->cap / 32 / 1024 * 1024) : e->cap;
-    for (int64_t off = 0; off < n; off += pass) {
+    // mesh mode: a configuration may queue many triangles per link, so a pass takes fewer configurations; the pass
+    // size adapts: an overflowing pass is redone at half the size (the engine remembers what worked)
+    if (e->mesh && e->mesh_pass <= 0) e->mesh_pass = std::max(1024, e->cap / 4 / 1024 * 1024);
+    for (int64_t off = 0; off < n;) {
+        const int64_t pass = e->mesh ? e->mesh_pass : e->cap;
         const int m = (int)std::min<int64_t>(pass, n - off);
         PassArgs a;
         fill_args(e, a, flags);
@@ -772,19 +775,25 @@ extern "C" int jg_check(jg_engine* e, const float* q, int64_t n, int dof, uint32
         prof_begin(e, 0, st);
         k_broadphase<BP_BLOCK><<<(m + BP_BLOCK - 1) / BP_BLOCK, BP_BLOCK, bp_smem(e, flags), st>>>(a);
         e->stats.kernel_launches += 1;
+        if (e->mesh) {   // secondary path: check the queue-overflow flag synchronously before going on
+            int err = 0;
+            prof_end(e, st);
+            CUDA_TRY(cudaMemcpyAsync(&err, e->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            if (err) {
+                CUDA_TRY(cudaMemsetAsync(e->d_err, 0, sizeof(int), st));
+                if (e->mesh_pass <= 1024)
+                    return fail(JG_ERR_NOMEM, "mesh mode: a triangle candidate queue overflowed even at 1024 configurations per pass "
+                                "(%d entries per link); create the engine with a larger `chunk`", e->cap);
+                e->mesh_pass = std::max(1024, e->mesh_pass / 2 / 1024 * 1024);
+                continue;   // redo this pass at the smaller size
+            }
+            prof_begin(e, 0, st);
+        }
         rc = run_narrow_and_finalize(e, a, m, flags, bits + off / 32, min_dist ? min_dist + off : nullptr,
                                      reason ? reason + off : nullptr, st);
         if (rc) return rc;
-    }
-    if (e->mesh) {   // secondary path: check the queue-overflow flag synchronously
-        int err = 0;
-        CUDA_TRY(cudaMemcpyAsync(&err, e->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-        if (err) {
-            cudaMemset(e->d_err, 0, sizeof(int));
-            return fail(JG_ERR_NOMEM, "mesh mode: a triangle candidate queue overflowed (more than %d candidates per link and pass); "
-                        "create the engine with a larger `chunk`", e->cap);
-        }
+        off += m;
     }
     return JG_OK;
 }
