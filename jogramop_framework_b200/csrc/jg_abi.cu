@@ -201,7 +201,8 @@ struct jg_engine {
     float mesh_margin = 0.f;
     Lbvh bvh;
     int* d_err = nullptr;
-    int mesh_pass = 0;                   // configurations per pass in mesh mode (adaptive)
+    int mesh_pass = 0;
+    int n_stash = 0;                     // link frames the broad phase stashes for the self pairs                   // configurations per pass in mesh mode (adaptive)
     float* d_qrest = nullptr;
     int* act_list = nullptr;              // [n_keys*cap]
     unsigned long long *champ_scene = nullptr, *champ_self = nullptr;   // [cap]
@@ -453,24 +454,36 @@ static int build_tables(jg_engine* e, const jg_robot* r, const jg_scene* sc) {
                               {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}});
     }
     e->n_scene_keys = (int)keys.size();
+    // self pairs sorted by their second link: the broad phase tests (la, lb) when the chain reaches lb, with la's frame
+    // taken from a shared-memory stash (only the pairs' first links are stashed)
     std::vector<SelfRec> selfs;
-    for (int k = 0; k < r->K; ++k) {
+    std::vector<int> order(r->K);
+    for (int k = 0; k < r->K; ++k) order[k] = k;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return r->self_pairs[2 * x + 1] < r->self_pairs[2 * y + 1]; });
+    for (int i = 0; i < r->L; ++i) { R.joints[i].self_first = 0; R.joints[i].self_count = 0; R.joints[i].stash_slot = -1; }
+    R.n_stash = 0;
+    for (int kk = 0; kk < r->K; ++kk) {
+        const int k = order[kk];
         const int la = r->self_pairs[2 * k], lb = r->self_pairs[2 * k + 1];
-        if (la < 0 || lb < 0 || la >= r->L || lb >= r->L)
-            return fail(JG_ERR_INVALID, "self pair %d: link ids (%d,%d) out of range (base link pairs unsupported)", k, la, lb);
+        if (la < 0 || lb < 0 || la >= r->L || lb >= r->L || la >= lb)
+            return fail(JG_ERR_INVALID, "self pair %d: link ids (%d,%d) must satisfy 0 <= first < second < %d", k, la, lb, r->L);
         const int sa = e->link_first_shape[la + 1], sb = e->link_first_shape[lb + 1];
         if (sa < 0 || sb < 0) return fail(JG_ERR_INVALID, "self pair %d: link without collision shape", k);
+        if (R.joints[la].stash_slot < 0) R.joints[la].stash_slot = R.n_stash++;
+        if (R.joints[lb].self_count == 0) R.joints[lb].self_first = (int)selfs.size();
+        R.joints[lb].self_count++;
         selfs.push_back(SelfRec{sa, sb, la, lb});
         KeyRec kr{R.shapes[sb].voff, R.shapes[sb].vn, R.shapes[sa].voff, R.shapes[sa].vn,
-                 R.shapes[sa].margin + R.shapes[sb].margin, KEY_SELF, R.shapes[sb].poff, R.shapes[sb].pn,
-                 R.shapes[sa].poff, R.shapes[sa].pn, R.shapes[sa].plane_margin + R.shapes[sb].plane_margin, 0,
-                 {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+                  R.shapes[sa].margin + R.shapes[sb].margin, KEY_SELF, R.shapes[sb].poff, R.shapes[sb].pn,
+                  R.shapes[sa].poff, R.shapes[sa].pn, R.shapes[sa].plane_margin + R.shapes[sb].plane_margin, 0,
+                  {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
         for (int c = 0; c < 3; ++c) {
             kr.a_c[c] = epa_box_c[sb][c]; kr.a_h[c] = epa_box_h[sb][c];
             kr.b_c[c] = epa_box_c[sa][c]; kr.b_h[c] = epa_box_h[sa][c];
         }
         keys.push_back(kr);
     }
+    e->n_stash = R.n_stash;
     e->n_keys = (int)keys.size();
     e->n_verts = (int)verts.size();
     for (const KeyRec& k : keys) e->max_msum = std::max(e->max_msum, k.msum);
@@ -547,7 +560,7 @@ constexpr int EPA_BIG_BLOCK = 512;  // overflow pass of the penetration depth: o
 
 static size_t bp_smem(const jg_engine* e, uint32_t flags) {
     size_t s = sizeof(RobotTab) + sizeof(PieceRec) * e->P + sizeof(float) * BP_BLOCK * e->dof;
-    if (flags & JG_SELF) s += sizeof(float) * 12 * e->L * BP_BLOCK;
+    if (flags & JG_SELF) s += sizeof(float) * 12 * e->n_stash * BP_BLOCK;
     return s;
 }
 
@@ -654,10 +667,15 @@ extern "C" void jg_engine_free(jg_engine* e) { engine_release(e); }
 extern "C" int jg_engine_device(const jg_engine* e) { return e ? e->device : JG_ERR_INVALID; }
 
 // ----------------------------------------------------------------------------------------------- passes
-static void fill_args(const jg_engine* e, PassArgs& a, uint32_t flags) {
+// want_dist = false: the caller only wants verdict bits.  The verdict is "some contact distance < threshold", so the
+// query distance shrinks to the threshold itself (pairs farther apart cannot change a bit: the broad phase drops
+// them and GJK stops as soon as a separating axis proves it) and penetration depth is never needed.  Same bits.
+static void fill_args(const jg_engine* e, PassArgs& a, uint32_t& flags, bool want_dist = true) {
     memset(&a, 0, sizeof a);
+    if (!want_dist) flags |= JG_NO_EPA;
     a.dof = e->dof; a.substeps = 1; a.flags = flags;
-    a.finger_open = e->prm.finger_open; a.qd = e->prm.query_distance; a.threshold = e->prm.threshold;
+    a.finger_open = e->prm.finger_open; a.threshold = e->prm.threshold;
+    a.qd = want_dist ? e->prm.query_distance : std::min(e->prm.query_distance, e->prm.threshold + 1e-6f);
     for (int k = 0; k < 4; ++k) a.plane[k] = e->plane[k];
     a.has_plane = e->has_plane ? 1 : 0;
     a.robot = e->d_robot; a.pieces = e->d_pieces; a.P = e->P; a.selfs = e->d_selfs; a.keys = e->d_keys;
@@ -768,7 +786,7 @@ extern "C" int jg_check(jg_engine* e, const float* q, int64_t n, int dof, uint32
         const int64_t pass = e->mesh ? e->mesh_pass : e->cap;
         const int m = (int)std::min<int64_t>(pass, n - off);
         PassArgs a;
-        fill_args(e, a, flags);
+        fill_args(e, a, flags, min_dist != nullptr);
         a.q = q + off * dof; a.n = m;
         CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * (4 * e->n_keys + 8), st));
         if (flags & JG_LIMITS) CUDA_TRY(cudaMemsetAsync(e->viol, 0, sizeof(uint32_t) * (e->cap / 32 + 1), st));
@@ -813,7 +831,7 @@ extern "C" int jg_check_edges(jg_engine* e, const float* qa, const float* qb, in
     for (int64_t off = 0; off < m; off += edges_per_pass) {
         const int me = (int)std::min<int64_t>(edges_per_pass, m - off);
         PassArgs a;
-        fill_args(e, a, flags);
+        fill_args(e, a, flags, min_dist != nullptr);
         a.q = qa + off * dof; a.qb = qb + off * dof; a.n = me * substeps; a.substeps = substeps;
         CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * (4 * e->n_keys + 8), st));
         if (flags & JG_LIMITS) CUDA_TRY(cudaMemsetAsync(e->viol, 0, sizeof(uint32_t) * (e->cap / 32 + 1), st));
@@ -901,7 +919,7 @@ extern "C" int jg_check_poses(jg_engine* e, const float* poses, int64_t n, int f
     for (int64_t off = 0; off < n; off += e->cap) {
         const int m = (int)std::min<int64_t>(e->cap, n - off);
         PassArgs a;
-        fill_args(e, a, flags);
+        fill_args(e, a, flags, min_dist != nullptr);
         a.n = m;
         CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * (4 * e->n_keys + 8), st));
         const size_t smem = sizeof(RobotTab) + sizeof(PieceRec) * e->P;

@@ -28,7 +28,8 @@ struct JointRec {
     int parent_sel;   // 0 previous link, 1 saved link, 2 base
     int save;         // keep this link's transform for later children
     int shape_first, shape_count;
-    int pad[3];
+    int self_first, self_count;   // self-collision pairs whose SECOND link is this one (sorted by second link)
+    int stash_slot;               // >= 0: this link is the first link of some pair: keep its frame in shared memory
 };
 
 struct ShapeRec {
@@ -41,7 +42,7 @@ struct ShapeRec {
 };
 
 struct RobotTab {
-    int L, S, dof, base_shape_first, base_shape_count, n_self, pad0, pad1;
+    int L, S, dof, base_shape_first, base_shape_count, n_self, n_stash, pad1;
     float qlo[MAX_DOF], qhi[MAX_DOF];
     JointRec joints[MAX_LINKS];
     ShapeRec shapes[MAX_SHAPES];
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(BLOCK) k_broadphase(const PassArgs a) {
     RobotTab* R = reinterpret_cast<RobotTab*>(smem_raw);
     PieceRec* pieces = reinterpret_cast<PieceRec*>(smem_raw + sizeof(RobotTab));
     float* qs = reinterpret_cast<float*>(smem_raw + sizeof(RobotTab) + sizeof(PieceRec) * a.P);
-    float* stash = qs + BLOCK * a.dof;   // [L][12][BLOCK], only with JG_SELF
+    float* stash = qs + BLOCK * a.dof;   // [n_stash][12][BLOCK], only with JG_SELF: frames of the pairs' first links
     const int tid = threadIdx.x;
     {
         const int* src = reinterpret_cast<const int*>(a.robot);
@@ -329,38 +330,32 @@ __global__ void __launch_bounds__(BLOCK) k_broadphase(const PassArgs a) {
         else cur = tf_mul(cur, loc);
         if (J.save) saved = cur;
         if (want_self) {
-            float* st = stash + (size_t)i * 12 * BLOCK + tid;
-            st[0 * BLOCK] = cur.r00; st[1 * BLOCK] = cur.r01; st[2 * BLOCK] = cur.r02;  st[3 * BLOCK] = cur.tx;
-            st[4 * BLOCK] = cur.r10; st[5 * BLOCK] = cur.r11; st[6 * BLOCK] = cur.r12;  st[7 * BLOCK] = cur.ty;
-            st[8 * BLOCK] = cur.r20; st[9 * BLOCK] = cur.r21; st[10 * BLOCK] = cur.r22; st[11 * BLOCK] = cur.tz;
+            // pairs (la, i): la's frame was stashed when the chain passed it; the pair is tested in la's frame
+            for (int k = J.self_first; k < J.self_first + J.self_count; ++k) {
+                const SelfRec sr = a.selfs[k];
+                const float* st = stash + (size_t)R->joints[sr.la].stash_slot * 12 * BLOCK + tid;
+                Tf Ta;
+                Ta.r00 = st[0 * BLOCK]; Ta.r01 = st[1 * BLOCK]; Ta.r02 = st[2 * BLOCK];  Ta.tx = st[3 * BLOCK];
+                Ta.r10 = st[4 * BLOCK]; Ta.r11 = st[5 * BLOCK]; Ta.r12 = st[6 * BLOCK];  Ta.ty = st[7 * BLOCK];
+                Ta.r20 = st[8 * BLOCK]; Ta.r21 = st[9 * BLOCK]; Ta.r22 = st[10 * BLOCK]; Ta.tz = st[11 * BLOCK];
+                const Tf rel = tf_inv_mul(Ta, cur);   // shape of link i expressed in the frame of link la
+                const ShapeRec& Sa = R->shapes[sr.sa];
+                const ShapeRec& Sb = R->shapes[sr.sb];
+                const float msum = Sa.margin + Sb.margin;
+                const float ov = aabb_overlap(rel, Sb.c, Sb.h, Sa.c, Sa.h);
+                const bool hit = valid && ov + a.qd + msum >= 0.f;
+                queue_push(a, hit, a.n_scene_keys + k, rel, out_idx, prio_of(ov, msum), a.champ_self);
+            }
+            if (J.stash_slot >= 0) {
+                float* st = stash + (size_t)J.stash_slot * 12 * BLOCK + tid;
+                st[0 * BLOCK] = cur.r00; st[1 * BLOCK] = cur.r01; st[2 * BLOCK] = cur.r02;  st[3 * BLOCK] = cur.tx;
+                st[4 * BLOCK] = cur.r10; st[5 * BLOCK] = cur.r11; st[6 * BLOCK] = cur.r12;  st[7 * BLOCK] = cur.ty;
+                st[8 * BLOCK] = cur.r20; st[9 * BLOCK] = cur.r21; st[10 * BLOCK] = cur.r22; st[11 * BLOCK] = cur.tz;
+            }
         }
         if (want_scene)
             for (int s = J.shape_first; s < J.shape_first + J.shape_count; ++s)
                 shape_vs_scene(a, R->shapes[s], s, pieces, cur, valid, out_idx);
-    }
-
-    if (want_self) {
-        for (int k = 0; k < R->n_self; ++k) {
-            const SelfRec sr = a.selfs[k];
-            Tf Ta, Tb;
-            {
-                const float* st = stash + (size_t)sr.la * 12 * BLOCK + tid;
-                Ta.r00 = st[0 * BLOCK]; Ta.r01 = st[1 * BLOCK]; Ta.r02 = st[2 * BLOCK];  Ta.tx = st[3 * BLOCK];
-                Ta.r10 = st[4 * BLOCK]; Ta.r11 = st[5 * BLOCK]; Ta.r12 = st[6 * BLOCK];  Ta.ty = st[7 * BLOCK];
-                Ta.r20 = st[8 * BLOCK]; Ta.r21 = st[9 * BLOCK]; Ta.r22 = st[10 * BLOCK]; Ta.tz = st[11 * BLOCK];
-                st = stash + (size_t)sr.lb * 12 * BLOCK + tid;
-                Tb.r00 = st[0 * BLOCK]; Tb.r01 = st[1 * BLOCK]; Tb.r02 = st[2 * BLOCK];  Tb.tx = st[3 * BLOCK];
-                Tb.r10 = st[4 * BLOCK]; Tb.r11 = st[5 * BLOCK]; Tb.r12 = st[6 * BLOCK];  Tb.ty = st[7 * BLOCK];
-                Tb.r20 = st[8 * BLOCK]; Tb.r21 = st[9 * BLOCK]; Tb.r22 = st[10 * BLOCK]; Tb.tz = st[11 * BLOCK];
-            }
-            const Tf rel = tf_inv_mul(Ta, Tb);   // shape of link lb expressed in the frame of link la
-            const ShapeRec& Sa = R->shapes[sr.sa];
-            const ShapeRec& Sb = R->shapes[sr.sb];
-            const float msum = Sa.margin + Sb.margin;
-            const float ov = aabb_overlap(rel, Sb.c, Sb.h, Sa.c, Sa.h);
-            const bool hit = valid && ov + a.qd + msum >= 0.f;
-            queue_push(a, hit, a.n_scene_keys + k, rel, out_idx, prio_of(ov, msum), a.champ_self);
-        }
     }
 }
 

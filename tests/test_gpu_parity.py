@@ -118,6 +118,24 @@ def test_mesh_mode_lbvh_parity(sid, robot, scene_loader):
     e.close()
 
 
+def test_verdict_only_mode_gives_the_same_bits(robot, scene_loader, engines):
+    """min_dist == NULL: the engine only proves / disproves 'some contact distance < threshold'.  Bits must be
+    identical to the full query's bits (same fp32 arithmetic up to early exits), reasons outside the band too."""
+    e = engines(11)
+    q = uniform_configs(robot, 200000, 23)
+    for fl in (3, 15, 4):
+        b_full, d_full, r_full = e.check(q, flags=fl, want_reason=True)
+        b_fast, d_none, r_fast = e.check(q, flags=fl, want_dist=False, want_reason=True)
+        assert d_none is None
+        clear = (d_full + 0.001).abs() > 1e-5
+        assert torch.equal(b_full[clear], b_fast[clear])
+        assert (b_full != b_fast).sum().item() <= 3
+        assert (r_full[clear] == r_fast[clear]).float().mean().item() > 0.9999
+    be, _ = e.check_edges(q[:2000], q[2000:4000], substeps=16, want_dist=False)
+    bf, df = e.check_edges(q[:2000], q[2000:4000], substeps=16)
+    assert (be != bf).sum().item() <= 1
+
+
 def test_scene_only_and_plane_only(robot, scene_loader, engines):
     e = engines(11)
     o = Oracle(robot, scene_loader(11))

@@ -55,10 +55,15 @@ def main():
             ms = timed(lambda: eng.check(q, flags=SCENE | PLANE | SELF | LIMITS, packed=True, want_reason=True))
             print(json.dumps({'config': 'filter (limits+self+scene)', 'scenario': sid, 'n': n, 'ms': ms,
                               'checks_per_s': n / ms * 1e3}), flush=True)
-            ms = timed(lambda: eng.check(q, flags=SCENE | PLANE, packed=True, want_dist=False) if False else
-                       eng.check(q, flags=SCENE | PLANE | 16, packed=True))
+            ms = timed(lambda: eng.check(q, flags=SCENE | PLANE | 16, packed=True))
             print(json.dumps({'config': 'verdict + clearance only (JG_NO_EPA)', 'scenario': sid, 'n': n, 'ms': ms,
                               'checks_per_s': n / ms * 1e3}), flush=True)
+            ms = timed(lambda: eng.check(q, flags=SCENE | PLANE, packed=True, want_dist=False))
+            print(json.dumps({'config': 'verdict bits only (min_dist = NULL)', 'scenario': sid, 'n': n, 'ms': ms,
+                              'checks_per_s': n / ms * 1e3}), flush=True)
+            ms = timed(lambda: eng.check(q, flags=SCENE | PLANE | SELF | LIMITS, packed=True, want_dist=False, want_reason=True))
+            print(json.dumps({'config': 'filter (limits+self+scene), verdict bits + reason only', 'scenario': sid, 'n': n,
+                              'ms': ms, 'checks_per_s': n / ms * 1e3}), flush=True)
             # config 5: free-floating gripper poses
             m = 10_000_000
             rng = np.random.default_rng(5000 + sid)
