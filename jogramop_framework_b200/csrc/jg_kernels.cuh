@@ -213,7 +213,7 @@ __device__ __forceinline__ void shape_vs_scene(const PassArgs& a, const ShapeRec
         const int key = s * (a.P + 1);
         const int lane = threadIdx.x & 31;
         if (valid)
-            lbvh_traverse(a.bvh_nodes, a.bvh_tri, a.bvh_n, qlo, qhi, [&](int tri) {
+            lbvh_traverse(a.bvh_nodes, a.bvh_tri, a.bvh_n, qlo, qhi, [&](int tri, float ov_infl) {
                 const unsigned m = __activemask();
                 const int leader = __ffs(m) - 1;
                 int base = 0;
@@ -227,6 +227,11 @@ __device__ __forceinline__ void shape_vs_scene(const PassArgs& a, const ShapeRec
                     a.q_r2[slot] = make_float4(T.r20, T.r21, T.r22, T.tz);
                     a.q_cfg[slot] = out_idx;
                     a.q_tri[slot] = tri;
+                    // bound for the champion-first staging: a triangle pair never reports less than -(margins), so
+                    // the bound only ranks the candidates (largest box overlap first); ov_infl includes the inflation
+                    const float prio = prio_of(ov_infl - infl, Sh.margin + a.mesh_margin);
+                    a.q_prio[slot] = prio;
+                    atomicMax(a.champ_scene + out_idx, ((unsigned long long)__float_as_uint(prio) << 32) | (unsigned)((key << 20) | idx));
                 } else {
                     *a.err_flag = 1;
                 }
@@ -625,8 +630,15 @@ __global__ void __launch_bounds__(BLOCK) k_select(const PassArgs a, int mode) {
             const int j = j0 + lane;
             bool sel = false;
             if (j < end) {
-                if (kind == KEY_PLANE || kind == KEY_MESH) {
+                if (kind == KEY_PLANE) {
                     sel = mode == SEL_GJK_CHAMP;
+                } else if (kind == KEY_MESH) {
+                    // a triangle pair reports at least -(margins): once the configuration is known to be that deep
+                    // (by another triangle or by the plane) no other triangle can lower its minimum
+                    const int cfg = a.q_cfg[kbase + j];
+                    const bool is_champ = (unsigned)(champ[cfg] & 0xFFFFFFFFull) == (unsigned)((key << 20) | j);
+                    if (mode == SEL_GJK_CHAMP) sel = is_champ;
+                    else if (mode == SEL_GJK_REST) sel = !is_champ && -dec_float(enc[cfg]) < a.keys[key].msum - 1e-6f;
                 } else {
                     const int slot = epa ? a.epa_slot[kbase + j] : j;
                     const int cfg = a.q_cfg[kbase + slot];

@@ -124,23 +124,26 @@ __global__ void k_lbvh_refit(const float4* __restrict__ tri_v, int n, BvhNode* _
     }
 }
 
-// Calls f(slot) for every triangle whose box overlaps [qlo, qhi].  Per-thread stack; depth of a 30-bit Morton tree
+// Calls f(slot, overlap) for every triangle whose box overlaps [qlo, qhi].  Per-thread stack; depth of a 30-bit Morton tree
 // with index tie-break is bounded by 64.
 template <class F>
 __device__ __forceinline__ void lbvh_traverse(const BvhNode* __restrict__ nodes, const float4* __restrict__ tri_v, int n,
                                               const float* qlo, const float* qhi, F f) {
     if (n <= 0) return;
-    auto tri_hits = [&](int slot) {
+    // leaf test; on a hit f(slot, ov) gets the smallest signed axis overlap of the query box and the triangle's box
+    auto leaf = [&](int slot) {
         float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
         for (int k = 0; k < 3; ++k) {
             const float4 p = tri_v[3 * slot + k];
             lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
             hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
         }
-        return lo[0] <= qhi[0] && hi[0] >= qlo[0] && lo[1] <= qhi[1] && hi[1] >= qlo[1] && lo[2] <= qhi[2] && hi[2] >= qlo[2];
+        const float ov = fminf(fminf(fminf(qhi[0], hi[0]) - fmaxf(qlo[0], lo[0]), fminf(qhi[1], hi[1]) - fmaxf(qlo[1], lo[1])),
+                               fminf(qhi[2], hi[2]) - fmaxf(qlo[2], lo[2]));
+        if (ov >= 0.f) f(slot, ov);
     };
     if (n == 1) {
-        if (tri_hits(0)) f(0);
+        leaf(0);
         return;
     }
     int stack[64];
@@ -151,8 +154,8 @@ __device__ __forceinline__ void lbvh_traverse(const BvhNode* __restrict__ nodes,
         if (!(N.lo[0] <= qhi[0] && N.hi[0] >= qlo[0] && N.lo[1] <= qhi[1] && N.hi[1] >= qlo[1] && N.lo[2] <= qhi[2] &&
               N.hi[2] >= qlo[2]))
             continue;
-        if (N.left < 0) { if (tri_hits(~N.left)) f(~N.left); } else if (sp < 64) stack[sp++] = N.left;
-        if (N.right < 0) { if (tri_hits(~N.right)) f(~N.right); } else if (sp < 64) stack[sp++] = N.right;
+        if (N.left < 0) leaf(~N.left); else if (sp < 64) stack[sp++] = N.left;
+        if (N.right < 0) leaf(~N.right); else if (sp < 64) stack[sp++] = N.right;
     }
 }
 
