@@ -136,6 +136,84 @@ def test_verdict_only_mode_gives_the_same_bits(robot, scene_loader, engines):
     assert (be != bf).sum().item() <= 1
 
 
+def test_fixed_base_panda_without_platform(scene_loader):
+    """panda.urdf (with_platform=False, simulation.py:136-139,161-164,453-455): 7 dof, a collision shape on the BASE
+    link (index -1), 25 self pairs, end effector = link 11."""
+    import os
+    from conftest import ROOT
+    from jogramop_framework_b200.engine import CollisionEngine
+    from jogramop_framework_b200.ingest import RobotModel
+    panda = RobotModel.load(os.path.join(ROOT, 'jogramop_framework_b200', 'data', 'robot_panda.npz'))
+    assert panda.shape_link[0] == -1 and len(panda.arm_joint_ids) == 7
+    sc = scene_loader(21)
+    e = CollisionEngine(panda, sc)
+    o = Oracle(panda, sc)
+    q = uniform_configs(panda, 20000, 5)
+    assert q.shape == (20000, 7)
+    fl = oracle.SCENE | oracle.PLANE | oracle.SELF | oracle.LIMITS
+    rb, rd = o.check(q.astype(np.float64), flags=fl)
+    bits, dist, _ = e.check(q, flags=fl)
+    compare(bits, dist, rb, rd)
+    assert np.abs(e.fk(q[:2000]).cpu().numpy() - o.fk(q[:2000].astype(np.float64))).max() <= FK_TOL
+    e.close()
+
+
+def test_degenerate_scenes(robot, scene_loader):
+    """No obstacle pieces (plane only), no plane (pieces only), and no scene at all (self-collision / FK only)."""
+    from jogramop_framework_b200.engine import CollisionEngine
+    sc = scene_loader(34)
+    q = uniform_configs(robot, 5000, 6)
+    plane_only = sc.subset([], with_plane=True)
+    e = CollisionEngine(robot, plane_only)
+    rb, rd = Oracle(robot, plane_only).check(q.astype(np.float64), flags=3)
+    bits, dist, _ = e.check(q, flags=3)
+    compare(bits, dist, rb, rd)
+    e.close()
+    no_plane = sc.subset([0, 1, 2], with_plane=False)
+    e = CollisionEngine(robot, no_plane)
+    rb, rd = Oracle(robot, no_plane).check(q.astype(np.float64), flags=3)
+    bits, dist, _ = e.check(q, flags=3)
+    compare(bits, dist, rb, rd)
+    e.close()
+    e = CollisionEngine(robot, None)
+    rb, rd = Oracle(robot, None).check(q.astype(np.float64), flags=oracle.SELF)
+    bits, dist, _ = e.check(q, flags=oracle.SELF | oracle.SCENE | oracle.PLANE)     # scene flags are no-ops without a scene
+    compare(bits, dist, rb, rd)
+    e.close()
+
+
+def test_invariances(robot, scene_loader):
+    """Properties the geometry must have: moving robot base and scene together changes nothing; the verdict is
+    monotone in the threshold; a smaller query distance only clamps the reported distance."""
+    from jogramop_framework_b200.engine import CollisionEngine
+    from jogramop_framework_b200.ingest import default_robot_pose
+    sc = scene_loader(43)
+    q = uniform_configs(robot, 20000, 43)
+    e = CollisionEngine(robot, sc)
+    b0, d0, _ = e.check(q, flags=3)
+    # shift the platform joints by (dy, dx) and the scene by the same vector in the robot frame
+    dy, dx = 0.125, -0.25
+    q2 = q.copy()
+    q2[:, 0] += dy
+    q2[:, 1] += dx
+    import copy
+    sc2 = copy.copy(sc)
+    sc2.piece_verts = sc.piece_verts + np.array([dx, dy, 0.0])
+    e2 = CollisionEngine(robot, sc2)
+    b2, d2, _ = e2.check(q2, flags=3)
+    assert (d0 - d2).abs().max().item() < 2e-5
+    assert (b0 != b2).sum().item() <= 2
+    e2.close()
+    # threshold monotonicity and query-distance clamping
+    e3 = CollisionEngine(robot, sc, threshold=0.004, query_distance=0.005)
+    b3, d3, _ = e3.check(q, flags=3)
+    assert (b3 | ~b0).all().item()
+    assert torch.allclose(d3, torch.clamp(d0, max=0.005), atol=2e-6)
+    assert torch.equal(b3, d3 < 0.004)
+    e3.close()
+    e.close()
+
+
 def test_scene_only_and_plane_only(robot, scene_loader, engines):
     e = engines(11)
     o = Oracle(robot, scene_loader(11))
