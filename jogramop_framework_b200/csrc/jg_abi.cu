@@ -728,11 +728,17 @@ static int run_narrow_and_finalize(jg_engine* e, const PassArgs& a, int n_out, u
     if (e->n_keys > 0) {
         for (int round = 0; round < 2; ++round) {
             prof_begin(e, 1, st);
-            k_select<256><<<e->sm_count * 4, 256, sel_smem, st>>>(a, round == 0 ? SEL_GJK_CHAMP : SEL_GJK_REST);
+            // the broad phase already wrote the stage-1 lists itself (thread-local champions) unless the champions were
+            // found with atomics (edge substeps, mesh queues)
+            const bool listed = round == 0 && a.substeps <= 1 && !a.mesh;
+            if (!listed) {
+                k_select<256><<<e->sm_count * 4, 256, sel_smem, st>>>(a, round == 0 ? SEL_GJK_CHAMP : SEL_GJK_REST);
+                e->stats.kernel_launches += 1;
+            }
             k_narrowphase<NP_BLOCK><<<e->np_blocks, NP_BLOCK, e->smem_narrow, st>>>(a);
             k_stage_reset<<<1, 256, 0, st>>>(a, 0, 4);      // stats[4] += GJK pairs run
             prof_end(e, st);
-            e->stats.kernel_launches += 3;
+            e->stats.kernel_launches += 2;
             if (epa) {
                 prof_begin(e, 2, st);
                 k_select<256><<<e->sm_count * 4, 256, sel_smem, st>>>(a, SEL_EPA_NEW);

@@ -157,16 +157,28 @@ __device__ __forceinline__ Tf joint_local(const JointRec& J, float val) {
     return O;
 }
 
+// A configuration's champion = its queued pair with the largest penetration bound.  All pairs of a configuration are
+// produced by ONE thread, so the thread keeps the running champion in a register (packed prio bits << 32 | key << 20 |
+// slot, compared as an integer) and publishes it once at the end (k_broadphase epilogue): no atomicMax per pair and no
+// selection kernel for the first stage.  Edge substeps of one edge are spread over threads: they keep the atomic path.
+struct Champ {
+    unsigned long long scene, self;
+};
+
 // warp-aggregated append of the lanes with `survive` to queue `key`.  prio = upper bound of the pair's total
-// penetration (0 for plane entries); the pair with the largest bound becomes the configuration's champion.
+// penetration.  `local` != nullptr: track the champion in the caller's register; else `champ` != nullptr: atomicMax.
+// stage1 = true (plane entries): every entry also goes straight into the key's stage-1 list.
 __device__ __forceinline__ void queue_push(const PassArgs& a, bool survive, int key, const Tf& T, int cfg, float prio,
-                                           unsigned long long* champ) {
+                                           unsigned long long* champ, unsigned long long* local, bool stage1) {
     const unsigned mask = __ballot_sync(0xFFFFFFFFu, survive);
     if (mask == 0) return;
     const int lane = threadIdx.x & 31;
     const int leader = __ffs(mask) - 1;
     int base = 0;
-    if (lane == leader) base = atomicAdd(a.counts + key, __popc(mask));
+    if (lane == leader) {
+        base = atomicAdd(a.counts + key, __popc(mask));
+        if (stage1) atomicAdd(cnt_act(a) + key, __popc(mask));   // same slots, same count: the list is the identity
+    }
     base = __shfl_sync(0xFFFFFFFFu, base, leader);
     if (survive) {
         const int idx = base + __popc(mask & ((1u << lane) - 1u));
@@ -176,8 +188,28 @@ __device__ __forceinline__ void queue_push(const PassArgs& a, bool survive, int 
         a.q_r2[slot] = make_float4(T.r20, T.r21, T.r22, T.tz);
         a.q_cfg[slot] = cfg;
         a.q_prio[slot] = prio;
-        if (champ) atomicMax(champ + cfg, ((unsigned long long)__float_as_uint(prio) << 32) | (unsigned)((key << 20) | idx));
+        if (stage1) a.act_list[slot] = idx;
+        const unsigned long long code = ((unsigned long long)__float_as_uint(prio) << 32) | (unsigned)((key << 20) | idx);
+        if (local) { if (code > *local) *local = code; }
+        else if (champ) atomicMax(champ + cfg, code);
     }
+}
+
+// publish a thread-local champion: remember it for the later stages and put it on its key's stage-1 list
+// (lanes of the warp that share a key reserve together)
+__device__ __forceinline__ void champ_publish(const PassArgs& a, unsigned long long code, unsigned long long* champ, int cfg,
+                                              bool valid) {
+    const bool have = valid && code != 0ull;
+    if (valid) champ[cfg] = code;
+    const unsigned act = __ballot_sync(0xFFFFFFFFu, have);
+    if (!have) return;
+    const int key = (int)((unsigned)(code & 0xFFFFFFFFull) >> 20), idx = (int)(code & 0xFFFFFull);
+    const unsigned peers = __match_any_sync(act, key);
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(cnt_act(a) + key, __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    a.act_list[(size_t)key * a.cap + base + __popc(peers & ((1u << lane) - 1u))] = idx;
 }
 
 // AABB of the shape (local centre c / half h) under T against a box (centre bc, half bh): smallest signed overlap over
@@ -198,7 +230,7 @@ __device__ __forceinline__ float prio_of(float ov, float msum) { return fmaxf(ov
 
 // scene + plane candidates of one shape placed by T (uniform control flow across the warp)
 __device__ __forceinline__ void shape_vs_scene(const PassArgs& a, const ShapeRec& Sh, int s, const PieceRec* pieces,
-                                               const Tf& T, bool valid, int out_idx) {
+                                               const Tf& T, bool valid, int out_idx, Champ* local) {
     if ((a.flags & 1u) && a.mesh) {
         // world box of the shape, inflated by everything a reported distance may span; every triangle whose box
         // overlaps it is a candidate (per-lane LBVH traversal; lanes that emit together share one atomicAdd)
@@ -244,7 +276,7 @@ __device__ __forceinline__ void shape_vs_scene(const PassArgs& a, const ShapeRec
             const bool hit = valid && ov + a.qd + msum >= 0.f;
             Tf Tc = T;   // vertices of the piece are stored relative to its AABB centre
             Tc.tx -= Pc.c[0]; Tc.ty -= Pc.c[1]; Tc.tz -= Pc.c[2];
-            queue_push(a, hit, s * (a.P + 1) + p, Tc, out_idx, prio_of(ov, msum), a.champ_scene);
+            queue_push(a, hit, s * (a.P + 1) + p, Tc, out_idx, prio_of(ov, msum), a.champ_scene, local ? &local->scene : nullptr, false);
         }
     }
     if ((a.flags & 2u) && a.has_plane) {
@@ -257,7 +289,7 @@ __device__ __forceinline__ void shape_vs_scene(const PassArgs& a, const ShapeRec
         const float low = fmaf(a.plane[0], cx, fmaf(a.plane[1], cy, fmaf(a.plane[2], cz, a.plane[3]))) - ext;
         // the plane vertices may exceed the core AABB by the embedded box margin: 2 mm slack
         const bool hit = valid && (low - 0.002f - Sh.plane_margin <= a.qd);
-        queue_push(a, hit, s * (a.P + 1) + a.P, T, out_idx, 0.f, nullptr);
+        queue_push(a, hit, s * (a.P + 1) + a.P, T, out_idx, 0.f, nullptr, nullptr, local != nullptr);
     }
 }
 
@@ -317,12 +349,16 @@ __global__ void __launch_bounds__(BLOCK) k_broadphase(const PassArgs a) {
     }
     const bool want_self = (a.flags & 4u) != 0;
     const bool want_scene = (a.flags & 3u) != 0;
+    // one thread owns all pairs of its configuration: champion in registers (not for edge substeps / mesh queues)
+    Champ champ;
+    champ.scene = champ.self = 0ull;
+    Champ* lc = (a.substeps <= 1 && !a.mesh) ? &champ : nullptr;
 
     // base-link shapes (link -1)
     Tf cur = tf_identity(), saved = tf_identity();
     if (want_scene)
         for (int s = R->base_shape_first; s < R->base_shape_first + R->base_shape_count; ++s)
-            shape_vs_scene(a, R->shapes[s], s, pieces, cur, valid, out_idx);
+            shape_vs_scene(a, R->shapes[s], s, pieces, cur, valid, out_idx, lc);
 
     for (int i = 0; i < R->L; ++i) {
         const JointRec& J = R->joints[i];
@@ -349,7 +385,7 @@ __global__ void __launch_bounds__(BLOCK) k_broadphase(const PassArgs a) {
                 const float msum = Sa.margin + Sb.margin;
                 const float ov = aabb_overlap(rel, Sb.c, Sb.h, Sa.c, Sa.h);
                 const bool hit = valid && ov + a.qd + msum >= 0.f;
-                queue_push(a, hit, a.n_scene_keys + k, rel, out_idx, prio_of(ov, msum), a.champ_self);
+                queue_push(a, hit, a.n_scene_keys + k, rel, out_idx, prio_of(ov, msum), a.champ_self, lc ? &lc->self : nullptr, false);
             }
             if (J.stash_slot >= 0) {
                 float* st = stash + (size_t)J.stash_slot * 12 * BLOCK + tid;
@@ -360,7 +396,11 @@ __global__ void __launch_bounds__(BLOCK) k_broadphase(const PassArgs a) {
         }
         if (want_scene)
             for (int s = J.shape_first; s < J.shape_first + J.shape_count; ++s)
-                shape_vs_scene(a, R->shapes[s], s, pieces, cur, valid, out_idx);
+                shape_vs_scene(a, R->shapes[s], s, pieces, cur, valid, out_idx, lc);
+    }
+    if (lc) {
+        if (want_scene) champ_publish(a, champ.scene, a.champ_scene, out_idx, valid);
+        if (want_self) champ_publish(a, champ.self, a.champ_self, out_idx, valid);
     }
 }
 
@@ -939,11 +979,14 @@ __global__ void __launch_bounds__(BLOCK) k_broadphase_poses(const PassArgs a, co
             Pz.tx = p[0]; Pz.ty = p[1]; Pz.tz = p[2];
         }
     }
+    Champ champ;
+    champ.scene = champ.self = 0ull;
     for (int k = 0; k < n_use; ++k) {
         const int s = use_shapes[k];
         const Tf T = tf_mul(Pz, rel[k]);
-        shape_vs_scene(a, R->shapes[s], s, pieces, T, valid, cfg);
+        shape_vs_scene(a, R->shapes[s], s, pieces, T, valid, cfg, &champ);
     }
+    champ_publish(a, champ.scene, a.champ_scene, cfg, valid);
 }
 
 // ------------------------------------------------------------------------------------------------ FK only

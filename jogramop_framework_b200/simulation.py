@@ -438,3 +438,69 @@ def _quat_from_matrix_torch(R):
     qy = torch.copysign(qy, m02 - m20)
     qz = torch.copysign(qz, m10 - m01)
     return torch.stack([qx, qy, qz, qw], dim=1)
+
+
+class JointTrajectory:
+    """Stand-in for ``burg.robots.JointTrajectory``: time stamps [s] and joint waypoints; iterating yields
+    (time_step, dt, target_pos, target_vel) like the reference's consumer (simulation.py:416-423)."""
+
+    def __init__(self, time_steps, waypoints):
+        self.time_steps = np.asarray(time_steps, dtype=np.float64)
+        self.joint_pos = np.asarray(waypoints, dtype=np.float64)
+        assert len(self.time_steps) == len(self.joint_pos)
+
+    def __len__(self):
+        return len(self.time_steps)
+
+    def __iter__(self):
+        dts = np.diff(self.time_steps, append=self.time_steps[-1])
+        vel = np.gradient(self.joint_pos, self.time_steps, axis=0) if len(self) > 1 else np.zeros_like(self.joint_pos)
+        for t, dt, p, v in zip(self.time_steps, dts, self.joint_pos, vel):
+            yield t, dt, p, v
+
+
+class TrajectoryPlanner:
+    """``simulation.py:475-535``: synchronised point-to-point motion with a trapezoidal velocity profile per joint
+    (the joint with the longest way sets the duration), sampled every ``dt`` -- the waypoint generator whose output
+    the batched collision check validates (``FrankaRobot.trajectory_in_collision``)."""
+
+    @staticmethod
+    def ptp(start_q, target_q, v_max=0.7, a_max=1.5, dt=1. / 20):
+        start_q, target_q = np.asarray(start_q, dtype=np.float64), np.asarray(target_q, dtype=np.float64)
+        assert len(target_q) == len(start_q)
+        if np.allclose(start_q, target_q):  # already at target
+            return JointTrajectory([0, dt], [start_q, target_q])
+        dist = np.abs(target_q - start_q)
+        d_max = dist.max()
+        if d_max < v_max ** 2 / a_max:      # too short to reach v_max: pure accelerate / decelerate triangle
+            v_max = np.sqrt(d_max * a_max)
+        T = (d_max * a_max + v_max ** 2) / (v_max * a_max)
+        steps = int(T // dt) + 1
+        # per joint: v = 1.5 d / T (capped), a = v^2 / (v T - d): every joint needs exactly T
+        v = np.minimum(1.5 * dist / T, v_max)
+        with np.errstate(divide='ignore', invalid='ignore'):
+            a = np.where(dist > 0, v ** 2 / (v * T - dist), 1.0)
+            t_acc = np.where(dist > 0, v / a, 0.0)
+        t = np.linspace(0, T, steps)[:, None]
+        s_acc = 0.5 * a * t ** 2
+        s_cruise = v * t - v ** 2 / (2 * a)
+        s_dec = (2 * a * v * T - 2 * v ** 2 - a ** 2 * (t - T) ** 2) / (2 * a)
+        s = np.where(t <= t_acc, s_acc, np.where(t <= T - t_acc, s_cruise, s_dec))
+        s = np.where(dist > 0, s, 0.0)
+        waypoints = start_q + np.sign(target_q - start_q) * s
+        assert np.allclose(waypoints[-1], target_q), \
+            f'waypoint interpolation went wrong, target pose is {target_q} but last waypoint is {waypoints[-1]}'
+        return JointTrajectory(t[:, 0], waypoints)
+
+
+def _trajectory_in_collision(self, trajectory, self_collision=True):
+    """Validate every waypoint of a JointTrajectory (or an [n,dof] array) with ONE batched check.
+    -> (collides: bool, index of the first colliding waypoint or -1, min_dist[n])."""
+    wp = trajectory.joint_pos if isinstance(trajectory, JointTrajectory) else np.asarray(trajectory, dtype=np.float64)
+    flags = _engine.SCENE | _engine.PLANE | (_engine.SELF if self_collision else 0)
+    bits, dist, _ = self._simulator._engine('full').check(wp.astype(np.float32), flags=flags)
+    hit = bits.cpu().numpy()
+    return bool(hit.any()), (int(np.argmax(hit)) if hit.any() else -1), dist.cpu().numpy()
+
+
+FrankaRobot.trajectory_in_collision = _trajectory_in_collision

@@ -112,6 +112,34 @@ def test_robot_state_and_error_conventions():
     assert r2.model.self_pairs.shape == (25, 2)
 
 
+def test_trajectory_planner_ptp_profile():
+    """simulation.py:480-535: synchronised trapezoids -- all joints arrive together, monotone, velocity and
+    acceleration limits respected, dt spacing, degenerate cases."""
+    from jogramop_framework_b200.simulation import TrajectoryPlanner
+    q0 = np.array([0.0, 0.0, 0.1, -0.5, 0.0, -2.0, 0.0, 1.5, 0.7])
+    q1 = np.array([0.5, -0.2, 0.1, 0.4, 1.0, -1.0, -0.3, 1.5, 2.0])
+    tr = TrajectoryPlanner.ptp(q0, q1)
+    wp, t = tr.joint_pos, tr.time_steps
+    assert np.allclose(wp[0], q0) and np.allclose(wp[-1], q1)
+    d_max = np.abs(q1 - q0).max()
+    T = (d_max * 1.5 + 0.7 ** 2) / (0.7 * 1.5)
+    assert t[-1] == pytest.approx(T) and len(t) == int(T // (1 / 20)) + 1
+    prog = (wp - q0) * np.sign(q1 - q0)
+    assert (np.diff(prog, axis=0) >= -1e-12).all()                      # monotone towards the target
+    vel = np.abs(np.diff(wp, axis=0)) / np.diff(t)[:, None]
+    assert vel.max() <= 0.7 + 1e-9
+    assert np.allclose(wp[:, 2], 0.1) and np.allclose(wp[:, 7], 1.5)    # joints that do not move stay put
+    # the slowest joint cruises at v_max in the middle of the motion
+    j = int(np.argmax(np.abs(q1 - q0)))
+    assert vel[len(vel) // 2, j] == pytest.approx(0.7, rel=1e-6)
+    short = TrajectoryPlanner.ptp(q0, q0 + 0.01)
+    assert np.allclose(short.joint_pos[-1], q0 + 0.01) and len(short) >= 2
+    same = TrajectoryPlanner.ptp(q0, q0)
+    assert len(same) == 2 and np.allclose(same.joint_pos, q0)
+    steps = list(tr)
+    assert len(steps) == len(tr) and len(steps[0]) == 4
+
+
 def test_timer_and_quaternion_helpers():
     t = util.Timer()
     t.start('a'); t.stop('a'); t.count('x'); t.count('x')
@@ -225,4 +253,10 @@ def test_batched_variants_and_filter(robot, scene_loader, golden):
         assert abs(float(gd[i]) - min(pd[9:12].min(), 0.01)) < 1e-4
     be, de = rob.edges_in_collision_batch(q[:100], q[100:200], substeps=8)
     assert be.shape == (100,) and de.dtype == torch.float32
+    # swept validation of a point-to-point trajectory (simulation.py:480-535 waypoints) with one batched check
+    from jogramop_framework_b200.simulation import TrajectoryPlanner
+    tr = TrajectoryPlanner.ptp(np.asarray(rob.home_conf), golden['ik_034'][0])
+    hit, first, dist = rob.trajectory_in_collision(tr)
+    rb2, rd2 = o.check(tr.joint_pos, flags=7)
+    assert np.abs(dist - rd2).max() < 1e-4 and (first == -1) == (not rb2[np.abs(rd2 + 0.001) > 1e-3].any() and not hit)
     sim.dismiss()
