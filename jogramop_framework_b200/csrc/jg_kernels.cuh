@@ -512,6 +512,7 @@ __global__ void __launch_bounds__(BLOCK) k_narrowphase(const PassArgs a) {
         GjkState S;
         Tf T = tf_identity();
         int cfg = 0, off = 0;
+        float best_total = -FLT_MAX;
         if (K.kind == KEY_MESH) {   // link hull vs one triangle per lane (registers); same lane refill, no penetration pass
             TriSupport tri;
             tri.p0 = tri.p1 = tri.p2 = mk(0.f, 0.f, 0.f);
@@ -562,6 +563,7 @@ __global__ void __launch_bounds__(BLOCK) k_narrowphase(const PassArgs a) {
                     T = load_entry(a, kbase + off, cfg);
                     gjk_init(S, mk(T.tx, T.ty, T.tz));
                     active = true;
+                    best_total = -dec_float(enc[cfg]);   // what is already proven for this configuration
                 }
                 next += min(__popc(need), avail);
             }
@@ -569,7 +571,13 @@ __global__ void __launch_bounds__(BLOCK) k_narrowphase(const PassArgs a) {
             // ---- one GJK iteration on every busy lane
             bool deep = false;
             if (active) {
-                const int st = gjk_step(S, A, K.a_n, SetSupport{B, K.b_n}, T, dmax);
+                int st = gjk_step(S, A, K.a_n, SetSupport{B, K.b_n}, T, dmax);
+                // exact early out: another pair of this configuration already penetrates deeper than this pair possibly
+                // can (hmin = smallest support value seen = upper bound of this pair's depth if it overlaps at all)
+                if (st == JG_GJK_RUNNING && best_total > 0.f && fmaxf(S.hmin, 0.f) + fmaxf(K.emsum, K.msum) + 0.004f <= best_total) {
+                    active = false;
+                    st = JG_GJK_RUNNING;
+                } else
                 if (st != JG_GJK_RUNNING) {
                     active = false;
                     if (st == JG_GJK_SEPARATED) {
@@ -768,6 +776,7 @@ __global__ void __launch_bounds__(BLOCK) k_penetration(const PassArgs a) {
         GjkState S;
         Tf T = tf_identity();
         int cfg = 0, myj = 0;
+        float best_total = -FLT_MAX;
         for (;;) {
             const unsigned need = __ballot_sync(0xFFFFFFFFu, phase == 0);
             const int avail = end - next;
@@ -777,6 +786,7 @@ __global__ void __launch_bounds__(BLOCK) k_penetration(const PassArgs a) {
                     myj = a.act_list[kbase + next + rank];
                     const size_t j = kbase + myj;
                     T = load_entry(a, kbase + a.epa_slot[j], cfg);
+                    best_total = -dec_float(enc[cfg]);
                     if (regjk) {
                         gjk_init(S, mk(T.tx, T.ty, T.tz));
                         phase = 1;
@@ -808,6 +818,9 @@ __global__ void __launch_bounds__(BLOCK) k_penetration(const PassArgs a) {
             } else if (phase == 2) {
                 const ThreadSupport sup = {A, K.ea_n, B, K.eb_n, T};
                 const int st = (a.flags & 0x40000000u) ? (int)JG_EPA_OVERFLOW : epa_step(X, sup);   // test hook
+                if (st == JG_EPA_RUNNING && X.ub + K.emsum + 1e-5f <= best_total) {
+                    phase = 0;   // exact early out: this pair's depth is bounded below what its configuration already has
+                } else
                 if (st == JG_EPA_DONE) {
                     // the cores overlap: never report less penetration than the margins
                     atomicMin(enc + cfg, enc_float(fminf(-(epa_result(X) + K.emsum), -K.msum)));
