@@ -272,8 +272,23 @@ __device__ __forceinline__ void shape_vs_scene(const PassArgs& a, const ShapeRec
         for (int p = 0; p < a.P; ++p) {
             const PieceRec& Pc = pieces[p];
             const float msum = Sh.margin + Pc.margin;
-            const float ov = aabb_overlap(T, Sh.c, Sh.h, Pc.c, Pc.h);
-            const bool hit = valid && ov + a.qd + msum >= 0.f;
+            float ov = aabb_overlap(T, Sh.c, Sh.h, Pc.c, Pc.h);
+            bool hit = valid && ov + a.qd + msum >= 0.f;
+            if (hit) {
+                // second look along the shape's own box axes (its local box is tight, the world box of a rotated link
+                // is not): culls false candidates and tightens the penetration bound that ranks the pairs
+                const float dx = fmaf(T.r00, Sh.c[0], fmaf(T.r01, Sh.c[1], fmaf(T.r02, Sh.c[2], T.tx))) - Pc.c[0];
+                const float dy = fmaf(T.r10, Sh.c[0], fmaf(T.r11, Sh.c[1], fmaf(T.r12, Sh.c[2], T.ty))) - Pc.c[1];
+                const float dz = fmaf(T.r20, Sh.c[0], fmaf(T.r21, Sh.c[1], fmaf(T.r22, Sh.c[2], T.tz))) - Pc.c[2];
+                const float o0 = Sh.h[0] + fmaf(fabsf(T.r00), Pc.h[0], fmaf(fabsf(T.r10), Pc.h[1], fabsf(T.r20) * Pc.h[2])) -
+                                 fabsf(fmaf(T.r00, dx, fmaf(T.r10, dy, T.r20 * dz)));
+                const float o1 = Sh.h[1] + fmaf(fabsf(T.r01), Pc.h[0], fmaf(fabsf(T.r11), Pc.h[1], fabsf(T.r21) * Pc.h[2])) -
+                                 fabsf(fmaf(T.r01, dx, fmaf(T.r11, dy, T.r21 * dz)));
+                const float o2 = Sh.h[2] + fmaf(fabsf(T.r02), Pc.h[0], fmaf(fabsf(T.r12), Pc.h[1], fabsf(T.r22) * Pc.h[2])) -
+                                 fabsf(fmaf(T.r02, dx, fmaf(T.r12, dy, T.r22 * dz)));
+                ov = fminf(ov, fminf(o0, fminf(o1, o2)));
+                hit = ov + a.qd + msum >= 0.f;
+            }
             Tf Tc = T;   // vertices of the piece are stored relative to its AABB centre
             Tc.tx -= Pc.c[0]; Tc.ty -= Pc.c[1]; Tc.tz -= Pc.c[2];
             queue_push(a, hit, s * (a.P + 1) + p, Tc, out_idx, prio_of(ov, msum), a.champ_scene, local ? &local->scene : nullptr, false);
