@@ -591,6 +591,8 @@ extern "C" jg_engine* jg_engine_create(const jg_robot* r, const jg_scene* sc, in
         return nullptr;
     }
     bool ok = cudaFuncSetAttribute(k_narrowphase<NP_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_penetration<416>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_penetration<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_penetration<352>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_penetration<320>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_penetration<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
@@ -616,9 +618,9 @@ extern "C" jg_engine* jg_engine_create(const jg_robot* r, const jg_scene* sc, in
         const size_t tables = sizeof(float4) * e->n_verts + sizeof(int) * ((e->n_keys + 2 + 3) & ~3);
         const size_t per_thread = sizeof(uint32_t) * EpaCompact<1>::WORDS;
         e->epa_threads = 0;
-        int want = 352;
+        int want = 416;
         if (const char* ev = getenv("JG_EPA_THREADS")) want = atoi(ev);   // tuning knob (experiments only)
-        for (int t : {352, 320, 256, 192, 128, 64})
+        for (int t : {416, 384, 352, 320, 256, 192, 128, 64})
             if (t <= want && tables + per_thread * t + 64 <= smem_max) { e->epa_threads = t; break; }
         if (!e->epa_threads) {
             fail(JG_ERR_INVALID, "scene too large for the shared-memory penetration pass (%zu B of tables)", tables);
@@ -717,6 +719,8 @@ static int run_narrow_and_finalize(jg_engine* e, const PassArgs& a, int n_out, u
     const size_t sel_smem = sizeof(int) * (2 * e->n_keys + 2);
     auto launch_penetration = [&]() {
         switch (e->epa_threads) {
+            case 416: k_penetration<416><<<e->epa_blocks, 416, e->smem_epa, st>>>(a); break;
+            case 384: k_penetration<384><<<e->epa_blocks, 384, e->smem_epa, st>>>(a); break;
             case 352: k_penetration<352><<<e->epa_blocks, 352, e->smem_epa, st>>>(a); break;
             case 320: k_penetration<320><<<e->epa_blocks, 320, e->smem_epa, st>>>(a); break;
             case 256: k_penetration<256><<<e->epa_blocks, 256, e->smem_epa, st>>>(a); break;

@@ -330,15 +330,14 @@ __device__ __forceinline__ float epa_result(const EpaStateT<E>& X) {
 
 // ---------------------------------------------------------------------------------------------- compact polytope
 // The fast kernel is bound by how many pairs fit in shared memory at once (its time scales 1/threads), so its
-// polytope is packed to 548 bytes: 18 vertices (3 words each), 32 faces (2 words each: offset d and one word with
-// three 5-bit vertex ids, three 5-bit neighbour faces and an alive bit), 16-bit flood-fill stack / horizon entries,
-// 8-bit removed list.  The neighbour's edge index is not stored: it is found from the shared vertex when the
-// neighbour is visited.  Visited marks are a 32-bit register.  14 expansions fit; larger polytopes overflow.
+// polytope is packed to 472 bytes: 18 vertices (3 words each), 32 faces (2 words each: offset d and one word with
+// three 5-bit vertex ids, three 5-bit neighbour faces and an alive bit).  The neighbour's edge index is not stored: it
+// is found from the shared vertex when the neighbour is visited.  Visited marks and the flood-fill scratch live in
+// registers.  14 expansions fit; larger polytopes overflow.
 template <int STRIDE>
 struct EpaCompact {
-    static constexpr int V = 18, F = 32, S = 12, H = 20, R = 12;
-    static constexpr int oP = 0, oFd = 3 * V, oFx = oFd + F, oSt = oFx + F, oHz = oSt + S / 2, oRm = oHz + H / 2,
-                         WORDS = oRm + R / 4;
+    static constexpr int V = 18, F = 32, S = 12, H = 24, R = 12;
+    static constexpr int oP = 0, oFd = 3 * V, oFx = oFd + F, WORDS = oFx + F;
     uint32_t* w;
     int nv, nf;
     __device__ __forceinline__ uint32_t& at(int k) const { return w[(size_t)k * STRIDE]; }
@@ -351,18 +350,29 @@ struct EpaCompact {
     __device__ __forceinline__ float fd(int f) const { return __uint_as_float(at(oFd + f)); }
     __device__ __forceinline__ void set_fd(int f, float d) const { at(oFd + f) = __float_as_uint(d); }
     __device__ __forceinline__ uint32_t& fx(int f) const { return at(oFx + f); }
-    // 16-bit / 8-bit packed scratch
-    __device__ __forceinline__ uint32_t get16(int base, int i) const { return (at(base + (i >> 1)) >> ((i & 1) * 16)) & 0xFFFFu; }
-    __device__ __forceinline__ void set16(int base, int i, uint32_t v) const {
-        uint32_t& x = at(base + (i >> 1));
-        const int sh = (i & 1) * 16;
-        x = (x & ~(0xFFFFu << sh)) | (v << sh);
+};
+
+// Flood-fill scratch of one expansion, held in REGISTERS as packed shift registers (the shared-memory version spent a
+// third of the kernel's instructions on 16-bit pack / unpack at 8 of 32 lanes): a 12-deep LIFO of 10-bit entries in
+// two 64-bit words, the removed faces (12 x 5 bits) in one, the horizon (24 x 7 bits) in three.
+struct EpaScratch {
+    unsigned long long st_lo, st_hi, rm, h0, h1, h2;
+    __device__ __forceinline__ void push(uint32_t e) { st_hi = (st_hi << 10) | (st_lo >> 54); st_lo = (st_lo << 10) | e; }
+    __device__ __forceinline__ uint32_t pop() {
+        const uint32_t e = (uint32_t)st_lo & 1023u;
+        st_lo = (st_lo >> 10) | (st_hi << 54);
+        st_hi >>= 10;
+        return e;
     }
-    __device__ __forceinline__ uint32_t get8(int base, int i) const { return (at(base + (i >> 2)) >> ((i & 3) * 8)) & 0xFFu; }
-    __device__ __forceinline__ void set8(int base, int i, uint32_t v) const {
-        uint32_t& x = at(base + (i >> 2));
-        const int sh = (i & 3) * 8;
-        x = (x & ~(0xFFu << sh)) | (v << sh);
+    __device__ __forceinline__ void rm_set(int i, uint32_t f) { rm |= (unsigned long long)f << (5 * i); }
+    __device__ __forceinline__ int rm_get(int i) const { return (int)((rm >> (5 * i)) & 31ull); }
+    __device__ __forceinline__ void hz_set(int i, uint32_t e) {
+        const unsigned long long v = (unsigned long long)e << (7 * (i & 7));
+        if (i < 8) h0 |= v; else if (i < 16) h1 |= v; else h2 |= v;
+    }
+    __device__ __forceinline__ uint32_t hz_get(int i) const {
+        const unsigned long long wv = i < 8 ? h0 : (i < 16 ? h1 : h2);
+        return (uint32_t)(wv >> (7 * (i & 7))) & 127u;
     }
 };
 // fx word: vertex k at bits 5k (k = 0..2), neighbour across edge k (c[k]->c[k+1]) at bits 15 + 5k, alive = bit 30
@@ -436,14 +446,18 @@ __device__ __forceinline__ int epa_step(EpaStateC<STRIDE>& X, const Sup& sup) {
     const int vi = P.nv;
     // ---- flood fill of the visible faces, horizon edges in loop order.  stack entry: face | start vertex << 5
     uint32_t visited = 1u << best;
+    EpaScratch sc;
+    sc.st_lo = sc.st_hi = sc.rm = sc.h0 = sc.h1 = sc.h2 = 0ull;
     int sp = 0, nh = 0, nr = 0;
     bool ok = true, over = false;
-    P.set8(E::oRm, nr++, (uint32_t)best);
-    P.set16(E::oSt, sp++, (uint32_t)cx_nbr(fxb, 2) | ((uint32_t)cx_vert(fxb, 0) << 5));
-    P.set16(E::oSt, sp++, (uint32_t)cx_nbr(fxb, 1) | ((uint32_t)cx_vert(fxb, 2) << 5));
-    P.set16(E::oSt, sp++, (uint32_t)cx_nbr(fxb, 0) | ((uint32_t)cx_vert(fxb, 1) << 5));
+    sc.rm_set(nr++, (uint32_t)best);
+    sc.push((uint32_t)cx_nbr(fxb, 2) | ((uint32_t)cx_vert(fxb, 0) << 5));
+    sc.push((uint32_t)cx_nbr(fxb, 1) | ((uint32_t)cx_vert(fxb, 2) << 5));
+    sc.push((uint32_t)cx_nbr(fxb, 0) | ((uint32_t)cx_vert(fxb, 1) << 5));
+    sp = 3;
     while (sp > 0) {
-        const uint32_t se = P.get16(E::oSt, --sp);
+        const uint32_t se = sc.pop();
+        --sp;
         const int f = (int)(se & 31u), v0 = (int)(se >> 5);
         if ((visited >> f) & 1u) { ok = false; break; }   // reached twice: inconsistent classification
         const uint32_t fx = P.fx(f);
@@ -457,15 +471,16 @@ __device__ __forceinline__ int epa_step(EpaStateC<STRIDE>& X, const Sup& sup) {
         }
         if (!vis) {
             if (nh >= E::H) { over = true; break; }
-            P.set16(E::oHz, nh++, (uint32_t)f | ((uint32_t)e << 5));
+            sc.hz_set(nh++, (uint32_t)f | ((uint32_t)e << 5));
         } else {
             if (nr >= E::R || sp + 2 > E::S) { over = true; break; }
             visited |= 1u << f;
-            P.set8(E::oRm, nr++, (uint32_t)f);
+            sc.rm_set(nr++, (uint32_t)f);
             const int e1 = e == 2 ? 0 : e + 1, e2 = e == 0 ? 2 : e - 1;
             // neighbour across edge k starts that edge (in its own orientation) at our vertex k+1
-            P.set16(E::oSt, sp++, (uint32_t)cx_nbr(fx, e2) | ((uint32_t)cx_vert(fx, e2 == 2 ? 0 : e2 + 1) << 5));
-            P.set16(E::oSt, sp++, (uint32_t)cx_nbr(fx, e1) | ((uint32_t)cx_vert(fx, e1 == 2 ? 0 : e1 + 1) << 5));
+            sc.push((uint32_t)cx_nbr(fx, e2) | ((uint32_t)cx_vert(fx, e2 == 2 ? 0 : e2 + 1) << 5));
+            sc.push((uint32_t)cx_nbr(fx, e1) | ((uint32_t)cx_vert(fx, e1 == 2 ? 0 : e1 + 1) << 5));
+            sp += 2;
         }
     }
     if (!over && ok && nh >= 3 && nh > nr + (E::F - P.nf)) over = true;
@@ -475,15 +490,15 @@ __device__ __forceinline__ int epa_step(EpaStateC<STRIDE>& X, const Sup& sup) {
     P.nv = vi + 1;
     // slots of the new faces: recycle removed ones (last removed first), then grow; the rest of the removed die
     const int nr0 = nr, nf0 = P.nf;
-    auto slot_of = [&](int j) -> int { return j < nr0 ? (int)P.get8(E::oRm, nr0 - 1 - j) : nf0 + (j - nr0); };
+    auto slot_of = [&](int j) -> int { return j < nr0 ? sc.rm_get(nr0 - 1 - j) : nf0 + (j - nr0); };
     if (nh > nr0) P.nf = nf0 + (nh - nr0);
     for (int i = 0; i < nr0 - nh; ++i) {
-        const int f = (int)P.get8(E::oRm, i);
+        const int f = sc.rm_get(i);
         P.fx(f) = 0u;
         P.set_fd(f, FLT_MAX);
     }
     {
-        uint32_t hcur = P.get16(E::oHz, 0);
+        uint32_t hcur = sc.hz_get(0);
         const uint32_t h0 = hcur;
         int prev_slot = slot_of(nh - 1), slot = slot_of(0);
         int f = (int)(hcur & 31u), e = (int)(hcur >> 5);
@@ -491,7 +506,7 @@ __device__ __forceinline__ int epa_step(EpaStateC<STRIDE>& X, const Sup& sup) {
         int ia = cx_vert(fxo, e == 2 ? 0 : e + 1);
         V3 pa = P.P(ia);
         for (int j = 0; j < nh; ++j) {
-            const uint32_t hnext = j + 1 < nh ? P.get16(E::oHz, j + 1) : h0;
+            const uint32_t hnext = j + 1 < nh ? sc.hz_get(j + 1) : h0;
             const int next_slot = j + 1 < nh ? slot_of(j + 1) : slot_of(0);
             const int ib = cx_vert(fxo, e);
             const V3 pb = P.P(ib);
