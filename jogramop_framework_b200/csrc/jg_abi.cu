@@ -1013,56 +1013,93 @@ extern "C" int jg_check_host(jg_engine* e, const float* q, int64_t n, int dof, u
     int rc = ensure_staging(e);
     if (rc) return rc;
     const bool pq = is_pinned(q), pb = is_pinned(bits), pd = dist && is_pinned(dist), pr = reason && is_pinned(reason);
-    jg_stats total{};
-    // host passes = engine passes: splitting a batch further would overlap its copies with its kernels, but every pass
-    // pays the fixed tails of the staged narrow phase (measured: 4 x 250 k is 40 % slower than 1 x 1 M end to end)
-    const int64_t hp = e->cap;
-    const int64_t n_pass = (n + hp - 1) / hp;
-    // software pipeline over passes: copy-in(i+1) || run(i) || copy-out(i-1); buffers alternate
+    if (e->mesh || n == 0) {   // secondary path: plain staged copy around the device entry point
+        float* dq = nullptr;
+        uint32_t* db = nullptr;
+        float* dd = nullptr;
+        uint8_t* dr = nullptr;
+        if (n == 0) return JG_OK;
+        CUDA_TRY(cudaMalloc(&dq, sizeof(float) * n * dof));
+        CUDA_TRY(cudaMalloc(&db, sizeof(uint32_t) * ((n + 31) / 32)));
+        if (dist) CUDA_TRY(cudaMalloc(&dd, sizeof(float) * n));
+        if (reason) CUDA_TRY(cudaMalloc(&dr, n));
+        CUDA_TRY(cudaMemcpyAsync(dq, q, sizeof(float) * n * dof, cudaMemcpyHostToDevice, e->s_run));
+        rc = jg_check(e, dq, n, dof, flags, db, dd, dr, e->s_run);
+        if (rc == JG_OK) {
+            CUDA_TRY(cudaMemcpyAsync(bits, db, sizeof(uint32_t) * ((n + 31) / 32), cudaMemcpyDeviceToHost, e->s_run));
+            if (dist) CUDA_TRY(cudaMemcpyAsync(dist, dd, sizeof(float) * n, cudaMemcpyDeviceToHost, e->s_run));
+            if (reason) CUDA_TRY(cudaMemcpyAsync(reason, dr, n, cudaMemcpyDeviceToHost, e->s_run));
+            CUDA_TRY(cudaStreamSynchronize(e->s_run));
+        }
+        cudaFree(dq); cudaFree(db); cudaFree(dd); cudaFree(dr);
+        return rc;
+    }
+    // One engine pass per `cap` configurations.  Within a pass the upload is cut into slices: the broad phase of slice
+    // i runs while slice i+1 is still crossing PCIe (the broad phase is per-configuration, so it can be launched
+    // slice by slice into the same queues); the staged narrow phase then runs once over the whole pass.  Results go
+    // back on a third stream while the next pass uploads.  Pageable host memory is staged through pinned buffers.
+    cudaStream_t st = e->s_run;
+    rc = begin_call(e, st);
+    if (rc) return rc;
+    e->stats.configs = n;
+    const int64_t n_pass = (n + e->cap - 1) / e->cap;
+    constexpr int SLICES = 4;
     for (int64_t i = 0; i < n_pass; ++i) {
         const int b = (int)(i & 1);
-        const int64_t off = i * hp;
-        const int m = (int)std::min<int64_t>(hp, n - off);
-        // buffer b was last used by pass i-2: its copy-out must be finished before we overwrite staging
-        if (i >= 2) CUDA_TRY(cudaEventSynchronize(e->ev_out[b]));
-        if (i >= 2) {   // drain pass i-2 results from pinned staging into pageable user memory
-            const int64_t o2 = (i - 2) * hp;
-            const int m2 = (int)hp;
-            if (!pb) memcpy(bits + o2 / 32, e->pin_bits[b], sizeof(uint32_t) * ((m2 + 31) / 32));
-            if (dist && !pd) memcpy(dist + o2, e->pin_dist[b], sizeof(float) * m2);
-            if (reason && !pr) memcpy(reason + o2, e->pin_reason[b], m2);
+        const int64_t off = i * e->cap;
+        const int m = (int)std::min<int64_t>(e->cap, n - off);
+        if (i >= 2) {   // buffer b was used by pass i-2: wait for its download, drain it into pageable user memory
+            CUDA_TRY(cudaEventSynchronize(e->ev_out[b]));
+            const int64_t o2 = (i - 2) * e->cap;
+            if (!pb) memcpy(bits + o2 / 32, e->pin_bits[b], sizeof(uint32_t) * (e->cap / 32));
+            if (dist && !pd) memcpy(dist + o2, e->pin_dist[b], sizeof(float) * e->cap);
+            if (reason && !pr) memcpy(reason + o2, e->pin_reason[b], e->cap);
         }
-        const float* src = q + off * dof;
-        if (!pq) { memcpy(e->pin_q[b], src, sizeof(float) * m * dof); src = e->pin_q[b]; }
-        CUDA_TRY(cudaMemcpyAsync(e->stage_q[b], src, sizeof(float) * m * dof, cudaMemcpyHostToDevice, e->s_in));
-        CUDA_TRY(cudaEventRecord(e->ev_in[b], e->s_in));
-        CUDA_TRY(cudaStreamWaitEvent(e->s_run, e->ev_in[b], 0));
-        rc = jg_check(e, e->stage_q[b], m, dof, flags, e->stage_bits[b], dist ? e->stage_dist[b] : nullptr,
-                      reason ? e->stage_reason[b] : nullptr, e->s_run);
+        PassArgs a;
+        uint32_t fl = flags;
+        fill_args(e, a, fl, dist != nullptr);
+        a.q = e->stage_q[b]; a.n = m;
+        CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * (4 * e->n_keys + 8), st));
+        if (fl & JG_LIMITS) CUDA_TRY(cudaMemsetAsync(e->viol, 0, sizeof(uint32_t) * (e->cap / 32 + 1), st));
+        const int slice = std::max(1024, ((m + SLICES - 1) / SLICES + 1023) / 1024 * 1024);
+        prof_begin(e, 0, st);
+        for (int c0 = 0; c0 < m; c0 += slice) {
+            const int c1 = std::min(m, c0 + slice);
+            const float* src = q + (off + c0) * dof;
+            if (!pq) {
+                memcpy(e->pin_q[b] + (size_t)c0 * dof, src, sizeof(float) * (c1 - c0) * dof);
+                src = e->pin_q[b] + (size_t)c0 * dof;
+            }
+            CUDA_TRY(cudaMemcpyAsync(e->stage_q[b] + (size_t)c0 * dof, src, sizeof(float) * (c1 - c0) * dof, cudaMemcpyHostToDevice, e->s_in));
+            CUDA_TRY(cudaEventRecord(e->ev_in[b], e->s_in));
+            CUDA_TRY(cudaStreamWaitEvent(st, e->ev_in[b], 0));
+            PassArgs as = a;
+            as.cfg_base = c0;
+            as.n = c1;     // configurations [c0, c1) of the pass
+            k_broadphase<BP_BLOCK><<<(c1 - c0 + BP_BLOCK - 1) / BP_BLOCK, BP_BLOCK, bp_smem(e, fl), st>>>(as);
+            e->stats.kernel_launches += 1;
+        }
+        rc = run_narrow_and_finalize(e, a, m, fl, e->stage_bits[b], dist ? e->stage_dist[b] : nullptr,
+                                     reason ? e->stage_reason[b] : nullptr, st);
         if (rc) return rc;
-        total.kernel_launches += e->stats.kernel_launches;
-        CUDA_TRY(cudaEventRecord(e->ev_run[b], e->s_run));
+        CUDA_TRY(cudaEventRecord(e->ev_run[b], st));
         CUDA_TRY(cudaStreamWaitEvent(e->s_out, e->ev_run[b], 0));
         CUDA_TRY(cudaMemcpyAsync(pb ? bits + off / 32 : e->pin_bits[b], e->stage_bits[b], sizeof(uint32_t) * ((m + 31) / 32),
                                  cudaMemcpyDeviceToHost, e->s_out));
         if (dist) CUDA_TRY(cudaMemcpyAsync(pd ? dist + off : e->pin_dist[b], e->stage_dist[b], sizeof(float) * m, cudaMemcpyDeviceToHost, e->s_out));
         if (reason) CUDA_TRY(cudaMemcpyAsync(pr ? reason + off : e->pin_reason[b], e->stage_reason[b], m, cudaMemcpyDeviceToHost, e->s_out));
         CUDA_TRY(cudaEventRecord(e->ev_out[b], e->s_out));
-        // the next pass's jg_check resets d_stats on s_run; the staging input of pass i must not be overwritten
-        // before its H2D finished: guaranteed by the ev_out wait above (copy-out follows run follows copy-in).
     }
     CUDA_TRY(cudaStreamSynchronize(e->s_out));
     for (int64_t i = std::max<int64_t>(0, n_pass - 2); i < n_pass; ++i) {
         const int b = (int)(i & 1);
-        const int64_t off = i * hp;
-        const int m = (int)std::min<int64_t>(hp, n - off);
+        const int64_t off = i * e->cap;
+        const int m = (int)std::min<int64_t>(e->cap, n - off);
         if (!pb) memcpy(bits + off / 32, e->pin_bits[b], sizeof(uint32_t) * ((m + 31) / 32));
         if (dist && !pd) memcpy(dist + off, e->pin_dist[b], sizeof(float) * m);
         if (reason && !pr) memcpy(reason + off, e->pin_reason[b], m);
     }
-    e->stats.configs = n;
-    e->stats.kernel_launches = total.kernel_launches;
-    e->last_stream = e->s_run;
+    e->last_stream = st;
     return JG_OK;
 }
 

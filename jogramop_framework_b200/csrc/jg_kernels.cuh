@@ -79,6 +79,8 @@ struct PassArgs {
     const float* q;    // [n,dof] (or qa for edges)
     const float* qb;   // edges: end configurations, else NULL
     int n;             // configurations in this pass (substep-expanded for edges)
+    int cfg_base;      // first configuration of THIS launch (the broad phase of a pass may be split into several
+                       // launches so that the host path can overlap it with the upload of the next slice)
     int dof;
     int substeps;      // 1, or substeps per edge
     uint32_t flags;
@@ -324,7 +326,7 @@ __global__ void __launch_bounds__(BLOCK) k_broadphase(const PassArgs a) {
         int* pd = reinterpret_cast<int*>(pieces);
         for (int i = tid; i < (int)(sizeof(PieceRec) / 4) * a.P; i += BLOCK) pd[i] = ps[i];
     }
-    const int cfg0 = blockIdx.x * BLOCK;
+    const int cfg0 = a.cfg_base + blockIdx.x * BLOCK;
     const int cfg = cfg0 + tid;
     const bool valid = cfg < a.n;
     const int dof = a.dof;
