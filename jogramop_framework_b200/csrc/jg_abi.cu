@@ -152,6 +152,10 @@ extern "C" jg_scene* jg_scene_create_mesh(int n_verts, const double* verts, int 
         fail(JG_ERR_INVALID, "jg_scene_create_mesh: bad arguments");
         return nullptr;
     }
+    if (n_tris >= 65536) {
+        fail(JG_ERR_INVALID, "jg_scene_create_mesh: at most 65535 triangles are supported (got %d)", n_tris);
+        return nullptr;
+    }
     for (int i = 0; i < 3 * n_tris; ++i)
         if (tris[i] < 0 || tris[i] >= n_verts) {
             fail(JG_ERR_INVALID, "jg_scene_create_mesh: triangle %d references vertex %d of %d", i / 3, tris[i], n_verts);
@@ -791,7 +795,7 @@ extern "C" int jg_check(jg_engine* e, const float* q, int64_t n, int dof, uint32
     e->stats.configs = n;
     // mesh mode: a configuration may queue many triangles per link, so a pass takes fewer configurations; the pass
     // size adapts: an overflowing pass is redone at half the size (the engine remembers what worked)
-    if (e->mesh && e->mesh_pass <= 0) e->mesh_pass = std::max(1024, e->cap / 4 / 1024 * 1024);
+    if (e->mesh && e->mesh_pass <= 0) e->mesh_pass = std::max(1024, e->cap / 2 / 1024 * 1024);
     for (int64_t off = 0; off < n;) {
         const int64_t pass = e->mesh ? e->mesh_pass : e->cap;
         const int m = (int)std::min<int64_t>(pass, n - off);

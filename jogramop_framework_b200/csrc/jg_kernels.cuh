@@ -246,30 +246,50 @@ __device__ __forceinline__ void shape_vs_scene(const PassArgs& a, const ShapeRec
         const float qlo[3] = {cx - hx, cy - hy, cz - hz}, qhi[3] = {cx + hx, cy + hy, cz + hz};
         const int key = s * (a.P + 1);
         const int lane = threadIdx.x & 31;
+        // candidates are first collected per lane, then the warp reserves its slots with ONE atomicAdd (an atomic per
+        // emitted triangle inside the divergent traversal was most of this kernel's time)
+        constexpr int MAXC = 32;
+        unsigned short cand[MAXC];
+        float cov[MAXC];
+        int nc = 0;
+        unsigned long long best = 0ull;
+        auto write_out = [&](int base) {   // entries cand[0..nc) -> queue slots [base, base+nc)
+            if (base + nc > a.cap) { *a.err_flag = 1; nc = max(0, min(nc, a.cap - base)); }
+            for (int i = 0; i < nc; ++i) {
+                const int idx = base + i;
+                const size_t slot = (size_t)key * a.cap + idx;
+                a.q_r0[slot] = make_float4(T.r00, T.r01, T.r02, T.tx);
+                a.q_r1[slot] = make_float4(T.r10, T.r11, T.r12, T.ty);
+                a.q_r2[slot] = make_float4(T.r20, T.r21, T.r22, T.tz);
+                a.q_cfg[slot] = out_idx;
+                a.q_tri[slot] = (int)cand[i];
+                // bound for the champion-first staging: a triangle pair never reports less than -(margins), so the
+                // bound only ranks the candidates (largest box overlap first); the overlap includes the inflation
+                const float prio = prio_of(cov[i] - infl, Sh.margin + a.mesh_margin);
+                a.q_prio[slot] = prio;
+                const unsigned long long code = ((unsigned long long)__float_as_uint(prio) << 32) | (unsigned)((key << 20) | idx);
+                if (code > best) best = code;
+            }
+            nc = 0;
+        };
         if (valid)
             lbvh_traverse(a.bvh_nodes, a.bvh_tri, a.bvh_n, qlo, qhi, [&](int tri, float ov_infl) {
-                const unsigned m = __activemask();
-                const int leader = __ffs(m) - 1;
-                int base = 0;
-                if (lane == leader) base = atomicAdd(a.counts + key, __popc(m));
-                base = __shfl_sync(m, base, leader);
-                const int idx = base + __popc(m & ((1u << lane) - 1u));
-                if (idx < a.cap) {
-                    const size_t slot = (size_t)key * a.cap + idx;
-                    a.q_r0[slot] = make_float4(T.r00, T.r01, T.r02, T.tx);
-                    a.q_r1[slot] = make_float4(T.r10, T.r11, T.r12, T.ty);
-                    a.q_r2[slot] = make_float4(T.r20, T.r21, T.r22, T.tz);
-                    a.q_cfg[slot] = out_idx;
-                    a.q_tri[slot] = tri;
-                    // bound for the champion-first staging: a triangle pair never reports less than -(margins), so
-                    // the bound only ranks the candidates (largest box overlap first); ov_infl includes the inflation
-                    const float prio = prio_of(ov_infl - infl, Sh.margin + a.mesh_margin);
-                    a.q_prio[slot] = prio;
-                    atomicMax(a.champ_scene + out_idx, ((unsigned long long)__float_as_uint(prio) << 32) | (unsigned)((key << 20) | idx));
-                } else {
-                    *a.err_flag = 1;
-                }
+                if (nc == MAXC) write_out(atomicAdd(a.counts + key, nc));   // rare: the lane's list is full, flush it alone
+                cand[nc] = (unsigned short)tri;
+                cov[nc] = ov_infl;
+                ++nc;
             });
+        int incl = nc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        int base = 0;
+        if (lane == 31 && incl > 0) base = atomicAdd(a.counts + key, incl);
+        base = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - nc;
+        write_out(base);
+        if (best) atomicMax(a.champ_scene + out_idx, best);
     } else if (a.flags & 1u) {
         for (int p = 0; p < a.P; ++p) {
             const PieceRec& Pc = pieces[p];
