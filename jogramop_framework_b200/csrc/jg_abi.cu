@@ -562,6 +562,11 @@ constexpr int BP_BLOCK = 128;   // broad phase: threads (= configurations) per b
 constexpr int NP_BLOCK = 256;   // narrow phase
 constexpr int EPA_BIG_BLOCK = 512;  // overflow pass of the penetration depth: one pair per warp, 16 warps per block
 
+static void launch_broadphase(const jg_engine* e, const PassArgs& a, int grid, size_t smem, cudaStream_t st) {
+    if (e->mesh) k_broadphase<BP_BLOCK, true><<<grid, BP_BLOCK, smem, st>>>(a);
+    else k_broadphase<BP_BLOCK, false><<<grid, BP_BLOCK, smem, st>>>(a);
+}
+
 static size_t bp_smem(const jg_engine* e, uint32_t flags) {
     size_t s = sizeof(RobotTab) + sizeof(PieceRec) * e->P + sizeof(float) * BP_BLOCK * e->dof;
     if (flags & JG_SELF) s += sizeof(float) * 12 * e->n_stash * BP_BLOCK;
@@ -604,8 +609,10 @@ extern "C" jg_engine* jg_engine_create(const jg_robot* r, const jg_scene* sc, in
     ok = ok && cudaFuncSetAttribute(k_penetration<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_penetration<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_penetration_big<EPA_BIG_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(k_broadphase<BP_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(k_broadphase_poses<BP_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_broadphase<BP_BLOCK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_broadphase<BP_BLOCK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_broadphase_poses<BP_BLOCK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_broadphase_poses<BP_BLOCK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess;
     if (!ok) {
         fail(JG_ERR_CUDA, "cudaFuncSetAttribute failed: %s (is this an sm_100 device?)", cudaGetErrorString(cudaGetLastError()));
         engine_release(e);
@@ -805,7 +812,7 @@ extern "C" int jg_check(jg_engine* e, const float* q, int64_t n, int dof, uint32
         CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * (4 * e->n_keys + 8), st));
         if (flags & JG_LIMITS) CUDA_TRY(cudaMemsetAsync(e->viol, 0, sizeof(uint32_t) * (e->cap / 32 + 1), st));
         prof_begin(e, 0, st);
-        k_broadphase<BP_BLOCK><<<(m + BP_BLOCK - 1) / BP_BLOCK, BP_BLOCK, bp_smem(e, flags), st>>>(a);
+        launch_broadphase(e, a, (m + BP_BLOCK - 1) / BP_BLOCK, bp_smem(e, flags), st);
         e->stats.kernel_launches += 1;
         if (e->mesh) {   // secondary path: check the queue-overflow flag synchronously before going on
             int err = 0;
@@ -851,7 +858,7 @@ extern "C" int jg_check_edges(jg_engine* e, const float* qa, const float* qb, in
         if (flags & JG_LIMITS) CUDA_TRY(cudaMemsetAsync(e->viol, 0, sizeof(uint32_t) * (e->cap / 32 + 1), st));
         prof_begin(e, 0, st);
         k_init_scratch<<<(me + 255) / 256, 256, 0, st>>>(e->enc_scene, e->enc_self, e->champ_scene, e->champ_self, me);
-        k_broadphase<BP_BLOCK><<<(a.n + BP_BLOCK - 1) / BP_BLOCK, BP_BLOCK, bp_smem(e, flags), st>>>(a);
+        launch_broadphase(e, a, (a.n + BP_BLOCK - 1) / BP_BLOCK, bp_smem(e, flags), st);
         e->stats.kernel_launches += 2;
         rc = run_narrow_and_finalize(e, a, me, flags, bits + off / 32, min_dist ? min_dist + off : nullptr, nullptr, st);
         if (rc) return rc;
@@ -938,8 +945,12 @@ extern "C" int jg_check_poses(jg_engine* e, const float* poses, int64_t n, int f
         CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * (4 * e->n_keys + 8), st));
         const size_t smem = sizeof(RobotTab) + sizeof(PieceRec) * e->P;
         prof_begin(e, 0, st);
-        k_broadphase_poses<BP_BLOCK><<<(m + BP_BLOCK - 1) / BP_BLOCK, BP_BLOCK, smem, st>>>(a, poses + off * stride, fmt, e->d_rel,
-                                                                                         e->d_use_shapes, (int)use.size());
+        if (e->mesh)
+            k_broadphase_poses<BP_BLOCK, true><<<(m + BP_BLOCK - 1) / BP_BLOCK, BP_BLOCK, smem, st>>>(
+                a, poses + off * stride, fmt, e->d_rel, e->d_use_shapes, (int)use.size());
+        else
+            k_broadphase_poses<BP_BLOCK, false><<<(m + BP_BLOCK - 1) / BP_BLOCK, BP_BLOCK, smem, st>>>(
+                a, poses + off * stride, fmt, e->d_rel, e->d_use_shapes, (int)use.size());
         e->stats.kernel_launches += 1;
         rc = run_narrow_and_finalize(e, a, m, flags, bits + off / 32, min_dist ? min_dist + off : nullptr, nullptr, st);
         if (rc) return rc;
@@ -1080,7 +1091,7 @@ extern "C" int jg_check_host(jg_engine* e, const float* q, int64_t n, int dof, u
             PassArgs as = a;
             as.cfg_base = c0;
             as.n = c1;     // configurations [c0, c1) of the pass
-            k_broadphase<BP_BLOCK><<<(c1 - c0 + BP_BLOCK - 1) / BP_BLOCK, BP_BLOCK, bp_smem(e, fl), st>>>(as);
+            launch_broadphase(e, as, (c1 - c0 + BP_BLOCK - 1) / BP_BLOCK, bp_smem(e, fl), st);
             e->stats.kernel_launches += 1;
         }
         rc = run_narrow_and_finalize(e, a, m, fl, e->stage_bits[b], dist ? e->stage_dist[b] : nullptr,

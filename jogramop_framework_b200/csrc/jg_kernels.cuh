@@ -230,10 +230,43 @@ __device__ __forceinline__ float aabb_overlap(const Tf& T, const float* c, const
 // smaller than the penetration geometry on each side
 __device__ __forceinline__ float prio_of(float ov, float msum) { return fmaxf(ov, 0.f) + msum + 0.0021f; }
 
+// (shape, piece) candidate test: world boxes first, then a second look along the shape's own box axes (its local box is
+// tight, the world box of a rotated link is not), which culls false candidates and tightens the penetration bound `ov`
+// that ranks the pairs
+__device__ __forceinline__ bool piece_test(const PassArgs& a, const ShapeRec& Sh, const PieceRec& Pc, const Tf& T, float& ov) {
+    const float msum = Sh.margin + Pc.margin;
+    ov = aabb_overlap(T, Sh.c, Sh.h, Pc.c, Pc.h);
+    if (!(ov + a.qd + msum >= 0.f)) return false;
+    const float dx = fmaf(T.r00, Sh.c[0], fmaf(T.r01, Sh.c[1], fmaf(T.r02, Sh.c[2], T.tx))) - Pc.c[0];
+    const float dy = fmaf(T.r10, Sh.c[0], fmaf(T.r11, Sh.c[1], fmaf(T.r12, Sh.c[2], T.ty))) - Pc.c[1];
+    const float dz = fmaf(T.r20, Sh.c[0], fmaf(T.r21, Sh.c[1], fmaf(T.r22, Sh.c[2], T.tz))) - Pc.c[2];
+    const float o0 = Sh.h[0] + fmaf(fabsf(T.r00), Pc.h[0], fmaf(fabsf(T.r10), Pc.h[1], fabsf(T.r20) * Pc.h[2])) -
+                     fabsf(fmaf(T.r00, dx, fmaf(T.r10, dy, T.r20 * dz)));
+    const float o1 = Sh.h[1] + fmaf(fabsf(T.r01), Pc.h[0], fmaf(fabsf(T.r11), Pc.h[1], fabsf(T.r21) * Pc.h[2])) -
+                     fabsf(fmaf(T.r01, dx, fmaf(T.r11, dy, T.r21 * dz)));
+    const float o2 = Sh.h[2] + fmaf(fabsf(T.r02), Pc.h[0], fmaf(fabsf(T.r12), Pc.h[1], fabsf(T.r22) * Pc.h[2])) -
+                     fabsf(fmaf(T.r02, dx, fmaf(T.r12, dy, T.r22 * dz)));
+    ov = fminf(ov, fminf(o0, fminf(o1, o2)));
+    return ov + a.qd + msum >= 0.f;
+}
+// plane candidate test (conservative): lowest point of the shape's bounding box above the plane
+__device__ __forceinline__ bool plane_test(const PassArgs& a, const ShapeRec& Sh, const Tf& T) {
+    const float cx = fmaf(T.r00, Sh.c[0], fmaf(T.r01, Sh.c[1], fmaf(T.r02, Sh.c[2], T.tx)));
+    const float cy = fmaf(T.r10, Sh.c[0], fmaf(T.r11, Sh.c[1], fmaf(T.r12, Sh.c[2], T.ty)));
+    const float cz = fmaf(T.r20, Sh.c[0], fmaf(T.r21, Sh.c[1], fmaf(T.r22, Sh.c[2], T.tz)));
+    const V3 nl = tf_rot_t(T, mk(a.plane[0], a.plane[1], a.plane[2]));
+    const float ext = fmaf(fabsf(nl.x), Sh.h[0], fmaf(fabsf(nl.y), Sh.h[1], fabsf(nl.z) * Sh.h[2]));
+    const float low = fmaf(a.plane[0], cx, fmaf(a.plane[1], cy, fmaf(a.plane[2], cz, a.plane[3]))) - ext;
+    // the plane vertices may exceed the core AABB by the embedded box margin: 2 mm slack
+    return low - 0.002f - Sh.plane_margin <= a.qd;
+}
+
 // scene + plane candidates of one shape placed by T (uniform control flow across the warp)
+// MESH is a compile-time switch: the triangle path's candidate lists must not cost the hull path registers
+template <bool MESH>
 __device__ __forceinline__ void shape_vs_scene(const PassArgs& a, const ShapeRec& Sh, int s, const PieceRec* pieces,
                                                const Tf& T, bool valid, int out_idx, Champ* local) {
-    if ((a.flags & 1u) && a.mesh) {
+    if (MESH && (a.flags & 1u)) {
         // world box of the shape, inflated by everything a reported distance may span; every triangle whose box
         // overlaps it is a candidate (per-lane LBVH traversal; lanes that emit together share one atomicAdd)
         const float infl = a.qd + Sh.margin + a.mesh_margin + 1e-5f;
@@ -290,47 +323,72 @@ __device__ __forceinline__ void shape_vs_scene(const PassArgs& a, const ShapeRec
         base = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - nc;
         write_out(base);
         if (best) atomicMax(a.champ_scene + out_idx, best);
-    } else if (a.flags & 1u) {
-        for (int p = 0; p < a.P; ++p) {
-            const PieceRec& Pc = pieces[p];
-            const float msum = Sh.margin + Pc.margin;
-            float ov = aabb_overlap(T, Sh.c, Sh.h, Pc.c, Pc.h);
-            bool hit = valid && ov + a.qd + msum >= 0.f;
-            if (hit) {
-                // second look along the shape's own box axes (its local box is tight, the world box of a rotated link
-                // is not): culls false candidates and tightens the penetration bound that ranks the pairs
-                const float dx = fmaf(T.r00, Sh.c[0], fmaf(T.r01, Sh.c[1], fmaf(T.r02, Sh.c[2], T.tx))) - Pc.c[0];
-                const float dy = fmaf(T.r10, Sh.c[0], fmaf(T.r11, Sh.c[1], fmaf(T.r12, Sh.c[2], T.ty))) - Pc.c[1];
-                const float dz = fmaf(T.r20, Sh.c[0], fmaf(T.r21, Sh.c[1], fmaf(T.r22, Sh.c[2], T.tz))) - Pc.c[2];
-                const float o0 = Sh.h[0] + fmaf(fabsf(T.r00), Pc.h[0], fmaf(fabsf(T.r10), Pc.h[1], fabsf(T.r20) * Pc.h[2])) -
-                                 fabsf(fmaf(T.r00, dx, fmaf(T.r10, dy, T.r20 * dz)));
-                const float o1 = Sh.h[1] + fmaf(fabsf(T.r01), Pc.h[0], fmaf(fabsf(T.r11), Pc.h[1], fabsf(T.r21) * Pc.h[2])) -
-                                 fabsf(fmaf(T.r01, dx, fmaf(T.r11, dy, T.r21 * dz)));
-                const float o2 = Sh.h[2] + fmaf(fabsf(T.r02), Pc.h[0], fmaf(fabsf(T.r12), Pc.h[1], fabsf(T.r22) * Pc.h[2])) -
-                                 fabsf(fmaf(T.r02, dx, fmaf(T.r12, dy, T.r22 * dz)));
-                ov = fminf(ov, fminf(o0, fminf(o1, o2)));
-                hit = ov + a.qd + msum >= 0.f;
-            }
-            Tf Tc = T;   // vertices of the piece are stored relative to its AABB centre
-            Tc.tx -= Pc.c[0]; Tc.ty -= Pc.c[1]; Tc.tz -= Pc.c[2];
-            queue_push(a, hit, s * (a.P + 1) + p, Tc, out_idx, prio_of(ov, msum), a.champ_scene, local ? &local->scene : nullptr, false);
-        }
     }
-    if ((a.flags & 2u) && a.has_plane) {
-        // conservative: lowest point of the shape's bounding box above the plane
-        const float cx = fmaf(T.r00, Sh.c[0], fmaf(T.r01, Sh.c[1], fmaf(T.r02, Sh.c[2], T.tx)));
-        const float cy = fmaf(T.r10, Sh.c[0], fmaf(T.r11, Sh.c[1], fmaf(T.r12, Sh.c[2], T.ty)));
-        const float cz = fmaf(T.r20, Sh.c[0], fmaf(T.r21, Sh.c[1], fmaf(T.r22, Sh.c[2], T.tz)));
-        const V3 nl = tf_rot_t(T, mk(a.plane[0], a.plane[1], a.plane[2]));
-        const float ext = fmaf(fabsf(nl.x), Sh.h[0], fmaf(fabsf(nl.y), Sh.h[1], fabsf(nl.z) * Sh.h[2]));
-        const float low = fmaf(a.plane[0], cx, fmaf(a.plane[1], cy, fmaf(a.plane[2], cz, a.plane[3]))) - ext;
-        // the plane vertices may exceed the core AABB by the embedded box margin: 2 mm slack
-        const bool hit = valid && (low - 0.002f - Sh.plane_margin <= a.qd);
-        queue_push(a, hit, s * (a.P + 1) + a.P, T, out_idx, 0.f, nullptr, nullptr, local != nullptr);
+    // Hull pieces + plane.  The slot reservation is an atomic with return (~1 us round trip under load); issued per
+    // (shape, piece) it was a third of this kernel's time.  So: first test ALL keys of the shape (bit k of `hm` = this
+    // lane hits key k; lane k keeps the warp's ballot for key k), then lanes 0..P reserve their key's slots side by
+    // side -- one round trip per shape -- and only then are the entries written.
+    const int lane = threadIdx.x & 31;
+    const int key0 = s * (a.P + 1);
+    const bool want_plane = (a.flags & 2u) && a.has_plane;
+    const int k_lo = (!MESH && (a.flags & 1u)) ? 0 : a.P, k_hi = want_plane ? a.P + 1 : a.P;
+    for (int c0 = k_lo; c0 < k_hi; c0 += 32) {   // chunks of 32 keys (one chunk unless a scene has > 31 pieces)
+        const int c1 = min(c0 + 32, k_hi);
+        unsigned hm = 0u, mymask = 0u;
+        for (int k = c0; k < c1; ++k) {
+            bool hit;
+            if (k < a.P) {
+                float ov;
+                hit = valid && piece_test(a, Sh, pieces[k], T, ov);
+            } else {
+                hit = valid && plane_test(a, Sh, T);
+            }
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
+            if (hit) hm |= 1u << (k - c0);
+            if (lane == k - c0) mymask = m;
+        }
+        int mybase = 0;
+        if (mymask != 0u) {
+            const int k = c0 + lane;
+            mybase = atomicAdd(a.counts + key0 + k, __popc(mymask));
+            // plane entries go straight onto the key's stage-1 list: same slots, same count (the list is the identity)
+            if (k == a.P && local != nullptr) atomicAdd(cnt_act(a) + key0 + k, __popc(mymask));
+        }
+        unsigned un = __reduce_or_sync(0xFFFFFFFFu, hm);
+        while (un != 0u) {
+            const int b = __ffs(un) - 1;
+            un &= un - 1u;
+            const unsigned m = __shfl_sync(0xFFFFFFFFu, mymask, b);
+            const int base = __shfl_sync(0xFFFFFFFFu, mybase, b);
+            if (!((hm >> b) & 1u)) continue;
+            const int k = c0 + b;
+            const int idx = base + __popc(m & ((1u << lane) - 1u));
+            const size_t slot = (size_t)(key0 + k) * a.cap + idx;
+            float prio = 0.f, ox = 0.f, oy = 0.f, oz = 0.f;
+            if (k < a.P) {
+                const PieceRec& Pc = pieces[k];
+                float ov;
+                piece_test(a, Sh, Pc, T, ov);
+                prio = prio_of(ov, Sh.margin + Pc.margin);
+                ox = Pc.c[0]; oy = Pc.c[1]; oz = Pc.c[2];   // vertices of the piece are stored relative to its AABB centre
+            }
+            a.q_r0[slot] = make_float4(T.r00, T.r01, T.r02, T.tx - ox);
+            a.q_r1[slot] = make_float4(T.r10, T.r11, T.r12, T.ty - oy);
+            a.q_r2[slot] = make_float4(T.r20, T.r21, T.r22, T.tz - oz);
+            a.q_cfg[slot] = out_idx;
+            a.q_prio[slot] = prio;
+            if (k < a.P) {
+                const unsigned long long code = ((unsigned long long)__float_as_uint(prio) << 32) | (unsigned)(((key0 + k) << 20) | idx);
+                if (local) { if (code > local->scene) local->scene = code; }
+                else atomicMax(a.champ_scene + out_idx, code);
+            } else if (local != nullptr) {
+                a.act_list[slot] = idx;
+            }
+        }
     }
 }
 
-template <int BLOCK>
+template <int BLOCK, bool MESH>
 __global__ void __launch_bounds__(BLOCK) k_broadphase(const PassArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RobotTab* R = reinterpret_cast<RobotTab*>(smem_raw);
@@ -389,13 +447,13 @@ __global__ void __launch_bounds__(BLOCK) k_broadphase(const PassArgs a) {
     // one thread owns all pairs of its configuration: champion in registers (not for edge substeps / mesh queues)
     Champ champ;
     champ.scene = champ.self = 0ull;
-    Champ* lc = (a.substeps <= 1 && !a.mesh) ? &champ : nullptr;
+    Champ* lc = (a.substeps <= 1 && !MESH) ? &champ : nullptr;
 
     // base-link shapes (link -1)
     Tf cur = tf_identity(), saved = tf_identity();
     if (want_scene)
         for (int s = R->base_shape_first; s < R->base_shape_first + R->base_shape_count; ++s)
-            shape_vs_scene(a, R->shapes[s], s, pieces, cur, valid, out_idx, lc);
+            shape_vs_scene<MESH>(a, R->shapes[s], s, pieces, cur, valid, out_idx, lc);
 
     for (int i = 0; i < R->L; ++i) {
         const JointRec& J = R->joints[i];
@@ -433,7 +491,7 @@ __global__ void __launch_bounds__(BLOCK) k_broadphase(const PassArgs a) {
         }
         if (want_scene)
             for (int s = J.shape_first; s < J.shape_first + J.shape_count; ++s)
-                shape_vs_scene(a, R->shapes[s], s, pieces, cur, valid, out_idx, lc);
+                shape_vs_scene<MESH>(a, R->shapes[s], s, pieces, cur, valid, out_idx, lc);
     }
     if (lc) {
         if (want_scene) champ_publish(a, champ.scene, a.champ_scene, out_idx, valid);
@@ -987,7 +1045,7 @@ __global__ void k_init_scratch(int* enc_scene, int* enc_self, unsigned long long
 
 // ------------------------------------------------------------------------------------------------ gripper poses
 // Free-floating gripper: one thread per pose of the end-effector link; the listed shapes ride on it rigidly.
-template <int BLOCK>
+template <int BLOCK, bool MESH>
 __global__ void __launch_bounds__(BLOCK) k_broadphase_poses(const PassArgs a, const float* __restrict__ poses, int fmt,
                                                             const Tf* __restrict__ rel, const int* __restrict__ use_shapes,
                                                             int n_use) {
@@ -1034,7 +1092,7 @@ __global__ void __launch_bounds__(BLOCK) k_broadphase_poses(const PassArgs a, co
     for (int k = 0; k < n_use; ++k) {
         const int s = use_shapes[k];
         const Tf T = tf_mul(Pz, rel[k]);
-        shape_vs_scene(a, R->shapes[s], s, pieces, T, valid, cfg, &champ);
+        shape_vs_scene<MESH>(a, R->shapes[s], s, pieces, T, valid, cfg, &champ);
     }
     champ_publish(a, champ.scene, a.champ_scene, cfg, valid);
 }
