@@ -283,6 +283,27 @@ def run_b200(args):
                      'polytopes_expanded_per_check': stats['epa_run'] / max(stats['configs'], 1)},
             'wall_s_timed_region': wall,
         }
+        if world == 1 and not args.no_count:
+            # audit of the nominal figure: executed work counted by the instrumented twin of the library, in a
+            # subprocess after the timed region (never timed, never the shipped path)
+            try:
+                import subprocess
+                env = dict(os.environ, JG_B200_LIB_VARIANT='count', CUDA_VISIBLE_DEVICES=os.environ.get('CUDA_VISIBLE_DEVICES', str(local)))
+                out = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'count_work.py'), '--scenario', str(args.scenario),
+                                      '--n', str(n), '--seed', '11', '--flags', str(int(flags))],
+                                     capture_output=True, text=True, timeout=600, env=env)
+                cw = json.loads(out.stdout.strip().splitlines()[-1])
+                ex_tf = checks_timed * cw['counted_narrow_flops_per_check'] / (nar_ms * 1e-3) / 1e12
+                line['roofline']['counted'] = {
+                    'executed_flops_per_check': cw['counted_narrow_flops_per_check'],
+                    'support_dots_per_check': cw['support_dots_per_check'],
+                    'gjk_iterations_per_check': cw['gjk_iterations_per_check'],
+                    'polytope_expansions_per_check': cw['polytope_expansions_per_check'],
+                    'executed_tflops': ex_tf, 'executed_frac': ex_tf / fp32_peak if fp32_peak else None,
+                    'flops_per_unit': cw['flops_per_unit'],
+                    'source': 'libjogramop_b200_count.so (-DJG_COUNT_WORK) on the same inputs, outside the timed region'}
+            except Exception as exc:   # the audit is optional evidence; the bench line stands without it
+                line['roofline']['counted'] = {'unavailable': repr(exc)[:200]}
         if world == 1 and not args.no_cpu_baseline:
             import oracle
             oflags = oracle.SCENE | oracle.PLANE | (oracle.NO_EPA if args.no_epa else 0)
@@ -307,6 +328,7 @@ def main():
     ap.add_argument('--chunk', type=int, default=0)
     ap.add_argument('--no-epa', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-count', action='store_true', help='skip the counted-work audit (instrumented library)')
     ap.add_argument('--cpu-budget', type=float, default=10.0, help='seconds of CPU work for the cpu_baseline sample')
     ap.add_argument('--ref-sample', type=int, default=200_000, help='configurations per step of the reference arm')
     args = ap.parse_args()

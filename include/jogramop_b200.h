@@ -44,7 +44,8 @@ enum {
     JG_ERR_INVALID = -1,   /* bad argument (NULL, dof mismatch, unsupported topology ...) */
     JG_ERR_CUDA = -2,      /* a CUDA runtime call failed */
     JG_ERR_NOMEM = -3,
-    JG_ERR_NODEVICE = -4   /* no usable CUDA device: there is NO CPU fallback */
+    JG_ERR_NODEVICE = -4,  /* no usable CUDA device: there is NO CPU fallback */
+    JG_ERR_UNSUPPORTED = -5 /* entry point not available in this build of the library */
 };
 
 /* what jg_check tests (scenario.py:109-119 order: limits, self-collision, scene collision) */
@@ -174,6 +175,13 @@ int jg_get_profile(jg_engine*, double ms[4], int64_t launches[4]);
 /* FP32 FMA micro-benchmark (roofline denominator of the narrow phase): dependent-chain-free FFMA loop on every
  * SM of `device`; returns the best of `reps` runs in TFLOP/s (2 flops per FMA). */
 int jg_measure_fp32_peak(int device, int reps, double* tflops);
+
+/* Work counters of the instrumented build (libjogramop_b200_count.so, compiled with -DJG_COUNT_WORK): executed support
+ * dot products, GJK iterations, polytope expansions, reserved -- accumulated on `device` since the last reset.  Used by
+ * bench.py to audit the nominal flops-per-check of the roofline with a counted figure.  The
+ * shipped library does not count: both calls return JG_ERR_UNSUPPORTED there. */
+int jg_work_counters(int device, uint64_t out[4]);
+int jg_work_counters_reset(int device);
 
 #ifdef __cplusplus
 }

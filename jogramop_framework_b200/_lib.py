@@ -18,7 +18,9 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
+    # JG_B200_LIB_VARIANT=count selects the instrumented twin (work counters; bench.py's flops audit runs it in a
+    # subprocess).  Everything else uses the shipped library.
+    path = _build.LIB_COUNT if os.environ.get('JG_B200_LIB_VARIANT') == 'count' else _build.LIB
     if not os.path.exists(path):
         raise JogramopError(
             f'{path} is missing: build it with `python -m jogramop_framework_b200.build` '
@@ -51,6 +53,8 @@ def load():
     L.jg_profile_enable.argtypes = [vp, i32]
     L.jg_get_profile.argtypes = [vp, vp, vp]
     L.jg_measure_fp32_peak.argtypes = [i32, i32, vp]
+    L.jg_work_counters.argtypes = [i32, vp]
+    L.jg_work_counters_reset.argtypes = [i32]
     _lib = L
     return L
 
@@ -75,4 +79,4 @@ EXPORTED_SYMBOLS = [
     'jg_default_params', 'jg_last_error', 'jg_abi_version', 'jg_device_count', 'jg_robot_create', 'jg_robot_free',
     'jg_scene_create', 'jg_scene_create_mesh', 'jg_scene_free', 'jg_engine_create', 'jg_engine_free', 'jg_engine_device', 'jg_fk', 'jg_check',
     'jg_check_edges', 'jg_check_poses', 'jg_check_host', 'jg_ik', 'jg_get_stats', 'jg_profile_enable', 'jg_get_profile',
-    'jg_measure_fp32_peak']
+    'jg_measure_fp32_peak', 'jg_work_counters', 'jg_work_counters_reset']

@@ -6,8 +6,11 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libjogramop_b200.so')
+# same sources with -DJG_COUNT_WORK: counts executed support dot products / iterations (bench.py's audit of the nominal
+# flops figure); never used for a timed or shipped path
+LIB_COUNT = os.path.join(HERE, 'libjogramop_b200_count.so')
 SOURCES = ['jg_abi.cu']
-HEADERS = ['jg_math.cuh', 'jg_gjk.cuh', 'jg_kernels.cuh', os.path.join('..', '..', 'include', 'jogramop_b200.h')]
+HEADERS = ['jg_math.cuh', 'jg_gjk.cuh', 'jg_epa.cuh', 'jg_lbvh.cuh', 'jg_kernels.cuh', os.path.join('..', '..', 'include', 'jogramop_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared']
 
@@ -19,21 +22,25 @@ def _nvcc():
     raise RuntimeError('nvcc not found: cannot build libjogramop_b200.so')
 
 
-def is_stale():
-    if not os.path.exists(LIB):
+def is_stale(lib=None):
+    lib = lib or LIB
+    if not os.path.exists(lib):
         return True
-    t = os.path.getmtime(LIB)
+    t = os.path.getmtime(lib)
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force=False, verbose=False):
-    """Compile the library if it is missing or older than its sources; returns its path."""
-    if not force and not is_stale():
-        return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB] + SOURCES
+def build(force=False, verbose=False, counting=False):
+    """Compile the library (or its instrumented twin) if it is missing or older than its sources; returns its path."""
+    lib = LIB_COUNT if counting else LIB
+    if not force and not is_stale(lib):
+        return lib
+    cmd = ([_nvcc()] + NVCC_FLAGS + (['-DJG_COUNT_WORK'] if counting else []) + (['-Xptxas', '-v'] if verbose else []) +
+           ['-o', lib] + SOURCES)
     subprocess.check_call(cmd, cwd=CSRC)
-    return LIB
+    return lib
 
 
 if __name__ == '__main__':
     print(build(force=True, verbose=True))
+    print(build(force=True, counting=True))

@@ -1167,6 +1167,34 @@ __global__ void __launch_bounds__(256) k_fma_peak(float* out, float a, float b, 
     out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }
 
+extern "C" int jg_work_counters(int device, uint64_t out[4]) {
+#ifdef JG_COUNT_WORK
+    if (!out) return fail(JG_ERR_INVALID, "jg_work_counters: NULL output");
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    unsigned long long h[JG_WORK_N];
+    CUDA_TRY(cudaMemcpyFromSymbol(h, g_jg_work, sizeof(h)));
+    for (int i = 0; i < 4; ++i) out[i] = h[i];
+    return JG_OK;
+#else
+    (void)device; (void)out;
+    return fail(JG_ERR_UNSUPPORTED, "jg_work_counters: this library was built without -DJG_COUNT_WORK");
+#endif
+}
+
+extern "C" int jg_work_counters_reset(int device) {
+#ifdef JG_COUNT_WORK
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    unsigned long long h[JG_WORK_N] = {0ull, 0ull, 0ull, 0ull};
+    CUDA_TRY(cudaMemcpyToSymbol(g_jg_work, h, sizeof(h)));
+    return JG_OK;
+#else
+    (void)device;
+    return fail(JG_ERR_UNSUPPORTED, "jg_work_counters_reset: this library was built without -DJG_COUNT_WORK");
+#endif
+}
+
 extern "C" int jg_measure_fp32_peak(int device, int reps, double* tflops) {
     if (!tflops) return fail(JG_ERR_INVALID, "jg_measure_fp32_peak: NULL output");
     CUDA_TRY(cudaSetDevice(device));

@@ -48,6 +48,7 @@ struct ThreadSupport {
     const float4* B; int nB;
     Tf T;
     __device__ __forceinline__ V3 operator()(V3 d, uint32_t& id) const { return support_md(A, nA, B, nB, T, d, id); }
+    __device__ __forceinline__ unsigned work_unit() const { return 1u; }   // (instrumented build) one expansion per thread
 };
 
 // Polytope storage.  All state lives in 32-bit words addressed as w[k * STRIDE]: STRIDE = 1 for a per-thread array
@@ -219,6 +220,7 @@ __device__ __forceinline__ int epa_step(EpaStateT<E>& X, const Sup& sup) {
     const V3 w = sup(n, id);
     X.ub = fminf(X.ub, dot(n, w));
     X.it += 1;
+    JG_WORK(JG_WORK_EPA_ITERS, sup.work_unit());
     if (X.ub - X.lb <= JG_EPA_TOL || X.it >= JG_EPA_MAX_ITER) return JG_EPA_DONE;
     bool dupl = false;
     for (int i = 0; i < P.nv; ++i) dupl |= (P.pid(i) == id);
@@ -440,6 +442,7 @@ __device__ __forceinline__ int epa_step(EpaStateC<STRIDE>& X, const Sup& sup) {
     const V3 w = sup(n, id);
     X.ub = fminf(X.ub, dot(n, w));
     X.it += 1;
+    JG_WORK(JG_WORK_EPA_ITERS, sup.work_unit());
     // (a support point that is already a polytope vertex cannot gain over the closest face: the bracket test ends it)
     if (X.ub - X.lb <= JG_EPA_TOL || X.it >= JG_EPA_MAX_ITER) return JG_EPA_DONE;
     if (P.nv >= E::V) return JG_EPA_OVERFLOW;

@@ -34,6 +34,7 @@ __device__ __forceinline__ float dot4(const float4 p, V3 d) { return fmaf(p.x, d
 
 __device__ __forceinline__ int support_scan(const float4* __restrict__ verts, int n, V3 d) {
     const int ng = (n + 3) >> 2;
+    JG_WORK(JG_WORK_DOTS, (unsigned)(4 * ng + 3));
     float best = -FLT_MAX;
     int bg = 0;
 #pragma unroll 2
@@ -137,6 +138,7 @@ struct SetSupport {
 struct TriSupport {
     V3 p0, p1, p2;
     __device__ __forceinline__ V3 operator()(V3 d, int& idx) const {
+        JG_WORK(JG_WORK_DOTS, 3u);
         const float s0 = dot(p0, d), s1 = dot(p1, d), s2 = dot(p2, d);
         idx = (s1 > s0) ? (s2 > s1 ? 2 : 1) : (s2 > s0 ? 2 : 0);
         return idx == 0 ? p0 : (idx == 1 ? p1 : p2);
@@ -148,6 +150,7 @@ __device__ __forceinline__ int gjk_step(GjkState& G, const float4* __restrict__ 
                                         float dmax) {
     Simplex& S = G.S;
     const V3 v = G.v;
+    JG_WORK(JG_WORK_GJK_ITERS, 1u);
     // support point of A - B in direction -v
     const V3 dl = tf_rot_t(T, -v);
     const int ia = support_scan(A, nA, dl);

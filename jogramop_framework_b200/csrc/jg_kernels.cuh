@@ -943,6 +943,7 @@ struct WarpSupport {
     __device__ __forceinline__ int scan(const float4* __restrict__ v, int n, V3 d) const {
         float best = -FLT_MAX;
         int bi = 0x7FFFFFFF;
+        JG_WORK(JG_WORK_DOTS, (unsigned)((n - lane + 31) / 32));
         for (int i = lane; i < n; i += 32) {
             const float s = dot4(v[i], d);
             if (s > best) { best = s; bi = i; }
@@ -962,6 +963,7 @@ struct WarpSupport {
         id = ((uint32_t)ia << 16) | (uint32_t)ib;
         return tf_apply(T, mk(pa.x, pa.y, pa.z)) - mk(pb.x, pb.y, pb.z);
     }
+    __device__ __forceinline__ unsigned work_unit() const { return lane == 0 ? 1u : 0u; }   // one expansion per WARP
 };
 
 template <int BLOCK>

@@ -22,6 +22,22 @@ static inline float4 make_float4(float x, float y, float z, float w) { float4 r 
 
 namespace jg {
 
+// Work counters of the INSTRUMENTED build (-DJG_COUNT_WORK, libjogramop_b200_count.so): executed support dot products,
+// GJK iterations, polytope expansions.  bench.py uses them to audit the nominal flops-per-check figure of the roofline
+// (SURVEY.md §8d); the shipped library compiles them away.
+enum { JG_WORK_DOTS = 0, JG_WORK_GJK_ITERS = 1, JG_WORK_EPA_ITERS = 2, JG_WORK_TRI_TESTS = 3, JG_WORK_N = 4 };
+#if defined(JG_COUNT_WORK) && !defined(JG_HOST_EMU)
+__device__ unsigned long long g_jg_work[JG_WORK_N];
+__device__ __forceinline__ void work_add(int slot, unsigned v) {
+    const unsigned m = __activemask();
+    const unsigned sum = __reduce_add_sync(m, v);
+    if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(&g_jg_work[slot], (unsigned long long)sum);
+}
+#define JG_WORK(slot, v) work_add(slot, v)
+#else
+#define JG_WORK(slot, v) ((void)0)
+#endif
+
 struct V3 {
     float x, y, z;
 };
