@@ -21,6 +21,7 @@ def load():
     # JG_B200_LIB_VARIANT=count selects the instrumented twin (work counters; bench.py's flops audit runs it in a
     # subprocess).  Everything else uses the shipped library.
     path = _build.LIB_COUNT if os.environ.get('JG_B200_LIB_VARIANT') == 'count' else _build.LIB
+    path = os.environ.get('JG_B200_LIB_PATH', path)   # development: an experimental build of the same sources
     if not os.path.exists(path):
         raise JogramopError(
             f'{path} is missing: build it with `python -m jogramop_framework_b200.build` '

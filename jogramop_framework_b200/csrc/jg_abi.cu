@@ -567,6 +567,8 @@ static void launch_broadphase(const jg_engine* e, const PassArgs& a, int grid, s
     else k_broadphase<BP_BLOCK, false><<<grid, BP_BLOCK, smem, st>>>(a);
 }
 
+#define JG_COUNTS_INTS(n_keys) (5 * (n_keys) + 8)   /* layout: jg_kernels.cuh cnt_*() */
+
 static size_t bp_smem(const jg_engine* e, uint32_t flags) {
     size_t s = sizeof(RobotTab) + sizeof(PieceRec) * e->P + sizeof(float) * BP_BLOCK * e->dof;
     if (flags & JG_SELF) s += sizeof(float) * 12 * e->n_stash * BP_BLOCK;
@@ -660,7 +662,7 @@ extern "C" jg_engine* jg_engine_create(const jg_robot* r, const jg_scene* sc, in
                cudaMalloc(&e->q_r2, sizeof(float4) * qn) == cudaSuccess && cudaMalloc(&e->q_cfg, sizeof(int) * qn) == cudaSuccess && cudaMalloc(&e->epa_slot, sizeof(int) * qn) == cudaSuccess && cudaMalloc(&e->epa_ids, sizeof(uint4) * qn) == cudaSuccess && cudaMalloc(&e->ovf_list, sizeof(int2) * cap) == cudaSuccess && cudaMalloc(&e->epa_prio, sizeof(float) * qn) == cudaSuccess && cudaMalloc(&e->q_prio, sizeof(float) * qn) == cudaSuccess &&
                cudaMalloc(&e->act_list, sizeof(int) * qn) == cudaSuccess && cudaMalloc(&e->champ_scene, sizeof(unsigned long long) * cap) == cudaSuccess &&
                cudaMalloc(&e->champ_self, sizeof(unsigned long long) * cap) == cudaSuccess &&
-               cudaMalloc(&e->counts, sizeof(int) * (4 * e->n_keys + 8)) == cudaSuccess &&
+               cudaMalloc(&e->counts, sizeof(int) * JG_COUNTS_INTS(e->n_keys)) == cudaSuccess &&
                cudaMalloc(&e->enc_scene, sizeof(int) * cap) == cudaSuccess && cudaMalloc(&e->enc_self, sizeof(int) * cap) == cudaSuccess &&
                cudaMalloc(&e->viol, sizeof(uint32_t) * (cap / 32 + 1)) == cudaSuccess &&
                cudaMalloc(&e->d_link_slot, sizeof(int) * MAX_LINKS) == cudaSuccess &&
@@ -809,7 +811,7 @@ extern "C" int jg_check(jg_engine* e, const float* q, int64_t n, int dof, uint32
         PassArgs a;
         fill_args(e, a, flags, min_dist != nullptr);
         a.q = q + off * dof; a.n = m;
-        CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * (4 * e->n_keys + 8), st));
+        CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * JG_COUNTS_INTS(e->n_keys), st));
         if (flags & JG_LIMITS) CUDA_TRY(cudaMemsetAsync(e->viol, 0, sizeof(uint32_t) * (e->cap / 32 + 1), st));
         prof_begin(e, 0, st);
         launch_broadphase(e, a, (m + BP_BLOCK - 1) / BP_BLOCK, bp_smem(e, flags), st);
@@ -854,7 +856,7 @@ extern "C" int jg_check_edges(jg_engine* e, const float* qa, const float* qb, in
         PassArgs a;
         fill_args(e, a, flags, min_dist != nullptr);
         a.q = qa + off * dof; a.qb = qb + off * dof; a.n = me * substeps; a.substeps = substeps;
-        CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * (4 * e->n_keys + 8), st));
+        CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * JG_COUNTS_INTS(e->n_keys), st));
         if (flags & JG_LIMITS) CUDA_TRY(cudaMemsetAsync(e->viol, 0, sizeof(uint32_t) * (e->cap / 32 + 1), st));
         prof_begin(e, 0, st);
         k_init_scratch<<<(me + 255) / 256, 256, 0, st>>>(e->enc_scene, e->enc_self, e->champ_scene, e->champ_self, me);
@@ -942,7 +944,7 @@ extern "C" int jg_check_poses(jg_engine* e, const float* poses, int64_t n, int f
         PassArgs a;
         fill_args(e, a, flags, min_dist != nullptr);
         a.n = m;
-        CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * (4 * e->n_keys + 8), st));
+        CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * JG_COUNTS_INTS(e->n_keys), st));
         const size_t smem = sizeof(RobotTab) + sizeof(PieceRec) * e->P;
         prof_begin(e, 0, st);
         if (e->mesh)
@@ -1074,7 +1076,7 @@ extern "C" int jg_check_host(jg_engine* e, const float* q, int64_t n, int dof, u
         uint32_t fl = flags;
         fill_args(e, a, fl, dist != nullptr);
         a.q = e->stage_q[b]; a.n = m;
-        CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * (4 * e->n_keys + 8), st));
+        CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * JG_COUNTS_INTS(e->n_keys), st));
         if (fl & JG_LIMITS) CUDA_TRY(cudaMemsetAsync(e->viol, 0, sizeof(uint32_t) * (e->cap / 32 + 1), st));
         const int slice = std::max(1024, ((m + SLICES - 1) / SLICES + 1023) / 1024 * 1024);
         prof_begin(e, 0, st);

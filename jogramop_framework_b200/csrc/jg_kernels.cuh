@@ -100,7 +100,7 @@ struct PassArgs {
     float4 *q_r0, *q_r1, *q_r2;
     int* q_cfg;
     int cap;           // queue capacity per key (= max configs per pass)
-    int* counts;       // 4*n_keys + 8 ints: pair-queue counts | penetration-queue counts | entries selected for the
+    int* counts;       // 5*n_keys + 8 ints (JG_COUNTS_INTS): pair-queue counts | penetration-queue counts | entries selected for the
                        // current stage | penetration entries already expanded | gjk range ctr, penetration range ctr,
                        // overflow-list length, select range ctr
     float* q_prio;     // [n_keys*cap] upper bound of the pair's total penetration (AABB overlap + margins)
@@ -133,6 +133,8 @@ __device__ __forceinline__ int* cnt_act(const PassArgs& a) { return a.counts + 2
 __device__ __forceinline__ int* cnt_done(const PassArgs& a) { return a.counts + 3 * a.n_keys; }
 enum { CTR_GJK = 0, CTR_EPA = 1, CTR_OVF = 2, CTR_SEL = 3 };
 __device__ __forceinline__ int* cnt_misc(const PassArgs& a) { return a.counts + 4 * a.n_keys; }
+// per-key cursors of the running narrow-phase stage (entries of the key's stage list handed out so far)
+__device__ __forceinline__ int* cnt_cur(const PassArgs& a) { return a.counts + 4 * a.n_keys + 8; }
 
 __device__ __forceinline__ Tf joint_local(const JointRec& J, float val) {
     Tf O;
@@ -500,24 +502,42 @@ __global__ void __launch_bounds__(BLOCK) k_broadphase(const PassArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------ narrow phase
-// Work distribution shared by the GJK and the penetration kernels.  A key's queue is cut into ranges of `G`
-// consecutive entries; warps pull ranges from a global counter (dynamic balance) and process a range with LANE
-// REFILL: whenever a lane finishes its pair it takes the next entry of the range, so every pass over the vertex
-// sets (the expensive, warp-uniform part of an iteration) runs with all lanes busy until the range drains.
-struct RangeSched {
-    int* prefix;   // smem [n_keys+1] exclusive scan of ranges per key
-    int G;         // entries per range (multiple of 32)
-    int total;     // total ranges
-};
+// Work distribution shared by the GJK and the penetration kernels: PER-KEY CURSORS with LANE REFILL.
+// Every lane of a warp must work on the same key (same two vertex sets -> broadcast reads), pairs differ wildly in
+// cost, and a stage has only a handful of pairs per lane -- so the unit of scheduling is the single entry:
+//   * a warp starts on the key at its proportional position in the stage's work and stays on it; it reserves 32
+//     entries at a time from the key's cursor (atomicAdd) and hands them to lanes as they go idle, so the warp-uniform
+//     part of an iteration (the vertex scans) runs with all lanes busy;
+//   * the next reservation is issued the moment the current one has been handed out and is only looked at when it is
+//     needed -- at least one iteration later -- so the round trip of the atomic is never waited for;
+//   * a key whose cursor passed its count is exhausted: the lanes drain (the only tail, once per key and warp) and
+//     the warp moves to the next key, in circular order, that still has entries.
+// sched_prefix: exclusive scan of the per-key entry counts into shared memory (warp 0 of the block).
+__device__ __forceinline__ void sched_prefix(const int* __restrict__ counts, int n_keys, int* prefix, int lane) {
+    int carry = 0;
+    for (int base = 0; base < n_keys; base += 32) {
+        const int k = base + lane;
+        const int t = k < n_keys ? counts[k] : 0;
+        int incl = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        if (k < n_keys) prefix[k] = carry + incl - t;
+        carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+    if (lane == 0) prefix[n_keys] = carry;
+}
 
-// called by warp 0 of the block; counts = per-key entry counts
+// range scheduler of the selection kernel (uniform cost per entry): a key's span is cut into ranges of G entries that
+// warps pull from one global counter.  called by warp 0 of the block; counts = per-key entry counts
 __device__ __forceinline__ void sched_build(const int* __restrict__ counts, int n_keys, int n_warps_total, int* prefix,
                                             int* g_out, int lane) {
     int tot = 0;
     for (int k = lane; k < n_keys; k += 32) tot += counts[k];
 #pragma unroll
     for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xFFFFFFFFu, tot, o);
-    // aim at ~4 ranges per warp so that the dynamic scheduler can balance keys of different cost
     int G = (tot / (n_warps_total * 4) + 31) & ~31;
     G = max(64, min(G, 2048));
     int carry = 0;
@@ -545,6 +565,63 @@ __device__ __forceinline__ int sched_find_key(const int* prefix, int n_keys, int
     return lo;
 }
 
+__device__ __forceinline__ int cursor_grab(int* cur, int n, int lane) {
+    int b = 0;
+    if (lane == 0) b = atomicAdd(cur, n);
+    return __shfl_sync(0xFFFFFFFFu, b, 0);
+}
+
+// first key at or after `from` (circular) whose cursor is still below its count, or -1: lanes probe 32 keys at a time
+__device__ __forceinline__ int sched_next_key(const int* __restrict__ counts, const int* cur, int n_keys, int from, int lane) {
+    for (int j = 0; j < n_keys; j += 32) {
+        int k = from + j + lane;
+        if (k >= n_keys) k -= n_keys;
+        const bool has = (j + lane < n_keys) && (*(const volatile int*)(cur + k) < counts[k]);
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, has);
+        if (m) {
+            int kk = from + j + (__ffs(m) - 1);
+            if (kk >= n_keys) kk -= n_keys;
+            return kk;
+        }
+    }
+    return -1;
+}
+
+// The refill loop of one key.  idle() / start(entry index in the key's stage list) act on the calling lane; step() runs
+// one iteration and is called by ALL lanes (converged) while any lane is busy.
+template <class Idle, class Start, class Step>
+__device__ __forceinline__ void refill_loop(int* cur, int cnt, int lane, Idle idle, Start start, Step step) {
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int next = 0, end = 0;
+    int pf = cursor_grab(cur, 32, lane);   // reservation in flight (its value is not looked at before it is needed)
+    bool pf_pending = true, exhausted = false;
+    for (;;) {
+        const unsigned need = __ballot_sync(0xFFFFFFFFu, idle());
+        if (need) {
+            if (next >= end && pf_pending) {
+                pf_pending = false;
+                if (pf < cnt) { next = pf; end = min(pf + 32, cnt); }
+                else exhausted = true;
+            }
+            const int avail = end - next;
+            if (avail > 0) {
+                const int rank = __popc(need & lt_mask);
+                if (idle() && rank < avail) start(next + rank);
+                next += min(__popc(need), avail);
+            }
+        }
+        if (!pf_pending && !exhausted && next >= end) {
+            pf = cursor_grab(cur, 32, lane);
+            pf_pending = true;
+        }
+        if (!__any_sync(0xFFFFFFFFu, !idle())) {
+            if (!pf_pending) break;   // exhausted and drained
+            continue;                 // nothing running: look at the reservation right away
+        }
+        step();
+    }
+}
+
 __device__ __forceinline__ Tf load_entry(const PassArgs& a, size_t slot, int& cfg) {
     const float4 r0 = a.q_r0[slot], r1 = a.q_r1[slot], r2 = a.q_r2[slot];
     cfg = a.q_cfg[slot];
@@ -569,32 +646,37 @@ __global__ void __launch_bounds__(BLOCK) k_narrowphase(const PassArgs a) {
         for (int i = tid; i < (int)(sizeof(KeyRec) / 4) * a.n_keys; i += BLOCK) kd[i] = ks[i];
     }
     const int* acounts = cnt_act(a);   // entries selected for this stage (k_select)
-    if (tid < 32) sched_build(acounts, a.n_keys, gridDim.x * (BLOCK / 32), prefix, prefix + a.n_keys + 1, lane);
+    if (tid < 32) sched_prefix(acounts, a.n_keys, prefix, lane);
     __syncthreads();
-    const int total = prefix[a.n_keys], G = prefix[a.n_keys + 1];
-    int* range_counter = cnt_misc(a) + CTR_GJK;
-    const unsigned lt_mask = (1u << lane) - 1u;
+    const int total = prefix[a.n_keys];
+    if (total == 0) return;
+    int* cur = cnt_cur(a);
     const bool want_epa = !(a.flags & 16u);
+    const int n_warps = gridDim.x * (BLOCK / 32), gw = blockIdx.x * (BLOCK / 32) + (tid >> 5);
+    const unsigned lt_mask = (1u << lane) - 1u;
 
+    // start at the key that holds this warp's proportional share of the stage, then go round the keys
+    int key = sched_find_key(prefix, a.n_keys, (int)((long long)gw * total / n_warps));
     for (;;) {
-        int r = 0;
-        if (lane == 0) r = atomicAdd(range_counter, 1);
-        r = __shfl_sync(0xFFFFFFFFu, r, 0);
-        if (r >= total) break;
-        const int key = sched_find_key(prefix, a.n_keys, r);
+        key = sched_next_key(acounts, cur, a.n_keys, key, lane);
+        if (key < 0) break;
         const KeyRec K = keys[key];
-        const int begin = (r - prefix[key]) * G;
-        const int end = min(begin + G, acounts[key]);
+        const int cnt = acounts[key];
         const size_t kbase = (size_t)key * a.cap;
         int* enc = K.kind == KEY_SELF ? a.enc_self : a.enc_scene;
 
-        if (K.kind == KEY_PLANE) {   // uniform cost per entry: plain strided loop
-            for (int i = begin + lane; i < end; i += 32) {
-                int cfg;
-                const Tf T = load_entry(a, kbase + a.act_list[kbase + i], cfg);
-                const float d = plane_distance(verts + K.a_off, K.a_n, T, mk(a.plane[0], a.plane[1], a.plane[2]),
-                                               a.plane[3]) - K.msum;
-                if (d <= a.qd) atomicMin(enc + cfg, enc_float(d));
+        if (K.kind == KEY_PLANE) {   // uniform cost per entry: plain strided loop over chunks of 256
+            for (;;) {
+                const int begin = cursor_grab(cur + key, 256, lane);
+                if (begin >= cnt) break;
+                const int end = min(begin + 256, cnt);
+                for (int i = begin + lane; i < end; i += 32) {
+                    int cfg;
+                    const Tf T = load_entry(a, kbase + a.act_list[kbase + i], cfg);
+                    const float d = plane_distance(verts + K.a_off, K.a_n, T, mk(a.plane[0], a.plane[1], a.plane[2]),
+                                                   a.plane[3]) - K.msum;
+                    if (d <= a.qd) atomicMin(enc + cfg, enc_float(d));
+                }
             }
             continue;
         }
@@ -602,7 +684,6 @@ __global__ void __launch_bounds__(BLOCK) k_narrowphase(const PassArgs a) {
         const float4* A = verts + K.a_off;
         const float4* B = verts + K.b_off;
         const float dmax = a.qd + K.msum;
-        int next = begin;
         bool active = false;
         GjkState S;
         Tf T = tf_identity();
@@ -611,28 +692,22 @@ __global__ void __launch_bounds__(BLOCK) k_narrowphase(const PassArgs a) {
         if (K.kind == KEY_MESH) {   // link hull vs one triangle per lane (registers); same lane refill, no penetration pass
             TriSupport tri;
             tri.p0 = tri.p1 = tri.p2 = mk(0.f, 0.f, 0.f);
-            for (;;) {
-                const unsigned need = __ballot_sync(0xFFFFFFFFu, !active);
-                const int avail = end - next;
-                if (need && avail > 0) {
-                    const int rank = __popc(need & lt_mask);
-                    if (!active && rank < avail) {
-                        off = a.act_list[kbase + next + rank];
-                        T = load_entry(a, kbase + off, cfg);
-                        const int t3 = 3 * a.q_tri[kbase + off];
-                        const float4 v0 = a.bvh_tri[t3], v1 = a.bvh_tri[t3 + 1], v2 = a.bvh_tri[t3 + 2];
-                        // work in a frame centred on the triangle (fp32 precision, like the centred pieces)
-                        const V3 c = mk((v0.x + v1.x + v2.x) * (1.f / 3.f), (v0.y + v1.y + v2.y) * (1.f / 3.f),
-                                        (v0.z + v1.z + v2.z) * (1.f / 3.f));
-                        tri.p0 = mk(v0.x, v0.y, v0.z) - c; tri.p1 = mk(v1.x, v1.y, v1.z) - c; tri.p2 = mk(v2.x, v2.y, v2.z) - c;
-                        T.tx -= c.x; T.ty -= c.y; T.tz -= c.z;
-                        gjk_init(S, mk(T.tx, T.ty, T.tz));
-                        active = true;
-                    }
-                    next += min(__popc(need), avail);
-                }
-                if (!__any_sync(0xFFFFFFFFu, active)) break;
-                if (active) {
+            refill_loop(cur + key, cnt, lane, [&]() { return !active; },
+                [&](int i) {
+                    off = a.act_list[kbase + i];
+                    T = load_entry(a, kbase + off, cfg);
+                    const int t3 = 3 * a.q_tri[kbase + off];
+                    const float4 v0 = a.bvh_tri[t3], v1 = a.bvh_tri[t3 + 1], v2 = a.bvh_tri[t3 + 2];
+                    // work in a frame centred on the triangle (fp32 precision, like the centred pieces)
+                    const V3 c = mk((v0.x + v1.x + v2.x) * (1.f / 3.f), (v0.y + v1.y + v2.y) * (1.f / 3.f),
+                                    (v0.z + v1.z + v2.z) * (1.f / 3.f));
+                    tri.p0 = mk(v0.x, v0.y, v0.z) - c; tri.p1 = mk(v1.x, v1.y, v1.z) - c; tri.p2 = mk(v2.x, v2.y, v2.z) - c;
+                    T.tx -= c.x; T.ty -= c.y; T.tz -= c.z;
+                    gjk_init(S, mk(T.tx, T.ty, T.tz));
+                    active = true;
+                },
+                [&]() {
+                    if (!active) return;
                     const int st = gjk_step(S, A, K.a_n, tri, T, dmax);
                     if (st != JG_GJK_RUNNING) {
                         active = false;
@@ -643,67 +718,59 @@ __global__ void __launch_bounds__(BLOCK) k_narrowphase(const PassArgs a) {
                             atomicMin(enc + cfg, enc_float(-K.msum));
                         }
                     }
-                }
-            }
+                });
             continue;
         }
-        for (;;) {
-            // ---- refill idle lanes from the range
-            const unsigned need = __ballot_sync(0xFFFFFFFFu, !active);
-            const int avail = end - next;
-            if (need && avail > 0) {
-                const int rank = __popc(need & lt_mask);
-                if (!active && rank < avail) {
-                    off = a.act_list[kbase + next + rank];
-                    T = load_entry(a, kbase + off, cfg);
-                    gjk_init(S, mk(T.tx, T.ty, T.tz));
-                    active = true;
-                    best_total = -dec_float(enc[cfg]);   // what is already proven for this configuration
-                }
-                next += min(__popc(need), avail);
-            }
-            if (!__any_sync(0xFFFFFFFFu, active)) break;
-            // ---- one GJK iteration on every busy lane
-            bool deep = false;
-            if (active) {
-                int st = gjk_step(S, A, K.a_n, SetSupport{B, K.b_n}, T, dmax);
-                // exact early out: another pair of this configuration already penetrates deeper than this pair possibly
-                // can (hmin = smallest support value seen = upper bound of this pair's depth if it overlaps at all)
-                if (st == JG_GJK_RUNNING && best_total > 0.f && fmaxf(S.hmin, 0.f) + fmaxf(K.emsum, K.msum) + 0.004f <= best_total) {
-                    active = false;
-                    st = JG_GJK_RUNNING;
-                } else
-                if (st != JG_GJK_RUNNING) {
-                    active = false;
-                    if (st == JG_GJK_SEPARATED) {
-                        const float d = sqrtf(S.vv) - K.msum;
-                        if (d <= a.qd) atomicMin(enc + cfg, enc_float(d));
-                    } else if (st == JG_GJK_PENETRATING) {
-                        if (want_epa) deep = true;
-                        else atomicMin(enc + cfg, enc_float(-K.msum));
+        refill_loop(cur + key, cnt, lane, [&]() { return !active; },
+            [&](int i) {
+                off = a.act_list[kbase + i];
+                T = load_entry(a, kbase + off, cfg);
+                gjk_init(S, mk(T.tx, T.ty, T.tz));
+                active = true;
+                best_total = -dec_float(enc[cfg]);   // what is already proven for this configuration
+            },
+            [&]() {
+                // ---- one GJK iteration on every busy lane
+                bool deep = false;
+                if (active) {
+                    int st = gjk_step(S, A, K.a_n, SetSupport{B, K.b_n}, T, dmax);
+                    // exact early out: another pair of this configuration already penetrates deeper than this pair possibly
+                    // can (hmin = smallest support value seen = upper bound of this pair's depth if it overlaps at all)
+                    if (st == JG_GJK_RUNNING && best_total > 0.f && fmaxf(S.hmin, 0.f) + fmaxf(K.emsum, K.msum) + 0.004f <= best_total) {
+                        active = false;
+                        st = JG_GJK_RUNNING;
+                    } else
+                    if (st != JG_GJK_RUNNING) {
+                        active = false;
+                        if (st == JG_GJK_SEPARATED) {
+                            const float d = sqrtf(S.vv) - K.msum;
+                            if (d <= a.qd) atomicMin(enc + cfg, enc_float(d));
+                        } else if (st == JG_GJK_PENETRATING) {
+                            if (want_epa) deep = true;
+                            else atomicMin(enc + cfg, enc_float(-K.msum));
+                        }
                     }
                 }
-            }
-            if (want_epa) {   // cores overlap: hand the pair (and its end simplex) to the penetration-depth pass
-                const unsigned m = __ballot_sync(0xFFFFFFFFu, deep);
-                if (m) {
-                    const int leader = __ffs(m) - 1;
-                    int base = 0;
-                    if (lane == leader) base = atomicAdd(cnt_epa(a) + key, __popc(m));
-                    base = __shfl_sync(0xFFFFFFFFu, base, leader);
-                    if (deep) {
-                        const int jj = base + __popc(m & lt_mask);
-                        const size_t j = kbase + jj;
-                        // bound of the total penetration: box overlap from the broad phase, tightened by the smallest
-                        // support value seen during GJK (+4 mm: margins of the penetration geometry vs the cores)
-                        a.epa_prio[j] = fminf(a.q_prio[kbase + off], fmaxf(S.hmin, 0.f) + fmaxf(K.emsum, K.msum) + 0.004f);
-                        a.epa_slot[j] = off;
-                        a.epa_ids[j] = make_uint4(S.S.n > 0 ? S.S.ia : 0xFFFFFFFFu, S.S.n > 1 ? S.S.ib : 0xFFFFFFFFu,
-                                                  S.S.n > 2 ? S.S.ic : 0xFFFFFFFFu, S.S.n > 3 ? S.S.id : 0xFFFFFFFFu);
+                if (want_epa) {   // cores overlap: hand the pair (and its end simplex) to the penetration-depth pass
+                    const unsigned m = __ballot_sync(0xFFFFFFFFu, deep);
+                    if (m) {
+                        const int leader = __ffs(m) - 1;
+                        int base = 0;
+                        if (lane == leader) base = atomicAdd(cnt_epa(a) + key, __popc(m));
+                        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                        if (deep) {
+                            const int jj = base + __popc(m & lt_mask);
+                            const size_t j = kbase + jj;
+                            // bound of the total penetration: box overlap from the broad phase, tightened by the smallest
+                            // support value seen during GJK (+4 mm: margins of the penetration geometry vs the cores)
+                            a.epa_prio[j] = fminf(a.q_prio[kbase + off], fmaxf(S.hmin, 0.f) + fmaxf(K.emsum, K.msum) + 0.004f);
+                            a.epa_slot[j] = off;
+                            a.epa_ids[j] = make_uint4(S.S.n > 0 ? S.S.ia : 0xFFFFFFFFu, S.S.n > 1 ? S.S.ib : 0xFFFFFFFFu,
+                                                      S.S.n > 2 ? S.S.ic : 0xFFFFFFFFu, S.S.n > 3 ? S.S.id : 0xFFFFFFFFu);
+                        }
                     }
                 }
-            }
-        }
+            });
     }
 }
 
@@ -818,6 +885,7 @@ __global__ void k_stage_reset(const PassArgs a, int mark_done, int stat_slot) {
     for (int k = threadIdx.x; k < a.n_keys; k += blockDim.x) {
         mine += cnt_act(a)[k];
         cnt_act(a)[k] = 0;
+        cnt_cur(a)[k] = 0;
         if (mark_done) cnt_done(a)[k] = cnt_epa(a)[k];
     }
     if (stat_slot >= 0 && mine) atomicAdd(&sum, mine);
@@ -839,95 +907,85 @@ __global__ void __launch_bounds__(BLOCK) k_penetration(const PassArgs a) {
     const int tid = threadIdx.x, lane = tid & 31;
     const int* ecounts = cnt_act(a);   // entries selected for this stage (k_select)
     for (int i = tid; i < a.n_verts; i += BLOCK) verts[i] = a.verts[i];
-    if (tid < 32) sched_build(ecounts, a.n_keys, gridDim.x * (BLOCK / 32), prefix, prefix + a.n_keys + 1, lane);
+    if (tid < 32) sched_prefix(ecounts, a.n_keys, prefix, lane);
     __syncthreads();
-    const int total = prefix[a.n_keys], G = prefix[a.n_keys + 1];
-    int* range_counter = cnt_misc(a) + CTR_EPA;
+    const int total = prefix[a.n_keys];
+    if (total == 0) return;
+    int* cur = cnt_cur(a);
     int* ovf_counter = cnt_misc(a) + CTR_OVF;
-    const unsigned lt_mask = (1u << lane) - 1u;
+    const int n_warps = gridDim.x * (BLOCK / 32), gw = blockIdx.x * (BLOCK / 32) + (tid >> 5);
 
     EpaStateC<BLOCK> X;   // compact polytope, interleaved across the block in shared memory (jg_epa.cuh)
     X.poly.w = poly_words + tid;
     X.poly.nv = X.poly.nf = 0;
     X.lb = 0.f; X.ub = FLT_MAX; X.it = 0;
 
+    int key = sched_find_key(prefix, a.n_keys, (int)((long long)gw * total / n_warps));
     for (;;) {
-        int r = 0;
-        if (lane == 0) r = atomicAdd(range_counter, 1);
-        r = __shfl_sync(0xFFFFFFFFu, r, 0);
-        if (r >= total) break;
-        const int key = sched_find_key(prefix, a.n_keys, r);
+        key = sched_next_key(ecounts, cur, a.n_keys, key, lane);
+        if (key < 0) break;
         const KeyRec K = a.keys[key];
-        const int begin = (r - prefix[key]) * G;
-        const int end = min(begin + G, ecounts[key]);
         const size_t kbase = (size_t)key * a.cap;
         int* enc = K.kind == KEY_SELF ? a.enc_self : a.enc_scene;
         const float4* A = verts + K.ea_off;
         const float4* B = verts + K.eb_off;
         const bool regjk = (K.ea_off != K.a_off) || (K.eb_off != K.b_off);   // warp-uniform
 
-        int next = begin;
         int phase = 0;   // 0 idle, 1 GJK on the penetration geometry, 2 expanding polytope
         GjkState S;
         Tf T = tf_identity();
         int cfg = 0, myj = 0;
         float best_total = -FLT_MAX;
-        for (;;) {
-            const unsigned need = __ballot_sync(0xFFFFFFFFu, phase == 0);
-            const int avail = end - next;
-            if (need && avail > 0) {
-                const int rank = __popc(need & lt_mask);
-                if (phase == 0 && rank < avail) {
-                    myj = a.act_list[kbase + next + rank];
-                    const size_t j = kbase + myj;
-                    T = load_entry(a, kbase + a.epa_slot[j], cfg);
-                    best_total = -dec_float(enc[cfg]);
-                    if (regjk) {
-                        gjk_init(S, mk(T.tx, T.ty, T.tz));
-                        phase = 1;
-                    } else {
-                        phase = 2;
-                        const ThreadSupport sup = {A, K.ea_n, B, K.eb_n, T};
-                        if (!epa_begin(X, sup, simplex_from_ids(A, B, T, a.epa_ids[j]))) {
-                            atomicMin(enc + cfg, enc_float(fminf(-K.emsum, -K.msum)));
-                            phase = 0;
-                        }
-                    }
-                }
-                next += min(__popc(need), avail);
-            }
-            if (!__any_sync(0xFFFFFFFFu, phase != 0)) break;
-            if (phase == 1) {
-                const int st = gjk_step(S, A, K.ea_n, SetSupport{B, K.eb_n}, T, 1e30f);
-                if (st == JG_GJK_PENETRATING) {
+        refill_loop(cur + key, ecounts[key], lane, [&]() { return phase == 0; },
+            [&](int i) {
+                myj = a.act_list[kbase + i];
+                const size_t j = kbase + myj;
+                T = load_entry(a, kbase + a.epa_slot[j], cfg);
+                best_total = -dec_float(enc[cfg]);
+                if (regjk) {
+                    gjk_init(S, mk(T.tx, T.ty, T.tz));
+                    phase = 1;
+                } else {
                     phase = 2;
                     const ThreadSupport sup = {A, K.ea_n, B, K.eb_n, T};
-                    if (!epa_begin(X, sup, S.S)) {
+                    if (!epa_begin(X, sup, simplex_from_ids(A, B, T, a.epa_ids[j]))) {
                         atomicMin(enc + cfg, enc_float(fminf(-K.emsum, -K.msum)));
                         phase = 0;
                     }
-                } else if (st != JG_GJK_RUNNING) {   // the penetration geometry does not overlap after all
-                    atomicMin(enc + cfg, enc_float(fminf(sqrtf(S.vv) - K.emsum, -K.msum)));
-                    phase = 0;
                 }
-            } else if (phase == 2) {
-                const ThreadSupport sup = {A, K.ea_n, B, K.eb_n, T};
-                const int st = (a.flags & 0x40000000u) ? (int)JG_EPA_OVERFLOW : epa_step(X, sup);   // test hook
-                if (st == JG_EPA_RUNNING && X.ub + K.emsum + 1e-5f <= best_total) {
-                    phase = 0;   // exact early out: this pair's depth is bounded below what its configuration already has
-                } else
-                if (st == JG_EPA_DONE) {
-                    // the cores overlap: never report less penetration than the margins
-                    atomicMin(enc + cfg, enc_float(fminf(-(epa_result(X) + K.emsum), -K.msum)));
-                    phase = 0;
-                } else if (st == JG_EPA_OVERFLOW) {   // rare large polytope: redo with per-thread storage
-                    const int o = atomicAdd(ovf_counter, 1);
-                    if (o < a.cap) a.ovf_list[o] = make_int2(key, myj);
-                    else atomicMin(enc + cfg, enc_float(fminf(-(epa_result(X) + K.emsum), -K.msum)));
-                    phase = 0;
+            },
+            [&]() {
+                if (phase == 1) {
+                    const int st = gjk_step(S, A, K.ea_n, SetSupport{B, K.eb_n}, T, 1e30f);
+                    if (st == JG_GJK_PENETRATING) {
+                        phase = 2;
+                        const ThreadSupport sup = {A, K.ea_n, B, K.eb_n, T};
+                        if (!epa_begin(X, sup, S.S)) {
+                            atomicMin(enc + cfg, enc_float(fminf(-K.emsum, -K.msum)));
+                            phase = 0;
+                        }
+                    } else if (st != JG_GJK_RUNNING) {   // the penetration geometry does not overlap after all
+                        atomicMin(enc + cfg, enc_float(fminf(sqrtf(S.vv) - K.emsum, -K.msum)));
+                        phase = 0;
+                    }
+                } else if (phase == 2) {
+                    const ThreadSupport sup = {A, K.ea_n, B, K.eb_n, T};
+                    const int st = (a.flags & 0x40000000u) ? (int)JG_EPA_OVERFLOW : epa_step(X, sup);   // test hook
+                    if (st == JG_EPA_RUNNING && X.ub + K.emsum + 1e-5f <= best_total) {
+                        phase = 0;   // exact early out: this pair's depth is bounded below what its configuration already has
+                    } else
+                    if (st == JG_EPA_DONE) {
+                        // the cores overlap: never report less penetration than the margins
+                        atomicMin(enc + cfg, enc_float(fminf(-(epa_result(X) + K.emsum), -K.msum)));
+                        phase = 0;
+                    } else if (st == JG_EPA_OVERFLOW) {   // rare large polytope: redo with per-thread storage
+                        const int o = atomicAdd(ovf_counter, 1);
+                        if (o < a.cap) a.ovf_list[o] = make_int2(key, myj);
+                        else atomicMin(enc + cfg, enc_float(fminf(-(epa_result(X) + K.emsum), -K.msum)));
+                        phase = 0;
+                    }
                 }
-            }
-        }
+            });
     }
 }
 
