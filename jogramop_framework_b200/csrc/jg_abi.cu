@@ -209,6 +209,7 @@ struct jg_engine {
     int n_stash = 0;                     // link frames the broad phase stashes for the self pairs                   // configurations per pass in mesh mode (adaptive)
     float* d_qrest = nullptr;
     int* act_list = nullptr;              // [n_keys*cap]
+    int2* act_meta = nullptr;             // [n_keys*cap]
     unsigned long long *champ_scene = nullptr, *champ_self = nullptr;   // [cap]
     int* counts = nullptr;                // [3*n_keys + 16], layout in jg_kernels.cuh PassArgs
     int *enc_scene = nullptr, *enc_self = nullptr;
@@ -289,7 +290,7 @@ static void engine_release(jg_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaFree(e->d_robot); cudaFree(e->d_pieces); cudaFree(e->d_selfs); cudaFree(e->d_keys); cudaFree(e->d_verts);
-    cudaFree(e->q_r0); cudaFree(e->q_r1); cudaFree(e->q_r2); cudaFree(e->q_cfg); cudaFree(e->epa_slot); cudaFree(e->epa_ids); cudaFree(e->ovf_list); cudaFree(e->epa_prio); cudaFree(e->q_prio); cudaFree(e->bvh.nodes); cudaFree(e->bvh.tri_v); cudaFree(e->bvh.tri_id); cudaFree(e->d_err); cudaFree(e->d_qrest); cudaFree(e->act_list); cudaFree(e->champ_scene); cudaFree(e->champ_self); cudaFree(e->counts);
+    cudaFree(e->q_r0); cudaFree(e->q_r1); cudaFree(e->q_r2); cudaFree(e->q_cfg); cudaFree(e->epa_slot); cudaFree(e->epa_ids); cudaFree(e->ovf_list); cudaFree(e->epa_prio); cudaFree(e->q_prio); cudaFree(e->bvh.nodes); cudaFree(e->bvh.tri_v); cudaFree(e->bvh.tri_id); cudaFree(e->d_err); cudaFree(e->d_qrest); cudaFree(e->act_list); cudaFree(e->act_meta); cudaFree(e->champ_scene); cudaFree(e->champ_self); cudaFree(e->counts);
     cudaFree(e->enc_scene); cudaFree(e->enc_self); cudaFree(e->viol); cudaFree(e->d_link_slot); cudaFree(e->d_rel);
     cudaFree(e->d_use_shapes); cudaFree(e->d_stats);
     for (int i = 0; i < 2; ++i) {
@@ -644,14 +645,14 @@ extern "C" jg_engine* jg_engine_create(const jg_robot* r, const jg_scene* sc, in
         e->smem_epa_big = sizeof(float4) * e->n_verts + sizeof(uint32_t) * EpaPolyBig::WORDS * (EPA_BIG_BLOCK / 32) + 64;
         e->epa_blocks = e->sm_count;
     }
-    // scratch arena: per-key queues of `cap` entries (72 B each).  Default: the largest power of two <= 2^20
+    // scratch arena: per-key queues of `cap` entries (92 B each).  Default: the largest power of two <= 2^20
     // configurations per pass whose arena stays within 16 GB and a quarter of the free device memory.
     int cap = e->prm.chunk;
     if (cap <= 0) {
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
         const size_t budget = std::min<size_t>((size_t)16 << 30, free_b / 4);
-        const size_t per_cfg = (size_t)std::max(e->n_keys, 1) * 84 + 48;
+        const size_t per_cfg = (size_t)std::max(e->n_keys, 1) * 92 + 48;
         cap = 1 << 20;
         while (cap > 4096 && (size_t)cap * per_cfg > budget) cap >>= 1;
     }
@@ -660,7 +661,7 @@ extern "C" jg_engine* jg_engine_create(const jg_robot* r, const jg_scene* sc, in
     const size_t qn = (size_t)std::max(e->n_keys, 1) * cap;
     bool okm = cudaMalloc(&e->q_r0, sizeof(float4) * qn) == cudaSuccess && cudaMalloc(&e->q_r1, sizeof(float4) * qn) == cudaSuccess &&
                cudaMalloc(&e->q_r2, sizeof(float4) * qn) == cudaSuccess && cudaMalloc(&e->q_cfg, sizeof(int) * qn) == cudaSuccess && cudaMalloc(&e->epa_slot, sizeof(int) * qn) == cudaSuccess && cudaMalloc(&e->epa_ids, sizeof(uint4) * qn) == cudaSuccess && cudaMalloc(&e->ovf_list, sizeof(int2) * cap) == cudaSuccess && cudaMalloc(&e->epa_prio, sizeof(float) * qn) == cudaSuccess && cudaMalloc(&e->q_prio, sizeof(float) * qn) == cudaSuccess &&
-               cudaMalloc(&e->act_list, sizeof(int) * qn) == cudaSuccess && cudaMalloc(&e->champ_scene, sizeof(unsigned long long) * cap) == cudaSuccess &&
+               cudaMalloc(&e->act_list, sizeof(int) * qn) == cudaSuccess && cudaMalloc(&e->act_meta, sizeof(int2) * qn) == cudaSuccess && cudaMalloc(&e->champ_scene, sizeof(unsigned long long) * cap) == cudaSuccess &&
                cudaMalloc(&e->champ_self, sizeof(unsigned long long) * cap) == cudaSuccess &&
                cudaMalloc(&e->counts, sizeof(int) * JG_COUNTS_INTS(e->n_keys)) == cudaSuccess &&
                cudaMalloc(&e->enc_scene, sizeof(int) * cap) == cudaSuccess && cudaMalloc(&e->enc_self, sizeof(int) * cap) == cudaSuccess &&
@@ -697,7 +698,7 @@ static void fill_args(const jg_engine* e, PassArgs& a, uint32_t& flags, bool wan
     a.n_keys = e->n_keys; a.n_scene_keys = e->n_scene_keys; a.verts = e->d_verts; a.n_verts = e->n_verts;
     a.q_r0 = e->q_r0; a.q_r1 = e->q_r1; a.q_r2 = e->q_r2; a.q_cfg = e->q_cfg; a.epa_slot = e->epa_slot; a.epa_ids = e->epa_ids; a.ovf_list = e->ovf_list; a.epa_prio = e->epa_prio; a.q_prio = e->q_prio; a.max_msum = e->max_msum; a.stats = e->d_stats;
     a.mesh = e->mesh ? 1 : 0; a.bvh_nodes = e->bvh.nodes; a.bvh_tri = e->bvh.tri_v; a.bvh_n = e->bvh.n_tris;
-    a.mesh_margin = e->mesh_margin; a.q_tri = e->epa_slot; a.err_flag = e->d_err; a.act_list = e->act_list; a.champ_scene = e->champ_scene; a.champ_self = e->champ_self; a.cap = e->cap; a.counts = e->counts;
+    a.mesh_margin = e->mesh_margin; a.q_tri = e->epa_slot; a.err_flag = e->d_err; a.act_list = e->act_list; a.act_meta = e->act_meta; a.champ_scene = e->champ_scene; a.champ_self = e->champ_self; a.cap = e->cap; a.counts = e->counts;
     a.enc_scene = e->enc_scene; a.enc_self = e->enc_self; a.viol = e->viol;
 }
 

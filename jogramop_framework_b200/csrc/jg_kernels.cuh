@@ -109,6 +109,8 @@ struct PassArgs {
     int2* ovf_list;    // [cap] (key, index in the penetration queue) of polytopes that outgrew shared memory
     float* epa_prio;   // [n_keys*cap] the same bound for the entries of the penetration queue
     int* act_list;     // [n_keys*cap] per key: queue indices selected for the current stage (k_select)
+    int2* act_meta;    // [n_keys*cap] beside act_list (hull / triangle keys): (pair-queue slot, configuration) of the entry,
+                       // so that a refilling lane does not chase list -> slot -> configuration through three loads
     unsigned long long *champ_scene, *champ_self;   // [cap] per configuration: (prio bits << 32 | key << 20 | slot) of the
                                                     // queued pair with the largest upper bound ("champion")
     float max_msum;    // largest margin sum over the keys (JG_NO_EPA pruning)
@@ -213,7 +215,9 @@ __device__ __forceinline__ void champ_publish(const PassArgs& a, unsigned long l
     int base = 0;
     if (lane == leader) base = atomicAdd(cnt_act(a) + key, __popc(peers));
     base = __shfl_sync(peers, base, leader);
-    a.act_list[(size_t)key * a.cap + base + __popc(peers & ((1u << lane) - 1u))] = idx;
+    const size_t li = (size_t)key * a.cap + base + __popc(peers & ((1u << lane) - 1u));
+    a.act_list[li] = idx;
+    a.act_meta[li] = make_int2(idx, cfg);
 }
 
 // AABB of the shape (local centre c / half h) under T against a box (centre bc, half bh): smallest signed overlap over
@@ -587,39 +591,66 @@ __device__ __forceinline__ int sched_next_key(const int* __restrict__ counts, co
     return -1;
 }
 
-// The refill loop of one key.  idle() / start(entry index in the key's stage list) act on the calling lane; step() runs
-// one iteration and is called by ALL lanes (converged) while any lane is busy.
+// The refill loop of one key.  idle() / start(list entry, pair-queue slot, configuration) act on the calling lane; step()
+// runs one iteration and is called by ALL lanes (converged) while any lane is busy.  Three reservations are in the
+// pipeline: `cur` is being handed out (its list entries + metadata sit in registers, lane l <-> entry cbase + l, and
+// reach the refilling lane by shuffle), `nxt` has its metadata loads in flight, `pf` is the atomic in flight.
 template <class Idle, class Start, class Step>
-__device__ __forceinline__ void refill_loop(int* cur, int cnt, int lane, Idle idle, Start start, Step step) {
+__device__ __forceinline__ void refill_loop(int* cur, int cnt, int lane, const int* __restrict__ list,
+                                            const int2* __restrict__ meta, Idle idle, Start start, Step step) {
     const unsigned lt_mask = (1u << lane) - 1u;
-    int next = 0, end = 0;
-    int pf = cursor_grab(cur, 32, lane);   // reservation in flight (its value is not looked at before it is needed)
+    int next = 0, end = 0, cbase = 0, cj = 0;
+    int2 cm = make_int2(0, 0);
+    int nbase = -1, nj = 0;
+    int2 nm = make_int2(0, 0);
+    int pf = cursor_grab(cur, 32, lane);
     bool pf_pending = true, exhausted = false;
     for (;;) {
         const unsigned need = __ballot_sync(0xFFFFFFFFu, idle());
-        if (need) {
-            if (next >= end && pf_pending) {
-                pf_pending = false;
-                if (pf < cnt) { next = pf; end = min(pf + 32, cnt); }
-                else exhausted = true;
+        if (need && next >= end) {
+            if (nbase >= 0) {   // promote the loaded interval
+                cbase = next = nbase; end = min(nbase + 32, cnt); cj = nj; cm = nm; nbase = -1;
             }
-            const int avail = end - next;
-            if (avail > 0) {
-                const int rank = __popc(need & lt_mask);
-                if (idle() && rank < avail) start(next + rank);
-                next += min(__popc(need), avail);
+            if (pf_pending) {   // its atomic was issued a whole interval ago
+                pf_pending = false;
+                if (pf < cnt) {
+                    nbase = pf;
+                    if (pf + lane < cnt) { nj = list[pf + lane]; nm = meta[pf + lane]; }
+                } else exhausted = true;
+            }
+            if (!exhausted) {
+                pf = cursor_grab(cur, 32, lane);
+                pf_pending = true;
+            }
+            if (next >= end && nbase >= 0) {   // start-up / starved: use the interval just loaded (waits for its loads)
+                cbase = next = nbase; end = min(nbase + 32, cnt); cj = nj; cm = nm; nbase = -1;
             }
         }
-        if (!pf_pending && !exhausted && next >= end) {
-            pf = cursor_grab(cur, 32, lane);
-            pf_pending = true;
+        const int avail = end - next;
+        if (need && avail > 0) {
+            const int rank = __popc(need & lt_mask);
+            const int src = (next - cbase + rank) & 31;
+            const int j = __shfl_sync(0xFFFFFFFFu, cj, src);
+            const int slot = __shfl_sync(0xFFFFFFFFu, cm.x, src), cfg = __shfl_sync(0xFFFFFFFFu, cm.y, src);
+            if (idle() && rank < avail) start(j, slot, cfg);
+            next += min(__popc(need), avail);
         }
         if (!__any_sync(0xFFFFFFFFu, !idle())) {
-            if (!pf_pending) break;   // exhausted and drained
-            continue;                 // nothing running: look at the reservation right away
+            if (exhausted && next >= end && nbase < 0) break;   // drained
+            continue;
         }
         step();
     }
+}
+
+// queue entry -> transform (the configuration index comes with the list metadata)
+__device__ __forceinline__ Tf load_tf(const PassArgs& a, size_t slot) {
+    const float4 r0 = a.q_r0[slot], r1 = a.q_r1[slot], r2 = a.q_r2[slot];
+    Tf T;
+    T.r00 = r0.x; T.r01 = r0.y; T.r02 = r0.z; T.tx = r0.w;
+    T.r10 = r1.x; T.r11 = r1.y; T.r12 = r1.z; T.ty = r1.w;
+    T.r20 = r2.x; T.r21 = r2.y; T.r22 = r2.z; T.tz = r2.w;
+    return T;
 }
 
 __device__ __forceinline__ Tf load_entry(const PassArgs& a, size_t slot, int& cfg) {
@@ -692,10 +723,11 @@ __global__ void __launch_bounds__(BLOCK) k_narrowphase(const PassArgs a) {
         if (K.kind == KEY_MESH) {   // link hull vs one triangle per lane (registers); same lane refill, no penetration pass
             TriSupport tri;
             tri.p0 = tri.p1 = tri.p2 = mk(0.f, 0.f, 0.f);
-            refill_loop(cur + key, cnt, lane, [&]() { return !active; },
-                [&](int i) {
-                    off = a.act_list[kbase + i];
-                    T = load_entry(a, kbase + off, cfg);
+            refill_loop(cur + key, cnt, lane, a.act_list + kbase, a.act_meta + kbase, [&]() { return !active; },
+                [&](int, int slot, int cfg_in) {
+                    off = slot;
+                    cfg = cfg_in;
+                    T = load_tf(a, kbase + off);
                     const int t3 = 3 * a.q_tri[kbase + off];
                     const float4 v0 = a.bvh_tri[t3], v1 = a.bvh_tri[t3 + 1], v2 = a.bvh_tri[t3 + 2];
                     // work in a frame centred on the triangle (fp32 precision, like the centred pieces)
@@ -721,13 +753,15 @@ __global__ void __launch_bounds__(BLOCK) k_narrowphase(const PassArgs a) {
                 });
             continue;
         }
-        refill_loop(cur + key, cnt, lane, [&]() { return !active; },
-            [&](int i) {
-                off = a.act_list[kbase + i];
-                T = load_entry(a, kbase + off, cfg);
+        refill_loop(cur + key, cnt, lane, a.act_list + kbase, a.act_meta + kbase, [&]() { return !active; },
+            [&](int, int slot, int c) {
+                off = slot;
+                cfg = c;
+                const int e0 = enc[cfg];   // what is already proven for this configuration
+                T = load_tf(a, kbase + off);
                 gjk_init(S, mk(T.tx, T.ty, T.tz));
                 active = true;
-                best_total = -dec_float(enc[cfg]);   // what is already proven for this configuration
+                best_total = -dec_float(e0);
             },
             [&]() {
                 // ---- one GJK iteration on every busy lane
@@ -839,19 +873,20 @@ __global__ void __launch_bounds__(BLOCK) k_select(const PassArgs a, int mode) {
         for (int j0 = begin; j0 < end; j0 += 32) {
             const int j = j0 + lane;
             bool sel = false;
+            int slot = j, cfg = 0;
             if (j < end) {
                 if (kind == KEY_PLANE) {
                     sel = mode == SEL_GJK_CHAMP;
                 } else if (kind == KEY_MESH) {
                     // a triangle pair reports at least -(margins): once the configuration is known to be that deep
                     // (by another triangle or by the plane) no other triangle can lower its minimum
-                    const int cfg = a.q_cfg[kbase + j];
+                    cfg = a.q_cfg[kbase + j];
                     const bool is_champ = (unsigned)(champ[cfg] & 0xFFFFFFFFull) == (unsigned)((key << 20) | j);
                     if (mode == SEL_GJK_CHAMP) sel = is_champ;
                     else if (mode == SEL_GJK_REST) sel = !is_champ && -dec_float(enc[cfg]) < a.keys[key].msum - 1e-6f;
                 } else {
-                    const int slot = epa ? a.epa_slot[kbase + j] : j;
-                    const int cfg = a.q_cfg[kbase + slot];
+                    slot = epa ? a.epa_slot[kbase + j] : j;
+                    cfg = a.q_cfg[kbase + slot];
                     if (mode == SEL_GJK_CHAMP) {
                         sel = (unsigned)(champ[cfg] & 0xFFFFFFFFull) == (unsigned)((key << 20) | slot);
                     } else {
@@ -869,7 +904,11 @@ __global__ void __launch_bounds__(BLOCK) k_select(const PassArgs a, int mode) {
                 int base = 0;
                 if (lane == leader) base = atomicAdd(acounts + key, __popc(m));
                 base = __shfl_sync(0xFFFFFFFFu, base, leader);
-                if (sel) a.act_list[kbase + base + __popc(m & lt_mask)] = j;
+                if (sel) {
+                    const size_t li = kbase + base + __popc(m & lt_mask);
+                    a.act_list[li] = j;
+                    if (kind != KEY_PLANE) a.act_meta[li] = make_int2(slot, cfg);
+                }
             }
         }
     }
@@ -936,12 +975,14 @@ __global__ void __launch_bounds__(BLOCK) k_penetration(const PassArgs a) {
         Tf T = tf_identity();
         int cfg = 0, myj = 0;
         float best_total = -FLT_MAX;
-        refill_loop(cur + key, ecounts[key], lane, [&]() { return phase == 0; },
-            [&](int i) {
-                myj = a.act_list[kbase + i];
+        refill_loop(cur + key, ecounts[key], lane, a.act_list + kbase, a.act_meta + kbase, [&]() { return phase == 0; },
+            [&](int jj, int slot, int c) {
+                myj = jj;
+                cfg = c;
                 const size_t j = kbase + myj;
-                T = load_entry(a, kbase + a.epa_slot[j], cfg);
-                best_total = -dec_float(enc[cfg]);
+                const int e0 = enc[cfg];
+                T = load_tf(a, kbase + slot);
+                best_total = -dec_float(e0);
                 if (regjk) {
                     gjk_init(S, mk(T.tx, T.ty, T.tz));
                     phase = 1;
