@@ -236,16 +236,29 @@ __device__ __forceinline__ float aabb_overlap(const Tf& T, const float* c, const
 // smaller than the penetration geometry on each side
 __device__ __forceinline__ float prio_of(float ov, float msum) { return fmaxf(ov, 0.f) + msum + 0.0021f; }
 
+// world-frame bounding box of a shape placed by T: computed once per shape, tested against every piece
+struct WorldBox {
+    float cx, cy, cz, hx, hy, hz;
+};
+__device__ __forceinline__ WorldBox world_box(const Tf& T, const ShapeRec& Sh) {
+    WorldBox w;
+    w.cx = fmaf(T.r00, Sh.c[0], fmaf(T.r01, Sh.c[1], fmaf(T.r02, Sh.c[2], T.tx)));
+    w.cy = fmaf(T.r10, Sh.c[0], fmaf(T.r11, Sh.c[1], fmaf(T.r12, Sh.c[2], T.ty)));
+    w.cz = fmaf(T.r20, Sh.c[0], fmaf(T.r21, Sh.c[1], fmaf(T.r22, Sh.c[2], T.tz)));
+    w.hx = fmaf(fabsf(T.r00), Sh.h[0], fmaf(fabsf(T.r01), Sh.h[1], fabsf(T.r02) * Sh.h[2]));
+    w.hy = fmaf(fabsf(T.r10), Sh.h[0], fmaf(fabsf(T.r11), Sh.h[1], fabsf(T.r12) * Sh.h[2]));
+    w.hz = fmaf(fabsf(T.r20), Sh.h[0], fmaf(fabsf(T.r21), Sh.h[1], fabsf(T.r22) * Sh.h[2]));
+    return w;
+}
 // (shape, piece) candidate test: world boxes first, then a second look along the shape's own box axes (its local box is
 // tight, the world box of a rotated link is not), which culls false candidates and tightens the penetration bound `ov`
 // that ranks the pairs
-__device__ __forceinline__ bool piece_test(const PassArgs& a, const ShapeRec& Sh, const PieceRec& Pc, const Tf& T, float& ov) {
+__device__ __forceinline__ bool piece_test(const PassArgs& a, const ShapeRec& Sh, const PieceRec& Pc, const Tf& T,
+                                           const WorldBox& w, float& ov) {
     const float msum = Sh.margin + Pc.margin;
-    ov = aabb_overlap(T, Sh.c, Sh.h, Pc.c, Pc.h);
+    const float dx = w.cx - Pc.c[0], dy = w.cy - Pc.c[1], dz = w.cz - Pc.c[2];
+    ov = fminf(fminf(w.hx + Pc.h[0] - fabsf(dx), w.hy + Pc.h[1] - fabsf(dy)), w.hz + Pc.h[2] - fabsf(dz));
     if (!(ov + a.qd + msum >= 0.f)) return false;
-    const float dx = fmaf(T.r00, Sh.c[0], fmaf(T.r01, Sh.c[1], fmaf(T.r02, Sh.c[2], T.tx))) - Pc.c[0];
-    const float dy = fmaf(T.r10, Sh.c[0], fmaf(T.r11, Sh.c[1], fmaf(T.r12, Sh.c[2], T.ty))) - Pc.c[1];
-    const float dz = fmaf(T.r20, Sh.c[0], fmaf(T.r21, Sh.c[1], fmaf(T.r22, Sh.c[2], T.tz))) - Pc.c[2];
     const float o0 = Sh.h[0] + fmaf(fabsf(T.r00), Pc.h[0], fmaf(fabsf(T.r10), Pc.h[1], fabsf(T.r20) * Pc.h[2])) -
                      fabsf(fmaf(T.r00, dx, fmaf(T.r10, dy, T.r20 * dz)));
     const float o1 = Sh.h[1] + fmaf(fabsf(T.r01), Pc.h[0], fmaf(fabsf(T.r11), Pc.h[1], fabsf(T.r21) * Pc.h[2])) -
@@ -256,13 +269,10 @@ __device__ __forceinline__ bool piece_test(const PassArgs& a, const ShapeRec& Sh
     return ov + a.qd + msum >= 0.f;
 }
 // plane candidate test (conservative): lowest point of the shape's bounding box above the plane
-__device__ __forceinline__ bool plane_test(const PassArgs& a, const ShapeRec& Sh, const Tf& T) {
-    const float cx = fmaf(T.r00, Sh.c[0], fmaf(T.r01, Sh.c[1], fmaf(T.r02, Sh.c[2], T.tx)));
-    const float cy = fmaf(T.r10, Sh.c[0], fmaf(T.r11, Sh.c[1], fmaf(T.r12, Sh.c[2], T.ty)));
-    const float cz = fmaf(T.r20, Sh.c[0], fmaf(T.r21, Sh.c[1], fmaf(T.r22, Sh.c[2], T.tz)));
+__device__ __forceinline__ bool plane_test(const PassArgs& a, const ShapeRec& Sh, const Tf& T, const WorldBox& w) {
     const V3 nl = tf_rot_t(T, mk(a.plane[0], a.plane[1], a.plane[2]));
     const float ext = fmaf(fabsf(nl.x), Sh.h[0], fmaf(fabsf(nl.y), Sh.h[1], fabsf(nl.z) * Sh.h[2]));
-    const float low = fmaf(a.plane[0], cx, fmaf(a.plane[1], cy, fmaf(a.plane[2], cz, a.plane[3]))) - ext;
+    const float low = fmaf(a.plane[0], w.cx, fmaf(a.plane[1], w.cy, fmaf(a.plane[2], w.cz, a.plane[3]))) - ext;
     // the plane vertices may exceed the core AABB by the embedded box margin: 2 mm slack
     return low - 0.002f - Sh.plane_margin <= a.qd;
 }
@@ -338,16 +348,23 @@ __device__ __forceinline__ void shape_vs_scene(const PassArgs& a, const ShapeRec
     const int key0 = s * (a.P + 1);
     const bool want_plane = (a.flags & 2u) && a.has_plane;
     const int k_lo = (!MESH && (a.flags & 1u)) ? 0 : a.P, k_hi = want_plane ? a.P + 1 : a.P;
+    const WorldBox wb = world_box(T, Sh);
     for (int c0 = k_lo; c0 < k_hi; c0 += 32) {   // chunks of 32 keys (one chunk unless a scene has > 31 pieces)
         const int c1 = min(c0 + 32, k_hi);
         unsigned hm = 0u, mymask = 0u;
+        int k_a = -1, k_b = -1;      // the lane's first two hits keep their box overlap (the bound that ranks the pair)
+        float ov_a = 0.f, ov_b = 0.f;
         for (int k = c0; k < c1; ++k) {
             bool hit;
             if (k < a.P) {
                 float ov;
-                hit = valid && piece_test(a, Sh, pieces[k], T, ov);
+                hit = valid && piece_test(a, Sh, pieces[k], T, wb, ov);
+                if (hit) {
+                    if (k_a < 0) { k_a = k; ov_a = ov; }
+                    else if (k_b < 0) { k_b = k; ov_b = ov; }
+                }
             } else {
-                hit = valid && plane_test(a, Sh, T);
+                hit = valid && plane_test(a, Sh, T, wb);
             }
             const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
             if (hit) hm |= 1u << (k - c0);
@@ -373,8 +390,8 @@ __device__ __forceinline__ void shape_vs_scene(const PassArgs& a, const ShapeRec
             float prio = 0.f, ox = 0.f, oy = 0.f, oz = 0.f;
             if (k < a.P) {
                 const PieceRec& Pc = pieces[k];
-                float ov;
-                piece_test(a, Sh, Pc, T, ov);
+                float ov = k == k_a ? ov_a : ov_b;
+                if (k != k_a && k != k_b) piece_test(a, Sh, Pc, T, wb, ov);   // third and later hits of one shape: rare
                 prio = prio_of(ov, Sh.margin + Pc.margin);
                 ox = Pc.c[0]; oy = Pc.c[1]; oz = Pc.c[2];   // vertices of the piece are stored relative to its AABB centre
             }
@@ -395,7 +412,7 @@ __device__ __forceinline__ void shape_vs_scene(const PassArgs& a, const ShapeRec
 }
 
 template <int BLOCK, bool MESH>
-__global__ void __launch_bounds__(BLOCK) k_broadphase(const PassArgs a) {
+__global__ void __launch_bounds__(BLOCK, 7) k_broadphase(const PassArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RobotTab* R = reinterpret_cast<RobotTab*>(smem_raw);
     PieceRec* pieces = reinterpret_cast<PieceRec*>(smem_raw + sizeof(RobotTab));
