@@ -182,6 +182,38 @@ def test_degenerate_scenes(robot, scene_loader):
     e.close()
 
 
+def test_scene_with_more_than_31_pieces(robot, scene_loader):
+    """The broad phase reserves the slots of a shape's keys with lanes 0..P: scenes with more than 31 pieces take
+    several 32-key chunks.  40 pieces = scenario 034's obstacles copied onto a grid around the robot."""
+    import copy
+    from jogramop_framework_b200.engine import CollisionEngine
+    sc = scene_loader(34)
+    parts, margins, bodies = [], [], []
+    shifts = [(0.0, 0.0)] + [(0.8 * i - 2.4, 1.2 * j - 1.2) for i in range(5) for j in range(3)]
+    for dx, dy in shifts:
+        for pi in range(sc.n_pieces):
+            parts.append(sc.piece(pi) + np.array([dx, dy, 0.0]))
+            margins.append(sc.piece_margin[pi])
+            bodies.append(sc.piece_body[pi])
+            if len(parts) == 40:
+                break
+        if len(parts) == 40:
+            break
+    assert len(parts) == 40
+    big = copy.copy(sc)
+    big.piece_verts = np.concatenate(parts)
+    big.piece_vert_offset = np.cumsum([0] + [len(x) for x in parts]).astype(np.int32)
+    big.piece_margin = np.asarray(margins, dtype=np.float64)
+    big.piece_body = np.asarray(bodies, dtype=np.int32)
+    q = uniform_configs(robot, 20000, 77)
+    e = CollisionEngine(robot, big)
+    rb, rd = Oracle(robot, big).check(q.astype(np.float64), flags=3)
+    bits, dist, _ = e.check(q, flags=3)
+    compare(bits, dist, rb, rd)
+    assert 0.2 < rb.mean() < 0.95
+    e.close()
+
+
 def test_invariances(robot, scene_loader):
     """Properties the geometry must have: moving robot base and scene together changes nothing; the verdict is
     monotone in the threshold; a smaller query distance only clamps the reported distance."""
