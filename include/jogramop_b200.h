@@ -161,6 +161,7 @@ typedef struct {
     int64_t gjk_run;          /* pair-queue entries the GJK stages really processed (incl. plane entries)    */
     int64_t epa_run;          /* polytopes the penetration stages really expanded (after bound pruning)      */
     int64_t kernel_launches;  /* kernels launched by the last call                                           */
+    int64_t overflow_run;     /* polytopes that outgrew the compact storage and were redone by the overflow kernel */
 } jg_stats;
 /* synchronises the engine's last stream and reads the device counters */
 int jg_get_stats(jg_engine*, jg_stats*);

@@ -67,7 +67,8 @@ class Params(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [('configs', C.c_int64), ('pairs', C.c_int64), ('plane_pairs', C.c_int64), ('self_pairs', C.c_int64),
-                ('epa_pairs', C.c_int64), ('gjk_run', C.c_int64), ('epa_run', C.c_int64), ('kernel_launches', C.c_int64)]
+                ('epa_pairs', C.c_int64), ('gjk_run', C.c_int64), ('epa_run', C.c_int64), ('kernel_launches', C.c_int64),
+                ('overflow_run', C.c_int64)]
 
 
 def check(rc, what=''):

@@ -719,7 +719,10 @@ __global__ void k_accumulate_stats(const int* counts, int n_scene_keys, int n_ke
     unsigned long long ep = 0;
     for (int k = threadIdx.x; k < n_keys; k += 32) ep += counts[n_keys + k];
     for (int o = 16; o; o >>= 1) ep += __shfl_xor_sync(0xFFFFFFFFu, ep, o);
-    if (threadIdx.x == 0) { stats[0] += h; stats[1] += pl; stats[2] += sf; stats[3] += ep; }
+    if (threadIdx.x == 0) {
+        stats[0] += h; stats[1] += pl; stats[2] += sf; stats[3] += ep;
+        stats[6] += (unsigned long long)counts[4 * n_keys + CTR_OVF];   // polytopes handed to the overflow kernel
+    }
 }
 
 // narrow phase + finalize of the pass described by `a` (queues already filled)
@@ -1134,6 +1137,7 @@ extern "C" int jg_get_stats(jg_engine* e, jg_stats* out) {
     out->epa_pairs = (int64_t)h[3];
     out->gjk_run = (int64_t)h[4];
     out->epa_run = (int64_t)h[5];
+    out->overflow_run = (int64_t)h[6];
     return JG_OK;
 }
 

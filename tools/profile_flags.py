@@ -24,4 +24,4 @@ for name, fl, wd in CASES:
     for _ in range(5): eng.check(q, flags=fl, packed=True, want_dist=wd)
     p = eng.get_profile(); eng.profile(False)
     st = eng.stats()
-    print(name, {k: round(v[0]/5,3) for k,v in p.items()}, 'total', round(sum(v[0] for v in p.values())/5,3), {k: st[k] for k in ('pairs','self_pairs','gjk_run','epa_run')})
+    print(name, {k: round(v[0]/5,3) for k,v in p.items()}, 'total', round(sum(v[0] for v in p.values())/5,3), {k: st[k] for k in ('pairs','self_pairs','gjk_run','epa_run','overflow_run')})
