@@ -156,6 +156,10 @@ def run_b200(args):
         raise SystemExit('bench.py: no CUDA device - the engine has no CPU fallback (use --impl reference for the CPU arm)')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    bound = None
+    if not os.environ.get('JG_NO_AFFINITY'):
+        from jogramop_framework_b200.dist import bind_to_gpu_cpus
+        bound = bind_to_gpu_cpus(local)    # pinned staging buffers of the host path end up on the GPU's NUMA node
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)
@@ -255,7 +259,8 @@ def run_b200(args):
                        'penetration_depth': 'clamped at -(marginA+marginB) (JG_NO_EPA)' if args.no_epa else 'EPA',
                        'l2': 'flushed between timed iterations (256 MB write)',
                        'collective': 'ncclAllGather of packed verdict bits' if world > 1 else 'none (1 GPU)',
-                       'pass_size': args.chunk or 'auto (<= 2^20 configurations per pass)'},
+                       'pass_size': args.chunk or 'auto (<= 2^20 configurations per pass)',
+                       'cpu_affinity': f'process bound to the {bound} CPUs local to its GPU (NVML)' if bound else 'not set'},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'checks/s', 'h2d_bytes_per_step': int(n * 36),
                     'd2h_bytes_per_step': int(n * 4 + words * 4)},
