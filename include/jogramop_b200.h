@@ -151,6 +151,15 @@ int jg_ik(jg_engine*, const float* targets, int64_t n, int ee_link, const float*
 int jg_check_host(jg_engine*, const float* q_host, int64_t n, int dof, uint32_t flags, uint32_t* bits_host,
                   float* min_dist_host, uint8_t* reason_host);
 
+/* Asynchronous form for callers that stream batches (a planner validating batch after batch): up to TWO batches in flight,
+ * so the upload of batch k+1 and the download of batch k overlap the kernels of the other batch.  n <= the pass
+ * capacity (2^20 configurations unless jg_params.chunk says otherwise); buffers must stay valid until the wait returns.
+ * jg_check_host_submit returns at once with a ticket; jg_check_host_wait blocks until that batch's results are in the
+ * host buffers.  A third submit before the oldest ticket was waited for is refused (JG_ERR_INVALID). */
+int jg_check_host_submit(jg_engine*, const float* q_host, int64_t n, int dof, uint32_t flags, uint32_t* bits_host,
+                         float* min_dist_host, uint8_t* reason_host, int64_t* ticket);
+int jg_check_host_wait(jg_engine*, int64_t ticket);
+
 /* ---- instrumentation ---- */
 typedef struct {
     int64_t configs;          /* configurations processed by the last jg_check* call                         */

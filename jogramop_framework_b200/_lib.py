@@ -49,6 +49,8 @@ def load():
     L.jg_check_edges.argtypes = [vp, vp, vp, i64, i32, i32, u32, vp, vp, vp]
     L.jg_check_poses.argtypes = [vp, vp, i64, i32, i32, vp, i32, u32, vp, vp, vp]
     L.jg_check_host.argtypes = [vp, vp, i64, i32, u32, vp, vp, vp]
+    L.jg_check_host_submit.argtypes = [vp, vp, i64, i32, u32, vp, vp, vp, vp]
+    L.jg_check_host_wait.argtypes = [vp, i64]
     L.jg_ik.argtypes = [vp, vp, i64, i32, vp, vp, i32, C.c_float, C.c_float, C.c_float, i32, vp, vp, vp]
     L.jg_get_stats.argtypes = [vp, vp]
     L.jg_profile_enable.argtypes = [vp, i32]
@@ -80,5 +82,5 @@ def check(rc, what=''):
 EXPORTED_SYMBOLS = [
     'jg_default_params', 'jg_last_error', 'jg_abi_version', 'jg_device_count', 'jg_robot_create', 'jg_robot_free',
     'jg_scene_create', 'jg_scene_create_mesh', 'jg_scene_free', 'jg_engine_create', 'jg_engine_free', 'jg_engine_device', 'jg_fk', 'jg_check',
-    'jg_check_edges', 'jg_check_poses', 'jg_check_host', 'jg_ik', 'jg_get_stats', 'jg_profile_enable', 'jg_get_profile',
+    'jg_check_edges', 'jg_check_poses', 'jg_check_host', 'jg_check_host_submit', 'jg_check_host_wait', 'jg_ik', 'jg_get_stats', 'jg_profile_enable', 'jg_get_profile',
     'jg_measure_fp32_peak', 'jg_work_counters', 'jg_work_counters_reset']

@@ -210,6 +210,9 @@ struct jg_engine {
     float* d_qrest = nullptr;
     int* act_list = nullptr;              // [n_keys*cap]
     int2* act_meta = nullptr;             // [n_keys*cap]
+    struct Pending { bool busy = false; int64_t n = 0; uint32_t* bits = nullptr; float* dist = nullptr; uint8_t* reason = nullptr;
+                     bool pb = false, pd = false, pr = false; } pending[2];   // jg_check_host_submit tickets (ticket & 1)
+    int64_t next_ticket = 0;
     unsigned long long *champ_scene = nullptr, *champ_self = nullptr;   // [cap]
     int* counts = nullptr;                // [3*n_keys + 16], layout in jg_kernels.cuh PassArgs
     int *enc_scene = nullptr, *enc_self = nullptr;
@@ -1025,6 +1028,50 @@ static bool is_pinned(const void* p) {
     return at.type == cudaMemoryTypeHost;
 }
 
+// One pass of the host path into staging buffer set `b`: sliced upload overlapped with the broad phase of the same pass,
+// staged narrow phase, download on the third stream; ev_out[b] fires when the results are in host memory.
+static int host_pass(jg_engine* e, int b, const float* q, int64_t off, int m, int dof, uint32_t flags, uint32_t* bits,
+                     float* dist, uint8_t* reason, bool pq, bool pb, bool pd, bool pr) {
+    cudaStream_t st = e->s_run;
+    constexpr int SLICES = 4;
+    int rc;
+    PassArgs a;
+    uint32_t fl = flags;
+    fill_args(e, a, fl, dist != nullptr);
+    a.q = e->stage_q[b]; a.n = m;
+    CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * JG_COUNTS_INTS(e->n_keys), st));
+    if (fl & JG_LIMITS) CUDA_TRY(cudaMemsetAsync(e->viol, 0, sizeof(uint32_t) * (e->cap / 32 + 1), st));
+    const int slice = std::max(1024, ((m + SLICES - 1) / SLICES + 1023) / 1024 * 1024);
+    prof_begin(e, 0, st);
+    for (int c0 = 0; c0 < m; c0 += slice) {
+        const int c1 = std::min(m, c0 + slice);
+        const float* src = q + (off + c0) * dof;
+        if (!pq) {
+            memcpy(e->pin_q[b] + (size_t)c0 * dof, src, sizeof(float) * (c1 - c0) * dof);
+            src = e->pin_q[b] + (size_t)c0 * dof;
+        }
+        CUDA_TRY(cudaMemcpyAsync(e->stage_q[b] + (size_t)c0 * dof, src, sizeof(float) * (c1 - c0) * dof, cudaMemcpyHostToDevice, e->s_in));
+        CUDA_TRY(cudaEventRecord(e->ev_in[b], e->s_in));
+        CUDA_TRY(cudaStreamWaitEvent(st, e->ev_in[b], 0));
+        PassArgs as = a;
+        as.cfg_base = c0;
+        as.n = c1;     // configurations [c0, c1) of the pass
+        launch_broadphase(e, as, (c1 - c0 + BP_BLOCK - 1) / BP_BLOCK, bp_smem(e, fl), st);
+        e->stats.kernel_launches += 1;
+    }
+    rc = run_narrow_and_finalize(e, a, m, fl, e->stage_bits[b], dist ? e->stage_dist[b] : nullptr,
+                                 reason ? e->stage_reason[b] : nullptr, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(e->ev_run[b], st));
+    CUDA_TRY(cudaStreamWaitEvent(e->s_out, e->ev_run[b], 0));
+    CUDA_TRY(cudaMemcpyAsync(pb ? bits + off / 32 : e->pin_bits[b], e->stage_bits[b], sizeof(uint32_t) * ((m + 31) / 32),
+                             cudaMemcpyDeviceToHost, e->s_out));
+    if (dist) CUDA_TRY(cudaMemcpyAsync(pd ? dist + off : e->pin_dist[b], e->stage_dist[b], sizeof(float) * m, cudaMemcpyDeviceToHost, e->s_out));
+    if (reason) CUDA_TRY(cudaMemcpyAsync(pr ? reason + off : e->pin_reason[b], e->stage_reason[b], m, cudaMemcpyDeviceToHost, e->s_out));
+    CUDA_TRY(cudaEventRecord(e->ev_out[b], e->s_out));
+    return JG_OK;
+}
+
 extern "C" int jg_check_host(jg_engine* e, const float* q, int64_t n, int dof, uint32_t flags, uint32_t* bits, float* dist,
                              uint8_t* reason) {
     if (!e) return fail(JG_ERR_INVALID, "jg_check_host: engine is NULL");
@@ -1033,6 +1080,8 @@ extern "C" int jg_check_host(jg_engine* e, const float* q, int64_t n, int dof, u
     CUDA_TRY(cudaSetDevice(e->device));
     int rc = ensure_staging(e);
     if (rc) return rc;
+    if (e->pending[0].busy || e->pending[1].busy)
+        return fail(JG_ERR_INVALID, "jg_check_host: batches submitted with jg_check_host_submit are still in flight");
     const bool pq = is_pinned(q), pb = is_pinned(bits), pd = dist && is_pinned(dist), pr = reason && is_pinned(reason);
     if (e->mesh || n == 0) {   // secondary path: plain staged copy around the device entry point
         float* dq = nullptr;
@@ -1064,7 +1113,6 @@ extern "C" int jg_check_host(jg_engine* e, const float* q, int64_t n, int dof, u
     if (rc) return rc;
     e->stats.configs = n;
     const int64_t n_pass = (n + e->cap - 1) / e->cap;
-    constexpr int SLICES = 4;
     for (int64_t i = 0; i < n_pass; ++i) {
         const int b = (int)(i & 1);
         const int64_t off = i * e->cap;
@@ -1076,40 +1124,8 @@ extern "C" int jg_check_host(jg_engine* e, const float* q, int64_t n, int dof, u
             if (dist && !pd) memcpy(dist + o2, e->pin_dist[b], sizeof(float) * e->cap);
             if (reason && !pr) memcpy(reason + o2, e->pin_reason[b], e->cap);
         }
-        PassArgs a;
-        uint32_t fl = flags;
-        fill_args(e, a, fl, dist != nullptr);
-        a.q = e->stage_q[b]; a.n = m;
-        CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * JG_COUNTS_INTS(e->n_keys), st));
-        if (fl & JG_LIMITS) CUDA_TRY(cudaMemsetAsync(e->viol, 0, sizeof(uint32_t) * (e->cap / 32 + 1), st));
-        const int slice = std::max(1024, ((m + SLICES - 1) / SLICES + 1023) / 1024 * 1024);
-        prof_begin(e, 0, st);
-        for (int c0 = 0; c0 < m; c0 += slice) {
-            const int c1 = std::min(m, c0 + slice);
-            const float* src = q + (off + c0) * dof;
-            if (!pq) {
-                memcpy(e->pin_q[b] + (size_t)c0 * dof, src, sizeof(float) * (c1 - c0) * dof);
-                src = e->pin_q[b] + (size_t)c0 * dof;
-            }
-            CUDA_TRY(cudaMemcpyAsync(e->stage_q[b] + (size_t)c0 * dof, src, sizeof(float) * (c1 - c0) * dof, cudaMemcpyHostToDevice, e->s_in));
-            CUDA_TRY(cudaEventRecord(e->ev_in[b], e->s_in));
-            CUDA_TRY(cudaStreamWaitEvent(st, e->ev_in[b], 0));
-            PassArgs as = a;
-            as.cfg_base = c0;
-            as.n = c1;     // configurations [c0, c1) of the pass
-            launch_broadphase(e, as, (c1 - c0 + BP_BLOCK - 1) / BP_BLOCK, bp_smem(e, fl), st);
-            e->stats.kernel_launches += 1;
-        }
-        rc = run_narrow_and_finalize(e, a, m, fl, e->stage_bits[b], dist ? e->stage_dist[b] : nullptr,
-                                     reason ? e->stage_reason[b] : nullptr, st);
+        rc = host_pass(e, b, q, off, m, dof, flags, bits, dist, reason, pq, pb, pd, pr);
         if (rc) return rc;
-        CUDA_TRY(cudaEventRecord(e->ev_run[b], st));
-        CUDA_TRY(cudaStreamWaitEvent(e->s_out, e->ev_run[b], 0));
-        CUDA_TRY(cudaMemcpyAsync(pb ? bits + off / 32 : e->pin_bits[b], e->stage_bits[b], sizeof(uint32_t) * ((m + 31) / 32),
-                                 cudaMemcpyDeviceToHost, e->s_out));
-        if (dist) CUDA_TRY(cudaMemcpyAsync(pd ? dist + off : e->pin_dist[b], e->stage_dist[b], sizeof(float) * m, cudaMemcpyDeviceToHost, e->s_out));
-        if (reason) CUDA_TRY(cudaMemcpyAsync(pr ? reason + off : e->pin_reason[b], e->stage_reason[b], m, cudaMemcpyDeviceToHost, e->s_out));
-        CUDA_TRY(cudaEventRecord(e->ev_out[b], e->s_out));
     }
     CUDA_TRY(cudaStreamSynchronize(e->s_out));
     for (int64_t i = std::max<int64_t>(0, n_pass - 2); i < n_pass; ++i) {
@@ -1121,6 +1137,52 @@ extern "C" int jg_check_host(jg_engine* e, const float* q, int64_t n, int dof, u
         if (reason && !pr) memcpy(reason + off, e->pin_reason[b], m);
     }
     e->last_stream = st;
+    return JG_OK;
+}
+
+// Asynchronous form of the host path for callers that stream batches: up to TWO batches in flight, so the upload of
+// batch k+1 and the download of batch k overlap the kernels of the other one (a synchronous call can only overlap
+// within its own batch).  n <= pass capacity; tickets alternate between the two staging buffer sets.
+extern "C" int jg_check_host_submit(jg_engine* e, const float* q, int64_t n, int dof, uint32_t flags, uint32_t* bits, float* dist,
+                                    uint8_t* reason, int64_t* ticket) {
+    if (!e || !ticket) return fail(JG_ERR_INVALID, "jg_check_host_submit: NULL engine / ticket");
+    if (dof != e->dof) return fail(JG_ERR_INVALID, "jg_check_host_submit: dof %d does not match the robot's %d", dof, e->dof);
+    if (n <= 0 || !q || !bits) return fail(JG_ERR_INVALID, "jg_check_host_submit: empty batch or NULL q/bits");
+    if (e->mesh) return fail(JG_ERR_UNSUPPORTED, "jg_check_host_submit: mesh-mode engines use jg_check_host");
+    if (n > e->cap) return fail(JG_ERR_INVALID, "jg_check_host_submit: %lld configurations exceed the pass capacity %d (use jg_check_host)",
+                                (long long)n, e->cap);
+    CUDA_TRY(cudaSetDevice(e->device));
+    int rc = ensure_staging(e);
+    if (rc) return rc;
+    const int b = (int)(e->next_ticket & 1);
+    if (e->pending[b].busy) return fail(JG_ERR_INVALID, "jg_check_host_submit: two batches are already in flight (wait for ticket %lld first)",
+                                        (long long)(e->next_ticket - 2));
+    rc = begin_call(e, e->s_run);
+    if (rc) return rc;
+    e->stats.configs = n;
+    jg_engine::Pending& P = e->pending[b];
+    P.n = n; P.bits = bits; P.dist = dist; P.reason = reason;
+    P.pb = is_pinned(bits); P.pd = dist && is_pinned(dist); P.pr = reason && is_pinned(reason);
+    rc = host_pass(e, b, q, 0, (int)n, dof, flags, bits, dist, reason, is_pinned(q), P.pb, P.pd, P.pr);
+    if (rc) return rc;
+    P.busy = true;
+    *ticket = e->next_ticket++;
+    e->last_stream = e->s_run;
+    return JG_OK;
+}
+
+extern "C" int jg_check_host_wait(jg_engine* e, int64_t ticket) {
+    if (!e) return fail(JG_ERR_INVALID, "jg_check_host_wait: engine is NULL");
+    if (ticket < 0 || ticket >= e->next_ticket) return fail(JG_ERR_INVALID, "jg_check_host_wait: unknown ticket %lld", (long long)ticket);
+    const int b = (int)(ticket & 1);
+    jg_engine::Pending& P = e->pending[b];
+    if (!P.busy || ticket + 2 < e->next_ticket) return JG_OK;   // already collected
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaEventSynchronize(e->ev_out[b]));
+    if (!P.pb) memcpy(P.bits, e->pin_bits[b], sizeof(uint32_t) * ((P.n + 31) / 32));
+    if (P.dist && !P.pd) memcpy(P.dist, e->pin_dist[b], sizeof(float) * P.n);
+    if (P.reason && !P.pr) memcpy(P.reason, e->pin_reason[b], P.n);
+    P.busy = false;
     return JG_OK;
 }
 

@@ -199,6 +199,33 @@ class CollisionEngine:
                    'jg_check_host')
         return out['bits'], out.get('dist'), out.get('reason')
 
+    def check_host_submit(self, q, flags=SCENE | PLANE, want_dist=True, want_reason=False, out=None):
+        """Asynchronous ``check_host`` for streams of batches: returns a ticket at once; at most two batches may be in
+        flight, so the copies of one batch overlap the kernels of the other.  ``q`` (and ``out``) must stay alive and
+        unchanged until ``check_host_wait(ticket)`` returned; pinned memory avoids the staging copy."""
+        if isinstance(q, torch.Tensor):
+            assert q.device.type == 'cpu' and q.dtype == torch.float32 and q.is_contiguous()
+            qn, qptr = q.shape[0], q.data_ptr()
+        else:
+            q = np.ascontiguousarray(q, dtype=np.float32)
+            qn, qptr = q.shape[0], q.ctypes.data
+        if out is None:
+            out = {'bits': torch.empty(((qn + 31) // 32,), dtype=torch.int32, pin_memory=True),
+                   'dist': torch.empty((qn,), dtype=torch.float32, pin_memory=True) if want_dist else None,
+                   'reason': torch.empty((qn,), dtype=torch.uint8, pin_memory=True) if want_reason else None}
+        t = C.c_int64(-1)
+        _lib.check(self._L.jg_check_host_submit(self._e, qptr, qn, self.dof, flags, out['bits'].data_ptr(),
+                                                out['dist'].data_ptr() if out.get('dist') is not None else None,
+                                                out['reason'].data_ptr() if out.get('reason') is not None else None,
+                                                C.byref(t)), 'jg_check_host_submit')
+        return {'ticket': t.value, 'q': q, 'out': out}
+
+    def check_host_wait(self, ticket):
+        """Block until the batch of ``ticket`` is in its host buffers -> (bits uint32 words, dist, reason)."""
+        _lib.check(self._L.jg_check_host_wait(self._e, ticket['ticket']), 'jg_check_host_wait')
+        out = ticket['out']
+        return out['bits'], out.get('dist'), out.get('reason')
+
     def ik(self, targets, q_rest, q_init=None, ee_link=None, iters=100, tol=1e-3, damping=0.05, null_gain=0.05,
            position_only=False):
         """Batched damped-least-squares IK.  targets: [n,4,4] / [n,3,4] poses of `ee_link` in the robot frame.

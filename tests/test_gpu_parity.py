@@ -372,6 +372,36 @@ def test_host_path_matches_device_path(robot, scene_loader, engines):
     assert torch.equal(wb2, wb) and torch.equal(wd2, wd)
 
 
+def test_async_host_path_two_batches_in_flight(robot, scene_loader, engines):
+    """jg_check_host_submit / _wait: results identical to the device path, tickets alternate buffer sets, a third
+    submit before a wait is refused, pageable buffers are drained at wait time."""
+    from jogramop_framework_b200._lib import JogramopError
+    from jogramop_framework_b200.engine import unpack_bits
+    e = engines(11, chunk=8192)
+    batches = [uniform_configs(robot, n, 30 + i) for i, n in enumerate([8192, 5000, 8192, 33, 7000])]
+    ref = [e.check(q, flags=15, want_reason=True) for q in batches]
+    pinned = [torch.from_numpy(q).pin_memory() for q in batches]
+    tickets = [e.check_host_submit(pinned[0], flags=15, want_reason=True), e.check_host_submit(pinned[1], flags=15, want_reason=True)]
+    with pytest.raises(JogramopError):
+        e.check_host_submit(pinned[2], flags=15, want_reason=True)
+    with pytest.raises(JogramopError):
+        e.check_host(pinned[2], flags=15)                  # the synchronous call refuses to share the buffers
+    got = []
+    for i in range(len(batches)):
+        got.append(e.check_host_wait(tickets[i]))
+        if i + 2 < len(batches):
+            src = pinned[i + 2] if i % 2 == 0 else batches[i + 2]      # pinned and pageable inputs
+            tickets.append(e.check_host_submit(src, flags=15, want_reason=True))
+    for (wb, wd, wr), (b1, d1, r1), q in zip(got, ref, batches):
+        assert torch.equal(unpack_bits(wb.cuda(), len(q)), b1)
+        assert torch.equal(wd.cuda(), d1) and torch.equal(wr.cuda(), r1)
+    assert e.check_host_wait(tickets[0])[0] is got[0][0]   # waiting twice is harmless
+    with pytest.raises(JogramopError):
+        e.check_host_submit(uniform_configs(robot, 8193, 1), flags=3)    # more than one pass: use check_host
+    wb, wd, _ = e.check_host(pinned[0], flags=15)          # synchronous path works again once everything is collected
+    assert torch.equal(unpack_bits(wb.cuda(), len(batches[0])), ref[0][0])
+
+
 def test_error_conventions(robot, scene_loader, engines):
     from jogramop_framework_b200._lib import JogramopError
     e = engines(34)
