@@ -887,44 +887,68 @@ __global__ void __launch_bounds__(BLOCK) k_select(const PassArgs a, int mode) {
         const size_t kbase = (size_t)key * a.cap;
         const unsigned long long* champ = kind == KEY_SELF ? a.champ_self : a.champ_scene;
         const int* enc = kind == KEY_SELF ? a.enc_self : a.enc_scene;
-        for (int j0 = begin; j0 < end; j0 += 32) {
-            const int j = j0 + lane;
-            bool sel = false;
-            int slot = j, cfg = 0;
-            if (j < end) {
+        // four entries per lane and step: their dependent load chains (entry -> configuration -> champion / proven
+        // distance) are independent of each other, which is what this latency-bound kernel needs
+        constexpr int U = 4;
+        for (int j0 = begin; j0 < end; j0 += 32 * U) {
+            int jj[U], slot[U], cfg[U];
+            bool sel[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                jj[u] = j0 + 32 * u + lane;
+                slot[u] = jj[u];
+                cfg[u] = 0;
+                sel[u] = false;
+                if (jj[u] < end && kind != KEY_PLANE) {
+                    if (kind != KEY_MESH && epa) slot[u] = a.epa_slot[kbase + jj[u]];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (jj[u] < end && kind != KEY_PLANE) cfg[u] = a.q_cfg[kbase + slot[u]];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (jj[u] >= end) continue;
+                const int j = jj[u];
                 if (kind == KEY_PLANE) {
-                    sel = mode == SEL_GJK_CHAMP;
+                    sel[u] = mode == SEL_GJK_CHAMP;
                 } else if (kind == KEY_MESH) {
                     // a triangle pair reports at least -(margins): once the configuration is known to be that deep
                     // (by another triangle or by the plane) no other triangle can lower its minimum
-                    cfg = a.q_cfg[kbase + j];
-                    const bool is_champ = (unsigned)(champ[cfg] & 0xFFFFFFFFull) == (unsigned)((key << 20) | j);
-                    if (mode == SEL_GJK_CHAMP) sel = is_champ;
-                    else if (mode == SEL_GJK_REST) sel = !is_champ && -dec_float(enc[cfg]) < a.keys[key].msum - 1e-6f;
+                    const bool is_champ = (unsigned)(champ[cfg[u]] & 0xFFFFFFFFull) == (unsigned)((key << 20) | j);
+                    if (mode == SEL_GJK_CHAMP) sel[u] = is_champ;
+                    else if (mode == SEL_GJK_REST) sel[u] = !is_champ && -dec_float(enc[cfg[u]]) < a.keys[key].msum - 1e-6f;
                 } else {
-                    slot = epa ? a.epa_slot[kbase + j] : j;
-                    cfg = a.q_cfg[kbase + slot];
                     if (mode == SEL_GJK_CHAMP) {
-                        sel = (unsigned)(champ[cfg] & 0xFFFFFFFFull) == (unsigned)((key << 20) | slot);
+                        sel[u] = (unsigned)(champ[cfg[u]] & 0xFFFFFFFFull) == (unsigned)((key << 20) | slot[u]);
                     } else {
-                        float best = -dec_float(enc[cfg]);          // proven total penetration (negative: none yet)
+                        float best = -dec_float(enc[cfg[u]]);       // proven total penetration (negative: none yet)
                         if (no_epa && best >= a.max_msum - 1e-6f) best = FLT_MAX;   // clamped mode: any overlap settles it
-                        sel = (epa ? a.epa_prio[kbase + j] : a.q_prio[kbase + slot]) > best;
+                        sel[u] = (epa ? a.epa_prio[kbase + j] : a.q_prio[kbase + slot[u]]) > best;
                         if (mode == SEL_GJK_REST)
-                            sel = sel && (unsigned)(champ[cfg] & 0xFFFFFFFFull) != (unsigned)((key << 20) | slot);
+                            sel[u] = sel[u] && (unsigned)(champ[cfg[u]] & 0xFFFFFFFFull) != (unsigned)((key << 20) | slot[u]);
                     }
                 }
             }
-            const unsigned m = __ballot_sync(0xFFFFFFFFu, sel);
-            if (m) {
-                const int leader = __ffs(m) - 1;
+            unsigned m[U];
+            int total_sel = 0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                m[u] = __ballot_sync(0xFFFFFFFFu, sel[u]);
+                total_sel += __popc(m[u]);
+            }
+            if (total_sel) {
                 int base = 0;
-                if (lane == leader) base = atomicAdd(acounts + key, __popc(m));
-                base = __shfl_sync(0xFFFFFFFFu, base, leader);
-                if (sel) {
-                    const size_t li = kbase + base + __popc(m & lt_mask);
-                    a.act_list[li] = j;
-                    if (kind != KEY_PLANE) a.act_meta[li] = make_int2(slot, cfg);
+                if (lane == 0) base = atomicAdd(acounts + key, total_sel);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (sel[u]) {
+                        const size_t li = kbase + base + __popc(m[u] & lt_mask);
+                        a.act_list[li] = jj[u];
+                        if (kind != KEY_PLANE) a.act_meta[li] = make_int2(slot[u], cfg[u]);
+                    }
+                    base += __popc(m[u]);
                 }
             }
         }
