@@ -133,7 +133,9 @@ int jg_check_edges(jg_engine*, const float* qa, const float* qb, int64_t m, int 
 
 /* ---- free-floating gripper (create_graspset.py:53-60 check_collisions) ----
  * poses: pose of link `ee_link` in the robot frame, fmt JG_POSE_MAT34 [n,12] or JG_POSE_POS_QUAT_XYZW [n,7];
- * the shapes of `links` (HOST ints) move rigidly with it (offsets from FK with params.finger_open). */
+ * the shapes of `links` (HOST ints) move rigidly with it (offsets from FK with params.finger_open).  On an engine whose
+ * scene was made with jg_scene_create_mesh the gripper is tested against the triangle surfaces (trimesh / fcl style;
+ * with triangle margin 0, min_dist <= -(hull margin) means the hull itself touches a surface). */
 int jg_check_poses(jg_engine*, const float* poses, int64_t n, int fmt, int ee_link, const int32_t* links,
                    int n_links, uint32_t flags, uint32_t* bits, float* min_dist, void* stream);
 

@@ -912,7 +912,6 @@ extern "C" int jg_check_poses(jg_engine* e, const float* poses, int64_t n, int f
     if (ee_link < 0 || ee_link >= e->L || !links || n_links <= 0) return fail(JG_ERR_INVALID, "jg_check_poses: bad link arguments");
     if (n < 0 || (n && (!poses || !bits))) return fail(JG_ERR_INVALID, "jg_check_poses: NULL poses/bits");
     flags &= (JG_SCENE | JG_PLANE | JG_NO_EPA);
-    if (e->mesh) return fail(JG_ERR_INVALID, "jg_check_poses: not available in mesh mode");
     cudaStream_t st = (cudaStream_t)stream;
     int rc = begin_call(e, st);
     if (rc) return rc;
@@ -946,8 +945,10 @@ extern "C" int jg_check_poses(jg_engine* e, const float* poses, int64_t n, int f
     CUDA_TRY(cudaMemcpyAsync(e->d_use_shapes, use.data(), sizeof(int) * use.size(), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));   // rel/use are stack-lifetime host vectors
     const int stride = fmt == JG_POSE_MAT34 ? 12 : 7;
-    for (int64_t off = 0; off < n; off += e->cap) {
-        const int m = (int)std::min<int64_t>(e->cap, n - off);
+    if (e->mesh && e->mesh_pass <= 0) e->mesh_pass = std::max(1024, e->cap / 2 / 1024 * 1024);
+    for (int64_t off = 0; off < n;) {
+        const int64_t pass = e->mesh ? e->mesh_pass : e->cap;   // mesh mode: adaptive pass size, see jg_check
+        const int m = (int)std::min<int64_t>(pass, n - off);
         PassArgs a;
         fill_args(e, a, flags, min_dist != nullptr);
         a.n = m;
@@ -961,8 +962,24 @@ extern "C" int jg_check_poses(jg_engine* e, const float* poses, int64_t n, int f
             k_broadphase_poses<BP_BLOCK, false><<<(m + BP_BLOCK - 1) / BP_BLOCK, BP_BLOCK, smem, st>>>(
                 a, poses + off * stride, fmt, e->d_rel, e->d_use_shapes, (int)use.size());
         e->stats.kernel_launches += 1;
+        if (e->mesh) {
+            int err = 0;
+            prof_end(e, st);
+            CUDA_TRY(cudaMemcpyAsync(&err, e->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            if (err) {
+                CUDA_TRY(cudaMemsetAsync(e->d_err, 0, sizeof(int), st));
+                if (e->mesh_pass <= 1024)
+                    return fail(JG_ERR_NOMEM, "mesh mode: a triangle candidate queue overflowed even at 1024 poses per pass "
+                                "(%d entries per link); create the engine with a larger `chunk`", e->cap);
+                e->mesh_pass = std::max(1024, e->mesh_pass / 2 / 1024 * 1024);
+                continue;
+            }
+            prof_begin(e, 0, st);
+        }
         rc = run_narrow_and_finalize(e, a, m, flags, bits + off / 32, min_dist ? min_dist + off : nullptr, nullptr, st);
         if (rc) return rc;
+        off += m;
     }
     return JG_OK;
 }

@@ -1231,12 +1231,13 @@ __global__ void __launch_bounds__(BLOCK) k_broadphase_poses(const PassArgs a, co
     }
     Champ champ;
     champ.scene = champ.self = 0ull;
+    Champ* lc = MESH ? nullptr : &champ;   // mesh queues find their champions with atomics (see k_broadphase)
     for (int k = 0; k < n_use; ++k) {
         const int s = use_shapes[k];
         const Tf T = tf_mul(Pz, rel[k]);
-        shape_vs_scene<MESH>(a, R->shapes[s], s, pieces, T, valid, cfg, &champ);
+        shape_vs_scene<MESH>(a, R->shapes[s], s, pieces, T, valid, cfg, lc);
     }
-    champ_publish(a, champ.scene, a.champ_scene, cfg, valid);
+    if (lc) champ_publish(a, champ.scene, a.champ_scene, cfg, valid);
 }
 
 // ------------------------------------------------------------------------------------------------ FK only

@@ -139,15 +139,19 @@ def target_mesh_world(scenario):
     return v, inv.reshape(-1, 3)
 
 
-def check_collisions(grasp_poses, scenario, open_scale=1.0):
+def check_collisions(grasp_poses, scenario, open_scale=1.0, surface_mesh=False):
     """``grasp_sampler.check_collisions(candidates, scene, gripper.mesh, with_plane=True)`` (create_graspset.py:53-60):
     0 = free, 1 = the gripper at that grasp collides with a scene body or the plane.  One batched GPU call; the gripper
     is the Panda hand + fingers placed through ``FrankaRobot.tf_grasp2ee`` (burg's procedural gripper mesh is not in the
-    reference tree)."""
+    reference tree).  ``surface_mesh=True`` tests against the triangle surfaces of the scene meshes instead of the convex
+    pieces (``GraspingSimulator.gripper_mesh_collision_batch``)."""
     from .simulation import FrankaRobot
     robot, sim = scenario.get_robot_and_sim()
     ee = np.asarray(grasp_poses, dtype=np.float64).reshape(-1, 4, 4) @ FrankaRobot.tf_grasp2ee
-    hit, _ = sim.gripper_in_collision_batch(ee, open_scale=open_scale, want_dist=False)
+    if surface_mesh:   # boolean mesh-surface mode (closer to trimesh / fcl): no margins, obstacle interiors are free
+        hit = sim.gripper_mesh_collision_batch(ee, open_scale=open_scale)
+    else:
+        hit, _ = sim.gripper_in_collision_batch(ee, open_scale=open_scale, want_dist=False)
     return hit.cpu().numpy().astype(np.int32)
 
 

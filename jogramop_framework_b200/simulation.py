@@ -117,8 +117,9 @@ class GraspingSimulator:
         m = self._scene_model.retarget(self._robot.pose)
         return m.subset(bodies, with_plane)
 
-    def _engine(self, key, bodies=None, with_plane=True, self_pairs=None, small=False):
-        """Cached CollisionEngine for (body subset, finger opening, self pair list)."""
+    def _engine(self, key, bodies=None, with_plane=True, self_pairs=None, small=False, mesh_margin=None):
+        """Cached CollisionEngine for (body subset, finger opening, self pair list); ``mesh_margin`` not None: mesh
+        mode (the scene's merged triangle mesh through the LBVH) with that triangle margin."""
         robot = self._robot
         if robot is None:
             raise JogramopError('no robot has been loaded into this simulator')
@@ -133,7 +134,8 @@ class GraspingSimulator:
                 bodies = [b for b in self._body_of_id.values() if b is not None]
             scene = self._scene_for(bodies, with_plane)
             self._engines[full_key] = _engine.CollisionEngine(
-                model, scene, device=self.device, finger_open=full_key[1], chunk=4096 if small else 0)
+                model, scene, device=self.device, finger_open=full_key[1], chunk=4096 if small else 0,
+                mesh_mode=mesh_margin is not None, mesh_margin=0.001 if mesh_margin is None else mesh_margin)
         return self._engines[full_key]
 
     # ------------------------------------------------------------------ reference API
@@ -206,6 +208,39 @@ class GraspingSimulator:
             eng = self._engine('full')
             links = [robot.end_effector_id - 3, *robot.finger_joint_ids]   # hand, left finger, right finger
             return eng.check_poses(T[:, :3, :].astype(np.float32), links=links, want_dist=want_dist)
+        finally:
+            robot._open_scale = old
+
+
+    def gripper_mesh_collision_batch(self, poses, open_scale=None):
+        """Boolean surface-mesh mode of the gripper filter (burg ``check_collisions`` -> trimesh / fcl
+        mesh-vs-mesh, create_graspset.py:53-60): does the gripper (convex hand + finger hulls, NO margins) touch the
+        triangle SURFACE of a scene mesh (export/obstacles.obj through the GPU-built LBVH) or reach the ground plane?
+
+        A hull-vs-triangle test per LBVH candidate (GJK with the triangle in registers) instead of fcl's
+        triangle-vs-triangle tests on a gripper mesh: for convex gripper parts the two agree except that a triangle
+        lying entirely INSIDE a part also counts as a hit here (fcl reports none: no surface crossing).  Unlike the
+        convex-piece model, the inside of an obstacle is free space.  Returns bool[n] (torch, engine device)."""
+        robot = self._robot
+        if robot is None:
+            raise JogramopError('load a FrankaRobot into the simulator first')
+        poses = np.asarray(poses, dtype=np.float64)
+        if poses.ndim == 2 and poses.shape[1] == 7:
+            T = np.stack([util.tf_from_pos_quat(p[:3], p[3:]) for p in poses]) if len(poses) else np.zeros((0, 4, 4))
+        else:
+            T = poses.reshape(-1, 4, 4)
+        T = np.linalg.inv(robot.pose) @ T
+        old = robot._open_scale
+        if open_scale is not None:
+            robot._open_scale = float(open_scale)
+        try:
+            eng = self._engine('surface-mesh', mesh_margin=0.0)
+            links = [robot.end_effector_id - 3, *robot.finger_joint_ids]
+            _, dist = eng.check_poses(T[:, :3, :].astype(np.float32), links=links, flags=_engine.SCENE | _engine.PLANE | _engine.NO_EPA)
+            # overlapping cores are reported as exactly -(hull margin + triangle margin) = -hull margin; anything
+            # larger means the hull itself is clear of the surface (the hull margin is not part of this mode)
+            msum = float(np.max(robot.model.shape_margin))
+            return dist <= -msum + 1e-6
         finally:
             robot._open_scale = old
 

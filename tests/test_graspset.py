@@ -93,3 +93,46 @@ def test_create_grasps_pipeline_on_gpu(tmp_path):
     free = (check_collisions(ref, s) == 0).mean()
     print(f'reference grasps.npy accepted by the Panda-hand collision model: {free:.3f}')
     assert 0.0 <= free <= 1.0
+
+
+@pytest.mark.gpu
+def test_surface_mesh_boolean_mode_on_gpu():
+    """gripper_mesh_collision_batch == the oracle's zero-margin hull-vs-triangle overlap test on the same poses, and is
+    implied by ... / implies the convex-piece verdict in the expected direction."""
+    import copy
+    import oracle
+    from jogramop_framework_b200.scenario import Scenario
+    s = Scenario(11)
+    robot, sim = s.get_robot_and_sim()
+    sc = s._scene_model
+    rng = np.random.default_rng(99)
+    n = 20000
+    v = sc.tri_verts
+    lo, hi = v.min(0) - 0.1, v.max(0) + 0.1
+    pos = lo + (hi - lo) * rng.random((n, 3))
+    quat = rng.normal(size=(n, 4))
+    quat /= np.linalg.norm(quat, axis=1, keepdims=True)
+    x, y, z, w = quat.T
+    R = np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                  2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                  2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], 1).reshape(n, 3, 3)
+    T_robot = np.tile(np.eye(4), (n, 1, 1))
+    T_robot[:, :3, :3], T_robot[:, :3, 3] = R, pos
+    T_world = robot.pose @ T_robot
+    hit = sim.gripper_mesh_collision_batch(T_world).cpu().numpy()
+    tri_scene = copy.copy(sc)
+    tri_scene.piece_verts = sc.tri_verts[sc.tris].reshape(-1, 3)
+    tri_scene.piece_vert_offset = (np.arange(len(sc.tris) + 1) * 3).astype(np.int32)
+    tri_scene.piece_body = sc.tri_body
+    tri_scene.piece_margin = np.zeros(len(sc.tris))
+    o = oracle.Oracle(robot.model, tri_scene)
+    links = [robot.end_effector_id - 3, *robot.finger_joint_ids]
+    _, rd = o.check_poses(T_robot, links=links, flags=oracle.SCENE | oracle.PLANE | oracle.NO_EPA)
+    ref = rd <= -0.001 + 1e-6
+    clear = np.abs(rd + 0.001) > 2e-5            # poses whose hull is not within 20 um of a surface
+    assert np.array_equal(hit[clear], ref[clear])
+    assert (hit != ref).sum() <= 5
+    assert 0.05 < ref.mean() < 0.9
+    # touching a surface implies colliding with the (solid, margin-inflated) convex pieces
+    solid, _ = sim.gripper_in_collision_batch(T_world)
+    assert (solid.cpu().numpy() | ~hit).mean() > 0.999
