@@ -736,7 +736,7 @@ __global__ void __launch_bounds__(BLOCK) k_narrowphase(const PassArgs a) {
         GjkState S;
         Tf T = tf_identity();
         int cfg = 0, off = 0;
-        float best_total = -FLT_MAX;
+        float best_total = -FLT_MAX, dmax_l = dmax;
         if (K.kind == KEY_MESH) {   // link hull vs one triangle per lane (registers); same lane refill, no penetration pass
             TriSupport tri;
             tri.p0 = tri.p1 = tri.p2 = mk(0.f, 0.f, 0.f);
@@ -779,12 +779,15 @@ __global__ void __launch_bounds__(BLOCK) k_narrowphase(const PassArgs a) {
                 gjk_init(S, mk(T.tx, T.ty, T.tz));
                 active = true;
                 best_total = -dec_float(e0);
+                // only a contact distance below the proven one can change the minimum: GJK may stop as soon as a
+                // separating axis shows the cores are further apart than that
+                dmax_l = fminf(dmax, fmaxf(K.msum - best_total, 0.f));
             },
             [&]() {
                 // ---- one GJK iteration on every busy lane
                 bool deep = false;
                 if (active) {
-                    int st = gjk_step(S, A, K.a_n, SetSupport{B, K.b_n}, T, dmax);
+                    int st = gjk_step(S, A, K.a_n, SetSupport{B, K.b_n}, T, dmax_l);
                     // exact early out: another pair of this configuration already penetrates deeper than this pair possibly
                     // can (hmin = smallest support value seen = upper bound of this pair's depth if it overlaps at all)
                     if (st == JG_GJK_RUNNING && best_total > 0.f && fmaxf(S.hmin, 0.f) + fmaxf(K.emsum, K.msum) + 0.004f <= best_total) {
