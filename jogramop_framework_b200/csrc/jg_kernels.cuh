@@ -107,6 +107,8 @@ struct PassArgs {
     int* epa_slot;     // [n_keys*cap] queue slots whose cores overlap (penetration-depth pass)
     uint4* epa_ids;    // [n_keys*cap] their GJK end simplices (vertex ids, 0xFFFFFFFF = unused)
     int2* ovf_list;    // [cap] (key, index in the penetration queue) of polytopes that outgrew shared memory
+    uint32_t* ovf_poly;  // [ovf_poly_cap][JG_OVF_WORDS] the compact polytope of the first ovf_poly_cap of them: the overflow
+    int ovf_poly_cap;    // kernel goes on from there instead of repeating the 14 expansions that filled it
     float* epa_prio;   // [n_keys*cap] the same bound for the entries of the penetration queue
     int* act_list;     // [n_keys*cap] per key: queue indices selected for the current stage (k_select)
     int2* act_meta;    // [n_keys*cap] beside act_list (hull / triangle keys): (pair-queue slot, configuration) of the entry,
@@ -134,6 +136,8 @@ __device__ __forceinline__ int* cnt_epa(const PassArgs& a) { return a.counts + a
 __device__ __forceinline__ int* cnt_act(const PassArgs& a) { return a.counts + 2 * a.n_keys; }
 __device__ __forceinline__ int* cnt_done(const PassArgs& a) { return a.counts + 3 * a.n_keys; }
 enum { CTR_GJK = 0, CTR_EPA = 1, CTR_OVF = 2, CTR_SEL = 3 };
+// hand-over record of an overflowing compact polytope: its words, then lb, ub, it, nv, nf (padded to 124)
+#define JG_OVF_WORDS 124
 __device__ __forceinline__ int* cnt_misc(const PassArgs& a) { return a.counts + 4 * a.n_keys; }
 // per-key cursors of the running narrow-phase stage (entries of the key's stage list handed out so far)
 __device__ __forceinline__ int* cnt_cur(const PassArgs& a) { return a.counts + 4 * a.n_keys + 8; }
@@ -1065,8 +1069,18 @@ __global__ void __launch_bounds__(BLOCK) k_penetration(const PassArgs a) {
                         phase = 0;
                     } else if (st == JG_EPA_OVERFLOW) {   // rare large polytope: redo with per-thread storage
                         const int o = atomicAdd(ovf_counter, 1);
-                        if (o < a.cap) a.ovf_list[o] = make_int2(key, myj);
-                        else atomicMin(enc + cfg, enc_float(fminf(-(epa_result(X) + K.emsum), -K.msum)));
+                        if (o < a.cap) {
+                            a.ovf_list[o] = make_int2(key, myj);
+                            if (o < a.ovf_poly_cap) {   // hand the polytope over (nothing was modified by the failed step)
+                                uint32_t* rec = a.ovf_poly + (size_t)o * JG_OVF_WORDS;
+                                for (int k = 0; k < EpaCompact<BLOCK>::WORDS; ++k) rec[k] = X.poly.at(k);
+                                rec[EpaCompact<BLOCK>::WORDS + 0] = __float_as_uint(X.lb);
+                                rec[EpaCompact<BLOCK>::WORDS + 1] = __float_as_uint(X.ub);
+                                rec[EpaCompact<BLOCK>::WORDS + 2] = (uint32_t)X.it;
+                                rec[EpaCompact<BLOCK>::WORDS + 3] = (uint32_t)X.poly.nv;
+                                rec[EpaCompact<BLOCK>::WORDS + 4] = (uint32_t)X.poly.nf;
+                            }
+                        } else atomicMin(enc + cfg, enc_float(fminf(-(epa_result(X) + K.emsum), -K.msum)));
                         phase = 0;
                     }
                 }
@@ -1132,6 +1146,47 @@ __global__ void __launch_bounds__(BLOCK) k_penetration_big(const PassArgs a) {
         Simplex sx;
         bool pen = true;
         float d = 0.f;
+        if (i < a.ovf_poly_cap) {
+            // continue the compact polytope: lane l converts vertex l and face l into the large storage class (the
+            // neighbour's edge index, which the compact form leaves out, is found from the shared vertex)
+            typedef EpaCompact<1> C;
+            const uint32_t* rec = a.ovf_poly + (size_t)i * JG_OVF_WORDS;
+            const int nv = (int)rec[C::WORDS + 3], nf = (int)rec[C::WORDS + 4];
+            __syncwarp();
+            if (lane < nv)   // vertex ids are not kept by the compact form: unique dummies (the bracket test ends the run)
+                X.poly.setP(lane, mk(__uint_as_float(rec[3 * lane]), __uint_as_float(rec[3 * lane + 1]), __uint_as_float(rec[3 * lane + 2])),
+                            0xFFFFFF00u + (uint32_t)lane);
+            if (lane < nf) {
+                const uint32_t fx = rec[C::oFx + lane];
+                uint32_t fv = 0u, fa = 0u;
+                float fd = FLT_MAX;
+                if ((fx >> 30) & 1u) {
+                    fv = (uint32_t)cx_vert(fx, 0) | ((uint32_t)cx_vert(fx, 1) << 8) | ((uint32_t)cx_vert(fx, 2) << 16) | (1u << 24);
+                    fd = __uint_as_float(rec[C::oFd + lane]);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const int g = cx_nbr(fx, k), vend = cx_vert(fx, k == 2 ? 0 : k + 1);
+                        const uint32_t fxg = rec[C::oFx + g];
+                        const int eg = cx_vert(fxg, 0) == vend ? 0 : (cx_vert(fxg, 1) == vend ? 1 : 2);
+                        fa |= ((uint32_t)g | ((uint32_t)eg << 8)) << (10 * k);
+                    }
+                }
+                X.poly.fv(lane) = fv;
+                X.poly.fa(lane) = fa;
+                X.poly.set_fd(lane, fd);
+            }
+            X.poly.nv = nv;
+            X.poly.nf = nf;
+            X.lb = __uint_as_float(rec[C::WORDS + 0]);
+            X.ub = __uint_as_float(rec[C::WORDS + 1]);
+            X.it = (int)rec[C::WORDS + 2];
+            __syncwarp();
+            while (epa_step(X, sup) == JG_EPA_RUNNING) { __syncwarp(); }
+            d = -(epa_result(X) + K.emsum);
+            __syncwarp();
+            if (lane == 0) atomicMin((K.kind == KEY_SELF ? a.enc_self : a.enc_scene) + cfg, enc_float(fminf(d, -K.msum)));
+            continue;
+        }
         if ((K.ea_off != K.a_off) || (K.eb_off != K.b_off)) {   // box: every lane reruns the (identical) GJK
             float dist;
             int it;

@@ -90,6 +90,13 @@ def test_overflow_kernel_parity(robot, scene_loader, engines):
     compare(bits, dist, rb, rd)
     bits2, dist2, _ = e.check(q, flags=oracle.SCENE | oracle.PLANE | oracle.SELF)
     assert (dist - dist2).abs().max().item() < 2e-5
+    # a smaller pass capacity has fewer hand-over records (capacity / 4 = 16384): the first overflows of the pass continue
+    # the compact polytope, the later ones restart from the GJK simplex -- both inside one pass.  (The overflow list
+    # itself holds `capacity` entries: with every polytope forced through it, the pass must stay below that.)
+    es = engines(11, chunk=65536)
+    bits3, dist3, _ = es.check(q, flags=oracle.SCENE | oracle.PLANE | oracle.SELF | 0x40000000)
+    compare(bits3, dist3, rb, rd)
+    assert 65536 // 4 < es.stats()['overflow_run'] < 65536
 
 
 @pytest.mark.parametrize('sid', [11, 34])
