@@ -104,9 +104,9 @@ def time_oracle(robot, scene, q, flags, n_threads, budget_s):
     rate = probe / (time.perf_counter() - t0)
     n = int(min(len(q), max(probe, rate * budget_s)))
     t0 = time.perf_counter()
-    o.check(q[:n].astype(np.float64), flags=flags, n_threads=n_threads)
+    rb, rd = o.check(q[:n].astype(np.float64), flags=flags, n_threads=n_threads)
     dt = time.perf_counter() - t0
-    return n / dt, n, (n_threads if n_threads > 0 else os.cpu_count())
+    return n / dt, n, (n_threads if n_threads > 0 else os.cpu_count()), rb, rd
 
 
 def run_reference(args):
@@ -334,10 +334,20 @@ def run_b200(args):
         if world == 1 and not args.no_cpu_baseline:
             import oracle
             oflags = oracle.SCENE | oracle.PLANE | (oracle.NO_EPA if args.no_epa else 0)
-            v, used, cores = time_oracle(robot, scene, q_host, oflags, 0, args.cpu_budget)
+            v, used, cores, rb, rd = time_oracle(robot, scene, q_host, oflags, 0, args.cpu_budget)
             line['cpu_baseline'] = {'value': v, 'unit': 'checks/s', 'cores': cores, 'kind': 'port',
                                     'sample': f'first {used} of the {n} configurations, all host threads; CPU oracle '
                                               'restatement (double precision) - pyBullet not installable in this image'}
+            # the oracle's answers for that sample are the checker of the timed path (not timed, not shipped)
+            gb, gd, _ = eng.check(q_dev[:used], flags=flags)
+            gb, gd = gb.cpu().numpy().astype(bool), gd.cpu().numpy().astype(np.float64)
+            outside = np.abs(rd + 0.001) > 1e-3
+            line['parity'] = {'checked': int(used), 'against': 'CPU oracle (double precision), same inputs',
+                              'verdict_mismatches_outside_1mm_band': int((gb[outside] != rb[outside]).sum()),
+                              'verdict_mismatches_inside_band': int((gb[~outside] != rb[~outside]).sum()),
+                              'configs_inside_band': int((~outside).sum()),
+                              'max_abs_distance_error_m': float(np.abs(gd - rd).max()),
+                              'collision_rate': float(rb.mean())}
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
