@@ -1,15 +1,21 @@
-// jg_kernels.cuh -- device tables and the three kernels of one collision-check pass.
+// jg_kernels.cuh -- device tables and the kernels of one collision-check pass.
 //
-//   k_broadphase  one thread per configuration: forward kinematics down the URDF chain (link transform in
-//                 registers), world AABB of every link shape vs obstacle-piece AABBs / plane / self pairs;
-//                 survivors are appended to per-(shape,piece) queues in HBM with warp-aggregated atomics.
-//   k_narrowphase persistent warps pull 32-entry tiles of ONE queue: every lane of the warp therefore runs GJK
-//                 on the same two vertex sets (shared-memory broadcast reads), each on its own configuration.
-//                 Result: atomicMin of the contact distance into the configuration's slot.
-//   k_finalize    per configuration: clamp at the query distance, threshold, ballot-pack the verdict bits.
+//   k_broadphase       one thread per configuration: forward kinematics down the URDF chain (link transform in
+//                      registers), world box of every link shape vs obstacle-piece boxes / plane / self pairs;
+//                      survivors go to per-(shape,piece) queues in HBM: all keys of a shape are tested first, then
+//                      lanes 0..P reserve the slots of their keys side by side (one atomic round trip per shape).
+//   k_select           builds the per-key index lists of a narrow-phase stage (champions / pairs that can still matter).
+//   k_narrowphase      GJK.  A warp works on ONE key at a time, so every lane runs on the same two vertex sets
+//                      (shared-memory broadcast reads), each on its own configuration; entries come from the key's
+//                      cursor through refill_loop (lane refill, prefetched reservations).  Result: atomicMin of the
+//                      contact distance into the configuration's slot; overlapping cores go to the penetration queue.
+//   k_penetration      expanding-polytope depth, one compact polytope per thread in shared memory, same scheduling.
+//   k_penetration_big  the few polytopes that outgrow the compact storage: one per warp, continued from a hand-over
+//                      record.
+//   k_finalize         per configuration: clamp at the query distance, threshold, ballot-pack the verdict bits.
 //
 // HBM layout of a pass over C configurations and K keys (key = shape*(P+1)+piece, plane = piece P, then the
-// self-collision pairs):   q_r0/q_r1/q_r2 float4[K*C] (rows of R with t in .w), q_cfg int[K*C], counts int[K].
+// self-collision pairs): see PassArgs below and DESIGN.md section 4.
 #pragma once
 #include "jg_epa.cuh"
 #include "jg_lbvh.cuh"
