@@ -31,9 +31,9 @@ sys.path.insert(0, ROOT)
 FLOPS_PER_CHECK = 1.5e4         # SURVEY §8d nominal algorithmic work per check, scenario 011
 FLOPS_PER_CHECK_NARROW = 1.28e4  # ... of which the narrow phase (W_np)
 # DRAM bytes (read + write) of the narrow-phase kernels of ONE pass over 1 M configurations of scenario 011, from the
-# ncu --set full capture profiles/r01_k_ncu_full_summary.csv (2 x k_narrowphase, 2 x k_penetration, 3 x k_select,
+# ncu --set full capture profiles/r01_m_ncu_full_summary.csv (2 x k_narrowphase, 2 x k_penetration, 3 x k_select,
 # k_penetration_big): 425.6 MB = 426 B per check, ~10x the algorithmic 40 B (pair queues), 4 % of HBM bandwidth
-NARROW_TRAFFIC_BYTES_PER_CHECK_NCU = 393.7
+NARROW_TRAFFIC_BYTES_PER_CHECK_NCU = 395.2
 BYTES_PER_CHECK = 40.125        # 36 B in + 4 B distance + 1 bit out
 
 
@@ -291,7 +291,7 @@ def run_b200(args):
                          'achieved': ach_tf, 'peak': fp32_peak,
                          'unit': 'TFLOP/s', 'frac': (ach_tf / fp32_peak) if (ach_tf and fp32_peak) else None,
                          'traffic': (NARROW_TRAFFIC_BYTES_PER_CHECK_NCU * n if (args.scenario == 11 and not args.no_epa) else None),
-                         'traffic_source': 'ncu dram__bytes_read.sum + dram__bytes_write.sum per pass, profiles/r01_k_ncu_full_summary.csv',
+                         'traffic_source': 'ncu dram__bytes_read.sum + dram__bytes_write.sum per pass, profiles/r01_m_ncu_full_summary.csv',
                          'peak_source': 'jg_measure_fp32_peak FMA micro-benchmark on this GPU',
                          'algorithmic_flops_per_check': FLOPS_PER_CHECK_NARROW,
                          'avg_launch_ms': nar_ms / np_n if np_n else None, 'launches': int(np_n),
