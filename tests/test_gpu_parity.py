@@ -453,3 +453,21 @@ def test_full_size_properties(robot, scene_loader, engines):
     idx = np.arange(0, 1_000_000, 50)
     rb, rd = o.check(q[idx].astype(np.float64), flags=3)
     compare(bits[torch.from_numpy(idx)], dist[torch.from_numpy(idx)], rb, rd)
+
+
+def test_batches_larger_than_one_pass(robot, scene_loader, engines):
+    """More configurations than the 2^20 pass capacity: the call splits into passes; results equal the per-slice calls and
+    the oracle on a sample that straddles the pass boundary.  Same through the host path (its passes are pipelined)."""
+    e = engines(11)
+    n = (1 << 20) + (1 << 19) + 77
+    q = uniform_configs(robot, n, 123)
+    bits, dist, _ = e.check(q, flags=3)
+    b0, d0, _ = e.check(q[:1 << 20], flags=3)
+    b1, d1, _ = e.check(q[1 << 20:], flags=3)
+    assert torch.equal(bits, torch.cat([b0, b1])) and torch.equal(dist, torch.cat([d0, d1]))
+    idx = np.concatenate([np.arange((1 << 20) - 3000, (1 << 20) + 3000), np.arange(n - 2000, n)])
+    rb, rd = Oracle(robot, scene_loader(11)).check(q[idx].astype(np.float64), flags=3)
+    compare(bits[torch.from_numpy(idx)], dist[torch.from_numpy(idx)], rb, rd)
+    from jogramop_framework_b200.engine import unpack_bits
+    wb, wd, _ = e.check_host(q, flags=3)                 # pageable input, two passes in the pipeline
+    assert torch.equal(unpack_bits(wb.cuda(), n), bits) and torch.equal(wd.cuda(), dist)
