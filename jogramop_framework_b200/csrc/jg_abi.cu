@@ -573,7 +573,7 @@ static void launch_broadphase(const jg_engine* e, const PassArgs& a, int grid, s
     else k_broadphase<BP_BLOCK, false><<<grid, BP_BLOCK, smem, st>>>(a);
 }
 
-#define JG_COUNTS_INTS(n_keys) (5 * (n_keys) + 8)   /* layout: jg_kernels.cuh cnt_*() */
+#define JG_COUNTS_INTS(n_keys) (7 * (n_keys) + 8)   /* layout: jg_kernels.cuh cnt_*() */
 
 static size_t bp_smem(const jg_engine* e, uint32_t flags) {
     size_t s = sizeof(RobotTab) + sizeof(PieceRec) * e->P + sizeof(float) * BP_BLOCK * e->dof;
@@ -708,7 +708,8 @@ static void fill_args(const jg_engine* e, PassArgs& a, uint32_t& flags, bool wan
     a.enc_scene = e->enc_scene; a.enc_self = e->enc_self; a.viol = e->viol;
 }
 
-__global__ void k_accumulate_stats(const int* counts, int n_scene_keys, int n_keys, int P, unsigned long long* stats) {
+__global__ void k_accumulate_stats(const int* counts, int n_scene_keys, int n_keys, int P, unsigned long long* stats,
+                                   int last_set, int last_slot) {
     // one warp; stats[0]=hull pairs, [1]=plane, [2]=self
     unsigned long long h = 0, pl = 0, sf = 0;
     for (int k = threadIdx.x; k < n_keys; k += 32) {
@@ -725,7 +726,12 @@ __global__ void k_accumulate_stats(const int* counts, int n_scene_keys, int n_ke
     unsigned long long ep = 0;
     for (int k = threadIdx.x; k < n_keys; k += 32) ep += counts[n_keys + k];
     for (int o = 16; o; o >>= 1) ep += __shfl_xor_sync(0xFFFFFFFFu, ep, o);
+    unsigned long long last = 0;
+    const int* lact = counts + (last_set ? 5 * n_keys + 8 : 2 * n_keys);
+    for (int k = threadIdx.x; k < n_keys; k += 32) last += lact[k];
+    for (int o = 16; o; o >>= 1) last += __shfl_xor_sync(0xFFFFFFFFu, last, o);
     if (threadIdx.x == 0) {
+        if (last_slot >= 0) stats[last_slot] += last;
         stats[0] += h; stats[1] += pl; stats[2] += sf; stats[3] += ep;
         stats[6] += (unsigned long long)counts[4 * n_keys + CTR_OVF];   // polytopes handed to the overflow kernel
     }
@@ -740,7 +746,7 @@ static int run_narrow_and_finalize(jg_engine* e, const PassArgs& a, int n_out, u
     // depth, then the rare large polytopes of both penetration stages.
     const bool epa = !(flags & JG_NO_EPA);
     const size_t sel_smem = sizeof(int) * (2 * e->n_keys + 2);
-    auto launch_penetration = [&]() {
+    auto launch_penetration = [&](const PassArgs& a) {
         switch (e->epa_threads) {
             case 416: k_penetration<416><<<e->epa_blocks, 416, e->smem_epa, st>>>(a); break;
             case 384: k_penetration<384><<<e->epa_blocks, 384, e->smem_epa, st>>>(a); break;
@@ -752,27 +758,37 @@ static int run_narrow_and_finalize(jg_engine* e, const PassArgs& a, int n_out, u
             default: k_penetration<64><<<e->epa_blocks, 64, e->smem_epa, st>>>(a); break;
         }
     };
+    // The stage lists live in two sets: every k_select builds the next stage's lists in one set and clears the set of
+    // the stage that has just finished (and books its entry count into stats[4] GJK pairs / stats[5] polytopes).
+    int set = 0, n_sel = 0, prev_slot = -1;
+    PassArgs as = a;
     if (e->n_keys > 0) {
         for (int round = 0; round < 2; ++round) {
             prof_begin(e, 1, st);
-            // the broad phase already wrote the stage-1 lists itself (thread-local champions) unless the champions were
-            // found with atomics (edge substeps, mesh queues)
+            // the broad phase already wrote the stage-1 lists itself (set 0, thread-local champions) unless the champions
+            // were found with atomics (edge substeps, mesh queues)
             const bool listed = round == 0 && a.substeps <= 1 && !a.mesh;
             if (!listed) {
-                k_select<256><<<e->sm_count * 4, 256, sel_smem, st>>>(a, round == 0 ? SEL_GJK_CHAMP : SEL_GJK_REST);
+                if (prev_slot >= 0) set ^= 1;
+                as.stage_set = set;
+                k_select<256><<<e->sm_count * 4, 256, sel_smem, st>>>(as, round == 0 ? SEL_GJK_CHAMP : SEL_GJK_REST, n_sel++,
+                                                                     prev_slot, round == 1 && epa ? 1 : 0);
                 e->stats.kernel_launches += 1;
             }
-            k_narrowphase<NP_BLOCK><<<e->np_blocks, NP_BLOCK, e->smem_narrow, st>>>(a);
-            k_stage_reset<<<1, 256, 0, st>>>(a, 0, 4);      // stats[4] += GJK pairs run
+            as.stage_set = set;
+            k_narrowphase<NP_BLOCK><<<e->np_blocks, NP_BLOCK, e->smem_narrow, st>>>(as);
+            prev_slot = 4;
             prof_end(e, st);
-            e->stats.kernel_launches += 2;
+            e->stats.kernel_launches += 1;
             if (epa) {
                 prof_begin(e, 2, st);
-                k_select<256><<<e->sm_count * 4, 256, sel_smem, st>>>(a, SEL_EPA_NEW);
-                launch_penetration();
-                k_stage_reset<<<1, 256, 0, st>>>(a, 1, 5);  // stats[5] += polytopes expanded; remember how far
+                set ^= 1;
+                as.stage_set = set;
+                k_select<256><<<e->sm_count * 4, 256, sel_smem, st>>>(as, SEL_EPA_NEW, n_sel++, prev_slot, 0);
+                launch_penetration(as);
+                prev_slot = 5;
                 prof_end(e, st);
-                e->stats.kernel_launches += 3;
+                e->stats.kernel_launches += 2;
             }
         }
         if (epa) {
@@ -784,7 +800,8 @@ static int run_narrow_and_finalize(jg_engine* e, const PassArgs& a, int n_out, u
     }
     prof_begin(e, 3, st);
     if (e->n_keys > 0) {
-        k_accumulate_stats<<<1, 32, 0, st>>>(e->counts, e->n_scene_keys, e->n_keys, e->P, e->d_stats);
+        // (also books the last stage, which no k_select followed)
+        k_accumulate_stats<<<1, 32, 0, st>>>(e->counts, e->n_scene_keys, e->n_keys, e->P, e->d_stats, set, prev_slot);
         e->stats.kernel_launches += 1;
     }
     k_finalize<<<(n_out + 255) / 256, 256, 0, st>>>(e->enc_scene, e->enc_self, e->viol, n_out, a.qd, a.threshold, flags, bits,

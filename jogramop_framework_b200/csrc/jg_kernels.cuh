@@ -89,6 +89,7 @@ struct PassArgs {
                        // launches so that the host path can overlap it with the upload of the next slice)
     int dof;
     int substeps;      // 1, or substeps per edge
+    int stage_set;     // which of the two stage-list sets (cnt_act / cnt_cur) this launch works on
     uint32_t flags;
     float finger_open, qd, threshold;
     float plane[4];
@@ -139,14 +140,19 @@ struct PassArgs {
 
 __device__ __forceinline__ int* cnt_pair(const PassArgs& a) { return a.counts; }
 __device__ __forceinline__ int* cnt_epa(const PassArgs& a) { return a.counts + a.n_keys; }
-__device__ __forceinline__ int* cnt_act(const PassArgs& a) { return a.counts + 2 * a.n_keys; }
+// Stage lists come in TWO sets (a.stage_set selects the one a kernel works on): k_select builds the lists of the next
+// stage in one set and, in passing, clears the set of the stage that has just finished -- no reset kernel in between.
+//   counts layout (JG_COUNTS_INTS = 7 K + 8 ints): pair | epa | act[0] | done | misc(8) | cur[0] | act[1] | cur[1]
+__device__ __forceinline__ int* cnt_act_of(const PassArgs& a, int set) { return a.counts + (set ? 5 * a.n_keys + 8 : 2 * a.n_keys); }
+__device__ __forceinline__ int* cnt_cur_of(const PassArgs& a, int set) { return a.counts + (set ? 6 * a.n_keys + 8 : 4 * a.n_keys + 8); }
+__device__ __forceinline__ int* cnt_act(const PassArgs& a) { return cnt_act_of(a, a.stage_set); }
 __device__ __forceinline__ int* cnt_done(const PassArgs& a) { return a.counts + 3 * a.n_keys; }
-enum { CTR_GJK = 0, CTR_EPA = 1, CTR_OVF = 2, CTR_SEL = 3 };
+enum { CTR_OVF = 2, CTR_SEL = 3 /* .. CTR_SEL + 3: one range counter per k_select launch of a pass */ };
 // hand-over record of an overflowing compact polytope: its words, then lb, ub, it, nv, nf (padded to 124)
 #define JG_OVF_WORDS 124
 __device__ __forceinline__ int* cnt_misc(const PassArgs& a) { return a.counts + 4 * a.n_keys; }
 // per-key cursors of the running narrow-phase stage (entries of the key's stage list handed out so far)
-__device__ __forceinline__ int* cnt_cur(const PassArgs& a) { return a.counts + 4 * a.n_keys + 8; }
+__device__ __forceinline__ int* cnt_cur(const PassArgs& a) { return cnt_cur_of(a, a.stage_set); }
 
 __device__ __forceinline__ Tf joint_local(const JointRec& J, float val) {
     Tf O;
@@ -870,7 +876,7 @@ __device__ __forceinline__ Simplex simplex_from_ids(const float4* __restrict__ A
 enum { SEL_GJK_CHAMP = 0, SEL_GJK_REST = 1, SEL_EPA_NEW = 2 };
 
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_select(const PassArgs a, int mode) {
+__global__ void __launch_bounds__(BLOCK) k_select(const PassArgs a, int mode, int sel_index, int prev_stat_slot, int mark_done) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int* prefix = reinterpret_cast<int*>(smem_raw);   // [n_keys + 2]
     int* span = prefix + a.n_keys + 2;                // [n_keys] entries to look at per key
@@ -883,8 +889,27 @@ __global__ void __launch_bounds__(BLOCK) k_select(const PassArgs a, int mode) {
     if (tid < 32) sched_build(span, a.n_keys, gridDim.x * (BLOCK / 32), prefix, prefix + a.n_keys + 1, lane);
     __syncthreads();
     const int total = prefix[a.n_keys], G = prefix[a.n_keys + 1];
-    int* range_counter = cnt_misc(a) + CTR_SEL;
+    int* range_counter = cnt_misc(a) + CTR_SEL + sel_index;
     int* acounts = cnt_act(a);
+    if (blockIdx.x == 0) {
+        // the stage that has just finished used the OTHER set: account for it (stats[prev_stat_slot] += entries it ran),
+        // clear it for the stage after this one, and -- after a penetration stage -- remember how far the penetration
+        // queue has been expanded.  Nothing else in this launch touches that set.
+        int* oact = cnt_act_of(a, a.stage_set ^ 1);
+        int* ocur = cnt_cur_of(a, a.stage_set ^ 1);
+        int mine = 0;
+        for (int k = tid; k < a.n_keys; k += BLOCK) {
+            mine += oact[k];
+            oact[k] = 0;
+            ocur[k] = 0;
+            if (mark_done) cnt_done(a)[k] = cnt_epa(a)[k];
+        }
+        if (prev_stat_slot >= 0) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, o);
+            if (lane == 0 && mine) atomicAdd(a.stats + prev_stat_slot, (unsigned long long)mine);
+        }
+    }
     const unsigned lt_mask = (1u << lane) - 1u;
     const bool no_epa = (a.flags & 16u) != 0;
     for (;;) {
@@ -965,29 +990,6 @@ __global__ void __launch_bounds__(BLOCK) k_select(const PassArgs a, int mode) {
                 }
             }
         }
-    }
-}
-
-// between stages: clear the selection counts and the range counters; `mark_done`: remember how much of the
-// penetration queue has been expanded
-__global__ void k_stage_reset(const PassArgs a, int mark_done, int stat_slot) {
-    __shared__ int sum;
-    if (threadIdx.x == 0) sum = 0;
-    __syncthreads();
-    int mine = 0;
-    for (int k = threadIdx.x; k < a.n_keys; k += blockDim.x) {
-        mine += cnt_act(a)[k];
-        cnt_act(a)[k] = 0;
-        cnt_cur(a)[k] = 0;
-        if (mark_done) cnt_done(a)[k] = cnt_epa(a)[k];
-    }
-    if (stat_slot >= 0 && mine) atomicAdd(&sum, mine);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (stat_slot >= 0) a.stats[stat_slot] += (unsigned long long)sum;   // entries the finished stage really ran
-        cnt_misc(a)[CTR_GJK] = 0;
-        cnt_misc(a)[CTR_EPA] = 0;
-        cnt_misc(a)[CTR_SEL] = 0;
     }
 }
 
