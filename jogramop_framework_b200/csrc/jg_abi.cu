@@ -708,35 +708,6 @@ static void fill_args(const jg_engine* e, PassArgs& a, uint32_t& flags, bool wan
     a.enc_scene = e->enc_scene; a.enc_self = e->enc_self; a.viol = e->viol;
 }
 
-__global__ void k_accumulate_stats(const int* counts, int n_scene_keys, int n_keys, int P, unsigned long long* stats,
-                                   int last_set, int last_slot) {
-    // one warp; stats[0]=hull pairs, [1]=plane, [2]=self
-    unsigned long long h = 0, pl = 0, sf = 0;
-    for (int k = threadIdx.x; k < n_keys; k += 32) {
-        const int c = counts[k];
-        if (k >= n_scene_keys) sf += c;
-        else if (k % (P + 1) == P) pl += c;
-        else h += c;
-    }
-    for (int o = 16; o; o >>= 1) {
-        h += __shfl_xor_sync(0xFFFFFFFFu, h, o);
-        pl += __shfl_xor_sync(0xFFFFFFFFu, pl, o);
-        sf += __shfl_xor_sync(0xFFFFFFFFu, sf, o);
-    }
-    unsigned long long ep = 0;
-    for (int k = threadIdx.x; k < n_keys; k += 32) ep += counts[n_keys + k];
-    for (int o = 16; o; o >>= 1) ep += __shfl_xor_sync(0xFFFFFFFFu, ep, o);
-    unsigned long long last = 0;
-    const int* lact = counts + (last_set ? 5 * n_keys + 8 : 2 * n_keys);
-    for (int k = threadIdx.x; k < n_keys; k += 32) last += lact[k];
-    for (int o = 16; o; o >>= 1) last += __shfl_xor_sync(0xFFFFFFFFu, last, o);
-    if (threadIdx.x == 0) {
-        if (last_slot >= 0) stats[last_slot] += last;
-        stats[0] += h; stats[1] += pl; stats[2] += sf; stats[3] += ep;
-        stats[6] += (unsigned long long)counts[4 * n_keys + CTR_OVF];   // polytopes handed to the overflow kernel
-    }
-}
-
 // narrow phase + finalize of the pass described by `a` (queues already filled)
 static int run_narrow_and_finalize(jg_engine* e, const PassArgs& a, int n_out, uint32_t flags, uint32_t* bits, float* dist,
                                    uint8_t* reason, cudaStream_t st) {
@@ -799,13 +770,12 @@ static int run_narrow_and_finalize(jg_engine* e, const PassArgs& a, int n_out, u
         }
     }
     prof_begin(e, 3, st);
-    if (e->n_keys > 0) {
-        // (also books the last stage, which no k_select followed)
-        k_accumulate_stats<<<1, 32, 0, st>>>(e->counts, e->n_scene_keys, e->n_keys, e->P, e->d_stats, set, prev_slot);
-        e->stats.kernel_launches += 1;
-    }
-    k_finalize<<<(n_out + 255) / 256, 256, 0, st>>>(e->enc_scene, e->enc_self, e->viol, n_out, a.qd, a.threshold, flags, bits,
-                                                    dist, reason);
+    // one extra block of k_finalize folds this pass's queue counters into the engine statistics (and books the last
+    // stage, which no k_select followed)
+    StatArgs sa = {nullptr, 0, 0, 0, nullptr, 0, -1};
+    if (e->n_keys > 0) sa = StatArgs{e->counts, e->n_scene_keys, e->n_keys, e->P, e->d_stats, set, prev_slot};
+    k_finalize<<<(n_out + 255) / 256 + 1, 256, 0, st>>>(e->enc_scene, e->enc_self, e->viol, n_out, a.qd, a.threshold, flags, bits,
+                                                        dist, reason, sa);
     e->stats.kernel_launches += 1;
     prof_end(e, st);
     CUDA_TRY(cudaGetLastError());

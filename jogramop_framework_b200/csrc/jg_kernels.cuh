@@ -1218,9 +1218,48 @@ __global__ void __launch_bounds__(BLOCK) k_penetration_big(const PassArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------ finalize
+// statistics of the pass: queue counters -> the engine's running totals (jg_get_stats)
+struct StatArgs {
+    const int* counts;      // NULL: nothing to account
+    int n_scene_keys, n_keys, P;
+    unsigned long long* stats;   // [0] hull pairs, [1] plane, [2] self, [3] overlapping, [4] GJK run, [5] polytopes, [6] overflows
+    int last_set, last_slot;     // stage-list set / statistics slot of the pass's last stage (no k_select followed it)
+};
+__device__ __forceinline__ void accumulate_stats(const StatArgs& t, int lane) {
+    const int n_keys = t.n_keys;
+    unsigned long long h = 0, pl = 0, sf = 0, ep = 0, last = 0;
+    const int* lact = t.counts + (t.last_set ? 5 * n_keys + 8 : 2 * n_keys);
+    for (int k = lane; k < n_keys; k += 32) {
+        const int c = t.counts[k];
+        if (k >= t.n_scene_keys) sf += c;
+        else if (k % (t.P + 1) == t.P) pl += c;
+        else h += c;
+        ep += t.counts[n_keys + k];
+        last += lact[k];
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        h += __shfl_xor_sync(0xFFFFFFFFu, h, o);
+        pl += __shfl_xor_sync(0xFFFFFFFFu, pl, o);
+        sf += __shfl_xor_sync(0xFFFFFFFFu, sf, o);
+        ep += __shfl_xor_sync(0xFFFFFFFFu, ep, o);
+        last += __shfl_xor_sync(0xFFFFFFFFu, last, o);
+    }
+    if (lane == 0) {
+        if (t.last_slot >= 0) t.stats[t.last_slot] += last;
+        t.stats[0] += h; t.stats[1] += pl; t.stats[2] += sf; t.stats[3] += ep;
+        t.stats[6] += (unsigned long long)t.counts[4 * n_keys + CTR_OVF];   // polytopes handed to the overflow kernel
+    }
+}
+
+// grid = ceil(n / 256) blocks for the configurations + ONE block that books the statistics
 __global__ void k_finalize(const int* __restrict__ enc_scene, const int* __restrict__ enc_self,
                            const uint32_t* __restrict__ viol, int n, float qd, float threshold, uint32_t flags,
-                           uint32_t* __restrict__ bits, float* __restrict__ dist, uint8_t* __restrict__ reason) {
+                           uint32_t* __restrict__ bits, float* __restrict__ dist, uint8_t* __restrict__ reason, const StatArgs st) {
+    if (blockIdx.x == gridDim.x - 1) {
+        if (st.counts != nullptr && threadIdx.x < 32) accumulate_stats(st, threadIdx.x);
+        return;
+    }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < n;
     float ds = FLT_MAX, dself = FLT_MAX;
