@@ -338,7 +338,32 @@ __device__ __forceinline__ void shape_vs_scene(const PassArgs& a, const ShapeRec
             nc = 0;
         };
         if (valid)
-            lbvh_traverse(a.bvh_nodes, a.bvh_tri, a.bvh_n, qlo, qhi, [&](int tri, float ov_infl) {
+            lbvh_traverse(a.bvh_nodes, a.bvh_tri, a.bvh_n, qlo, qhi, [&](int tri, float ov_infl, V3 p0, V3 p1, V3 p2) {
+                // separating axes beyond the world boxes (conservative: a culled triangle is provably further than the
+                // inflation from the shape's box): the triangle's plane, then the three axes of the shape's own box.
+                // One third of the candidates goes away here (13.9 instead of 20.9 per configuration in scenario 011).
+                const V3 cw = mk(cx, cy, cz);
+                const V3 a0 = mk(T.r00, T.r10, T.r20), a1 = mk(T.r01, T.r11, T.r21), a2 = mk(T.r02, T.r12, T.r22);
+                const V3 nt = cross(p1 - p0, p2 - p0);
+                const float l2 = norm2(nt);
+                if (l2 > 1e-24f) {
+                    const float r = fabsf(dot(nt, a0)) * Sh.h[0] + fabsf(dot(nt, a1)) * Sh.h[1] + fabsf(dot(nt, a2)) * Sh.h[2];
+                    const float dc = fabsf(dot(nt, cw - p0));
+                    if (dc > r + infl * sqrtf(l2)) return;
+                }
+                const V3 d0 = p0 - cw, d1 = p1 - cw, d2 = p2 - cw;
+                {
+                    const float t0 = dot(a0, d0), t1 = dot(a0, d1), t2 = dot(a0, d2), lim = Sh.h[0] + infl;
+                    if (fminf(t0, fminf(t1, t2)) > lim || fmaxf(t0, fmaxf(t1, t2)) < -lim) return;
+                }
+                {
+                    const float t0 = dot(a1, d0), t1 = dot(a1, d1), t2 = dot(a1, d2), lim = Sh.h[1] + infl;
+                    if (fminf(t0, fminf(t1, t2)) > lim || fmaxf(t0, fmaxf(t1, t2)) < -lim) return;
+                }
+                {
+                    const float t0 = dot(a2, d0), t1 = dot(a2, d1), t2 = dot(a2, d2), lim = Sh.h[2] + infl;
+                    if (fminf(t0, fminf(t1, t2)) > lim || fmaxf(t0, fmaxf(t1, t2)) < -lim) return;
+                }
                 if (nc == MAXC) write_out(atomicAdd(a.counts + key, nc));   // rare: the lane's list is full, flush it alone
                 cand[nc] = (unsigned short)tri;
                 cov[nc] = ov_infl;

@@ -124,23 +124,21 @@ __global__ void k_lbvh_refit(const float4* __restrict__ tri_v, int n, BvhNode* _
     }
 }
 
-// Calls f(slot, overlap) for every triangle whose box overlaps [qlo, qhi].  Per-thread stack; depth of a 30-bit Morton tree
-// with index tie-break is bounded by 64.
+// Calls f(slot, overlap, p0, p1, p2) for every triangle whose box overlaps [qlo, qhi] (the vertices come along so that the
+// caller can apply further separating-axis tests).  Per-thread stack; depth of a 30-bit Morton tree with index
+// tie-break is bounded by 64.
 template <class F>
 __device__ __forceinline__ void lbvh_traverse(const BvhNode* __restrict__ nodes, const float4* __restrict__ tri_v, int n,
                                               const float* qlo, const float* qhi, F f) {
     if (n <= 0) return;
     // leaf test; on a hit f(slot, ov) gets the smallest signed axis overlap of the query box and the triangle's box
     auto leaf = [&](int slot) {
-        float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-        for (int k = 0; k < 3; ++k) {
-            const float4 p = tri_v[3 * slot + k];
-            lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
-            hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
-        }
+        const float4 p0 = tri_v[3 * slot], p1 = tri_v[3 * slot + 1], p2 = tri_v[3 * slot + 2];
+        const float lo[3] = {fminf(p0.x, fminf(p1.x, p2.x)), fminf(p0.y, fminf(p1.y, p2.y)), fminf(p0.z, fminf(p1.z, p2.z))};
+        const float hi[3] = {fmaxf(p0.x, fmaxf(p1.x, p2.x)), fmaxf(p0.y, fmaxf(p1.y, p2.y)), fmaxf(p0.z, fmaxf(p1.z, p2.z))};
         const float ov = fminf(fminf(fminf(qhi[0], hi[0]) - fmaxf(qlo[0], lo[0]), fminf(qhi[1], hi[1]) - fmaxf(qlo[1], lo[1])),
                                fminf(qhi[2], hi[2]) - fmaxf(qlo[2], lo[2]));
-        if (ov >= 0.f) f(slot, ov);
+        if (ov >= 0.f) f(slot, ov, mk(p0.x, p0.y, p0.z), mk(p1.x, p1.y, p1.z), mk(p2.x, p2.y, p2.z));
     };
     if (n == 1) {
         leaf(0);

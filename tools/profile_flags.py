@@ -25,3 +25,13 @@ for name, fl, wd in CASES:
     p = eng.get_profile(); eng.profile(False)
     st = eng.stats()
     print(name, {k: round(v[0]/5,3) for k,v in p.items()}, 'total', round(sum(v[0] for v in p.values())/5,3), {k: st[k] for k in ('pairs','self_pairs','gjk_run','epa_run','overflow_run')})
+
+if len(sys.argv) <= 1 or sys.argv[1] == 'mesh':
+    em = CollisionEngine(robot, scene, mesh_mode=True)
+    for _ in range(3): em.check(q, flags=3, packed=True)
+    torch.cuda.synchronize()
+    em.profile(True)
+    for _ in range(5): em.check(q, flags=3, packed=True)
+    p = em.get_profile(); em.profile(False)
+    st = em.stats()
+    print('mesh mode', {k: round(v[0]/5,3) for k,v in p.items()}, 'total', round(sum(v[0] for v in p.values())/5,3), {k: st[k] for k in ('pairs','gjk_run','kernel_launches')})
