@@ -41,6 +41,20 @@ def build(force=False, verbose=False, counting=False):
     return lib
 
 
+def build_all(force=False):
+    """Both libraries, compiled side by side when both are stale (each nvcc run takes about a minute)."""
+    stale = [c for c in (False, True) if force or is_stale(LIB_COUNT if c else LIB)]
+    procs = []
+    for c in stale:
+        lib = LIB_COUNT if c else LIB
+        cmd = [_nvcc()] + NVCC_FLAGS + (['-DJG_COUNT_WORK'] if c else []) + ['-o', lib] + SOURCES
+        procs.append((lib, subprocess.Popen(cmd, cwd=CSRC)))
+    for lib, p in procs:
+        if p.wait() != 0:
+            raise RuntimeError(f'nvcc failed for {lib}')
+    return LIB, LIB_COUNT
+
+
 if __name__ == '__main__':
     print(build(force=True, verbose=True))
     print(build(force=True, counting=True))
