@@ -35,3 +35,20 @@ if len(sys.argv) <= 1 or sys.argv[1] == 'mesh':
     p = em.get_profile(); em.profile(False)
     st = em.stats()
     print('mesh mode', {k: round(v[0]/5,3) for k,v in p.items()}, 'total', round(sum(v[0] for v in p.values())/5,3), {k: st[k] for k in ('pairs','gjk_run','kernel_launches')})
+
+if len(sys.argv) <= 1 or sys.argv[1] == 'edges':
+    sc34 = SceneModel.load(os.path.join(DATA, 'scene_034.npz'))
+    ee = CollisionEngine(robot, sc34)
+    m = 1 << 14
+    rng = np.random.default_rng(34)
+    qa = (lim[:, 0] + (lim[:, 1] - lim[:, 0]) * rng.random((m, 9))).astype(np.float32)
+    qb = np.clip(qa + (np.random.default_rng(3400).random((m, 9)) - 0.5).astype(np.float32) * 0.5, lim[:, 0], lim[:, 1]).astype(np.float32)
+    qa, qb = torch.from_numpy(qa).cuda(), torch.from_numpy(qb).cuda()
+    for want in (True, False):
+        for _ in range(3): ee.check_edges(qa, qb, substeps=64, packed=True, want_dist=want)
+        torch.cuda.synchronize()
+        ee.profile(True)
+        for _ in range(5): ee.check_edges(qa, qb, substeps=64, packed=True, want_dist=want)
+        p = ee.get_profile(); ee.profile(False)
+        st = ee.stats()
+        print('edges 2^14 x 64' + ('' if want else ' (bits only)'), {k: round(v[0]/5,3) for k,v in p.items()}, 'total', round(sum(v[0] for v in p.values())/5,3), {k: st[k] for k in ('pairs','gjk_run','epa_run','kernel_launches')})
