@@ -93,6 +93,9 @@ def main():
             print(json.dumps({'config': 4, 'scenario': sid, 'edges': m, 'substeps': 64, 'ms': ms,
                               'checks_per_s': m * 64 / ms * 1e3, 'edges_per_s': m / ms * 1e3,
                               'edge_collision_rate': bits.float().mean().item()}), flush=True)
+            ms = timed(lambda: eng.check_edges(qa_d, qb_d, substeps=64, packed=True, want_dist=False), reps=3, warm=2)
+            print(json.dumps({'config': '4, verdict bits only (what an RRT edge validation needs)', 'scenario': sid, 'edges': m,
+                              'substeps': 64, 'ms': ms, 'checks_per_s': m * 64 / ms * 1e3, 'edges_per_s': m / ms * 1e3}), flush=True)
         eng.close()
 
 

@@ -123,7 +123,20 @@ def main():
     ms, allw = timed(run_edges)
     hit = torch.bitwise_and(allw.view(-1, 1) >> torch.arange(32, device=dev, dtype=torch.int32), 1).sum().item() / n_edges
     emit(config=4, scenario=34, edges=n_edges, substeps=64, n_gpus=world, ms=ms, checks_per_s=n_edges * 64 / ms * 1e3,
-         edges_per_s=n_edges / ms * 1e3, edge_collision_rate=hit)
+         edges_per_s=n_edges / ms * 1e3, edge_collision_rate=hit, outputs='verdict bit + min distance over the substeps')
+
+    def run_edges_bits():
+        words = torch.empty(((hi - lo) + 31) // 32, dtype=torch.int32, device=dev)
+        for c0 in range(0, hi - lo, ECH):
+            c1 = min(c0 + ECH, hi - lo)
+            b, _ = eng.check_edges(qa[c0:c1], qb[c0:c1], substeps=64, packed=True, want_dist=False)
+            words[c0 // 32:c0 // 32 + b.numel()] = b
+        return gather_bits(words, n_edges)
+
+    ms, allw2 = timed(run_edges_bits)
+    emit(config=4, scenario=34, edges=n_edges, substeps=64, n_gpus=world, ms=ms, checks_per_s=n_edges * 64 / ms * 1e3,
+         edges_per_s=n_edges / ms * 1e3, outputs='verdict bit only (what an RRT edge validation needs)',
+         same_verdicts_as_distance_mode=bool(torch.equal(allw, allw2)))
     del eng
 
     # ---- config 5
