@@ -205,7 +205,10 @@ __device__ __forceinline__ int gjk_step(GjkState& G, const float4* __restrict__ 
             const V3 nrm = cross(x - A0, y - A0);
             const float sp = -dot(A0, nrm);
             const float sd = dot(z - A0, nrm);
-            const bool outside = !(sp * sd > 0.f);
+            // a flat tetrahedron (the support point repeats a simplex point through another vertex pair, or lies in the
+            // plane of the others) has sd = rounding noise of either sign: never evidence that the origin is inside
+            const bool flat = sd * sd <= 1e-12f * norm2(nrm) * norm2(z - A0);
+            const bool outside = flat || !(sp * sd > 0.f);
             if (outside) {
                 any_out = true;
                 int mask;

@@ -327,7 +327,12 @@ static int closest_tetra(simplex* s, v3* vout) {
         v3 n = cross(sub(b, a), sub(c, a));
         double sp = -dot(a, n);          /* origin side */
         double sd = dot(sub(d, a), n);   /* opposite vertex side */
-        int outside = (sd == 0.0) ? 1 : (sp * sd < 0.0);
+        /* A flat tetrahedron (the new support point repeats a simplex point through another vertex pair, or lies in
+         * the plane of the other three) has sd = rounding noise of either sign: the "same side" test is then
+         * meaningless and four lucky signs would report an overlap that is not there.  Such a face is treated like
+         * sd == 0: a candidate for the closest feature, never evidence that the origin is inside. */
+        int flat = fabs(sd) <= 1e-12 * sqrt(norm2(n) * norm2(sub(d, a)));
+        int outside = flat ? 1 : (sp * sd < 0.0);
         if (!outside) continue;
         outside_any = 1;
         int mask;

@@ -471,3 +471,16 @@ def test_batches_larger_than_one_pass(robot, scene_loader, engines):
     from jogramop_framework_b200.engine import unpack_bits
     wb, wd, _ = e.check_host(q, flags=3)                 # pageable input, two passes in the pipeline
     assert torch.equal(unpack_bits(wb.cuda(), n), bits) and torch.equal(wd.cuda(), dist)
+
+
+@pytest.mark.parametrize('sid', [s for s in SCENARIO_IDS if s not in (11, 21, 34, 43, 45)])
+def test_remaining_scenarios_parity(sid, robot, scene_loader):
+    """The 15 scenarios test_scene_parity does not cover: scene + plane + self + limits on 20 000 configurations each."""
+    from jogramop_framework_b200.engine import CollisionEngine
+    e = CollisionEngine(robot, scene_loader(sid))
+    q = uniform_configs(robot, 20000, 1000 + sid)
+    fl = oracle.SCENE | oracle.PLANE | oracle.SELF | oracle.LIMITS
+    rb, rd = Oracle(robot, scene_loader(sid)).check(q.astype(np.float64), flags=fl)
+    bits, dist, _ = e.check(q, flags=fl)
+    compare(bits, dist, rb, rd)
+    e.close()
