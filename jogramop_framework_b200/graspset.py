@@ -128,6 +128,49 @@ class AntipodalGraspSampler:
         return np.stack(poses), np.stack(contacts)
 
 
+def _box(lo, hi):
+    lo, hi = np.asarray(lo, float), np.asarray(hi, float)
+    return np.array([[x, y, z] for x in (lo[0], hi[0]) for y in (lo[1], hi[1]) for z in (lo[2], hi[2])])
+
+
+def burg_gripper_model(opening_width=0.08, finger_length=0.05, finger_thickness=0.003, stem_length=0.0):
+    """burg's simplified two-finger gripper (``burg.gripper.TwoFingerGripperVisualisation(opening_width=0.08)``,
+    create_graspset.py:53) as a RobotModel of convex boxes in the GRASP frame (x = closing direction, z = from the finger
+    tips back towards the gripper base; ``FrankaRobot.tf_grasp2ee`` maps it to the end-effector frame):
+
+        finger 1   x in [-w/2 - t, -w/2]   y in [-t/2, t/2]   z in [0, l]
+        finger 2   x in [ w/2,  w/2 + t]   y in [-t/2, t/2]   z in [0, l]
+        bridge     x in [-w/2 - t, w/2 + t], y in [-t/2, t/2], z in [l, l + t]
+        stem       (optional) x, y in [-t/2, t/2], z in [l + t, l + t + stem_length]
+
+    burg_toolkit is not vendored, so the mesh itself is not in the reference tree; the layout (two bar fingers outside
+    the opening joined by a bar) and the numbers w = 0.08 (given by the call site), l = 0.05, t = 0.003 were RECOVERED
+    from the reference's own 20 x 200 kept grasps (``scenarios/*/grasps.npy``, 4 000 poses that passed burg's filter;
+    tools/fit_burg_gripper.py): in the grasp frame the scene surfaces leave exactly this region empty -- the finger
+    lines x = +-0.04 are never crossed for z in [0, 0.0535] but are reached down to z = -0.0001, the segment between
+    them is crossed in 30 grasps at z = 0.048 and in none for z in [0.050, 0.062], and the void is < 6 mm wide in x and
+    < 4 mm in y.  Nothing above z = 0.077 on the centre line can belong to the gripper (68 kept grasps have target
+    surface there), so a stem, if burg's mesh has one, is shorter than 24 mm: ``stem_length`` defaults to 0.
+    All margins are zero: the model is meant for the boolean surface-mesh mode (trimesh / fcl semantics)."""
+    from . import ingest
+    w, l, t = float(opening_width), float(finger_length), float(finger_thickness)
+    parts = [_box([-w / 2 - t, -t / 2, 0], [-w / 2, t / 2, l]), _box([w / 2, -t / 2, 0], [w / 2 + t, t / 2, l]),
+             _box([-w / 2 - t, -t / 2, l], [w / 2 + t, t / 2, l + t])]
+    if stem_length > 0:
+        parts.append(_box([-t / 2, -t / 2, l + t], [t / 2, t / 2, l + t + stem_length]))
+    S = len(parts)
+    off = (np.arange(S + 1) * 8).astype(np.int32)
+    verts = np.concatenate(parts)
+    return ingest.RobotModel(
+        name='burg_two_finger_gripper', link_names=['grasp_frame'], joint_names=['grasp_frame_joint'],
+        joint_type=np.array([ingest.JOINT_PRISMATIC], np.int32), joint_parent=np.array([-1], np.int32),
+        joint_origin=np.eye(4)[None].copy(), joint_axis=np.array([[0.0, 0.0, 1.0]]), joint_limits=np.zeros((1, 2)),
+        shape_link=np.zeros(S, np.int32), shape_type=np.full(S, ingest.SHAPE_HULL, np.int32), shape_margin=np.zeros(S),
+        shape_vert_offset=off, core_verts=verts, shape_plane_offset=off.copy(), plane_verts=verts.copy(),
+        shape_plane_margin=np.zeros(S), arm_joint_ids=[0], finger_joint_ids=[], end_effector_id=0,
+        self_pairs=np.zeros((0, 2), np.int32))
+
+
 def target_mesh_world(scenario):
     """Triangle mesh (verts [V,3], tris [F,3]) of the scenario's target object in the WORLD frame."""
     sc = scenario._scene_model
@@ -139,29 +182,40 @@ def target_mesh_world(scenario):
     return v, inv.reshape(-1, 3)
 
 
-def check_collisions(grasp_poses, scenario, open_scale=1.0, surface_mesh=False):
+def check_collisions(grasp_poses, scenario, open_scale=1.0, surface_mesh=False, gripper='burg', sim=None):
     """``grasp_sampler.check_collisions(candidates, scene, gripper.mesh, with_plane=True)`` (create_graspset.py:53-60):
-    0 = free, 1 = the gripper at that grasp collides with a scene body or the plane.  One batched GPU call; the gripper
-    is the Panda hand + fingers placed through ``FrankaRobot.tf_grasp2ee`` (burg's procedural gripper mesh is not in the
-    reference tree).  ``surface_mesh=True`` tests against the triangle surfaces of the scene meshes instead of the convex
-    pieces (``GraspingSimulator.gripper_mesh_collision_batch``)."""
+    0 = free, 1 = the gripper at that grasp collides with a scene body or the plane.  One batched GPU call.
+
+    ``gripper='burg'`` (default, the reference's filter): burg's two-finger gripper (``burg_gripper_model``) against
+    the surfaces of the scene's ``mesh_fn`` meshes, boolean (``GraspingSimulator.burg_gripper_collision_batch``).  All
+    4 000 grasps the reference ships pass it (tests/test_graspset.py).
+    ``gripper='panda'``: the real Panda hand + finger hulls placed through ``FrankaRobot.tf_grasp2ee`` -- stricter (the
+    fingers are 2 cm wide and reach deeper): against the convex pieces with Bullet margins, or with
+    ``surface_mesh=True`` against the triangle surfaces of export/obstacles.obj without margins."""
+    if gripper == 'burg':
+        if sim is None:
+            sim = scenario.get_robot_and_sim()[1]
+        return sim.burg_gripper_collision_batch(grasp_poses).cpu().numpy().astype(np.int32)
+    if gripper != 'panda':
+        raise ValueError("gripper must be 'burg' or 'panda'")
     from .simulation import FrankaRobot
-    robot, sim = scenario.get_robot_and_sim()
+    if sim is None:
+        sim = scenario.get_robot_and_sim()[1]
     ee = np.asarray(grasp_poses, dtype=np.float64).reshape(-1, 4, 4) @ FrankaRobot.tf_grasp2ee
-    if surface_mesh:   # boolean mesh-surface mode (closer to trimesh / fcl): no margins, obstacle interiors are free
+    if surface_mesh:   # boolean mesh-surface mode: no margins, obstacle interiors are free
         hit = sim.gripper_mesh_collision_batch(ee, open_scale=open_scale)
     else:
         hit, _ = sim.gripper_in_collision_batch(ee, open_scale=open_scale, want_dist=False)
     return hit.cpu().numpy().astype(np.int32)
 
 
-def create_grasps(scenario, n_candidates=2000, keep=200, gripper_width=0.08, seed=None, save_fn=None):
+def create_grasps(scenario, n_candidates=2000, keep=200, gripper_width=0.08, seed=None, save_fn=None, gripper='burg'):
     """``create_graspset.create_grasps`` (27-70) for a loaded ``Scenario``: sample, filter, keep a random subset,
     optionally save ``grasps.npy``.  Returns (grasps [m,4,4] world, number of candidates, number collision-free)."""
     sampler = AntipodalGraspSampler(n_orientations=7, only_grasp_from_above=True, no_contact_below_z=None, seed=seed)
     verts, tris = target_mesh_world(scenario)
     candidates, _ = sampler.sample(verts, tris, n=n_candidates, max_gripper_width=gripper_width)
-    collisions = check_collisions(candidates, scenario)
+    collisions = check_collisions(candidates, scenario, gripper=gripper)
     grasps = candidates[collisions == 0]
     n_free = len(grasps)
     if len(grasps) > keep:

@@ -351,6 +351,7 @@ class SceneObject:
     pose: np.ndarray
     vhacd_fn: str = None
     is_target: bool = False
+    mesh_fn: str = None          # the library's ``mesh_fn``: what burg's ``ObjectInstance.get_mesh()`` returns
 
 
 @dataclass
@@ -455,6 +456,7 @@ def load_object_library(lib_fn):
         out[o['identifier']] = {
             'vhacd_fn': os.path.join(base, o['vhacd_fn']) if o.get('vhacd_fn') else None,
             'urdf_fn': os.path.join(base, o['urdf_fn']) if o.get('urdf_fn') else None,
+            'mesh_fn': os.path.join(base, o['mesh_fn']) if o.get('mesh_fn') else None,
             'scale': o.get('scale', 1.0),
         }
     return out
@@ -472,7 +474,7 @@ def load_scene_yaml(scene_fn):
         t = e['object_type']
         if t not in lib:
             raise KeyError(f'object type {t} not in object library {lib_fn}')
-        return SceneObject(t, np.asarray(e['pose'], dtype=np.float64), lib[t]['vhacd_fn'], is_target)
+        return SceneObject(t, np.asarray(e['pose'], dtype=np.float64), lib[t]['vhacd_fn'], is_target, lib[t]['mesh_fn'])
     scene = SceneDescription(
         objects=[inst(e, True) for e in (y.get('objects') or [])],
         bg_objects=[inst(e, False) for e in (y.get('bg_objects') or [])],
@@ -530,6 +532,41 @@ def build_scene_model(scene, robot_pose, name='scene', ungrouped_obj_policy='sin
         tri_body=np.concatenate(tb) if tb else np.zeros(0, np.int32),
         plane=np.array([robot_pose[2, 0], robot_pose[2, 1], robot_pose[2, 2], robot_pose[2, 3]]),
         has_plane=with_plane)
+
+
+def merge_meshes(bodies, robot_pose, name='visual'):
+    """``bodies``: [(vertices [n,3] in the object's mesh frame, triangles [m,3], pose 4x4 world, is_target)] -> a SceneModel
+    that carries ONLY the merged triangle mesh (robot frame) and the plane: the scene as burg's
+    ``AntipodalGraspSampler.check_collisions`` sees it (``obj.get_mesh()`` of every object and bg object: the library's
+    ``mesh_fn`` meshes, not the VHACD pieces; create_graspset.py:54-59).  For mesh-mode engines."""
+    robot_pose = np.asarray(robot_pose, dtype=np.float64)
+    to_robot = np.linalg.inv(robot_pose)
+    tv, tf_, tb, is_t, names = [], [], [], [], []
+    n_tv = 0
+    for b, (v, f, pose, target) in enumerate(bodies):
+        T = to_robot @ np.asarray(pose, dtype=np.float64)
+        tv.append(np.asarray(v, dtype=np.float64) @ T[:3, :3].T + T[:3, 3])
+        tf_.append(np.asarray(f, dtype=np.int64) + n_tv)
+        tb.append(np.full(len(f), b, np.int32))
+        n_tv += len(v)
+        is_t.append(bool(target))
+        names.append(f'body{b}')
+    return SceneModel(
+        name=name, robot_pose=robot_pose, piece_vert_offset=np.zeros(1, np.int32), piece_verts=np.zeros((0, 3)),
+        piece_body=np.zeros(0, np.int32), piece_margin=np.zeros(0), body_names=names,
+        body_is_target=np.asarray(is_t, bool), tri_verts=np.concatenate(tv) if tv else np.zeros((0, 3)),
+        tris=(np.concatenate(tf_) if tf_ else np.zeros((0, 3))).astype(np.int32),
+        tri_body=np.concatenate(tb) if tb else np.zeros(0, np.int32),
+        plane=np.array([robot_pose[2, 0], robot_pose[2, 1], robot_pose[2, 2], robot_pose[2, 3]]), has_plane=True)
+
+
+def read_obj_mesh(path):
+    """Whole OBJ file as one welded-as-written triangle mesh (all groups merged): (vertices, triangles)."""
+    shapes = read_obj_shapes(path)
+    v = np.concatenate([s[0] for s in shapes])
+    off = np.cumsum([0] + [len(s[0]) for s in shapes])
+    f = np.concatenate([s[1] + o for s, o in zip(shapes, off)])
+    return v, f
 
 
 def default_robot_pose():

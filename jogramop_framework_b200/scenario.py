@@ -82,6 +82,25 @@ class Scenario:
         self.gs = GraspSet.from_poses(grasps)
         print(f'loaded {len(self.gs)} grasps')
         self.select_indices = None  # for grasp set sub-selection
+        self._visual_model = None
+
+    def visual_scene_model(self):
+        """The scene as burg's ``AntipodalGraspSampler.check_collisions`` sees it (create_graspset.py:54-59): the
+        library's ``mesh_fn`` mesh of every object and bg object, merged, in the robot frame, plus the plane -- a
+        SceneModel for mesh-mode engines (``GraspingSimulator.burg_gripper_collision_batch``)."""
+        if self._visual_model is None:
+            bodies = []
+            baked = None
+            for o in list(self.scene.objects) + list(self.scene.bg_objects):
+                if getattr(o, 'mesh_fn', None):
+                    v, f = ingest.read_obj_mesh(o.mesh_fn)
+                else:
+                    if baked is None:
+                        baked = np.load(os.path.join(_DATA, 'visual_meshes.npz'), allow_pickle=False)
+                    v, f = baked[f'v_{o.object_type}'], baked[f'f_{o.object_type}']
+                bodies.append((v, f, o.pose, o.is_target))
+            self._visual_model = ingest.merge_meshes(bodies, self.robot_pose, name=f'{self.id:03d}_visual')
+        return self._visual_model
 
     @property
     def grasp_poses(self):
@@ -105,6 +124,7 @@ class Scenario:
         sim = GraspingSimulator(verbose=with_gui, device=self.device)
         sim.add_scene(self._scene_model)
         sim.scene = self.scene
+        sim._visual_model_fn = self.visual_scene_model
         robot = FrankaRobot(sim, self.robot_pose, with_platform=self.with_platform)
         return robot, sim
 

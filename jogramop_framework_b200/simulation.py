@@ -60,6 +60,8 @@ class GraspingSimulator:
         self._next_id = 1
         self._robot = None
         self._engines = {}
+        self._gripper_engines = {}
+        self._visual_model_fn = None                     # () -> SceneModel of the visual (mesh_fn) meshes, set by Scenario
         self.scene = None
 
     # ------------------------------------------------------------------ scene
@@ -92,9 +94,10 @@ class GraspingSimulator:
         self._engines.clear()
 
     def dismiss(self):
-        for e in self._engines.values():
+        for e in list(self._engines.values()) + list(self._gripper_engines.values()):
             e.close()
         self._engines.clear()
+        self._gripper_engines.clear()
 
     # ------------------------------------------------------------------ engines
     def _register_robot(self, robot):
@@ -243,6 +246,34 @@ class GraspingSimulator:
             return dist <= -msum + 1e-6
         finally:
             robot._open_scale = old
+
+
+    def burg_gripper_collision_batch(self, grasp_poses, opening_width=0.08, visual_model=None, **gripper_kw):
+        """The grasp filter of the reference, on the reference's own terms (create_graspset.py:53-59):
+        ``check_collisions(candidates, scene, TwoFingerGripperVisualisation(opening_width).mesh, with_plane=True)`` =
+        does burg's two-finger gripper, placed at each GRASP pose (burg convention, world frame, [n,4,4]), touch the
+        surface of any scene mesh (the library's ``mesh_fn`` meshes) or the plane.  Boolean, no margins (trimesh / fcl).
+
+        The gripper is ``graspset.burg_gripper_model`` (three zero-margin boxes, geometry recovered from the 4 000 kept
+        grasps the reference ships); the scene is the merged visual mesh behind the GPU-built LBVH; one batched
+        ``jg_check_poses`` call, verdict bits straight from the kernel (threshold 1e-6: touching counts).
+        Returns bool[n] (torch, engine device).  No robot needs to be loaded."""
+        from .graspset import burg_gripper_model
+        if visual_model is None:
+            if self._visual_model_fn is None:
+                raise JogramopError('burg_gripper_collision_batch needs the scene\'s visual meshes (Scenario.get_robot_and_sim '
+                                    'provides them; or pass visual_model=)')
+            visual_model = self._visual_model_fn()
+        key = (id(visual_model), float(opening_width), tuple(sorted(gripper_kw.items())))
+        if key not in self._gripper_engines:
+            model = burg_gripper_model(opening_width=opening_width, **gripper_kw)
+            self._gripper_engines[key] = _engine.CollisionEngine(
+                model, visual_model, device=self.device, threshold=1e-6, query_distance=0.01, finger_open=0.0,
+                mesh_mode=True, mesh_margin=0.0)
+        eng = self._gripper_engines[key]
+        T = np.linalg.inv(visual_model.robot_pose) @ np.asarray(grasp_poses, dtype=np.float64).reshape(-1, 4, 4)
+        hit, _ = eng.check_poses(T[:, :3, :].astype(np.float32), links=[0], ee_link=0, want_dist=False)
+        return hit
 
 
 class FrankaRobot:

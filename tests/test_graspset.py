@@ -74,6 +74,104 @@ def test_target_mesh_of_a_scenario_is_graspable():
     assert (g[:, 2, 2] > -1e-9).all()
 
 
+SCENARIO_IDS = [11, 12, 13, 14, 15, 21, 22, 23, 24, 25, 31, 32, 33, 34, 35, 41, 42, 43, 44, 45]
+
+
+def tri_piece_scene(sc):
+    """A mesh SceneModel as the oracle takes it: every triangle is a zero-margin convex piece."""
+    import copy
+    m = copy.copy(sc)
+    m.piece_verts = sc.tri_verts[sc.tris].reshape(-1, 3)
+    m.piece_vert_offset = (np.arange(len(sc.tris) + 1) * 3).astype(np.int32)
+    m.piece_body = sc.tri_body
+    m.piece_margin = np.zeros(len(sc.tris))
+    return m
+
+
+def oracle_burg_filter(scenario, grasps_world, **gripper_kw):
+    """burg's check_collisions restated on the CPU: zero-margin gripper boxes vs every triangle of the visual meshes +
+    plane (oracle GJK, double precision).  -> (collides bool[n], distance[n])"""
+    import oracle
+    from jogramop_framework_b200.graspset import burg_gripper_model
+    sc = scenario.visual_scene_model()
+    o = oracle.Oracle(burg_gripper_model(**gripper_kw), tri_piece_scene(sc))
+    T = np.linalg.inv(sc.robot_pose) @ np.asarray(grasps_world, dtype=np.float64)
+    _, d = o.check_poses(T, links=[0], ee_link=0, flags=oracle.SCENE | oracle.PLANE | oracle.NO_EPA, threshold=1e-9)
+    return d <= 1e-9, d
+
+
+def reference_grasps(scenario):
+    """The scenario's ``grasps.npy`` (burg convention, world frame): 200 poses that passed the reference's filter."""
+    from jogramop_framework_b200.simulation import FrankaRobot
+    return scenario.gs.poses @ np.linalg.inv(FrankaRobot.tf_grasp2ee)
+
+
+def test_burg_gripper_accepts_the_references_own_grasps_g8():
+    """SURVEY G8 as a pin: the 20 x 200 grasps the reference ships all passed
+    ``check_collisions(candidates, scene, TwoFingerGripperVisualisation(0.08).mesh, with_plane=True)``
+    (create_graspset.py:53-60), so the restated filter (oracle arithmetic) must accept them -- and the pin is
+    two-sided: every perturbation of the recovered gripper geometry starts rejecting them."""
+    from jogramop_framework_b200.scenario import Scenario
+    scen = {sid: Scenario(sid) for sid in SCENARIO_IDS}
+    total = 0
+    for sid, s in scen.items():
+        hit, _ = oracle_burg_filter(s, reference_grasps(s))
+        assert len(hit) == 200 and hit.mean() <= 0.01, (sid, int(hit.sum()))
+        total += int(hit.sum())
+    assert total == 0     # measured: none of the 4 000
+    # two-sided: thicker bars, a lower bridge, a wider / narrower opening, finger tips 1 mm further out -> rejections
+    sub = [11, 21, 31, 34, 41, 45]
+
+    def rejected(shift=0.0, **kw):
+        n = 0
+        for sid in sub:
+            g = reference_grasps(scen[sid]).copy()
+            g[:, :3, 3] += shift * g[:, :3, 2]
+            n += int(oracle_burg_filter(scen[sid], g, **kw)[0].sum())
+        return n
+    assert rejected() == 0
+    assert rejected(finger_thickness=0.004) >= 20
+    assert rejected(finger_length=0.048) >= 10
+    assert rejected(opening_width=0.082) >= 10
+    assert rejected(opening_width=0.070) >= 3
+    assert rejected(shift=-0.001) >= 15       # the whole gripper 1 mm towards the object
+    assert rejected(shift=-0.02) >= 600       # bridge inside the object: "obviously penetrating"
+
+
+@pytest.mark.gpu
+def test_burg_gripper_filter_on_gpu_matches_reference_grasps_and_oracle():
+    """The product path (burg gripper boxes vs the LBVH over the visual meshes, jg_check_poses on a zero-margin mesh-mode
+    engine): accepts >= 99 % of every scenario's reference grasps (G8), rejects pushed-in poses, and agrees with the
+    oracle pose by pose outside a 20 um band around touching."""
+    from jogramop_framework_b200.graspset import check_collisions
+    from jogramop_framework_b200.scenario import Scenario
+    rng = np.random.default_rng(8)
+    n_free = n_all = 0
+    for sid in SCENARIO_IDS:
+        s = Scenario(sid)
+        _, sim = s.get_robot_and_sim()
+        g = reference_grasps(s)
+        hit = check_collisions(g, s, sim=sim)
+        assert hit.shape == (200,) and (hit == 0).mean() >= 0.99, (sid, int(hit.sum()))
+        n_free += int((hit == 0).sum())
+        n_all += len(hit)
+        # pushed 2 cm towards the object + jittered poses: a mix of verdicts, compared with the oracle one by one
+        pushed = g.copy()
+        pushed[:, :3, 3] -= 0.02 * pushed[:, :3, 2]
+        jit = g.copy()
+        jit[:, :3, 3] += rng.normal(scale=0.01, size=(200, 3))
+        test = np.concatenate([pushed, jit])
+        got = check_collisions(test, s, sim=sim).astype(bool)
+        ref, d = oracle_burg_filter(s, test)
+        clear = np.abs(d) > 2e-5
+        assert np.array_equal(got[clear], ref[clear]), (sid, int((got != ref)[clear].sum()))
+        assert (got != ref).sum() <= 3
+        assert got[:200].mean() >= 0.85       # pushed-in poses are rejected
+        sim.dismiss()
+    print(f'G8: {n_free} of {n_all} reference grasps accepted by the burg-gripper filter on the GPU')
+    assert n_free >= 0.995 * n_all
+
+
 @pytest.mark.gpu
 def test_create_grasps_pipeline_on_gpu(tmp_path):
     from jogramop_framework_b200.graspset import check_collisions, create_grasps
@@ -86,13 +184,15 @@ def test_create_grasps_pipeline_on_gpu(tmp_path):
     assert (check_collisions(grasps, s) == 0).all()                 # what is kept is collision-free
     again, _, _ = create_grasps(s, n_candidates=2000, keep=200, seed=7)
     assert np.array_equal(grasps, again)
-    # The reference's own annotations were filtered with burg's procedural gripper mesh, which is not in the reference
-    # tree; under this repo's model (Panda hand + finger hulls on panda_grasptarget) the fingers reach ~1 cm deeper, so
-    # most of them touch the target (tools/grasp_model_gap.py: 011 14 % free, 034 50 %).  Informational, not a parity bar.
-    ref = s.gs.poses @ np.linalg.inv(type(s.get_robot_and_sim()[0]).tf_grasp2ee)
-    free = (check_collisions(ref, s) == 0).mean()
-    print(f'reference grasps.npy accepted by the Panda-hand collision model: {free:.3f}')
-    assert 0.0 <= free <= 1.0
+    # the stricter model (real Panda hand + finger hulls, Bullet margins) is still selectable; the reference's own
+    # annotations mostly fail it (the real fingers are 2 cm wide and reach deeper than burg's 3 mm bars)
+    ref = reference_grasps(s)
+    free_panda = (check_collisions(ref, s, gripper='panda') == 0).mean()
+    free_burg = (check_collisions(ref, s) == 0).mean()
+    print(f'reference grasps.npy accepted: burg gripper {free_burg:.3f}, Panda hand hulls {free_panda:.3f}')
+    assert free_burg >= 0.99 and free_panda < free_burg
+    with pytest.raises(ValueError):
+        check_collisions(ref, s, gripper='robotiq')
 
 
 @pytest.mark.gpu

@@ -14,6 +14,8 @@ Outputs
   jogramop_framework_b200/data/scene_<id>.npz                   SceneModel (+ grasps_world)
   jogramop_framework_b200/data/scene_045_singlehull.npz         045 with the stale one-piece gate (quirk Q1)
   jogramop_framework_b200/data/gate_0_54_pieces.npz             recovered 2-piece gate decomposition
+  jogramop_framework_b200/data/visual_meshes.npz                the library's ``mesh_fn`` meshes of every object type used
+                                                                by a scenario (what burg's check_collisions tests against)
   tests/golden/export_golden.npz                                 export/*.csv, obstacles.obj triangles, per scenario
 """
 import os
@@ -67,10 +69,16 @@ def main():
 
     golden = {}
     pose = I.default_robot_pose()
+    visual = {}
     for sid in SCENARIO_IDS:
         sdir = os.path.join(ref, 'scenarios', f'{sid:03d}')
         scene, _ = I.load_scene_yaml(os.path.join(sdir, 'scene.yaml'))
         grasps = np.load(os.path.join(sdir, 'grasps.npy'), allow_pickle=True).astype(np.float32)
+        for o in list(scene.objects) + list(scene.bg_objects):
+            if o.object_type not in visual:
+                v, f = I.read_obj_mesh(o.mesh_fn)
+                used, inv = np.unique(f.reshape(-1), return_inverse=True)     # drop unreferenced vertices
+                visual[o.object_type] = (v[used].astype(np.float32), inv.reshape(-1, 3).astype(np.int32))
         variants = [(f'scene_{sid:03d}.npz', {'gate_0_54': list(zip(gate_v, gate_f))})]
         if sid == 45:
             variants.append((f'scene_{sid:03d}_singlehull.npz', None))
@@ -95,6 +103,9 @@ def main():
         (v, f), = I.read_obj_shapes(os.path.join(exp, 'obstacles.obj'))
         golden[f'obstacles_tris_{sid:03d}'] = v[f].astype(np.float64)
     np.savez_compressed(os.path.join(gold, 'export_golden.npz'), **golden)
+    np.savez_compressed(os.path.join(data, 'visual_meshes.npz'), types=np.array(sorted(visual)),
+                        **{f'v_{t}': visual[t][0] for t in visual}, **{f'f_{t}': visual[t][1] for t in visual})
+    print('visual meshes:', {t: (len(v), len(f)) for t, (v, f) in visual.items()})
     print('golden IK rows:', sum(len(golden[f'ik_{s:03d}']) for s in SCENARIO_IDS))
 
 
