@@ -76,7 +76,8 @@ extern "C" jg_robot* jg_robot_create(int L, const int32_t* joint_type, const int
                                      const int32_t* plane_off, const double* plane_v, const double* plane_margin,
                                      int K, const int32_t* self_pairs) {
     if (L <= 0 || L > MAX_LINKS || S < 0 || S > MAX_SHAPES || dof <= 0 || dof > MAX_DOF || !joint_type ||
-        !joint_parent || !joint_origin || !joint_axis || !joint_qidx || !q_limits || (S && (!shape_link || !shape_off)) ||
+        !joint_parent || !joint_origin || !joint_axis || !joint_qidx || !q_limits ||
+        (S && (!shape_link || !shape_off || !shape_margin || !core || !plane_off || !plane_v || !plane_margin)) ||
         K < 0 || (K && !self_pairs)) {
         fail(JG_ERR_INVALID, "jg_robot_create: bad sizes (L=%d<=%d, S=%d<=%d, dof=%d<=%d) or NULL table", L, MAX_LINKS, S,
              MAX_SHAPES, dof, MAX_DOF);
@@ -192,7 +193,8 @@ struct jg_engine {
     KeyRec* d_keys = nullptr;
     float4* d_verts = nullptr;
     // scratch arena
-    int cap = 0;                          // configurations per pass
+    int cap = 0;                          // configurations per pass the arena currently holds (grows on demand up to cap_max)
+    int cap_max = 0;                      // largest pass: jg_params.chunk, or what fits the memory budget (<= 2^20)
     float4 *q_r0 = nullptr, *q_r1 = nullptr, *q_r2 = nullptr;
     int* q_cfg = nullptr;
     int* epa_slot = nullptr;              // [n_keys*cap]
@@ -202,7 +204,8 @@ struct jg_engine {
     int ovf_poly_cap = 0;
     float* epa_prio = nullptr;            // [n_keys*cap]
     float* q_prio = nullptr;              // [n_keys*cap]
-    float max_msum = 0.f;
+    float max_msum = 0.f, min_msum = 0.f;
+    cudaEvent_t ev_order = nullptr;      // orders a call on a new stream after the previous call's work (shared scratch arena)
     bool mesh = false;
     float mesh_margin = 0.f;
     Lbvh bvh;
@@ -233,11 +236,13 @@ struct jg_engine {
     float* pin_dist[2] = {nullptr, nullptr};
     uint8_t* pin_reason[2] = {nullptr, nullptr};
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_run[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
-    bool staging_ready = false;
+    bool staging_ready = false;          // streams + events exist
+    int staging_cap = 0;                 // pass size the staging buffers were allocated for
     // stats
     jg_stats stats{};
     unsigned long long* d_stats = nullptr;       // [8]
     cudaStream_t last_stream = nullptr;
+    bool have_last_stream = false;
     int sm_count = 148;
     int np_blocks = 0, epa_blocks = 0, epa_threads = 0;
     size_t smem_narrow = 0, smem_epa = 0, smem_epa_big = 0;
@@ -291,17 +296,38 @@ static void prof_collect(jg_engine* e) {
     e->prof_used = 0;
 }
 
+template <class T>
+static void free_dev(T*& p) { cudaFree(p); p = nullptr; }
+template <class T>
+static void free_pin(T*& p) { cudaFreeHost(p); p = nullptr; }
+
+// the per-pass scratch arena (everything sized by e->cap)
+static void arena_free(jg_engine* e) {
+    free_dev(e->q_r0); free_dev(e->q_r1); free_dev(e->q_r2); free_dev(e->q_cfg); free_dev(e->epa_slot); free_dev(e->epa_ids);
+    free_dev(e->ovf_list); free_dev(e->ovf_poly); free_dev(e->epa_prio); free_dev(e->q_prio); free_dev(e->act_list);
+    free_dev(e->act_meta); free_dev(e->champ_scene); free_dev(e->champ_self); free_dev(e->enc_scene); free_dev(e->enc_self);
+    free_dev(e->viol);
+    e->cap = 0;
+}
+// staging buffers of the host path (sized by e->cap as well)
+static void staging_free(jg_engine* e) {
+    for (int i = 0; i < 2; ++i) {
+        free_dev(e->stage_q[i]); free_dev(e->stage_bits[i]); free_dev(e->stage_dist[i]); free_dev(e->stage_reason[i]);
+        free_pin(e->pin_q[i]); free_pin(e->pin_bits[i]); free_pin(e->pin_dist[i]); free_pin(e->pin_reason[i]);
+    }
+    e->staging_cap = 0;
+}
+
 static void engine_release(jg_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaFree(e->d_robot); cudaFree(e->d_pieces); cudaFree(e->d_selfs); cudaFree(e->d_keys); cudaFree(e->d_verts);
-    cudaFree(e->q_r0); cudaFree(e->q_r1); cudaFree(e->q_r2); cudaFree(e->q_cfg); cudaFree(e->epa_slot); cudaFree(e->epa_ids); cudaFree(e->ovf_list); cudaFree(e->ovf_poly); cudaFree(e->epa_prio); cudaFree(e->q_prio); cudaFree(e->bvh.nodes); cudaFree(e->bvh.tri_v); cudaFree(e->bvh.tri_id); cudaFree(e->d_err); cudaFree(e->d_qrest); cudaFree(e->act_list); cudaFree(e->act_meta); cudaFree(e->champ_scene); cudaFree(e->champ_self); cudaFree(e->counts);
-    cudaFree(e->enc_scene); cudaFree(e->enc_self); cudaFree(e->viol); cudaFree(e->d_link_slot); cudaFree(e->d_rel);
+    arena_free(e);
+    cudaFree(e->bvh.nodes); cudaFree(e->bvh.tri_v); cudaFree(e->bvh.tri_id); cudaFree(e->d_err); cudaFree(e->d_qrest); cudaFree(e->counts);
+    cudaFree(e->d_link_slot); cudaFree(e->d_rel);
     cudaFree(e->d_use_shapes); cudaFree(e->d_stats);
+    staging_free(e);
     for (int i = 0; i < 2; ++i) {
-        cudaFree(e->stage_q[i]); cudaFree(e->stage_bits[i]); cudaFree(e->stage_dist[i]); cudaFree(e->stage_reason[i]);
-        cudaFreeHost(e->pin_q[i]); cudaFreeHost(e->pin_bits[i]); cudaFreeHost(e->pin_dist[i]);
-        cudaFreeHost(e->pin_reason[i]);
         if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
         if (e->ev_run[i]) cudaEventDestroy(e->ev_run[i]);
         if (e->ev_out[i]) cudaEventDestroy(e->ev_out[i]);
@@ -310,6 +336,7 @@ static void engine_release(jg_engine* e) {
     if (e->s_run) cudaStreamDestroy(e->s_run);
     if (e->s_out) cudaStreamDestroy(e->s_out);
     for (cudaEvent_t ev : e->prof_ev) cudaEventDestroy(ev);
+    if (e->ev_order) cudaEventDestroy(e->ev_order);
     delete e;
 }
 
@@ -477,35 +504,48 @@ static int build_tables(jg_engine* e, const jg_robot* r, const jg_scene* sc) {
         const int la = r->self_pairs[2 * k], lb = r->self_pairs[2 * k + 1];
         if (la < 0 || lb < 0 || la >= r->L || lb >= r->L || la >= lb)
             return fail(JG_ERR_INVALID, "self pair %d: link ids (%d,%d) must satisfy 0 <= first < second < %d", k, la, lb, r->L);
-        const int sa = e->link_first_shape[la + 1], sb = e->link_first_shape[lb + 1];
-        if (sa < 0 || sb < 0) return fail(JG_ERR_INVALID, "self pair %d: link without collision shape", k);
+        if (e->link_first_shape[la + 1] < 0 || e->link_first_shape[lb + 1] < 0)
+            return fail(JG_ERR_INVALID, "self pair %d: link without collision shape", k);
         if (R.joints[la].stash_slot < 0) R.joints[la].stash_slot = R.n_stash++;
-        if (R.joints[lb].self_count == 0) R.joints[lb].self_first = (int)selfs.size();
-        R.joints[lb].self_count++;
-        selfs.push_back(SelfRec{sa, sb, la, lb});
-        KeyRec kr{R.shapes[sb].voff, R.shapes[sb].vn, R.shapes[sa].voff, R.shapes[sa].vn,
-                  R.shapes[sa].margin + R.shapes[sb].margin, KEY_SELF, R.shapes[sb].poff, R.shapes[sb].pn,
-                  R.shapes[sa].poff, R.shapes[sa].pn, R.shapes[sa].plane_margin + R.shapes[sb].plane_margin, 0,
-                  {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-        for (int c = 0; c < 3; ++c) {
-            kr.a_c[c] = epa_box_c[sb][c]; kr.a_h[c] = epa_box_h[sb][c];
-            kr.b_c[c] = epa_box_c[sa][c]; kr.b_h[c] = epa_box_h[sa][c];
+        // getClosestPoints(linkA, linkB) covers every collision shape of both links: one key per shape combination
+        for (int sa = 0; sa < r->S; ++sa) {
+            if (r->shape_link[sa] != la) continue;
+            for (int sb = 0; sb < r->S; ++sb) {
+                if (r->shape_link[sb] != lb) continue;
+                if (R.joints[lb].self_count == 0) R.joints[lb].self_first = (int)selfs.size();
+                R.joints[lb].self_count++;
+                selfs.push_back(SelfRec{sa, sb, la, lb});
+                KeyRec kr{R.shapes[sb].voff, R.shapes[sb].vn, R.shapes[sa].voff, R.shapes[sa].vn,
+                          R.shapes[sa].margin + R.shapes[sb].margin, KEY_SELF, R.shapes[sb].poff, R.shapes[sb].pn,
+                          R.shapes[sa].poff, R.shapes[sa].pn, R.shapes[sa].plane_margin + R.shapes[sb].plane_margin, 0,
+                          {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+                for (int c = 0; c < 3; ++c) {
+                    kr.a_c[c] = epa_box_c[sb][c]; kr.a_h[c] = epa_box_h[sb][c];
+                    kr.b_c[c] = epa_box_c[sa][c]; kr.b_h[c] = epa_box_h[sa][c];
+                }
+                keys.push_back(kr);
+            }
         }
-        keys.push_back(kr);
     }
+    R.n_self = (int)selfs.size();
     e->n_stash = R.n_stash;
     e->n_keys = (int)keys.size();
     e->n_verts = (int)verts.size();
-    for (const KeyRec& k : keys) e->max_msum = std::max(e->max_msum, k.msum);
+    e->min_msum = FLT_MAX;
+    for (const KeyRec& k : keys) {
+        e->max_msum = std::max(e->max_msum, k.msum);
+        if (k.kind != KEY_PLANE) e->min_msum = std::min(e->min_msum, k.msum);
+    }
+    // champion codes pack (key << 20 | queue slot) into 32 bits: 11 bits of key, 20 bits of slot (cap <= 2^20)
     if (e->n_keys >= 2048) return fail(JG_ERR_INVALID, "too many (shape, piece) keys (%d >= 2048)", e->n_keys);
-    e->K = r->K;
+    e->K = (int)selfs.size();
 
     CUDA_TRY(cudaMalloc(&e->d_robot, sizeof(RobotTab)));
     CUDA_TRY(cudaMemcpy(e->d_robot, &R, sizeof(RobotTab), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc(&e->d_pieces, sizeof(PieceRec) * std::max(P, 1)));
     if (P) CUDA_TRY(cudaMemcpy(e->d_pieces, pieces.data(), sizeof(PieceRec) * P, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMalloc(&e->d_selfs, sizeof(SelfRec) * std::max(r->K, 1)));
-    if (r->K) CUDA_TRY(cudaMemcpy(e->d_selfs, selfs.data(), sizeof(SelfRec) * r->K, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&e->d_selfs, sizeof(SelfRec) * std::max<size_t>(selfs.size(), 1)));
+    if (!selfs.empty()) CUDA_TRY(cudaMemcpy(e->d_selfs, selfs.data(), sizeof(SelfRec) * selfs.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc(&e->d_keys, sizeof(KeyRec) * std::max(e->n_keys, 1)));
     if (e->n_keys) CUDA_TRY(cudaMemcpy(e->d_keys, keys.data(), sizeof(KeyRec) * e->n_keys, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc(&e->d_verts, sizeof(float4) * std::max(e->n_verts, 1)));
@@ -581,6 +621,48 @@ static size_t bp_smem(const jg_engine* e, uint32_t flags) {
     return s;
 }
 
+static int arena_alloc(jg_engine* e, int cap) {
+    e->cap = cap;
+    e->ovf_poly_cap = std::min(std::max(cap / 4, 1), 65536);   // hand-over records (496 B each); later overflows restart
+    const size_t qn = (size_t)std::max(e->n_keys, 1) * cap;
+    bool okm = cudaMalloc(&e->q_r0, sizeof(float4) * qn) == cudaSuccess && cudaMalloc(&e->q_r1, sizeof(float4) * qn) == cudaSuccess &&
+               cudaMalloc(&e->q_r2, sizeof(float4) * qn) == cudaSuccess && cudaMalloc(&e->q_cfg, sizeof(int) * qn) == cudaSuccess &&
+               cudaMalloc(&e->epa_slot, sizeof(int) * qn) == cudaSuccess && cudaMalloc(&e->epa_ids, sizeof(uint4) * qn) == cudaSuccess &&
+               cudaMalloc(&e->ovf_list, sizeof(int2) * cap) == cudaSuccess &&
+               cudaMalloc(&e->ovf_poly, sizeof(uint32_t) * JG_OVF_WORDS * (size_t)e->ovf_poly_cap) == cudaSuccess &&
+               cudaMalloc(&e->epa_prio, sizeof(float) * qn) == cudaSuccess && cudaMalloc(&e->q_prio, sizeof(float) * qn) == cudaSuccess &&
+               cudaMalloc(&e->act_list, sizeof(int) * qn) == cudaSuccess && cudaMalloc(&e->act_meta, sizeof(int2) * qn) == cudaSuccess &&
+               cudaMalloc(&e->champ_scene, sizeof(unsigned long long) * cap) == cudaSuccess &&
+               cudaMalloc(&e->champ_self, sizeof(unsigned long long) * cap) == cudaSuccess &&
+               cudaMalloc(&e->enc_scene, sizeof(int) * cap) == cudaSuccess && cudaMalloc(&e->enc_self, sizeof(int) * cap) == cudaSuccess &&
+               cudaMalloc(&e->viol, sizeof(uint32_t) * (cap / 32 + 1)) == cudaSuccess;
+    if (!okm) {
+        const int rc = fail(JG_ERR_NOMEM, "scratch allocation failed (%zu queue entries): %s", qn, cudaGetErrorString(cudaGetLastError()));
+        arena_free(e);
+        return rc;
+    }
+    return JG_OK;
+}
+
+static int drain_pending(jg_engine* e);
+
+// make the arena hold passes of min(want, cap_max) configurations (power-of-two growth; everything in flight is
+// finished first: growth is a rare set-up event, not part of a steady-state call)
+static int ensure_arena(jg_engine* e, int64_t want) {
+    const int need = (int)std::min<int64_t>(e->cap_max, std::max<int64_t>(want, 1));
+    if (need <= e->cap) return JG_OK;
+    int cap = std::max(e->cap, 1024);
+    while (cap < need) cap <<= 1;
+    cap = std::min(cap, e->cap_max);
+    int rc = drain_pending(e);
+    if (rc) return rc;
+    CUDA_TRY(cudaDeviceSynchronize());
+    arena_free(e);
+    staging_free(e);
+    e->mesh_pass = 0;
+    return arena_alloc(e, cap);
+}
+
 extern "C" jg_engine* jg_engine_create(const jg_robot* r, const jg_scene* sc, int device, const jg_params* prm) {
     if (!r) { fail(JG_ERR_INVALID, "jg_engine_create: robot is NULL"); return nullptr; }
     int ndev = 0;
@@ -653,6 +735,11 @@ extern "C" jg_engine* jg_engine_create(const jg_robot* r, const jg_scene* sc, in
     // scratch arena: per-key queues of `cap` entries (92 B each).  Default: the largest power of two <= 2^20
     // configurations per pass whose arena stays within 16 GB and a quarter of the free device memory.
     int cap = e->prm.chunk;
+    if (cap > (1 << 20)) {   // queue slots are packed into 20 bits of the champion codes (queue_push / champ_publish / k_select)
+        fail(JG_ERR_INVALID, "jg_params.chunk = %d exceeds the maximum pass size 2^20 = 1048576 (larger batches are cut into passes)", cap);
+        engine_release(e);
+        return nullptr;
+    }
     if (cap <= 0) {
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
@@ -661,23 +748,22 @@ extern "C" jg_engine* jg_engine_create(const jg_robot* r, const jg_scene* sc, in
         cap = 1 << 20;
         while (cap > 4096 && (size_t)cap * per_cfg > budget) cap >>= 1;
     }
-    cap = (cap + 1023) / 1024 * 1024;
-    e->cap = cap;
-    e->ovf_poly_cap = std::min(std::max(cap / 4, 1), 65536);   // hand-over records (496 B each); later overflows restart
-    const size_t qn = (size_t)std::max(e->n_keys, 1) * cap;
-    bool okm = cudaMalloc(&e->q_r0, sizeof(float4) * qn) == cudaSuccess && cudaMalloc(&e->q_r1, sizeof(float4) * qn) == cudaSuccess &&
-               cudaMalloc(&e->q_r2, sizeof(float4) * qn) == cudaSuccess && cudaMalloc(&e->q_cfg, sizeof(int) * qn) == cudaSuccess && cudaMalloc(&e->epa_slot, sizeof(int) * qn) == cudaSuccess && cudaMalloc(&e->epa_ids, sizeof(uint4) * qn) == cudaSuccess && cudaMalloc(&e->ovf_list, sizeof(int2) * cap) == cudaSuccess && cudaMalloc(&e->ovf_poly, sizeof(uint32_t) * JG_OVF_WORDS * (size_t)e->ovf_poly_cap) == cudaSuccess && cudaMalloc(&e->epa_prio, sizeof(float) * qn) == cudaSuccess && cudaMalloc(&e->q_prio, sizeof(float) * qn) == cudaSuccess &&
-               cudaMalloc(&e->act_list, sizeof(int) * qn) == cudaSuccess && cudaMalloc(&e->act_meta, sizeof(int2) * qn) == cudaSuccess && cudaMalloc(&e->champ_scene, sizeof(unsigned long long) * cap) == cudaSuccess &&
-               cudaMalloc(&e->champ_self, sizeof(unsigned long long) * cap) == cudaSuccess &&
-               cudaMalloc(&e->counts, sizeof(int) * JG_COUNTS_INTS(e->n_keys)) == cudaSuccess &&
-               cudaMalloc(&e->enc_scene, sizeof(int) * cap) == cudaSuccess && cudaMalloc(&e->enc_self, sizeof(int) * cap) == cudaSuccess &&
-               cudaMalloc(&e->viol, sizeof(uint32_t) * (cap / 32 + 1)) == cudaSuccess &&
+    cap = std::min((cap + 1023) / 1024 * 1024, 1 << 20);
+    static_assert((1 << 20) - 1 == 0xFFFFF, "slot field of the champion code");
+    e->cap_max = cap;
+    bool okm = cudaMalloc(&e->counts, sizeof(int) * JG_COUNTS_INTS(e->n_keys)) == cudaSuccess &&
                cudaMalloc(&e->d_link_slot, sizeof(int) * MAX_LINKS) == cudaSuccess &&
                cudaMalloc(&e->d_rel, sizeof(Tf) * MAX_SHAPES) == cudaSuccess &&
                cudaMalloc(&e->d_use_shapes, sizeof(int) * MAX_SHAPES) == cudaSuccess &&
                cudaMalloc(&e->d_stats, sizeof(unsigned long long) * 8) == cudaSuccess && cudaMalloc(&e->d_err, sizeof(int)) == cudaSuccess && cudaMalloc(&e->d_qrest, sizeof(float) * MAX_DOF) == cudaSuccess;
     if (!okm) {
-        fail(JG_ERR_NOMEM, "scratch allocation failed (%zu queue entries): %s", qn, cudaGetErrorString(cudaGetLastError()));
+        fail(JG_ERR_NOMEM, "table allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        engine_release(e);
+        return nullptr;
+    }
+    // an explicit chunk is allocated at once; the automatic size starts small (single-shot queries of the drop-in API
+    // never need more) and grows with the batches that actually arrive (ensure_arena)
+    if (arena_alloc(e, e->prm.chunk > 0 ? e->cap_max : std::min(e->cap_max, 4096)) != JG_OK) {
         engine_release(e);
         return nullptr;
     }
@@ -692,9 +778,12 @@ extern "C" int jg_engine_device(const jg_engine* e) { return e ? e->device : JG_
 // want_dist = false: the caller only wants verdict bits.  The verdict is "some contact distance < threshold", so the
 // query distance shrinks to the threshold itself (pairs farther apart cannot change a bit: the broad phase drops
 // them and GJK stops as soon as a separating axis proves it) and penetration depth is never needed.  Same bits.
+// The shortcut is exact only while every overlap is a collision: overlapping cores report exactly -(margin sum), so the
+// threshold must lie above -(smallest margin sum); for a lower threshold (a free parameter of links_in_collision /
+// are_in_collision) the penetration stages stay on and only the distance output is dropped.
 static void fill_args(const jg_engine* e, PassArgs& a, uint32_t& flags, bool want_dist = true) {
     memset(&a, 0, sizeof a);
-    if (!want_dist) flags |= JG_NO_EPA;
+    if (!want_dist && (e->mesh || e->n_keys == 0 || e->prm.threshold > -e->min_msum + 1e-6f)) flags |= JG_NO_EPA;
     a.dof = e->dof; a.substeps = 1; a.flags = flags;
     a.finger_open = e->prm.finger_open; a.threshold = e->prm.threshold;
     a.qd = want_dist ? e->prm.query_distance : std::min(e->prm.query_distance, e->prm.threshold + 1e-6f);
@@ -782,8 +871,17 @@ static int run_narrow_and_finalize(jg_engine* e, const PassArgs& a, int n_out, u
     return JG_OK;
 }
 
+// All entry points share ONE scratch arena (queues, counters, per-configuration slots).  Calls on the same stream are
+// ordered by the stream; a call on a DIFFERENT stream than the previous one (torch stream after the library's own
+// host-path stream, or the other way round) first waits for everything the previous call enqueued.
 static int begin_call(jg_engine* e, cudaStream_t st) {
     CUDA_TRY(cudaSetDevice(e->device));
+    if (e->have_last_stream && st != e->last_stream) {
+        if (!e->ev_order) CUDA_TRY(cudaEventCreateWithFlags(&e->ev_order, cudaEventDisableTiming));
+        if (cudaEventRecord(e->ev_order, e->last_stream) == cudaSuccess) CUDA_TRY(cudaStreamWaitEvent(st, e->ev_order, 0));
+        else cudaGetLastError();   // the previous stream no longer exists: its work has completed
+    }
+    e->have_last_stream = true;
     e->stats = jg_stats{};
     e->last_stream = st;
     CUDA_TRY(cudaMemsetAsync(e->d_stats, 0, sizeof(unsigned long long) * 8, st));
@@ -796,7 +894,10 @@ extern "C" int jg_check(jg_engine* e, const float* q, int64_t n, int dof, uint32
     if (dof != e->dof) return fail(JG_ERR_INVALID, "jg_check: dof %d does not match the robot's %d", dof, e->dof);
     if (n < 0 || (n && (!q || !bits))) return fail(JG_ERR_INVALID, "jg_check: NULL q/bits");
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = begin_call(e, st);
+    CUDA_TRY(cudaSetDevice(e->device));
+    int rc = ensure_arena(e, n);
+    if (rc) return rc;
+    rc = begin_call(e, st);
     if (rc) return rc;
     e->stats.configs = n;
     // mesh mode: a configuration may queue many triangles per link, so a pass takes fewer configurations; the pass
@@ -822,7 +923,7 @@ extern "C" int jg_check(jg_engine* e, const float* q, int64_t n, int dof, uint32
                 CUDA_TRY(cudaMemsetAsync(e->d_err, 0, sizeof(int), st));
                 if (e->mesh_pass <= 1024)
                     return fail(JG_ERR_NOMEM, "mesh mode: a triangle candidate queue overflowed even at 1024 configurations per pass "
-                                "(%d entries per link); create the engine with a larger `chunk`", e->cap);
+                                "(%d entries per link shape; chunk is already at most 2^20): simplify the obstacle mesh", e->cap);
                 e->mesh_pass = std::max(1024, e->mesh_pass / 2 / 1024 * 1024);
                 continue;   // redo this pass at the smaller size
             }
@@ -840,11 +941,14 @@ extern "C" int jg_check_edges(jg_engine* e, const float* qa, const float* qb, in
                               uint32_t flags, uint32_t* bits, float* min_dist, void* stream) {
     if (!e) return fail(JG_ERR_INVALID, "jg_check_edges: engine is NULL");
     if (dof != e->dof) return fail(JG_ERR_INVALID, "jg_check_edges: dof %d does not match the robot's %d", dof, e->dof);
-    if (substeps < 2 || substeps > e->cap / 32) return fail(JG_ERR_INVALID, "jg_check_edges: substeps %d out of range [2,%d]", substeps, e->cap / 32);
+    if (substeps < 2 || substeps > e->cap_max / 32) return fail(JG_ERR_INVALID, "jg_check_edges: substeps %d out of range [2,%d]", substeps, e->cap_max / 32);
     if (e->mesh) return fail(JG_ERR_INVALID, "jg_check_edges: not available in mesh mode");
     if (m < 0 || (m && (!qa || !qb || !bits))) return fail(JG_ERR_INVALID, "jg_check_edges: NULL qa/qb/bits");
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = begin_call(e, st);
+    CUDA_TRY(cudaSetDevice(e->device));
+    int rc = ensure_arena(e, std::max<int64_t>(m, 32) * substeps);
+    if (rc) return rc;
+    rc = begin_call(e, st);
     if (rc) return rc;
     e->stats.configs = m * substeps;
     const int edges_per_pass = (e->cap / substeps) / 32 * 32;   // keep packed words aligned across passes
@@ -903,7 +1007,10 @@ extern "C" int jg_check_poses(jg_engine* e, const float* poses, int64_t n, int f
     if (n < 0 || (n && (!poses || !bits))) return fail(JG_ERR_INVALID, "jg_check_poses: NULL poses/bits");
     flags &= (JG_SCENE | JG_PLANE | JG_NO_EPA);
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = begin_call(e, st);
+    CUDA_TRY(cudaSetDevice(e->device));
+    int rc = ensure_arena(e, n);
+    if (rc) return rc;
+    rc = begin_call(e, st);
     if (rc) return rc;
     e->stats.configs = n;
     // rigid offsets rel_s = inv(T_ee) * T_link(s)
@@ -961,7 +1068,7 @@ extern "C" int jg_check_poses(jg_engine* e, const float* poses, int64_t n, int f
                 CUDA_TRY(cudaMemsetAsync(e->d_err, 0, sizeof(int), st));
                 if (e->mesh_pass <= 1024)
                     return fail(JG_ERR_NOMEM, "mesh mode: a triangle candidate queue overflowed even at 1024 poses per pass "
-                                "(%d entries per link); create the engine with a larger `chunk`", e->cap);
+                                "(%d entries per link shape; chunk is already at most 2^20): simplify the obstacle mesh", e->cap);
                 e->mesh_pass = std::max(1024, e->mesh_pass / 2 / 1024 * 1024);
                 continue;
             }
@@ -1007,10 +1114,19 @@ extern "C" int jg_fk(jg_engine* e, const float* q, int64_t n, int dof, const int
 
 // ----------------------------------------------------------------------------------------------- host path
 static int ensure_staging(jg_engine* e) {
-    if (e->staging_ready) return JG_OK;
-    CUDA_TRY(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&e->s_run, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
+    if (!e->staging_ready) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&e->s_run, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CUDA_TRY(cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&e->ev_run[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&e->ev_out[i], cudaEventDisableTiming));
+        }
+        e->staging_ready = true;
+    }
+    if (e->staging_cap == e->cap) return JG_OK;
+    staging_free(e);
     for (int i = 0; i < 2; ++i) {
         CUDA_TRY(cudaMalloc(&e->stage_q[i], sizeof(float) * e->cap * e->dof));
         CUDA_TRY(cudaMalloc(&e->stage_bits[i], sizeof(uint32_t) * (e->cap / 32)));
@@ -1020,11 +1136,8 @@ static int ensure_staging(jg_engine* e) {
         CUDA_TRY(cudaMallocHost(&e->pin_bits[i], sizeof(uint32_t) * (e->cap / 32)));
         CUDA_TRY(cudaMallocHost(&e->pin_dist[i], sizeof(float) * e->cap));
         CUDA_TRY(cudaMallocHost(&e->pin_reason[i], e->cap));
-        CUDA_TRY(cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&e->ev_run[i], cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&e->ev_out[i], cudaEventDisableTiming));
     }
-    e->staging_ready = true;
+    e->staging_cap = e->cap;
     return JG_OK;
 }
 
@@ -1085,10 +1198,12 @@ extern "C" int jg_check_host(jg_engine* e, const float* q, int64_t n, int dof, u
     if (dof != e->dof) return fail(JG_ERR_INVALID, "jg_check_host: dof %d does not match the robot's %d", dof, e->dof);
     if (n < 0 || (n && (!q || !bits))) return fail(JG_ERR_INVALID, "jg_check_host: NULL q/bits");
     CUDA_TRY(cudaSetDevice(e->device));
-    int rc = ensure_staging(e);
-    if (rc) return rc;
     if (e->pending[0].busy || e->pending[1].busy)
         return fail(JG_ERR_INVALID, "jg_check_host: batches submitted with jg_check_host_submit are still in flight");
+    int rc = ensure_arena(e, n);
+    if (rc) return rc;
+    rc = ensure_staging(e);
+    if (rc) return rc;
     const bool pq = is_pinned(q), pb = is_pinned(bits), pd = dist && is_pinned(dist), pr = reason && is_pinned(reason);
     if (e->mesh || n == 0) {   // secondary path: plain staged copy around the device entry point
         float* dq = nullptr;
@@ -1156,10 +1271,12 @@ extern "C" int jg_check_host_submit(jg_engine* e, const float* q, int64_t n, int
     if (dof != e->dof) return fail(JG_ERR_INVALID, "jg_check_host_submit: dof %d does not match the robot's %d", dof, e->dof);
     if (n <= 0 || !q || !bits) return fail(JG_ERR_INVALID, "jg_check_host_submit: empty batch or NULL q/bits");
     if (e->mesh) return fail(JG_ERR_UNSUPPORTED, "jg_check_host_submit: mesh-mode engines use jg_check_host");
-    if (n > e->cap) return fail(JG_ERR_INVALID, "jg_check_host_submit: %lld configurations exceed the pass capacity %d (use jg_check_host)",
-                                (long long)n, e->cap);
+    if (n > e->cap_max) return fail(JG_ERR_INVALID, "jg_check_host_submit: %lld configurations exceed the pass capacity %d (use jg_check_host)",
+                                    (long long)n, e->cap_max);
     CUDA_TRY(cudaSetDevice(e->device));
-    int rc = ensure_staging(e);
+    int rc = ensure_arena(e, n);
+    if (rc) return rc;
+    rc = ensure_staging(e);
     if (rc) return rc;
     const int b = (int)(e->next_ticket & 1);
     if (e->pending[b].busy) return fail(JG_ERR_INVALID, "jg_check_host_submit: two batches are already in flight (wait for ticket %lld first)",
@@ -1190,6 +1307,14 @@ extern "C" int jg_check_host_wait(jg_engine* e, int64_t ticket) {
     if (P.dist && !P.pd) memcpy(P.dist, e->pin_dist[b], sizeof(float) * P.n);
     if (P.reason && !P.pr) memcpy(P.reason, e->pin_reason[b], P.n);
     P.busy = false;
+    return JG_OK;
+}
+
+static int drain_pending(jg_engine* e) {
+    for (int64_t t = std::max<int64_t>(0, e->next_ticket - 2); t < e->next_ticket; ++t) {
+        const int rc = jg_check_host_wait(e, t);
+        if (rc) return rc;
+    }
     return JG_OK;
 }
 

@@ -772,7 +772,7 @@ __global__ void __launch_bounds__(BLOCK) k_narrowphase(const PassArgs a) {
 
         const float4* A = verts + K.a_off;
         const float4* B = verts + K.b_off;
-        const float dmax = a.qd + K.msum;
+        const float dmax = fmaxf(a.qd + K.msum, 0.f);   // cores apart at all => contact distance > -msum
         bool active = false;
         GjkState S;
         Tf T = tf_identity();

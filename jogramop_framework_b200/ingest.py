@@ -416,6 +416,13 @@ class SceneModel:
         m.piece_body = self.piece_body[keep]
         m.piece_margin = self.piece_margin[keep]
         m.has_plane = bool(with_plane and self.has_plane)
+        # the merged triangle mesh follows the same body selection (mesh-mode engines)
+        sel = np.isin(self.tri_body, list(set(bodies)))
+        tris = self.tris[sel]
+        used, inv = np.unique(tris.reshape(-1), return_inverse=True)
+        m.tri_verts = self.tri_verts[used] if len(used) else np.zeros((0, 3))
+        m.tris = inv.reshape(-1, 3).astype(np.int32)
+        m.tri_body = self.tri_body[sel]
         return m
 
     def to_dict(self):

@@ -137,8 +137,9 @@ class Scenario:
         """The check half of ``get_ik_solutions`` (scenario.py:105-125) as ONE batched call: joint limits, then
         self-collision, then scene collision, with the reference's counters.  ``candidates``: [n,dof] (rows may be
         None-free only).  Returns (accepted [m,dof] float64, reason uint8[n], Timer)."""
+        own_sim = None
         if robot is None:
-            robot, _ = self.get_robot_and_sim()
+            robot, own_sim = self.get_robot_and_sim()
         candidates = np.asarray(candidates, dtype=np.float64).reshape(-1, len(robot.arm_joint_ids))
         count = util.Timer()
         count.start('perform checks')
@@ -150,6 +151,8 @@ class Scenario:
             k = int((reason == code).sum())
             if k:
                 count.count(key, k)
+        if own_sim is not None:
+            own_sim.dismiss()      # engines of a simulator created here are released with it (robot <-> simulator is a cycle)
         return candidates[reason == 0], reason, count
 
     def get_ik_solutions(self):
@@ -190,6 +193,7 @@ class Scenario:
             if target_conf is not None:
                 ik_solutions.append(target_conf)
         count.print()
+        sim.dismiss()
         return np.array(ik_solutions)
 
     def get_ik_solutions_batch(self, restarts=8, seed=0):
@@ -209,4 +213,5 @@ class Scenario:
         _, _, reason = robot.check_batch(q.astype(np.float32), want_dist=False)
         ok = (err <= 0.015) & (reason.cpu().numpy() == 0)
         idx = np.nonzero(ok)[0]
+        sim.dismiss()
         return q[idx], idx % n

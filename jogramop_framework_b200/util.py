@@ -13,34 +13,42 @@ SCENARIO_IDS = [11, 12, 13, 14, 15, 21, 22, 23, 24, 25, 31, 32, 33, 34, 35, 41, 
 
 
 class Timer:
-    """util.py:13-49: accumulating wall-clock timers and occurrence counters with the same print() summary."""
+    """Interface of the reference's ``util.Timer`` (util.py:13-49; used by ``Scenario.get_ik_solutions``,
+    scenario.py:94-127): ``start(key)`` / ``stop(key)`` accumulate elapsed seconds per key over any number of
+    intervals, ``count(key)`` counts occurrences, ``print()`` writes the summary in the reference's layout.
+    Own implementation: elapsed time is kept separately from the start stamp of a running interval (monotonic
+    ``perf_counter``), so ``timers`` always holds finished seconds; ``count`` takes an increment for batched callers."""
+
+    _RULE = 33
 
     def __init__(self):
-        self.timers = {}
-        self.counters = {}
+        self.timers = {}      # key -> accumulated seconds of finished intervals
+        self.counters = {}    # key -> occurrences
+        self._running = {}    # key -> perf_counter() stamp of the open interval
 
     def start(self, key):
-        if key not in self.timers.keys():
-            self.timers[key] = -time.time()
-        else:
-            self.timers[key] -= time.time()
+        self.timers.setdefault(key, 0.0)
+        self._running[key] = time.perf_counter()
 
     def stop(self, key):
-        if key not in self.timers.keys():
+        now = time.perf_counter()
+        if key not in self._running:
             raise ValueError('attempting to stop timer that has not been started')
-        self.timers[key] += time.time()
+        self.timers[key] += now - self._running.pop(key)
 
     def count(self, key, n=1):
         self.counters[key] = self.counters.get(key, 0) + n
 
+    def summary(self):
+        """-> {'timings': {key: seconds}, 'counters': {key: n}} (what ``print`` shows)."""
+        return {'timings': dict(self.timers), 'counters': dict(self.counters)}
+
     def print(self):
-        print('************ TIMINGS ************')
-        for key, val in self.timers.items():
-            print(f'\t{key}:\t{val:.2f}s')
-        print('*********** COUNTERS ************')
-        for key, val in self.counters.items():
-            print(f'\t{key}:\t{val}x')
-        print('*********************************')
+        for title, rows, unit, fmt in ((' TIMINGS ', self.timers, 's', '{:.2f}'), (' COUNTERS ', self.counters, 'x', '{}')):
+            print(title.center(self._RULE, '*'))
+            for key, val in rows.items():
+                print('\t' + key + ':\t' + fmt.format(val) + unit)
+        print('*' * self._RULE)
 
 
 def quaternion_from_rotation_matrix(rot_mat):

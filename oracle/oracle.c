@@ -619,14 +619,19 @@ static double self_min_distance(const orc_robot* r, const tf* links, double qd, 
     double dmin = INFINITY;
     for (int k = 0; k < r->K; ++k) {
         int la = r->self_pairs[2 * k], lb = r->self_pairs[2 * k + 1];
-        int sa = r->link_shape[la + 1], sb = r->link_shape[lb + 1];
         double d = INFINITY;
-        if (sa >= 0 && sb >= 0) {
-            const tf* Ta = la >= 0 ? &links[la] : &TF_ID;
-            const tf* Tb = lb >= 0 ? &links[lb] : &TF_ID;
-            d = shape_vs_hull(r, sa, Ta, r->core + 3 * r->shape_off[sb], r->shape_off[sb + 1] - r->shape_off[sb], Tb,
-                              r->shape_margin[sb], r->plane_v + 3 * r->plane_off[sb],
-                              r->plane_off[sb + 1] - r->plane_off[sb], r->plane_margin[sb], qd, flags);
+        /* getClosestPoints(body, body, 0.01, linkA, linkB) reports points of EVERY collision shape of both links */
+        for (int sa = 0; sa < r->S; ++sa) {
+            if (r->shape_link[sa] != la) continue;
+            for (int sb = 0; sb < r->S; ++sb) {
+                if (r->shape_link[sb] != lb) continue;
+                const tf* Ta = la >= 0 ? &links[la] : &TF_ID;
+                const tf* Tb = lb >= 0 ? &links[lb] : &TF_ID;
+                double dd = shape_vs_hull(r, sa, Ta, r->core + 3 * r->shape_off[sb], r->shape_off[sb + 1] - r->shape_off[sb], Tb,
+                                          r->shape_margin[sb], r->plane_v + 3 * r->plane_off[sb],
+                                          r->plane_off[sb + 1] - r->plane_off[sb], r->plane_margin[sb], qd, flags);
+                if (dd < d) d = dd;
+            }
         }
         if (per_pair) per_pair[k] = d;
         if (d < dmin) dmin = d;
