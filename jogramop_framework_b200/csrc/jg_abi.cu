@@ -628,7 +628,7 @@ static int arena_alloc(jg_engine* e, int cap) {
     bool okm = cudaMalloc(&e->q_r0, sizeof(float4) * qn) == cudaSuccess && cudaMalloc(&e->q_r1, sizeof(float4) * qn) == cudaSuccess &&
                cudaMalloc(&e->q_r2, sizeof(float4) * qn) == cudaSuccess && cudaMalloc(&e->q_cfg, sizeof(int) * qn) == cudaSuccess &&
                cudaMalloc(&e->epa_slot, sizeof(int) * qn) == cudaSuccess && cudaMalloc(&e->epa_ids, sizeof(uint4) * qn) == cudaSuccess &&
-               cudaMalloc(&e->ovf_list, sizeof(int2) * cap) == cudaSuccess &&
+               cudaMalloc(&e->ovf_list, sizeof(int2) * 4 * (size_t)cap) == cudaSuccess &&
                cudaMalloc(&e->ovf_poly, sizeof(uint32_t) * JG_OVF_WORDS * (size_t)e->ovf_poly_cap) == cudaSuccess &&
                cudaMalloc(&e->epa_prio, sizeof(float) * qn) == cudaSuccess && cudaMalloc(&e->q_prio, sizeof(float) * qn) == cudaSuccess &&
                cudaMalloc(&e->act_list, sizeof(int) * qn) == cudaSuccess && cudaMalloc(&e->act_meta, sizeof(int2) * qn) == cudaSuccess &&
@@ -791,7 +791,7 @@ static void fill_args(const jg_engine* e, PassArgs& a, uint32_t& flags, bool wan
     a.has_plane = e->has_plane ? 1 : 0;
     a.robot = e->d_robot; a.pieces = e->d_pieces; a.P = e->P; a.selfs = e->d_selfs; a.keys = e->d_keys;
     a.n_keys = e->n_keys; a.n_scene_keys = e->n_scene_keys; a.verts = e->d_verts; a.n_verts = e->n_verts;
-    a.q_r0 = e->q_r0; a.q_r1 = e->q_r1; a.q_r2 = e->q_r2; a.q_cfg = e->q_cfg; a.epa_slot = e->epa_slot; a.epa_ids = e->epa_ids; a.ovf_list = e->ovf_list; a.ovf_poly = e->ovf_poly; a.ovf_poly_cap = e->ovf_poly_cap; a.epa_prio = e->epa_prio; a.q_prio = e->q_prio; a.max_msum = e->max_msum; a.stats = e->d_stats;
+    a.q_r0 = e->q_r0; a.q_r1 = e->q_r1; a.q_r2 = e->q_r2; a.q_cfg = e->q_cfg; a.epa_slot = e->epa_slot; a.epa_ids = e->epa_ids; a.ovf_list = e->ovf_list; a.ovf_cap = 4 * e->cap; a.ovf_poly = e->ovf_poly; a.ovf_poly_cap = e->ovf_poly_cap; a.epa_prio = e->epa_prio; a.q_prio = e->q_prio; a.max_msum = e->max_msum; a.stats = e->d_stats;
     a.mesh = e->mesh ? 1 : 0; a.bvh_nodes = e->bvh.nodes; a.bvh_tri = e->bvh.tri_v; a.bvh_n = e->bvh.n_tris;
     a.mesh_margin = e->mesh_margin; a.q_tri = e->epa_slot; a.err_flag = e->d_err; a.act_list = e->act_list; a.act_meta = e->act_meta; a.champ_scene = e->champ_scene; a.champ_self = e->champ_self; a.cap = e->cap; a.counts = e->counts;
     a.enc_scene = e->enc_scene; a.enc_self = e->enc_self; a.viol = e->viol;
@@ -888,6 +888,28 @@ static int begin_call(jg_engine* e, cudaStream_t st) {
     return JG_OK;
 }
 
+// Mesh mode: a (pose, link shape) may queue many triangle candidates, so a pass takes fewer configurations than the
+// per-key queue capacity; the pass size adapts.  Called when the broad phase of a pass reported a queue overflow:
+// halve the pass, or -- at the smallest pass -- grow the arena (while it is below cap_max).  > 0: redo the pass.
+static int mesh_overflow_retry(jg_engine* e, cudaStream_t st, const char* who) {
+    CUDA_TRY(cudaMemsetAsync(e->d_err, 0, sizeof(int), st));
+    if (e->mesh_pass > 256) {
+        e->mesh_pass = std::max(256, e->mesh_pass / 2 / 32 * 32);
+        return 1;
+    }
+    if (e->cap < e->cap_max) {
+        const int rc = ensure_arena(e, std::min<int64_t>(e->cap_max, (int64_t)e->cap * 4));
+        if (rc) return rc;
+        e->mesh_pass = std::max(256, std::min(e->cap / 16, 65536) / 32 * 32);
+        return 1;
+    }
+    return fail(JG_ERR_NOMEM, "%s: mesh mode: a triangle candidate queue overflowed even at 256 configurations per pass "
+                "(%d entries per link shape, the maximum): simplify the obstacle mesh", who, e->cap);
+}
+static void mesh_first_pass(jg_engine* e) {
+    if (e->mesh && e->mesh_pass <= 0) e->mesh_pass = std::max(256, std::min(e->cap / 16, 65536) / 32 * 32);
+}
+
 extern "C" int jg_check(jg_engine* e, const float* q, int64_t n, int dof, uint32_t flags, uint32_t* bits, float* min_dist,
                         uint8_t* reason, void* stream) {
     if (!e) return fail(JG_ERR_INVALID, "jg_check: engine is NULL");
@@ -895,14 +917,12 @@ extern "C" int jg_check(jg_engine* e, const float* q, int64_t n, int dof, uint32
     if (n < 0 || (n && (!q || !bits))) return fail(JG_ERR_INVALID, "jg_check: NULL q/bits");
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaSetDevice(e->device));
-    int rc = ensure_arena(e, n);
+    int rc = ensure_arena(e, e->mesh ? n * 16 : n);
     if (rc) return rc;
     rc = begin_call(e, st);
     if (rc) return rc;
     e->stats.configs = n;
-    // mesh mode: a configuration may queue many triangles per link, so a pass takes fewer configurations; the pass
-    // size adapts: an overflowing pass is redone at half the size (the engine remembers what worked)
-    if (e->mesh && e->mesh_pass <= 0) e->mesh_pass = std::max(1024, e->cap / 2 / 1024 * 1024);
+    mesh_first_pass(e);
     for (int64_t off = 0; off < n;) {
         const int64_t pass = e->mesh ? e->mesh_pass : e->cap;
         const int m = (int)std::min<int64_t>(pass, n - off);
@@ -920,11 +940,8 @@ extern "C" int jg_check(jg_engine* e, const float* q, int64_t n, int dof, uint32
             CUDA_TRY(cudaMemcpyAsync(&err, e->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
             if (err) {
-                CUDA_TRY(cudaMemsetAsync(e->d_err, 0, sizeof(int), st));
-                if (e->mesh_pass <= 1024)
-                    return fail(JG_ERR_NOMEM, "mesh mode: a triangle candidate queue overflowed even at 1024 configurations per pass "
-                                "(%d entries per link shape; chunk is already at most 2^20): simplify the obstacle mesh", e->cap);
-                e->mesh_pass = std::max(1024, e->mesh_pass / 2 / 1024 * 1024);
+                rc = mesh_overflow_retry(e, st, "jg_check");
+                if (rc < 0) return rc;
                 continue;   // redo this pass at the smaller size
             }
             prof_begin(e, 0, st);
@@ -1008,7 +1025,7 @@ extern "C" int jg_check_poses(jg_engine* e, const float* poses, int64_t n, int f
     flags &= (JG_SCENE | JG_PLANE | JG_NO_EPA);
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaSetDevice(e->device));
-    int rc = ensure_arena(e, n);
+    int rc = ensure_arena(e, e->mesh ? n * 16 : n);
     if (rc) return rc;
     rc = begin_call(e, st);
     if (rc) return rc;
@@ -1042,9 +1059,9 @@ extern "C" int jg_check_poses(jg_engine* e, const float* poses, int64_t n, int f
     CUDA_TRY(cudaMemcpyAsync(e->d_use_shapes, use.data(), sizeof(int) * use.size(), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));   // rel/use are stack-lifetime host vectors
     const int stride = fmt == JG_POSE_MAT34 ? 12 : 7;
-    if (e->mesh && e->mesh_pass <= 0) e->mesh_pass = std::max(1024, e->cap / 2 / 1024 * 1024);
+    mesh_first_pass(e);
     for (int64_t off = 0; off < n;) {
-        const int64_t pass = e->mesh ? e->mesh_pass : e->cap;   // mesh mode: adaptive pass size, see jg_check
+        const int64_t pass = e->mesh ? e->mesh_pass : e->cap;   // mesh mode: adaptive pass size, see mesh_overflow_retry
         const int m = (int)std::min<int64_t>(pass, n - off);
         PassArgs a;
         fill_args(e, a, flags, min_dist != nullptr);
@@ -1065,11 +1082,8 @@ extern "C" int jg_check_poses(jg_engine* e, const float* poses, int64_t n, int f
             CUDA_TRY(cudaMemcpyAsync(&err, e->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
             if (err) {
-                CUDA_TRY(cudaMemsetAsync(e->d_err, 0, sizeof(int), st));
-                if (e->mesh_pass <= 1024)
-                    return fail(JG_ERR_NOMEM, "mesh mode: a triangle candidate queue overflowed even at 1024 poses per pass "
-                                "(%d entries per link shape; chunk is already at most 2^20): simplify the obstacle mesh", e->cap);
-                e->mesh_pass = std::max(1024, e->mesh_pass / 2 / 1024 * 1024);
+                rc = mesh_overflow_retry(e, st, "jg_check_poses");
+                if (rc < 0) return rc;
                 continue;
             }
             prof_begin(e, 0, st);

@@ -113,7 +113,8 @@ struct PassArgs {
     float* q_prio;     // [n_keys*cap] upper bound of the pair's total penetration (AABB overlap + margins)
     int* epa_slot;     // [n_keys*cap] queue slots whose cores overlap (penetration-depth pass)
     uint4* epa_ids;    // [n_keys*cap] their GJK end simplices (vertex ids, 0xFFFFFFFF = unused)
-    int2* ovf_list;    // [cap] (key, index in the penetration queue) of polytopes that outgrew shared memory
+    int2* ovf_list;    // [ovf_cap] (key, index in the penetration queue) of polytopes that outgrew shared memory
+    int ovf_cap;       // = 4 * cap: a pass may hand more polytopes to the overflow kernel than it has configurations
     uint32_t* ovf_poly;  // [ovf_poly_cap][JG_OVF_WORDS] the compact polytope of the first ovf_poly_cap of them: the overflow
     int ovf_poly_cap;    // kernel goes on from there instead of repeating the 14 expansions that filled it
     float* epa_prio;   // [n_keys*cap] the same bound for the entries of the penetration queue
@@ -1102,7 +1103,7 @@ __global__ void __launch_bounds__(BLOCK) k_penetration(const PassArgs a) {
                         phase = 0;
                     } else if (st == JG_EPA_OVERFLOW) {   // rare large polytope: redo with per-thread storage
                         const int o = atomicAdd(ovf_counter, 1);
-                        if (o < a.cap) {
+                        if (o < a.ovf_cap) {
                             a.ovf_list[o] = make_int2(key, myj);
                             if (o < a.ovf_poly_cap) {   // hand the polytope over (nothing was modified by the failed step)
                                 uint32_t* rec = a.ovf_poly + (size_t)o * JG_OVF_WORDS;
@@ -1161,7 +1162,7 @@ __global__ void __launch_bounds__(BLOCK) k_penetration_big(const PassArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* verts = reinterpret_cast<float4*>(smem_raw);
     uint32_t* poly_words = reinterpret_cast<uint32_t*>(smem_raw + sizeof(float4) * a.n_verts);
-    const int n = min(cnt_misc(a)[CTR_OVF], a.cap);
+    const int n = min(cnt_misc(a)[CTR_OVF], a.ovf_cap);
     if (n == 0) return;
     for (int i = threadIdx.x; i < a.n_verts; i += BLOCK) verts[i] = a.verts[i];
     __syncthreads();
@@ -1557,6 +1558,18 @@ __global__ void __launch_bounds__(BLOCK) k_ik(const IkArgs a) {
             } else if (j < dof && jtype[j] == 2) {
                 Jc[j][0] = jax[j].x; Jc[j][1] = jax[j].y; Jc[j][2] = jax[j].z; Jc[j][3] = 0.f; Jc[j][4] = 0.f; Jc[j][5] = 0.f;
             } else {
+                for (int r = 0; r < 6; ++r) Jc[j][r] = 0.f;
+            }
+        }
+        // active set: a joint that sits on a limit and that the task gradient J^T e pushes further out cannot move; with
+        // its column left in, the damped step keeps spending itself against the clamp (the commonest way a start ends
+        // short of a reachable pose).  Take it out of this iteration's Jacobian.
+        for (int j = 0; j < dof; ++j) {
+            float g = 0.f;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) g = fmaf(Jc[j][r], e6[r], g);
+            if ((q[j] <= R->qlo[j] && g < 0.f) || (q[j] >= R->qhi[j] && g > 0.f)) {
+#pragma unroll
                 for (int r = 0; r < 6; ++r) Jc[j][r] = 0.f;
             }
         }

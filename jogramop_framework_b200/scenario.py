@@ -196,21 +196,43 @@ class Scenario:
         sim.dismiss()
         return np.array(ik_solutions)
 
-    def get_ik_solutions_batch(self, restarts=8, seed=0):
-        """Batched variant: all grasps (x ``restarts`` start configurations: home + uniform samples) go through ONE IK
-        launch and ONE filter launch.  Returns (accepted [m,dof], grasp index of each accepted row)."""
-        robot, sim = self.get_robot_and_sim()
+    def ik_start_configurations(self, robot, restarts, seed=0):
+        """Start configurations for ``restarts`` IK attempts per grasp -> [restarts * n, dof] (attempt-major).  A 9-dof
+        arm has a 3-dimensional solution manifold per grasp and only a small part of it is collision-free (the hardest
+        reference grasps: ~1 % of the converged attempts), so the batched variant covers it by sampling: attempt 0
+        starts at home (the reference's start), odd attempts uniformly inside the joint limits, even attempts with the
+        mobile base placed 0.25-0.8 m from the grasp, joint 1 turned towards it and the arm jittered around home."""
         n = len(self.gs)
         lim = robot.arm_joint_limits()
+        home = np.asarray(robot.home_conf, dtype=np.float64)
         rng = np.random.default_rng(seed)
-        starts = [np.tile(np.asarray(robot.home_conf), (n, 1))]
-        for _ in range(restarts - 1):
-            starts.append(lim[:, 0] + (lim[:, 1] - lim[:, 0]) * rng.random((n, len(lim))))
-        q0 = np.concatenate(starts).astype(np.float32)
+        T = np.linalg.inv(robot.pose) @ self.gs.poses            # targets in the robot frame
+        starts = [np.tile(home, (n, 1))]
+        for r in range(1, restarts):
+            if r % 2 == 1 or not self.with_platform:
+                starts.append(lim[:, 0] + (lim[:, 1] - lim[:, 0]) * rng.random((n, len(lim))))
+                continue
+            q = np.tile(home, (n, 1))
+            rad, phi = rng.uniform(0.25, 0.8, n), rng.uniform(0, 2 * np.pi, n)
+            q[:, 1] = np.clip(T[:, 0, 3] - rad * np.cos(phi), lim[1, 0], lim[1, 1])      # base_joint_x is q[1] (quirk Q2)
+            q[:, 0] = np.clip(T[:, 1, 3] - rad * np.sin(phi), lim[0, 0], lim[0, 1])      # base_joint_y is q[0]
+            q[:, 2] = np.arctan2(T[:, 1, 3] - q[:, 0], T[:, 0, 3] - q[:, 1]) + rng.normal(0, 0.3, n)
+            q[:, 3:] += rng.normal(0, 0.4, (n, q.shape[1] - 3))
+            starts.append(np.clip(q, lim[:, 0], lim[:, 1]))
+        return np.concatenate(starts)
+
+    def get_ik_solutions_batch(self, restarts=256, seed=0):
+        """Batched variant: all grasps x ``restarts`` start configurations (``ik_start_configurations``) go through ONE
+        IK launch and ONE filter launch (limits, self-collision, scene).  Returns (accepted [m,dof], grasp index of each
+        accepted row).  With 256 restarts every scenario yields at least as many distinct grasps as the reference's
+        ``grasp_IK_solutions.csv`` holds (tests/test_export_and_ik.py, profiles/r02_ik_g6_counts.txt)."""
+        robot, sim = self.get_robot_and_sim()
+        n = len(self.gs)
+        q0 = self.ik_start_configurations(robot, restarts, seed).astype(np.float32)
         poses = np.tile(self.gs.poses, (restarts, 1, 1))
         q, err = robot.inverse_kinematics_batch(poses, q_init=q0)
+        _, _, reason = robot.check_batch(q, want_dist=False)
         q, err = q.cpu().numpy().astype(np.float64), err.cpu().numpy()
-        _, _, reason = robot.check_batch(q.astype(np.float32), want_dist=False)
         ok = (err <= 0.015) & (reason.cpu().numpy() == 0)
         idx = np.nonzero(ok)[0]
         sim.dismiss()

@@ -99,3 +99,49 @@ def test_get_ik_solutions_end_to_end(robot, golden, scene_loader):
         assert bits.mean() < 0.05
         lim = robot.joint_limits[robot.arm_joint_ids]
         assert (sols_b >= lim[:, 0] - 1e-6).all() and (sols_b <= lim[:, 1] + 1e-6).all()
+
+
+REF_G6 = {11: 1, 12: 3, 13: 0, 14: 1, 15: 0, 21: 1, 22: 4, 23: 2, 24: 1, 25: 1, 31: 10, 32: 11, 33: 15, 34: 15, 35: 8,
+          41: 0, 42: 5, 43: 2, 44: 5, 45: 4}    # rows of scenarios/*/export/grasp_IK_solutions.csv
+
+
+def _reached(o, robot, rows, grasps_robot):
+    T = o.fk(rows)[:, robot.end_effector_id]
+    pe = np.linalg.norm(grasps_robot[None, :, :3, 3] - T[:, None, :, 3], axis=2)
+    Rrel = np.einsum('gij,nkj->ngik', grasps_robot[:, :3, :3], T[:, :, :3])
+    ang = np.degrees(np.arccos(np.clip((np.trace(Rrel, axis1=2, axis2=3) - 1) / 2, -1, 1)))
+    e = pe + ang / 1000
+    return e.argmin(1), e.min(1), e
+
+
+@pytest.mark.gpu
+def test_ik_outcomes_against_the_references_recorded_outcomes_g6(robot, golden, scene_loader):
+    """G6 as a pin (simulation.py:251-310 + scenario.py:82-129): for all 20 scenarios the batched IK + filter must
+    (a) return only rows that the oracle accepts (limits, self-collision, scene) and that reach one of the 200 grasps
+    within the reference's acceptance threshold, and (b) accept at least as many distinct grasps as the reference's
+    grasp_IK_solutions.csv holds; most of the very grasps the reference reached are recovered as well."""
+    import oracle
+    found = n_ref = 0
+    for sid, n_rows in REF_G6.items():
+        s = Scenario(sid)
+        o = oracle.Oracle(robot, scene_loader(sid))
+        gr = np.linalg.inv(s.robot_pose) @ s.gs.poses
+        ref_rows = golden[f'ik_{sid:03d}'].reshape(-1, 9)
+        assert len(ref_rows) == n_rows
+        ref_g = set(_reached(o, robot, ref_rows, gr)[0].tolist()) if n_rows else set()
+        q, gi = s.get_ik_solutions_batch(restarts=256)
+        got = set(gi.tolist())
+        if len(q):
+            rows = q.astype(np.float32).astype(np.float64)
+            bits, dist = o.check(rows, flags=7)
+            assert (np.abs(dist[bits] + 0.001) < 1e-3).all() and bits.mean() < 0.05     # fp32 vs fp64 only inside the band
+            lim = robot.joint_limits[robot.arm_joint_ids]
+            assert (q >= lim[:, 0] - 1e-6).all() and (q <= lim[:, 1] + 1e-6).all()
+            e_target = _reached(o, robot, rows, gr)[2][np.arange(len(rows)), gi]    # error to the grasp each row was solved for
+            assert (e_target <= 0.0152).all()
+        print(f'{sid:03d}: reference {n_rows} rows / {len(ref_g)} grasps; batched x256: {len(q)} rows / {len(got)} grasps, '
+              f'{len(ref_g & got)} of the reference\'s grasps')
+        assert len(got) >= len(ref_g), sid
+        found += len(ref_g & got)
+        n_ref += len(ref_g)
+    assert n_ref == 89 and found >= 80, found
