@@ -15,6 +15,14 @@ timed region.
             `roofline_hbm` gives the HBM view of the whole pass.
 `cpu_baseline`: the double-precision CPU oracle ("port": pybullet is not installable in this image) on the host cores.
 `--impl reference`: the same oracle, all host threads, bounded samples, as the reference arm.
+
+Timing (all on the device, max over ranks): ONE CUDA-event pair around the K timed steps on the launching stream, after a
+barrier + synchronize; the steps rotate over 4 different 1 M input batches (144 MB > the 126 MB L2; the pass's own queue
+traffic evicts the rest), so no step finds its inputs in L2.  With N > 1 the kernels write their packed verdict words
+straight into the rank's slot of the all-gather buffer and the all-gather of step k runs on a side stream under the
+kernels of step k+1; the timed region ends when the last gather has finished.
+`soak`    : the same step looped for 2 s with NVML clock samples every 5 ms (sustained SM clock of THIS workload).
+`configs` : BASELINE.json configs 3 / 4 / 5 measured after the timed region (N = 1), each with a parity sample.
 """
 import argparse
 import json
@@ -30,11 +38,11 @@ sys.path.insert(0, ROOT)
 
 FLOPS_PER_CHECK = 1.5e4         # SURVEY §8d nominal algorithmic work per check, scenario 011
 FLOPS_PER_CHECK_NARROW = 1.28e4  # ... of which the narrow phase (W_np)
-# DRAM bytes (read + write) of the narrow-phase kernels of ONE pass over 1 M configurations of scenario 011, from the
-# ncu --set full capture profiles/r01_m_ncu_full_summary.csv (2 x k_narrowphase, 2 x k_penetration, 3 x k_select,
-# k_penetration_big): 425.6 MB = 426 B per check, ~10x the algorithmic 40 B (pair queues), 4 % of HBM bandwidth
-NARROW_TRAFFIC_BYTES_PER_CHECK_NCU = 395.2
+# DRAM traffic per pass comes from profiles/r02_traffic.json (tools/ncu_summary.py --traffic on an `ncu --set full` capture
+# of this very command; the file names the commit it was taken at) -- never a constant in this file.
+TRAFFIC_FILE = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
 BYTES_PER_CHECK = 40.125        # 36 B in + 4 B distance + 1 bit out
+SCENARIO_IDS = [11, 12, 13, 14, 15, 21, 22, 23, 24, 25, 31, 32, 33, 34, 35, 41, 42, 43, 44, 45]   # util.py:10
 
 
 def load_models(scenario):
@@ -51,17 +59,22 @@ def make_configs(robot, n, seed):
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock / throttle reasons of one GPU every 100 ms while the timed region runs."""
+    """Samples SM clock / throttle reasons of one GPU through NVML every `period` seconds while a timed region runs."""
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.005):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz, self._stop_evt = index, [], set(), None, threading.Event()
+        self.period = period
         self.ok = False
         try:
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = index
+            if visible and len(visible.split(',')) > index and visible.split(',')[index].strip().isdigit():
+                phys = int(visible.split(',')[index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
             self.ok = True
         except Exception:
@@ -84,14 +97,15 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop_evt.wait(0.1)
+            self._stop_evt.wait(self.period)
 
     def stop(self):
         self._stop_evt.set()
         if self.is_alive():
             self.join(timeout=2)
         med = float(np.median(self.samples)) if self.samples else None
-        return {'sm_mhz': med, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons), 'samples': len(self.samples)}
+        return {'sm_mhz': med, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons), 'samples': len(self.samples),
+                'sm_mhz_min': float(min(self.samples)) if self.samples else None, 'period_ms': 1e3 * self.period}
 
 
 def time_oracle(robot, scene, q, flags, n_threads, budget_s):
@@ -144,6 +158,164 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def random_poses(rng, lo, hi, m):
+    pos = (lo + (hi - lo) * rng.random((m, 3))).astype(np.float32)
+    quat = rng.normal(size=(m, 4)).astype(np.float32)
+    return np.concatenate([pos, quat], 1)
+
+
+def quat_poses_to_mat(pq):
+    p = pq[:, :3].astype(np.float64)
+    qn = pq[:, 3:].astype(np.float64)
+    qn /= np.linalg.norm(qn, axis=1, keepdims=True)
+    x, y, z, w = qn.T
+    R = np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w), 2 * (x * y + z * w),
+                  1 - 2 * (x * x + z * z), 2 * (y * z - x * w), 2 * (x * z - y * w), 2 * (y * z + x * w),
+                  1 - 2 * (x * x + y * y)], 1).reshape(-1, 3, 3)
+    return np.concatenate([R, p[:, :, None]], 2)
+
+
+def bench_other_configs(robot, dev, budget_s=1.0):
+    """BASELINE.json configs 3, 4 and 5 on ONE GPU, outside the headline's timed region: CUDA events around `reps`
+    repetitions after warm-up, plus a parity sample against the CPU oracle for each (the checker, never the timed path)."""
+    import torch
+    import oracle
+    from jogramop_framework_b200.engine import CollisionEngine, SCENE, PLANE
+    from jogramop_framework_b200.ingest import SceneModel
+    data = os.path.join(ROOT, 'jogramop_framework_b200', 'data')
+    lim = robot.joint_limits[robot.arm_joint_ids]
+    out = {}
+
+    def timed(fn, reps=3, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    def parity(gb, gd, rb, rd):
+        gb = gb.cpu().numpy().astype(bool)
+        outside = np.abs(rd + 0.001) > 1e-3
+        r = {'checked': int(len(rb)), 'verdict_mismatches_outside_1mm_band': int((gb[outside] != rb[outside]).sum()),
+             'verdict_mismatches_inside_band': int((gb[~outside] != rb[~outside]).sum())}
+        if gd is not None:
+            r['max_abs_distance_error_m'] = float(np.abs(gd.cpu().numpy().astype(np.float64) - rd).max())
+        return r
+
+    # ---- config 3: every scenario, 1 M configurations each on this GPU (the full-size run is 10 M each over 8 GPUs:
+    #      tools/bench_sharded.py; per-GPU work is the same per configuration)
+    n3 = 1_000_000
+    ms3, rates = 0.0, {}
+    for sid in SCENARIO_IDS:
+        scene = SceneModel.load(os.path.join(data, f'scene_{sid:03d}.npz'))
+        eng = CollisionEngine(robot, scene, device=dev.index)
+        q = torch.from_numpy(make_configs(robot, n3, sid)).to(dev)
+        ms = timed(lambda: eng.check(q, flags=SCENE | PLANE, packed=True), reps=2, warm=2)
+        ms3 += ms
+        rates[f'{sid:03d}'] = n3 / ms * 1e3
+        eng.close()
+        del eng, q
+    out['config3_all_20_scenarios'] = {
+        'workload': f'{len(SCENARIO_IDS)} scenarios x {n3} uniform configurations (seed = scenario id), bit + min distance, 1 GPU',
+        'checks_per_s': len(SCENARIO_IDS) * n3 / ms3 * 1e3, 'ms_total': ms3,
+        'slowest_scenario_checks_per_s': min(rates.values()), 'fastest_scenario_checks_per_s': max(rates.values()),
+        'parity': 'tests/test_gpu_sweeps.py::test_sweep_all_flags_every_scenario (50 000 per scenario vs the oracle)'}
+
+    # ---- config 4: scenario 034, 1 M edges x 64 substeps
+    scene = SceneModel.load(os.path.join(data, 'scene_034.npz'))
+    eng = CollisionEngine(robot, scene, device=dev.index)
+    m = 1_000_000
+    qa = make_configs(robot, m, 34)
+    qb = np.clip(qa + np.random.default_rng(3400).uniform(-0.25, 0.25, qa.shape), lim[:, 0], lim[:, 1]).astype(np.float32)
+    qa_d, qb_d = torch.from_numpy(qa).to(dev), torch.from_numpy(qb).to(dev)
+    ms_d = timed(lambda: eng.check_edges(qa_d, qb_d, substeps=64, packed=True))
+    ms_v = timed(lambda: eng.check_edges(qa_d, qb_d, substeps=64, packed=True, want_dist=False))
+    k = 2000
+    o = oracle.Oracle(robot, scene)
+    rb, rd = o.check_edges(qa[:k].astype(np.float64), qb[:k].astype(np.float64), substeps=64)
+    gb, gd = eng.check_edges(qa_d[:k], qb_d[:k], substeps=64)
+    gbv, _ = eng.check_edges(qa_d[:k], qb_d[:k], substeps=64, want_dist=False)
+    bits_all, _ = eng.check_edges(qa_d, qb_d, substeps=64)
+    out['config4_edges'] = {
+        'workload': 'scenario 034: 1 000 000 edges x 64 interpolated substeps (qa seed 34, qb = clip(qa + U(-0.25, 0.25)) seed 3400); '
+                    'checks counted = edges x 64, no early-exit credit',
+        'verdict_and_distance': {'ms': ms_d, 'substep_checks_per_s': m * 64 / ms_d * 1e3, 'edges_per_s': m / ms_d * 1e3,
+                                 'parity': parity(gb, gd, rb, rd)},
+        'verdict_only': {'ms': ms_v, 'substep_checks_per_s': m * 64 / ms_v * 1e3, 'edges_per_s': m / ms_v * 1e3,
+                         'parity': parity(gbv, None, rb, rd)},
+        'edge_collision_rate': float(bits_all.float().mean().item())}
+    eng.close()
+    del qa_d, qb_d
+
+    # ---- config 5: scenario 011, 10 M free-floating gripper poses
+    scene = SceneModel.load(os.path.join(data, 'scene_011.npz'))
+    eng = CollisionEngine(robot, scene, device=dev.index)
+    m = 10_000_000
+    tgt = scene.piece(0)
+    lo, hi = tgt.min(0) - 0.25, tgt.max(0) + 0.25
+    pq = random_poses(np.random.default_rng(5011), lo, hi, m)
+    pq_d = torch.from_numpy(pq).to(dev)
+    links = [robot.end_effector_id - 3, *robot.finger_joint_ids]
+    ms_p = timed(lambda: eng.check_poses(pq_d, links=links, packed=True))
+    k = 20000
+    T = quat_poses_to_mat(pq[:k])
+    o = oracle.Oracle(robot, scene)
+    rb, rd = o.check_poses(T, links=links, flags=3)
+    gb, gd = eng.check_poses(pq_d[:k], links=links)
+    bits_all, _ = eng.check_poses(pq_d, links=links)
+    c5 = {'workload': 'scenario 011: 10 000 000 free-floating gripper poses (position uniform in the target box + 0.25 m, '
+                      'uniform rotations, seed 5011) vs target + obstacles + plane',
+          'panda_hand_hulls': {'model': 'panda_hand + two finger hulls at 0.04, Bullet margins, convex pieces, bit + signed distance',
+                               'ms': ms_p, 'poses_per_s': m / ms_p * 1e3, 'collision_rate': float(bits_all.float().mean().item()),
+                               'parity': parity(gb, gd, rb, rd)}}
+    eng.close()
+    # the reference's own filter (create_graspset.py:53-59): burg two-finger gripper vs the visual meshes, boolean
+    try:
+        from jogramop_framework_b200.scenario import Scenario
+        from jogramop_framework_b200.simulation import GraspingSimulator
+        from jogramop_framework_b200.graspset import burg_gripper_model
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            scn = Scenario(11, device=dev.index)
+        vis = scn.visual_scene_model()
+        sim = GraspingSimulator(device=dev.index)
+        mb = 2_000_000
+        Tw = scn.robot_pose @ np.concatenate([quat_poses_to_mat(pq[:mb]), np.tile([[[0, 0, 0, 1.0]]], (mb, 1, 1))], 1)
+        sim.burg_gripper_collision_batch(Tw[:1000], visual_model=vis)        # builds the engine + LBVH
+        geng = next(iter(sim._gripper_engines.values()))
+        Tr = torch.from_numpy(np.ascontiguousarray(quat_poses_to_mat(pq[:mb]).astype(np.float32))).to(dev)
+        ms_b = timed(lambda: geng.check_poses(Tr, links=[0], ee_link=0, want_dist=False, packed=True), reps=2, warm=1)
+        hit, _ = geng.check_poses(Tr[:5000], links=[0], ee_link=0, want_dist=False)
+        import copy
+        tri = copy.copy(vis)
+        tri.piece_verts = vis.tri_verts[vis.tris].reshape(-1, 3)
+        tri.piece_vert_offset = (np.arange(len(vis.tris) + 1) * 3).astype(np.int32)
+        tri.piece_body, tri.piece_margin = vis.tri_body, np.zeros(len(vis.tris))
+        og = oracle.Oracle(burg_gripper_model(), tri)
+        _, dd = og.check_poses(quat_poses_to_mat(pq[:5000]), links=[0], ee_link=0,
+                               flags=oracle.SCENE | oracle.PLANE | oracle.NO_EPA, threshold=1e-9)
+        hb, rbg = hit.cpu().numpy().astype(bool), dd <= 1e-9
+        touching = (dd > 1e-9) & (dd <= 2e-5)          # clear of every surface by less than 20 um: either verdict is fine
+        c5['burg_gripper_visual_meshes'] = {
+            'model': 'burg two-finger gripper (3 zero-margin boxes) vs the mesh_fn meshes behind the GPU-built LBVH '
+                     f'({len(vis.tris)} triangles) + plane, boolean (the reference filter); {mb} of the 10 M poses',
+            'ms': ms_b, 'poses_per_s': mb / ms_b * 1e3, 'collision_rate': float(hb.mean()),
+            'parity': {'checked': 5000, 'verdict_mismatches': int((hb != rbg).sum()),
+                       'verdict_mismatches_outside_20um_band': int((hb != rbg)[~touching].sum()),
+                       'poses_within_20um_of_touching': int(touching.sum())}}
+        sim.dismiss()
+    except Exception as exc:
+        c5['burg_gripper_visual_meshes'] = {'unavailable': repr(exc)[:300]}
+    out['config5_gripper_poses'] = c5
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -166,49 +338,68 @@ def run_b200(args):
     robot, scene = load_models(args.scenario)
     flags = SCENE | PLANE | (NO_EPA if args.no_epa else 0)
     n = args.n
-    q_host = make_configs(robot, n, 11 + 1000 * rank)
+    ROT = 4                                    # rotating input batches: 4 x 36 MB > L2
+    q_hosts = [make_configs(robot, n, 11 + 1000 * rank + 7919 * r) for r in range(ROT)]
+    q_host = q_hosts[0]
     eng = CollisionEngine(robot, scene, device=local, chunk=args.chunk)
-    q_dev = torch.from_numpy(q_host).to(dev)
+    q_devs = [torch.from_numpy(q).to(dev) for q in q_hosts]
+    q_dev = q_devs[0]
     words = (n + 31) // 32
-    gathered = torch.empty((world * words,), dtype=torch.int32, device=dev)
-    my_slot = gathered[rank * words:(rank + 1) * words]
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)   # > 126 MB L2
+    # the receive buffers of the all-gather, double-buffered; the kernels write into this rank's slot of one of them
+    gathered = [torch.zeros((world * words,), dtype=torch.int32, device=dev) for _ in range(2)]
+    slots = [g[rank * words:(rank + 1) * words] for g in gathered]
+    dist_out = torch.empty((n,), dtype=torch.float32, device=dev)
+    side = torch.cuda.Stream(device=dev)
+    ev_check = [torch.cuda.Event() for _ in range(2)]
+    ev_gather = [torch.cuda.Event() for _ in range(2)]
+    gather_pending = [False, False]
 
     fp32_peak = measure_fp32_peak(local) if rank == 0 else None
 
-    def step():
-        bits, d, _ = eng.check(q_dev, flags=flags, packed=True)
+    def step(i):
+        b = i & 1
+        main = torch.cuda.current_stream(dev)
+        if gather_pending[b]:
+            main.wait_event(ev_gather[b])      # the gather of step i-2 read this slot: long finished
+        eng.check(q_devs[i % ROT], flags=flags, packed=True, bits_out=slots[b], dist_out=dist_out)
         if world > 1:
-            my_slot.copy_(bits)
-            dist.all_gather_into_tensor(gathered, my_slot)
-        return bits, d
+            ev_check[b].record(main)
+            side.wait_event(ev_check[b])
+            with torch.cuda.stream(side):      # the all-gather of step i runs under the kernels of step i+1
+                dist.all_gather_into_tensor(gathered[b], slots[b])
+                ev_gather[b].record(side)
+            gather_pending[b] = True
+
+    def drain():
+        torch.cuda.current_stream(dev).wait_stream(side)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    drain()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
     eng.profile(True)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     wall0 = time.perf_counter()
+    ev0.record()
     for s in range(args.steps):
-        flush.zero_()                   # evict the 36 MB input from L2 between timed iterations
-        ev[s][0].record()
-        step()
-        ev[s][1].record()
+        step(s)
+    drain()                                     # the timed region ends when the last all-gather has finished
+    ev1.record()
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
     prof = eng.get_profile()
     eng.profile(False)
     stats = eng.stats()
-    ms = sum(a.elapsed_time(b) for a, b in ev)
+    ms = ev0.elapsed_time(ev1)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -216,15 +407,16 @@ def run_b200(args):
     value = world * n * args.steps / (ms_total * 1e-3)
 
     # ---- end to end through the host-buffer entry point
-    q_pin = torch.from_numpy(q_host).pin_memory()
+    q_pins = [torch.from_numpy(q).pin_memory() for q in q_hosts]
+    q_pin = q_pins[0]
     out = {'bits': torch.empty((words,), dtype=torch.int32, pin_memory=True),
            'dist': torch.empty((n,), dtype=torch.float32, pin_memory=True), 'reason': None}
     for _ in range(2):
         eng.check_host(q_pin, flags=flags, out=out)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        eng.check_host(q_pin, flags=flags, out=out)      # returns when the results are in host memory
+    for s_i in range(args.steps):
+        eng.check_host(q_pins[s_i % ROT], flags=flags, out=out)      # returns when the results are in host memory
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -239,9 +431,9 @@ def run_b200(args):
     eng.check_host_wait(eng.check_host_submit(q_pin, flags=flags, out=outs[0]))
     barrier()
     t0 = time.perf_counter()
-    tk = eng.check_host_submit(q_pin, flags=flags, out=outs[0])
+    tk = eng.check_host_submit(q_pins[0], flags=flags, out=outs[0])
     for s_i in range(1, args.steps):
-        nxt = eng.check_host_submit(q_pin, flags=flags, out=outs[s_i & 1])
+        nxt = eng.check_host_submit(q_pins[s_i % ROT], flags=flags, out=outs[s_i & 1])
         eng.check_host_wait(tk)
         tk = nxt
     eng.check_host_wait(tk)
@@ -268,16 +460,27 @@ def run_b200(args):
         except Exception:
             pass
         hbm_peak = peaks.get('hbm_gbs', 6650.0)
+        traffic = None
+        try:
+            with open(TRAFFIC_FILE) as fh:
+                traffic = json.load(fh)
+        except Exception:
+            pass
+        use_traffic = traffic is not None and args.scenario == 11 and not args.no_epa and n == traffic.get('configs_per_pass')
+        step_tf = value / world * FLOPS_PER_CHECK / 1e12
         line = {
             'metric': 'configuration collision checks/sec', 'value': value, 'unit': 'checks/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_total / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': f'scenario {args.scenario:03d}: {n} uniformly sampled mobile-Panda configurations per GPU, '
                                    'collision bit + signed min distance (SCENE+PLANE)',
-                       'configs_per_gpu': n, 'seed': '11 + 1000*rank', 'flags': int(flags),
+                       'configs_per_gpu': n, 'seed': '11 + 1000*rank (+ 7919*r for the rotating batches r = 1..3)', 'flags': int(flags),
                        'penetration_depth': 'clamped at -(marginA+marginB) (JG_NO_EPA)' if args.no_epa else 'EPA',
-                       'l2': 'flushed between timed iterations (256 MB write)',
-                       'collective': 'ncclAllGather of packed verdict bits' if world > 1 else 'none (1 GPU)',
+                       'l2': f'inputs larger than L2: the steps rotate over {ROT} different {n}-configuration batches '
+                             f'({ROT * n * 36 / 1e6:.0f} MB > 126 MB L2); one CUDA-event pair around all timed steps',
+                       'collective': ('ncclAllGather of the packed verdict bits, in place (the kernels write into the rank\'s slot), '
+                                      'on a side stream under the next step\'s kernels; the timed region ends after the last gather')
+                       if world > 1 else 'none (1 GPU)',
                        'pass_size': args.chunk or 'auto (<= 2^20 configurations per pass)',
                        'cpu_affinity': f'process bound to the {bound} CPUs local to its GPU (NVML)' if bound else 'not set'},
             'clocks': clocks,
@@ -290,13 +493,23 @@ def run_b200(args):
             'roofline': {'bound': 'fp32', 'kernel': 'narrow phase (k_narrowphase GJK stages + k_penetration stages)',
                          'achieved': ach_tf, 'peak': fp32_peak,
                          'unit': 'TFLOP/s', 'frac': (ach_tf / fp32_peak) if (ach_tf and fp32_peak) else None,
-                         'traffic': (NARROW_TRAFFIC_BYTES_PER_CHECK_NCU * n if (args.scenario == 11 and not args.no_epa) else None),
-                         'traffic_source': 'ncu dram__bytes_read.sum + dram__bytes_write.sum per pass, profiles/r01_m_ncu_full_summary.csv',
+                         'traffic': traffic.get('whole_pass_bytes') if use_traffic else None,
+                         'traffic_detail': ({'source': 'profiles/r02_traffic.json: ncu --set full, dram__bytes_read.sum + '
+                                                       'dram__bytes_write.sum summed over ALL kernels of one pass',
+                                             'commit': traffic.get('commit'), 'per_kernel_bytes': traffic.get('per_kernel_bytes'),
+                                             'narrow_phase_bytes': traffic.get('narrow_phase_bytes'),
+                                             'algorithmic_bytes': BYTES_PER_CHECK * n,
+                                             'ratio_to_algorithmic': traffic.get('whole_pass_bytes') / (BYTES_PER_CHECK * n)}
+                                            if use_traffic else None),
                          'peak_source': 'jg_measure_fp32_peak FMA micro-benchmark on this GPU',
                          'algorithmic_flops_per_check': FLOPS_PER_CHECK_NARROW,
                          'avg_launch_ms': nar_ms / np_n if np_n else None, 'launches': int(np_n),
+                         'whole_step': {'flops_per_check': FLOPS_PER_CHECK, 'achieved': step_tf,
+                                        'frac': step_tf / fp32_peak if fp32_peak else None,
+                                        'note': 'SURVEY 8(d): checks/s per GPU x 1.5e4 nominal flops / FP32 peak'},
                          'note': 'algorithmic = nominal work of an unpruned narrow phase; the champion-first pruning '
-                                 'executes far fewer flops, so frac is work-avoided + pipe-utilisation combined'},
+                                 'executes far fewer flops, so frac is work-avoided + pipe-utilisation combined; '
+                                 'counted.executed_frac is the pipe utilisation alone'},
             'roofline_hbm': {'bound': 'hbm', 'achieved': checks_timed * BYTES_PER_CHECK / (ms_total * 1e-3) / 1e9,
                              'peak': hbm_peak, 'unit': 'GB/s',
                              'frac': checks_timed * BYTES_PER_CHECK / (ms_total * 1e-3) / 1e9 / hbm_peak,
@@ -310,6 +523,41 @@ def run_b200(args):
                      'polytopes_expanded_per_check': stats['epa_run'] / max(stats['configs'], 1)},
             'wall_s_timed_region': wall,
         }
+        if world == 1 and not args.no_extras:
+            # ---- the pass as ONE CUDA-graph launch (engine.capture_check), same rotating inputs
+            try:
+                graphs = [eng.capture_check(q, flags=flags) for q in q_devs]
+                for g in graphs:
+                    g[0]()
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for s_i in range(args.steps):
+                    graphs[s_i % ROT][0]()
+                b.record()
+                torch.cuda.synchronize()
+                gms = a.elapsed_time(b) / args.steps
+                same = torch.equal(graphs[0][1], eng.check(q_devs[0], flags=flags, packed=True)[0])
+                line['cuda_graph'] = {'value': n / gms * 1e3, 'ms_per_step': gms, 'api': 'CollisionEngine.capture_check: '
+                                      'the pass replayed as one graph launch', 'bits_identical_to_plain_launches': bool(same)}
+                del graphs
+            except Exception as exc:
+                line['cuda_graph'] = {'unavailable': repr(exc)[:200]}
+            # ---- soak: the same step looped for 2 s, NVML clock samples every 5 ms
+            soak = ClockSampler(local)
+            soak.start()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            k = 0
+            while time.perf_counter() - t0 < args.soak:
+                for _ in range(20):
+                    eng.check(q_devs[k % ROT], flags=flags, packed=True, bits_out=slots[0], dist_out=dist_out)
+                    k += 1
+                torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            sc = soak.stop()
+            line['soak'] = {'seconds': dt, 'steps': k, 'value': k * n / dt, 'unit': 'checks/s (wall clock incl. one sync per 20 steps)',
+                            'clocks': sc}
         if world == 1 and not args.no_count:
             # audit of the nominal figure: executed work counted by the instrumented twin of the library, in a
             # subprocess after the timed region (never timed, never the shipped path)
@@ -337,7 +585,9 @@ def run_b200(args):
             v, used, cores, rb, rd = time_oracle(robot, scene, q_host, oflags, 0, args.cpu_budget)
             line['cpu_baseline'] = {'value': v, 'unit': 'checks/s', 'cores': cores, 'kind': 'port',
                                     'sample': f'first {used} of the {n} configurations, all host threads; CPU oracle '
-                                              'restatement (double precision) - pyBullet not installable in this image'}
+                                              'restatement (double precision) - pyBullet not installable in this image; '
+                                              'the oracle itself is pinned by the reference\'s golden artefacts '
+                                              '(known-negatives only, see BASELINE.md)'}
             # the oracle's answers for that sample are the checker of the timed path (not timed, not shipped)
             gb, gd, _ = eng.check(q_dev[:used], flags=flags)
             gb, gd = gb.cpu().numpy().astype(bool), gd.cpu().numpy().astype(np.float64)
@@ -348,6 +598,14 @@ def run_b200(args):
                               'configs_inside_band': int((~outside).sum()),
                               'max_abs_distance_error_m': float(np.abs(gd - rd).max()),
                               'collision_rate': float(rb.mean())}
+        if world == 1 and not args.no_extras:
+            eng.close()
+            del q_devs, q_pins
+            torch.cuda.empty_cache()
+            try:
+                line['configs'] = bench_other_configs(robot, dev)
+            except Exception as exc:
+                line['configs'] = {'unavailable': repr(exc)[:300]}
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
@@ -366,6 +624,8 @@ def main():
     ap.add_argument('--no-epa', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-count', action='store_true', help='skip the counted-work audit (instrumented library)')
+    ap.add_argument('--no-extras', action='store_true', help='skip the CUDA-graph line, the soak and the configs 3/4/5 block')
+    ap.add_argument('--soak', type=float, default=2.0, help='seconds of the soak loop (sustained clocks)')
     ap.add_argument('--cpu-budget', type=float, default=10.0, help='seconds of CPU work for the cpu_baseline sample')
     ap.add_argument('--ref-sample', type=int, default=200_000, help='configurations per step of the reference arm')
     args = ap.parse_args()

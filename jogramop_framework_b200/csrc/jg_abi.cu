@@ -876,14 +876,20 @@ static int run_narrow_and_finalize(jg_engine* e, const PassArgs& a, int n_out, u
 // host-path stream, or the other way round) first waits for everything the previous call enqueued.
 static int begin_call(jg_engine* e, cudaStream_t st) {
     CUDA_TRY(cudaSetDevice(e->device));
-    if (e->have_last_stream && st != e->last_stream) {
-        if (!e->ev_order) CUDA_TRY(cudaEventCreateWithFlags(&e->ev_order, cudaEventDisableTiming));
-        if (cudaEventRecord(e->ev_order, e->last_stream) == cudaSuccess) CUDA_TRY(cudaStreamWaitEvent(st, e->ev_order, 0));
-        else cudaGetLastError();   // the previous stream no longer exists: its work has completed
+    // a stream that is being captured into a CUDA graph cannot wait on uncaptured work: the caller synchronises before
+    // the capture (CollisionEngine.capture_check does) and orders the replays against other calls itself
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    const bool capturing = cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive;
+    if (!capturing) {
+        if (e->have_last_stream && st != e->last_stream) {
+            if (!e->ev_order) CUDA_TRY(cudaEventCreateWithFlags(&e->ev_order, cudaEventDisableTiming));
+            if (cudaEventRecord(e->ev_order, e->last_stream) == cudaSuccess) CUDA_TRY(cudaStreamWaitEvent(st, e->ev_order, 0));
+            else cudaGetLastError();   // the previous stream no longer exists: its work has completed
+        }
+        e->have_last_stream = true;
+        e->last_stream = st;
     }
-    e->have_last_stream = true;
     e->stats = jg_stats{};
-    e->last_stream = st;
     CUDA_TRY(cudaMemsetAsync(e->d_stats, 0, sizeof(unsigned long long) * 8, st));
     return JG_OK;
 }

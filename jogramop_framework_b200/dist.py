@@ -47,15 +47,53 @@ def gather_distances(local_dist, n_total, group=None, fill=0.0):
     return out[:n_total]
 
 
+class GatherBuffer:
+    """The receive buffer of the verdict all-gather, allocated ONCE: ``slot`` is this rank's part of it, and it is what
+    the collision kernels write their packed words into (``engine.check(..., bits_out=buf.slot)``), so the collective
+    runs in place -- no copy between the finalize kernel and the all-gather."""
+
+    def __init__(self, n_total, device, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n_total = n_total
+        self.words_per_rank = shard_size(n_total, self.world) // 32
+        self.all = torch.zeros((self.world * self.words_per_rank,), dtype=torch.int32, device=device)
+        self.slot = self.all[self.rank * self.words_per_rank:(self.rank + 1) * self.words_per_rank]
+
+    def gather(self, async_op=False):
+        """All ranks' slots -> ``self.all`` (in place).  Returns the words of the n_total configurations (a view), or
+        the work handle when ``async_op``."""
+        if self.world > 1:
+            w = dist.all_gather_into_tensor(self.all, self.slot, group=self.group, async_op=async_op)
+            if async_op:
+                return w
+        return self.all[:(self.n_total + 31) // 32]
+
+
+_gather_buffers = {}
+
+
 def check_sharded(engine, q_all, flags, group=None, want_dist=False):
     """Every rank passes the SAME full batch (or just needs its own rows): checks its shard on its GPU and returns the
-    verdict words (and optionally distances) of the whole batch on every rank."""
+    verdict words (and optionally distances) of the whole batch on every rank.  The kernels write straight into the
+    rank's slot of a cached gather buffer (valid until the next call with the same batch size)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     n = len(q_all)
     lo, hi = shard_bounds(n, world, rank)
-    bits, d, _ = engine.check(q_all[lo:hi], flags=flags, want_dist=want_dist, packed=True)
-    words = gather_bits(bits, n, group)
+    key = (n, str(engine.device), id(group))
+    buf = _gather_buffers.get(key)
+    if buf is None:
+        buf = _gather_buffers[key] = GatherBuffer(n, engine.device, group)
+    if hi - lo < buf.words_per_rank * 32:
+        buf.slot.zero_()          # ragged last shard: words beyond it stay zero
+    d = None
+    if hi > lo:
+        _, d, _ = engine.check(q_all[lo:hi], flags=flags, want_dist=want_dist, packed=True, bits_out=buf.slot)
+    elif want_dist:
+        d = torch.zeros((0,), dtype=torch.float32, device=engine.device)
+    words = buf.gather()
     return (words, gather_distances(d, n, group)) if want_dist else (words, None)
 
 

@@ -127,18 +127,56 @@ class CollisionEngine:
                                      out.data_ptr(), self._stream()), 'jg_fk')
         return out
 
-    def check(self, q, flags=SCENE | PLANE, want_dist=True, want_reason=False, packed=False):
-        """-> (collides bool[n] (or packed int32 words), min_dist fp32[n] | None, reason uint8[n] | None)."""
+    def check(self, q, flags=SCENE | PLANE, want_dist=True, want_reason=False, packed=False, bits_out=None, dist_out=None):
+        """-> (collides bool[n] (or packed int32 words), min_dist fp32[n] | None, reason uint8[n] | None).
+        ``bits_out`` / ``dist_out``: preallocated device tensors the kernels write into directly (int32 words, at least
+        ceil(n/32); fp32 [n]) -- e.g. this rank's slot of an all-gather buffer (``dist.GatherBuffer``), so that no copy
+        sits between the finalize kernel and the collective."""
         q = self._dev_f32(q, self.dof)
         n = q.shape[0]
-        bits = torch.empty(((n + 31) // 32,), device=self.device, dtype=torch.int32)
-        dist = torch.empty((n,), device=self.device, dtype=torch.float32) if want_dist else None
+        words = (n + 31) // 32
+        if bits_out is not None:
+            assert bits_out.dtype == torch.int32 and bits_out.is_contiguous() and bits_out.numel() >= words and \
+                bits_out.device == self.device, 'bits_out must be a contiguous int32 device tensor of >= ceil(n/32) words'
+            bits = bits_out[:words]
+        else:
+            bits = torch.empty((words,), device=self.device, dtype=torch.int32)
+        if dist_out is not None:
+            assert dist_out.dtype == torch.float32 and dist_out.is_contiguous() and dist_out.numel() >= n and \
+                dist_out.device == self.device
+            dist, want_dist = dist_out[:n], True
+        else:
+            dist = torch.empty((n,), device=self.device, dtype=torch.float32) if want_dist else None
         reason = torch.empty((n,), device=self.device, dtype=torch.uint8) if want_reason else None
         with torch.cuda.device(self.device):
             _lib.check(self._L.jg_check(self._e, q.data_ptr(), n, self.dof, flags, bits.data_ptr(),
                                         dist.data_ptr() if want_dist else None,
                                         reason.data_ptr() if want_reason else None, self._stream()), 'jg_check')
         return (bits if packed else unpack_bits(bits, n)), dist, reason
+
+    def capture_check(self, q, flags=SCENE | PLANE, want_dist=True, want_reason=False):
+        """Capture one ``check`` of the device tensor ``q`` [n,dof] (n <= one pass) into a CUDA graph: the ~10 launches of
+        a pass replay as ONE graph launch.  Returns (replay, bits, dist, reason): calling ``replay()`` re-runs the pass
+        on the current contents of ``q`` and overwrites the returned output tensors (packed int32 words, fp32, uint8).
+        Worth it for small batches issued over and over (a planner validating batch after batch), where launch gaps
+        are a visible share of the pass."""
+        assert isinstance(q, torch.Tensor) and q.is_cuda and q.dtype == torch.float32 and q.is_contiguous()
+        n = q.shape[0]
+        bits = torch.empty(((n + 31) // 32,), device=self.device, dtype=torch.int32)
+        dist = torch.empty((n,), device=self.device, dtype=torch.float32) if want_dist else None
+        reason = torch.empty((n,), device=self.device, dtype=torch.uint8) if want_reason else None
+
+        def run():
+            _lib.check(self._L.jg_check(self._e, q.data_ptr(), n, self.dof, flags, bits.data_ptr(),
+                                        dist.data_ptr() if want_dist else None,
+                                        reason.data_ptr() if want_reason else None, self._stream()), 'jg_check')
+        with torch.cuda.device(self.device):
+            run()                                   # grows the arena to its final size outside the capture
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                run()
+        return g.replay, bits, dist, reason
 
     def check_edges(self, qa, qb, substeps=64, flags=SCENE | PLANE, want_dist=True, packed=False):
         qa, qb = self._dev_f32(qa, self.dof), self._dev_f32(qb, self.dof)

@@ -53,11 +53,14 @@ def _worker(rank, world, port, n, q, expected_words, expected_dist):
         scene = SceneModel.load(os.path.join(data, 'scene_034.npz'))
         o = oracle.Oracle(robot, scene)
 
-        class OracleAsEngine:   # same call shape as CollisionEngine.check(packed=True)
-            def check(self, qq, flags, want_dist, packed):
-                b, d = o.check(np.asarray(qq, dtype=np.float64), flags=flags, n_threads=1) if len(qq) else \
-                    (np.zeros(0, bool), np.zeros(0))
-                return torch.from_numpy(jd.pack_bits_numpy(b).copy()), torch.from_numpy(d.astype(np.float32)), None
+        class OracleAsEngine:   # same call shape as CollisionEngine.check(packed=True, bits_out=slot)
+            device = torch.device('cpu')
+
+            def check(self, qq, flags, want_dist, packed, bits_out):
+                b, d = o.check(np.asarray(qq, dtype=np.float64), flags=flags, n_threads=1)
+                w = torch.from_numpy(jd.pack_bits_numpy(b).copy())
+                bits_out[:len(w)].copy_(w)      # the kernels write straight into the rank's slot of the gather buffer
+                return bits_out[:len(w)], torch.from_numpy(d.astype(np.float32)), None
 
         words, d = jd.check_sharded(OracleAsEngine(), q, flags=3, want_dist=True)
         assert torch.equal(words, torch.from_numpy(expected_words)), f'rank {rank}: gathered bitmask differs'
