@@ -369,6 +369,12 @@ static int build_tables(jg_engine* e, const jg_robot* r, const jg_scene* sc) {
         J.axis[0] = (float)ax; J.axis[1] = (float)ay; J.axis[2] = (float)az;
         J.type = r->joint_type[i];
         J.qidx = r->joint_qidx[i];
+        {
+            const float I12[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+            bool ident = true;
+            for (int k = 0; k < 12; ++k) ident = ident && J.o[k] == I12[k];
+            J.fast = (ident ? 1 : 0) | ((J.type == JG_JOINT_REVOLUTE && J.axis[0] == 0.f && J.axis[1] == 0.f && J.axis[2] == 1.f) ? 2 : 0);
+        }
         const int p = r->joint_parent[i];
         if (p == -1) J.parent_sel = 2;
         else if (p == i - 1) J.parent_sel = 0;

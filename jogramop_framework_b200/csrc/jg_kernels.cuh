@@ -22,6 +22,9 @@
 
 namespace jg {
 
+#ifndef JG_BP_OCC
+#define JG_BP_OCC 7   /* resident blocks per SM the broad phase is compiled for (register budget) */
+#endif
 constexpr int MAX_LINKS = 24;
 constexpr int MAX_SHAPES = 24;
 constexpr int MAX_DOF = 16;
@@ -36,6 +39,7 @@ struct JointRec {
     int shape_first, shape_count;
     int self_first, self_count;   // self-collision pairs whose SECOND link is this one (sorted by second link)
     int stash_slot;               // >= 0: this link is the first link of some pair: keep its frame in shared memory
+    int fast;                     // bit 0: the origin is the identity; bit 1: revolute about +z of the joint frame
 };
 
 struct ShapeRec {
@@ -54,12 +58,15 @@ struct RobotTab {
     ShapeRec shapes[MAX_SHAPES];
 };
 
-struct PieceRec {
+static_assert(sizeof(RobotTab) % 16 == 0, "the piece table follows the robot table in shared memory and is read in 16-byte words");
+
+struct __align__(16) PieceRec {
     float c[3], h[3];  // AABB centre / half extents (robot frame); vertices are stored relative to c
     float margin;
     int voff, vn;
     int pad[3];
 };
+static_assert(sizeof(PieceRec) == 48, "PieceRec is read as three 16-byte words");
 
 struct SelfRec {
     int sa, sb;        // shape ids (sa = shape of the first link: the static "B" side of the GJK)
@@ -178,6 +185,35 @@ __device__ __forceinline__ Tf joint_local(const JointRec& J, float val) {
         O.tz = fmaf(O.r20, ax, fmaf(O.r21, ay, fmaf(O.r22, az, O.tz)));
     }
     return O;
+}
+
+// parent frame x joint origin x joint motion, specialised for what the chains of this repo are made of: identity origins
+// (the platform joints) and revolutes about the joint frame's z axis (every Panda joint): the z rotation only mixes the
+// first two columns of (parent x origin).  Anything else takes the generic path.
+__device__ __forceinline__ Tf chain_step(const Tf& par, const JointRec& J, float val) {
+    if (J.type == 1 && !(J.fast & 2)) return tf_mul(par, joint_local(J, val));
+    Tf A = par;
+    if (!(J.fast & 1)) {
+        Tf O;
+        O.r00 = J.o[0]; O.r01 = J.o[1]; O.r02 = J.o[2];  O.tx = J.o[3];
+        O.r10 = J.o[4]; O.r11 = J.o[5]; O.r12 = J.o[6];  O.ty = J.o[7];
+        O.r20 = J.o[8]; O.r21 = J.o[9]; O.r22 = J.o[10]; O.tz = J.o[11];
+        A = tf_mul(par, O);
+    }
+    if (J.type == 1) {
+        float s, c;
+        sincosf(val, &s, &c);
+        const float a00 = A.r00, a10 = A.r10, a20 = A.r20;
+        A.r00 = fmaf(c, a00, s * A.r01);  A.r01 = fmaf(c, A.r01, -s * a00);
+        A.r10 = fmaf(c, a10, s * A.r11);  A.r11 = fmaf(c, A.r11, -s * a10);
+        A.r20 = fmaf(c, a20, s * A.r21);  A.r21 = fmaf(c, A.r21, -s * a20);
+    } else if (J.type == 2) {
+        const float ax = J.axis[0] * val, ay = J.axis[1] * val, az = J.axis[2] * val;
+        A.tx = fmaf(A.r00, ax, fmaf(A.r01, ay, fmaf(A.r02, az, A.tx)));
+        A.ty = fmaf(A.r10, ax, fmaf(A.r11, ay, fmaf(A.r12, az, A.ty)));
+        A.tz = fmaf(A.r20, ax, fmaf(A.r21, ay, fmaf(A.r22, az, A.tz)));
+    }
+    return A;
 }
 
 // A configuration's champion = its queued pair with the largest penetration bound.  All pairs of a configuration are
@@ -393,25 +429,39 @@ __device__ __forceinline__ void shape_vs_scene(const PassArgs& a, const ShapeRec
     const WorldBox wb = world_box(T, Sh);
     for (int c0 = k_lo; c0 < k_hi; c0 += 32) {   // chunks of 32 keys (one chunk unless a scene has > 31 pieces)
         const int c1 = min(c0 + 32, k_hi);
-        unsigned hm = 0u, mymask = 0u;
+        // (1) every lane tests ITS shape against all keys of the chunk on its own: the cheap first look (world boxes) in
+        // a straight loop without votes, then the second look (shape's own box axes) only on the few survivors.  Bit k of
+        // `hm` = this lane hits key c0 + k.
+        unsigned hm = 0u;
         int k_a = -1, k_b = -1;      // the lane's first two hits keep their box overlap (the bound that ranks the pair)
         float ov_a = 0.f, ov_b = 0.f;
-        for (int k = c0; k < c1; ++k) {
-            bool hit;
-            if (k < a.P) {
-                float ov;
-                hit = valid && piece_test(a, Sh, pieces[k], T, wb, ov);
-                if (hit) {
-                    if (k_a < 0) { k_a = k; ov_a = ov; }
-                    else if (k_b < 0) { k_b = k; ov_b = ov; }
-                }
-            } else {
-                hit = valid && plane_test(a, Sh, T, wb);
+        if (valid) {
+            const int pe = min(c1, a.P);
+            const float slack = a.qd + Sh.margin;
+            for (int k = c0; k < pe; ++k) {
+                // box + margin of the piece in two 16-byte broadcast reads: (c0 c1 c2 h0) (h1 h2 margin .)
+                const float4 pa = reinterpret_cast<const float4*>(pieces + k)[0], pb = reinterpret_cast<const float4*>(pieces + k)[1];
+                const float ov1 = fminf(fminf(wb.hx + pa.w - fabsf(wb.cx - pa.x), wb.hy + pb.x - fabsf(wb.cy - pa.y)),
+                                        wb.hz + pb.y - fabsf(wb.cz - pa.z));
+                if (ov1 + slack + pb.z >= 0.f) hm |= 1u << (k - c0);
             }
-            const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
-            if (hit) hm |= 1u << (k - c0);
-            if (lane == k - c0) mymask = m;
+            for (unsigned h2 = hm; h2 != 0u; h2 &= h2 - 1u) {
+                const int b = __ffs(h2) - 1;
+                float ov;
+                if (!piece_test(a, Sh, pieces[c0 + b], T, wb, ov)) hm &= ~(1u << b);
+                else if (k_a < 0) { k_a = c0 + b; ov_a = ov; }
+                else if (k_b < 0) { k_b = c0 + b; ov_b = ov; }
+            }
+            if (c1 > a.P && plane_test(a, Sh, T, wb)) hm |= 1u << (a.P - c0);
         }
+        // (2) one vote per key that ANY lane hit (lane k keeps the warp's ballot of key k) ...
+        unsigned mymask = 0u;
+        for (unsigned un = __reduce_or_sync(0xFFFFFFFFu, hm); un != 0u; un &= un - 1u) {
+            const int b = __ffs(un) - 1;
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, (hm >> b) & 1u);
+            if (lane == b) mymask = m;
+        }
+        // (3) ... lanes 0..P reserve the slots of their keys side by side: ONE atomic round trip per shape
         int mybase = 0;
         if (mymask != 0u) {
             const int k = c0 + lane;
@@ -419,13 +469,17 @@ __device__ __forceinline__ void shape_vs_scene(const PassArgs& a, const ShapeRec
             // plane entries go straight onto the key's stage-1 list: same slots, same count (the list is the identity)
             if (k == a.P && local != nullptr) atomicAdd(cnt_act(a) + key0 + k, __popc(mymask));
         }
-        unsigned un = __reduce_or_sync(0xFFFFFFFFu, hm);
-        while (un != 0u) {
-            const int b = __ffs(un) - 1;
-            un &= un - 1u;
+        // (4) every lane writes ITS OWN hits (lanes work on different keys side by side; the key's ballot and base come
+        // from the lane that reserved it by a shuffle with a per-lane source)
+        const int rounds = __reduce_max_sync(0xFFFFFFFFu, __popc(hm));
+        unsigned mine = hm;
+        for (int it = 0; it < rounds; ++it) {
+            const bool have = mine != 0u;
+            const int b = have ? __ffs(mine) - 1 : 0;
+            mine &= mine - 1u;
             const unsigned m = __shfl_sync(0xFFFFFFFFu, mymask, b);
             const int base = __shfl_sync(0xFFFFFFFFu, mybase, b);
-            if (!((hm >> b) & 1u)) continue;
+            if (!have) continue;
             const int k = c0 + b;
             const int idx = base + __popc(m & ((1u << lane) - 1u));
             const size_t slot = (size_t)(key0 + k) * a.cap + idx;
@@ -454,7 +508,7 @@ __device__ __forceinline__ void shape_vs_scene(const PassArgs& a, const ShapeRec
 }
 
 template <int BLOCK, bool MESH>
-__global__ void __launch_bounds__(BLOCK, 7) k_broadphase(const PassArgs a) {
+__global__ void __launch_bounds__(BLOCK, JG_BP_OCC) k_broadphase(const PassArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RobotTab* R = reinterpret_cast<RobotTab*>(smem_raw);
     PieceRec* pieces = reinterpret_cast<PieceRec*>(smem_raw + sizeof(RobotTab));
@@ -525,10 +579,9 @@ __global__ void __launch_bounds__(BLOCK, 7) k_broadphase(const PassArgs a) {
         float val = 0.f;
         if (J.qidx >= 0) val = qs[J.qidx * BLOCK + tid];
         else if (J.qidx == -2) val = a.finger_open;
-        const Tf loc = joint_local(J, val);
-        if (J.parent_sel == 1) cur = tf_mul(saved, loc);
-        else if (J.parent_sel == 2) cur = loc;
-        else cur = tf_mul(cur, loc);
+        if (J.parent_sel == 1) cur = chain_step(saved, J, val);
+        else if (J.parent_sel == 2) cur = joint_local(J, val);
+        else cur = chain_step(cur, J, val);
         if (J.save) saved = cur;
         if (want_self) {
             // pairs (la, i): la's frame was stashed when the chain passed it; the pair is tested in la's frame
@@ -1399,10 +1452,9 @@ __global__ void __launch_bounds__(BLOCK) k_fk(const RobotTab* __restrict__ robot
         float val = 0.f;
         if (J.qidx >= 0) val = qs[J.qidx * BLOCK + tid];
         else if (J.qidx == -2) val = finger_open;
-        const Tf loc = joint_local(J, val);
-        if (J.parent_sel == 1) cur = tf_mul(saved, loc);
-        else if (J.parent_sel == 2) cur = loc;
-        else cur = tf_mul(cur, loc);
+        if (J.parent_sel == 1) cur = chain_step(saved, J, val);
+        else if (J.parent_sel == 2) cur = joint_local(J, val);
+        else cur = chain_step(cur, J, val);
         if (J.save) saved = cur;
         const int slot = link_slot[i];
         if (slot >= 0) {

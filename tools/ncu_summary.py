@@ -42,7 +42,7 @@ def traffic(commit, n_configs, report):
         return float(r[i].replace(',', '')) * scale.get(units[i], 1.0)
     per, total, narrow = [], 0.0, 0.0
     for r in rows[2:]:
-        name = r[ik].split('(')[0].split('<')[0].replace('jg::', '')
+        name = r[ik].split('(')[0].split('<')[0].replace('jg::', '').replace('void ', '').strip()
         b = val(r, ir) + val(r, iw)
         per.append({'kernel': name, 'read': val(r, ir), 'write': val(r, iw), 'time': r[it] + ' ' + units[it]})
         total += b
