@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define JG_ABI_VERSION 1
+#define JG_ABI_VERSION 2
 
 typedef struct jg_robot jg_robot;
 typedef struct jg_scene jg_scene;
@@ -103,6 +103,64 @@ jg_scene* jg_scene_create(int n_pieces, const int32_t* piece_vert_offset, const 
 jg_scene* jg_scene_create_mesh(int n_verts, const double* verts, int n_tris, const int32_t* tris, double margin,
                                const double* plane);
 void jg_scene_free(jg_scene*);
+
+/* ---- file-level loaders: the same handles straight from the reference's own files, for callers without Python
+ *      (the sister C++ planners, README.md:52-56).  Replace pybullet.loadURDF (simulation.py:137-144) and
+ *      burg Scene.from_yaml + SimulatorBase.add_scene (scenario.py:24,64); semantics of SURVEY.md Appendix A/C/E:
+ *      one convex hull (margin 0.001) per OBJ `o`/`g` shape, a file without groups is ONE shape, <box> embeds its
+ *      margin, link i = child of joint i (depth first, file order), pieces in the ROBOT frame
+ *      inv(robot_pose) @ pose @ v with objects first, then bg_objects (create_cpp_export.py:36,41,60-61), plane z_world = 0.
+ * jg_robot_load: `urdf_path` = robots/franka_panda/{mobile_panda,panda}.urdf; mesh filenames are relative to `mesh_root`
+ *   (NULL = the URDF's directory).  Configuration vector = the movable joints in link order except joints whose name
+ *   contains "finger" (these follow params.finger_open): [base_y, base_x, j1..j7] for the mobile Panda
+ *   (simulation.py:159).  Self-collision pairs = FrankaRobot.in_self_collision's (simulation.py:439-464).
+ * jg_scene_load: `scene_yaml` = scenarios/<id>/scene.yaml (its object_library_fn is followed);  robot_pose = row-major
+ *   4x4 world pose of the robot base, NULL = Scenario.default_robot_pose() (scenario.py:69-80).  Objects with
+ *   scale != 1 are refused (JG_ERR_UNSUPPORTED, create_cpp_export.py:33-34).
+ * jg_scene_load_ex: ungrouped_obj_policy for OBJ files without groups: JG_OBJ_SINGLE_HULL (pyBullet's reading) or
+ *   JG_OBJ_CONNECTED_COMPONENTS (one hull per connected component: SURVEY quirk Q1, the stale gate_0_54_vhacd.obj).
+ * jg_scene_load_mesh: the scene as one triangle mesh (mesh mode): JG_MESH_VHACD = the merged vhacd files (what
+ *   create_cpp_export.py writes as export/obstacles.obj), JG_MESH_VISUAL = the library's mesh_fn meshes (what burg's
+ *   check_collisions tests against, create_graspset.py:54-59). */
+enum { JG_OBJ_SINGLE_HULL = 0, JG_OBJ_CONNECTED_COMPONENTS = 1 };
+enum { JG_MESH_VHACD = 0, JG_MESH_VISUAL = 1 };
+jg_robot* jg_robot_load(const char* urdf_path, const char* mesh_root);
+jg_scene* jg_scene_load(const char* scene_yaml, const double robot_pose[16]);
+jg_scene* jg_scene_load_ex(const char* scene_yaml, const double robot_pose[16], int ungrouped_obj_policy);
+jg_scene* jg_scene_load_mesh(const char* scene_yaml, const double robot_pose[16], int mesh_source, double margin);
+
+/* read-only views of a handle's tables (valid until the handle is freed): what a C caller needs to size its buffers,
+ * and what the tests compare with the Python ingestion */
+typedef struct {
+    int n_links, n_shapes, dof, n_self_pairs;
+    int ee_link;                     /* end-effector link (panda_grasptarget: 14 / 11) or -1 when unknown */
+    const int32_t *joint_type, *joint_parent, *joint_qidx;
+    const double *joint_origin, *joint_axis, *q_limits;
+    const int32_t* shape_link;
+    const double* shape_margin;
+    const int32_t* shape_vert_offset;
+    const double* core_verts;
+    const int32_t* shape_plane_offset;
+    const double* plane_verts;
+    const double* shape_plane_margin;
+    const int32_t* self_pairs;
+} jg_robot_desc;
+typedef struct {
+    int n_pieces;
+    const int32_t* piece_vert_offset;
+    const double* piece_verts;
+    const double* piece_margin;
+    const int32_t* piece_body;       /* body index of every piece (loaded scenes; NULL otherwise) */
+    int n_bodies, n_target_bodies;   /* bodies 0 .. n_target_bodies-1 are the scene's `objects` (grasp targets) */
+    int has_plane;
+    double plane[4];
+    int is_mesh, n_mesh_verts, n_mesh_tris;
+    const float* mesh_verts;
+    const int32_t* mesh_tris;
+} jg_scene_desc;
+int jg_robot_describe(const jg_robot*, jg_robot_desc* out);
+int jg_robot_link_index(const jg_robot*, const char* link_name);   /* link id, or a negative JG_ERR_* */
+int jg_scene_describe(const jg_scene*, jg_scene_desc* out);
 
 /* ---- engine: uploads hulls / pieces to HBM on `device`, owns the scratch arena ---- */
 jg_engine* jg_engine_create(const jg_robot*, const jg_scene* /* may be NULL: FK / self-collision only */,

@@ -40,6 +40,17 @@ def load():
     L.jg_scene_create_mesh.restype = vp
     L.jg_scene_create_mesh.argtypes = [i32, vp, i32, vp, f64, vp]
     L.jg_scene_free.argtypes = [vp]
+    L.jg_robot_load.restype = vp
+    L.jg_robot_load.argtypes = [C.c_char_p, C.c_char_p]
+    L.jg_scene_load.restype = vp
+    L.jg_scene_load.argtypes = [C.c_char_p, vp]
+    L.jg_scene_load_ex.restype = vp
+    L.jg_scene_load_ex.argtypes = [C.c_char_p, vp, i32]
+    L.jg_scene_load_mesh.restype = vp
+    L.jg_scene_load_mesh.argtypes = [C.c_char_p, vp, i32, f64]
+    L.jg_robot_describe.argtypes = [vp, vp]
+    L.jg_robot_link_index.argtypes = [vp, C.c_char_p]
+    L.jg_scene_describe.argtypes = [vp, vp]
     L.jg_engine_create.restype = vp
     L.jg_engine_create.argtypes = [vp, vp, i32, vp]
     L.jg_engine_free.argtypes = [vp]
@@ -67,6 +78,22 @@ class Params(C.Structure):
                 ('chunk', C.c_int32)]
 
 
+class RobotDesc(C.Structure):
+    _P, _D = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+    _fields_ = [('n_links', C.c_int), ('n_shapes', C.c_int), ('dof', C.c_int), ('n_self_pairs', C.c_int), ('ee_link', C.c_int),
+                ('joint_type', _P), ('joint_parent', _P), ('joint_qidx', _P), ('joint_origin', _D), ('joint_axis', _D),
+                ('q_limits', _D), ('shape_link', _P), ('shape_margin', _D), ('shape_vert_offset', _P), ('core_verts', _D),
+                ('shape_plane_offset', _P), ('plane_verts', _D), ('shape_plane_margin', _D), ('self_pairs', _P)]
+
+
+class SceneDesc(C.Structure):
+    _P, _D = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+    _fields_ = [('n_pieces', C.c_int), ('piece_vert_offset', _P), ('piece_verts', _D), ('piece_margin', _D), ('piece_body', _P),
+                ('n_bodies', C.c_int), ('n_target_bodies', C.c_int), ('has_plane', C.c_int), ('plane', C.c_double * 4),
+                ('is_mesh', C.c_int), ('n_mesh_verts', C.c_int), ('n_mesh_tris', C.c_int),
+                ('mesh_verts', C.POINTER(C.c_float)), ('mesh_tris', _P)]
+
+
 class Stats(C.Structure):
     _fields_ = [('configs', C.c_int64), ('pairs', C.c_int64), ('plane_pairs', C.c_int64), ('self_pairs', C.c_int64),
                 ('epa_pairs', C.c_int64), ('gjk_run', C.c_int64), ('epa_run', C.c_int64), ('kernel_launches', C.c_int64),
@@ -81,6 +108,7 @@ def check(rc, what=''):
 
 EXPORTED_SYMBOLS = [
     'jg_default_params', 'jg_last_error', 'jg_abi_version', 'jg_device_count', 'jg_robot_create', 'jg_robot_free',
-    'jg_scene_create', 'jg_scene_create_mesh', 'jg_scene_free', 'jg_engine_create', 'jg_engine_free', 'jg_engine_device', 'jg_fk', 'jg_check',
+    'jg_scene_create', 'jg_scene_create_mesh', 'jg_scene_free', 'jg_robot_load', 'jg_scene_load', 'jg_scene_load_ex', 'jg_scene_load_mesh',
+    'jg_robot_describe', 'jg_robot_link_index', 'jg_scene_describe', 'jg_engine_create', 'jg_engine_free', 'jg_engine_device', 'jg_fk', 'jg_check',
     'jg_check_edges', 'jg_check_poses', 'jg_check_host', 'jg_check_host_submit', 'jg_check_host_wait', 'jg_ik', 'jg_get_stats', 'jg_profile_enable', 'jg_get_profile',
     'jg_measure_fp32_peak', 'jg_work_counters', 'jg_work_counters_reset']

@@ -13,12 +13,14 @@
 #include <vector>
 
 #include "../../include/jogramop_b200.h"
+#include "jg_handles.h"
 #include "jg_kernels.cuh"
 
 using namespace jg;
 
 // ----------------------------------------------------------------------------------------------- errors
 static thread_local std::string g_err;
+int jg_fail(int code, const char* fmt, ...);
 static int fail(int code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
@@ -34,6 +36,15 @@ static int fail(int code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail(JG_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_));   \
     } while (0)
 
+int jg_fail(int code, const char* fmt, ...) {   // for the other translation units of the library
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
 extern "C" const char* jg_last_error(void) { return g_err.c_str(); }
 extern "C" int jg_abi_version(void) { return JG_ABI_VERSION; }
 extern "C" void jg_default_params(jg_params* p) {
@@ -51,24 +62,6 @@ extern "C" int jg_device_count(void) {
 }
 
 // ----------------------------------------------------------------------------------------------- handles
-struct jg_robot {
-    int L = 0, S = 0, dof = 0, K = 0;
-    std::vector<int> joint_type, joint_parent, joint_qidx, shape_link, shape_off, plane_off, self_pairs;
-    std::vector<double> joint_origin, joint_axis, q_limits, shape_margin, core, plane_v, plane_margin;
-};
-
-struct jg_scene {
-    int P = 0;
-    std::vector<int> off;
-    std::vector<double> v, margin;
-    bool is_mesh = false;              // triangle soup behind an LBVH instead of convex pieces
-    std::vector<float> mesh_v;         // [n,3]
-    std::vector<int> mesh_t;           // [m,3]
-    double mesh_margin = 0.001;
-    bool has_plane = false;
-    double plane[4] = {0, 0, 1, 0};
-};
-
 extern "C" jg_robot* jg_robot_create(int L, const int32_t* joint_type, const int32_t* joint_parent,
                                      const double* joint_origin, const double* joint_axis, const int32_t* joint_qidx,
                                      const double* q_limits, int dof, int S, const int32_t* shape_link,

@@ -20,6 +20,23 @@
 #include "jg_epa.cuh"
 #include "jg_lbvh.cuh"
 
+// JG_DEBUG_BOUNDS build (libjogramop_b200_bounds.so): every index into a queue, a stage list or the overflow records is
+// checked on the device before it is used; a violation prints what and where and traps (the launch fails, the test
+// fails).  compute-sanitizer is not available on the GPU pool, so the GPU suite is run once per round against this
+// build instead (profiles/r02_bounds_run.txt).  The shipped library compiles the checks away.
+#if defined(JG_DEBUG_BOUNDS) && !defined(JG_HOST_EMU)
+#define JG_BOUNDS(cond, what)                                                                                       \
+    do {                                                                                                            \
+        if (!(cond)) {                                                                                              \
+            printf("JG_DEBUG_BOUNDS: %s violated at %s:%d (block %d thread %d)\n", what, __FILE__, __LINE__, (int)blockIdx.x, \
+                   (int)threadIdx.x);                                                                                \
+            __trap();                                                                                               \
+        }                                                                                                           \
+    } while (0)
+#else
+#define JG_BOUNDS(cond, what) ((void)0)
+#endif
+
 namespace jg {
 
 #ifndef JG_BP_OCC
@@ -241,6 +258,7 @@ __device__ __forceinline__ void queue_push(const PassArgs& a, bool survive, int 
     base = __shfl_sync(0xFFFFFFFFu, base, leader);
     if (survive) {
         const int idx = base + __popc(mask & ((1u << lane) - 1u));
+        JG_BOUNDS(idx >= 0 && idx < a.cap && key >= 0 && key < a.n_keys, "pair-queue slot (queue_push)");
         const size_t slot = (size_t)key * a.cap + idx;
         a.q_r0[slot] = make_float4(T.r00, T.r01, T.r02, T.tx);
         a.q_r1[slot] = make_float4(T.r10, T.r11, T.r12, T.ty);
@@ -268,6 +286,7 @@ __device__ __forceinline__ void champ_publish(const PassArgs& a, unsigned long l
     int base = 0;
     if (lane == leader) base = atomicAdd(cnt_act(a) + key, __popc(peers));
     base = __shfl_sync(peers, base, leader);
+    JG_BOUNDS(key >= 0 && key < a.n_keys && base + __popc(peers) <= a.cap && idx < a.cap, "stage-1 list slot (champ_publish)");
     const size_t li = (size_t)key * a.cap + base + __popc(peers & ((1u << lane) - 1u));
     a.act_list[li] = idx;
     a.act_meta[li] = make_int2(idx, cfg);
@@ -482,6 +501,7 @@ __device__ __forceinline__ void shape_vs_scene(const PassArgs& a, const ShapeRec
             if (!have) continue;
             const int k = c0 + b;
             const int idx = base + __popc(m & ((1u << lane) - 1u));
+            JG_BOUNDS(idx >= 0 && idx < a.cap && key0 + k < a.n_scene_keys && ((m >> lane) & 1u), "pair-queue slot (broad phase)");
             const size_t slot = (size_t)(key0 + k) * a.cap + idx;
             float prio = 0.f, ox = 0.f, oy = 0.f, oz = 0.f;
             if (k < a.P) {
@@ -869,6 +889,7 @@ __global__ void __launch_bounds__(BLOCK) k_narrowphase(const PassArgs a) {
             [&](int, int slot, int c) {
                 off = slot;
                 cfg = c;
+                JG_BOUNDS(slot >= 0 && slot < a.cap && c >= 0 && c < a.cap, "stage list entry (GJK refill)");
                 const int e0 = enc[cfg];   // what is already proven for this configuration
                 T = load_tf(a, kbase + off);
                 gjk_init(S, mk(T.tx, T.ty, T.tz));
@@ -909,6 +930,7 @@ __global__ void __launch_bounds__(BLOCK) k_narrowphase(const PassArgs a) {
                         base = __shfl_sync(0xFFFFFFFFu, base, leader);
                         if (deep) {
                             const int jj = base + __popc(m & lt_mask);
+                            JG_BOUNDS(jj >= 0 && jj < a.cap && off >= 0 && off < a.cap, "penetration-queue slot");
                             const size_t j = kbase + jj;
                             // bound of the total penetration: box overlap from the broad phase, tightened by the smallest
                             // support value seen during GJK (+4 mm: margins of the penetration geometry vs the cores)
@@ -1061,6 +1083,8 @@ __global__ void __launch_bounds__(BLOCK) k_select(const PassArgs a, int mode, in
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     if (sel[u]) {
+                        JG_BOUNDS(base + __popc(m[u] & lt_mask) < a.cap && jj[u] < a.cap && slot[u] >= 0 && slot[u] < a.cap &&
+                                      cfg[u] >= 0 && cfg[u] < a.cap, "stage list slot (k_select)");
                         const size_t li = kbase + base + __popc(m[u] & lt_mask);
                         a.act_list[li] = jj[u];
                         if (kind != KEY_PLANE) a.act_meta[li] = make_int2(slot[u], cfg[u]);
@@ -1114,6 +1138,7 @@ __global__ void __launch_bounds__(BLOCK) k_penetration(const PassArgs a) {
             [&](int jj, int slot, int c) {
                 myj = jj;
                 cfg = c;
+                JG_BOUNDS(jj >= 0 && jj < a.cap && slot >= 0 && slot < a.cap && c >= 0 && c < a.cap, "stage list entry (penetration refill)");
                 const size_t j = kbase + myj;
                 const int e0 = enc[cfg];
                 T = load_tf(a, kbase + slot);
@@ -1224,6 +1249,7 @@ __global__ void __launch_bounds__(BLOCK) k_penetration_big(const PassArgs a) {
     X.poly.w = poly_words + (size_t)warp * EpaPolyBig::WORDS;
     for (int i = blockIdx.x * (BLOCK / 32) + warp; i < n; i += gridDim.x * (BLOCK / 32)) {
         const int2 e = a.ovf_list[i];
+        JG_BOUNDS(e.x >= 0 && e.x < a.n_keys && e.y >= 0 && e.y < a.cap, "overflow list entry");
         const KeyRec K = a.keys[e.x];
         const size_t kbase = (size_t)e.x * a.cap;
         const size_t j = kbase + e.y;

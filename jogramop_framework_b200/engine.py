@@ -85,6 +85,11 @@ class CollisionEngine:
             raise _lib.JogramopError('jg_engine_create: ' + L.jg_last_error().decode())
         self.threshold, self.query_distance, self.finger_open = threshold, query_distance, finger_open
 
+    @property
+    def handle(self):
+        """The ``jg_engine*`` as an integer: what ``torch.ops.jogramop.*`` (torch_ops.py) and C callers take."""
+        return int(self._e)
+
     def close(self):
         L = self._L
         if getattr(self, '_e', None):

@@ -579,3 +579,117 @@ def read_obj_mesh(path):
 def default_robot_pose():
     """scenario.py:69-80."""
     return np.array([[0.0, -1.0, 0.0, 1.0], [1.0, 0.0, 0.0, 0.0], [0.0, 0.0, 1.0, 0.05], [0.0, 0.0, 0.0, 1.0]])
+
+
+# --------------------------------------------------------------------------- writers (hand a model to file-based callers)
+def _hull_faces(v):
+    """Triangles of the convex hull of v [n,3] (indices into v); a flat / tiny set gets a fan so every vertex is used."""
+    from scipy.spatial import ConvexHull, QhullError
+    if len(v) >= 4:
+        try:
+            return ConvexHull(v).simplices
+        except QhullError:
+            pass
+    return np.array([[0, i, i + 1] for i in range(1, max(len(v) - 1, 2))]) % max(len(v), 1)
+
+
+def _matrix_to_rpy(R):
+    """Inverse of rpy_to_matrix (URDF fixed-axis XYZ)."""
+    pitch = -np.arcsin(np.clip(R[2, 0], -1.0, 1.0))
+    if abs(np.cos(pitch)) > 1e-9:
+        return np.arctan2(R[2, 1], R[2, 2]), pitch, np.arctan2(R[1, 0], R[0, 0])
+    return np.arctan2(-R[1, 2], R[1, 1]), pitch, 0.0
+
+
+def export_robot_urdf(model, out_dir, name='robot'):
+    """Write a RobotModel as ``<out_dir>/<name>.urdf`` + one OBJ per hull shape (``meshes/shape_<s>.obj``: the hull
+    vertices and the hull's triangles), so that file-based callers -- ``jg_robot_load`` of the C-ABI, the sister C++
+    planners -- get exactly this collision model.  Boxes are written as ``<box>`` (they must be axis-aligned in their
+    link frame, as the mobile platform is).  Returns the URDF path."""
+    os.makedirs(os.path.join(out_dir, 'meshes'), exist_ok=True)
+    base_name = 'base_link_export'
+    lines = ['<?xml version="1.0" ?>', f'<robot name="{name}">']
+
+    def collisions(link):
+        out = []
+        for s in np.nonzero(model.shape_link == link)[0]:
+            if model.shape_type[s] == SHAPE_BOX:
+                e = model.shape_plane_verts(s)
+                lo, hi = e.min(0), e.max(0)
+                if len(e) != 8 or not np.allclose(np.sort(np.unique(np.round(e, 12), axis=0), axis=0).shape, (8, 3)):
+                    raise NotImplementedError('only axis-aligned boxes can be exported')
+                c, size = [float(x) for x in 0.5 * (lo + hi)], [float(x) for x in hi - lo]
+                out.append(f'    <collision><origin xyz="{c[0]!r} {c[1]!r} {c[2]!r}" rpy="0 0 0"/>'
+                           f'<geometry><box size="{size[0]!r} {size[1]!r} {size[2]!r}"/></geometry></collision>')
+            else:
+                v = model.shape_verts(s)
+                fn = os.path.join('meshes', f'shape_{s}.obj')
+                with open(os.path.join(out_dir, fn), 'w') as fh:
+                    fh.write(f'o shape_{s}\n')
+                    for p in v:
+                        fh.write(f'v {float(p[0])!r} {float(p[1])!r} {float(p[2])!r}\n')
+                    for t in _hull_faces(v):
+                        fh.write(f'f {t[0] + 1} {t[1] + 1} {t[2] + 1}\n')
+                out.append(f'    <collision><origin xyz="0 0 0" rpy="0 0 0"/><geometry><mesh filename="{fn}"/></geometry></collision>')
+        return out
+
+    lines += [f'  <link name="{base_name}">'] + collisions(-1) + ['  </link>']
+    for i, ln in enumerate(model.link_names):
+        lines += [f'  <link name="{ln}">'] + collisions(i) + ['  </link>']
+    types = {JOINT_FIXED: 'fixed', JOINT_REVOLUTE: 'revolute', JOINT_PRISMATIC: 'prismatic'}
+    for i, jn in enumerate(model.joint_names):
+        T = model.joint_origin[i]
+        r, p, y = _matrix_to_rpy(T[:3, :3])
+        parent = base_name if model.joint_parent[i] < 0 else model.link_names[model.joint_parent[i]]
+        lines.append(f'  <joint name="{jn}" type="{types[int(model.joint_type[i])]}">')
+        lines.append(f'    <origin xyz="{float(T[0, 3])!r} {float(T[1, 3])!r} {float(T[2, 3])!r}" rpy="{float(r)!r} {float(p)!r} {float(y)!r}"/>')
+        lines.append(f'    <parent link="{parent}"/><child link="{model.link_names[i]}"/>')
+        if model.joint_type[i] != JOINT_FIXED:
+            a = model.joint_axis[i]
+            lines.append(f'    <axis xyz="{float(a[0])!r} {float(a[1])!r} {float(a[2])!r}"/>')
+            lines.append(f'    <limit lower="{float(model.joint_limits[i, 0])!r}" upper="{float(model.joint_limits[i, 1])!r}" effort="0" velocity="0"/>')
+        lines.append('  </joint>')
+    lines.append('</robot>')
+    path = os.path.join(out_dir, f'{name}.urdf')
+    with open(path, 'w') as fh:
+        fh.write('\n'.join(lines) + '\n')
+    return path
+
+
+def export_scene_files(scene_model, out_dir, scenario='000'):
+    """Write a SceneModel as ``scenarios/<scenario>/scene.yaml`` + ``object_library/object_library.yaml`` + one OBJ per
+    body (its convex pieces as ``o`` groups, robot-frame coordinates; every body is placed with pose = robot_pose, so
+    loading with that robot pose reproduces the model).  Returns the scene.yaml path."""
+    lib_dir = os.path.join(out_dir, 'object_library')
+    sc_dir = os.path.join(out_dir, 'scenarios', str(scenario))
+    os.makedirs(os.path.join(lib_dir, 'vhacd'), exist_ok=True)
+    os.makedirs(sc_dir, exist_ok=True)
+    lib = ['description: exported by jogramop_framework_b200.ingest.export_scene_files', 'name: export', 'objects:']
+    entries = {True: [], False: []}
+    for b, (bname, is_t) in enumerate(zip(scene_model.body_names, scene_model.body_is_target)):
+        ident = f'body{b}_{bname}'
+        fn = os.path.join('vhacd', f'{ident}.obj')
+        n_v = 0
+        with open(os.path.join(lib_dir, fn), 'w') as fh:
+            for p in np.nonzero(scene_model.piece_body == b)[0]:
+                v = scene_model.piece(p)
+                fh.write(f'o piece_{p}\n')
+                for x in v:
+                    fh.write(f'v {float(x[0])!r} {float(x[1])!r} {float(x[2])!r}\n')
+                for t in _hull_faces(v):
+                    fh.write(f'f {t[0] + 1 + n_v} {t[1] + 1 + n_v} {t[2] + 1 + n_v}\n')
+                n_v += len(v)
+        lib += [f'- identifier: {ident}', f'  mesh_fn: {fn}', f'  name: {ident}', '  scale: 1.0', '  thumbnail_fn: null',
+                f'  vhacd_fn: {fn}']
+        pose = ['  pose:'] + [('  - - ' if c == 0 else '    - ') + repr(float(scene_model.robot_pose[r, c]))
+                              for r in range(4) for c in range(4)]
+        entries[bool(is_t)] += [f'- object_type: {ident}'] + pose
+    with open(os.path.join(lib_dir, 'object_library.yaml'), 'w') as fh:
+        fh.write('\n'.join(lib) + '\n')
+    y = ['bg_objects:' + ('' if entries[False] else ' []')] + entries[False] + ['ground_area_x: 2', 'ground_area_y: 2',
+         'object_library_fn: ../../object_library/object_library.yaml', 'objects:' + ('' if entries[True] else ' []')] + \
+        entries[True] + ['printout: null', 'yaml_file_type: Scene', "yaml_file_version: '1.0'"]
+    path = os.path.join(sc_dir, 'scene.yaml')
+    with open(path, 'w') as fh:
+        fh.write('\n'.join(y) + '\n')
+    return path
