@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(L, s), f'{s} declared in include/jogramop_b200.h but not exported'
     assert sorted(_lib.EXPORTED_SYMBOLS) == syms
-    assert L.jg_abi_version() == 1
+    assert L.jg_abi_version() == 2
 
 
 def test_default_params_and_error_channel():
