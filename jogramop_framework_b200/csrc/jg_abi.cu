@@ -204,6 +204,8 @@ struct jg_engine {
     Lbvh bvh;
     int* d_err = nullptr;
     int mesh_pass = 0;
+    float4* mesh_T = nullptr;            // [mesh_cfg_cap * S * 3] shape transforms of a mesh-mode pass (queries of k_mesh_traverse)
+    int mesh_cfg_cap = 0;                // configurations (substep-expanded) a mesh-mode pass may hold
     int n_stash = 0;                     // link frames the broad phase stashes for the self pairs                   // configurations per pass in mesh mode (adaptive)
     float* d_qrest = nullptr;
     int* act_list = nullptr;              // [n_keys*cap]
@@ -299,7 +301,7 @@ static void arena_free(jg_engine* e) {
     free_dev(e->q_r0); free_dev(e->q_r1); free_dev(e->q_r2); free_dev(e->q_cfg); free_dev(e->epa_slot); free_dev(e->epa_ids);
     free_dev(e->ovf_list); free_dev(e->ovf_poly); free_dev(e->epa_prio); free_dev(e->q_prio); free_dev(e->act_list);
     free_dev(e->act_meta); free_dev(e->champ_scene); free_dev(e->champ_self); free_dev(e->enc_scene); free_dev(e->enc_self);
-    free_dev(e->viol);
+    free_dev(e->viol); free_dev(e->mesh_T);
     e->cap = 0;
 }
 // staging buffers of the host path (sized by e->cap as well)
@@ -404,6 +406,21 @@ static int build_tables(jg_engine* e, const jg_robot* r, const jg_scene* sc) {
             verts.push_back(make_float4((float)r->core[3 * i], (float)r->core[3 * i + 1], (float)r->core[3 * i + 2], 0.f));
         pad4();
         Sh.link = r->shape_link[s];
+        {   // exactly the 8 corners of its local box?  (exact box-vs-triangle tests in the boolean mesh mode)
+            int seen = 0;
+            bool box = Sh.vn == 8;
+            for (int i = r->shape_off[s]; box && i < r->shape_off[s + 1]; ++i) {
+                int code = 0;
+                for (int k = 0; k < 3; ++k) {
+                    const double v = r->core[3 * i + k];
+                    if (std::fabs(v - lo[k]) <= 1e-12) code |= 0;
+                    else if (std::fabs(v - hi[k]) <= 1e-12) code |= 1 << k;
+                    else box = false;
+                }
+                seen |= 1 << code;
+            }
+            Sh.is_box = (box && seen == 0xFF) ? 1 : 0;
+        }
         // plane / EPA vertices: share the core range when identical (hulls), else append (boxes)
         const int pn = r->plane_off[s + 1] - r->plane_off[s];
         bool same = pn == Sh.vn;
@@ -635,6 +652,10 @@ static int arena_alloc(jg_engine* e, int cap) {
                cudaMalloc(&e->champ_self, sizeof(unsigned long long) * cap) == cudaSuccess &&
                cudaMalloc(&e->enc_scene, sizeof(int) * cap) == cudaSuccess && cudaMalloc(&e->enc_self, sizeof(int) * cap) == cudaSuccess &&
                cudaMalloc(&e->viol, sizeof(uint32_t) * (cap / 32 + 1)) == cudaSuccess;
+    if (okm && e->mesh) {
+        e->mesh_cfg_cap = std::min(cap, 1 << 19);    // 48 B per (configuration, shape): 300 MB at 12 shapes
+        okm = cudaMalloc(&e->mesh_T, sizeof(float4) * 3 * (size_t)e->mesh_cfg_cap * std::max(e->S, 1)) == cudaSuccess;
+    }
     if (!okm) {
         const int rc = fail(JG_ERR_NOMEM, "scratch allocation failed (%zu queue entries): %s", qn, cudaGetErrorString(cudaGetLastError()));
         arena_free(e);
@@ -656,8 +677,7 @@ static int ensure_arena(jg_engine* e, int64_t want) {
     int rc = drain_pending(e);
     if (rc) return rc;
     CUDA_TRY(cudaDeviceSynchronize());
-    arena_free(e);
-    staging_free(e);
+    arena_free(e);      // (the host path's staging buffers are separate: ensure_staging grows them when a host call needs it)
     e->mesh_pass = 0;
     return arena_alloc(e, cap);
 }
@@ -792,7 +812,7 @@ static void fill_args(const jg_engine* e, PassArgs& a, uint32_t& flags, bool wan
     a.n_keys = e->n_keys; a.n_scene_keys = e->n_scene_keys; a.verts = e->d_verts; a.n_verts = e->n_verts;
     a.q_r0 = e->q_r0; a.q_r1 = e->q_r1; a.q_r2 = e->q_r2; a.q_cfg = e->q_cfg; a.epa_slot = e->epa_slot; a.epa_ids = e->epa_ids; a.ovf_list = e->ovf_list; a.ovf_cap = 4 * e->cap; a.ovf_poly = e->ovf_poly; a.ovf_poly_cap = e->ovf_poly_cap; a.epa_prio = e->epa_prio; a.q_prio = e->q_prio; a.max_msum = e->max_msum; a.stats = e->d_stats;
     a.mesh = e->mesh ? 1 : 0; a.bvh_nodes = e->bvh.nodes; a.bvh_tri = e->bvh.tri_v; a.bvh_n = e->bvh.n_tris;
-    a.mesh_margin = e->mesh_margin; a.q_tri = e->epa_slot; a.err_flag = e->d_err; a.act_list = e->act_list; a.act_meta = e->act_meta; a.champ_scene = e->champ_scene; a.champ_self = e->champ_self; a.cap = e->cap; a.counts = e->counts;
+    a.mesh_margin = e->mesh_margin; a.mesh_T = e->mesh_T; a.mesh_n_use = e->S; a.q_tri = e->epa_slot; a.err_flag = e->d_err; a.act_list = e->act_list; a.act_meta = e->act_meta; a.champ_scene = e->champ_scene; a.champ_self = e->champ_self; a.cap = e->cap; a.counts = e->counts;
     a.enc_scene = e->enc_scene; a.enc_self = e->enc_self; a.viol = e->viol;
 }
 
@@ -894,25 +914,65 @@ static int begin_call(jg_engine* e, cudaStream_t st) {
 }
 
 // Mesh mode: a (pose, link shape) may queue many triangle candidates, so a pass takes fewer configurations than the
-// per-key queue capacity; the pass size adapts.  Called when the broad phase of a pass reported a queue overflow:
-// halve the pass, or -- at the smallest pass -- grow the arena (while it is below cap_max).  > 0: redo the pass.
-static int mesh_overflow_retry(jg_engine* e, cudaStream_t st, const char* who) {
+// per-key queue capacity; the pass size adapts.  Called when a pass reported a queue overflow: halve the pass, or -- at
+// the smallest pass -- grow the arena (while it is below cap_max).  > 0: redo the pass.
+static int mesh_overflow_retry(jg_engine* e, cudaStream_t st, const char* who, int min_pass = 256) {
     CUDA_TRY(cudaMemsetAsync(e->d_err, 0, sizeof(int), st));
-    if (e->mesh_pass > 256) {
-        e->mesh_pass = std::max(256, e->mesh_pass / 2 / 32 * 32);
+    if (e->mesh_pass > min_pass) {
+        e->mesh_pass = std::max(min_pass, e->mesh_pass / 2 / 32 * 32);
         return 1;
     }
     if (e->cap < e->cap_max) {
         const int rc = ensure_arena(e, std::min<int64_t>(e->cap_max, (int64_t)e->cap * 4));
         if (rc) return rc;
-        e->mesh_pass = std::max(256, std::min(e->cap / 16, 65536) / 32 * 32);
+        e->mesh_pass = std::max(min_pass, std::min(e->cap / 2, e->mesh_cfg_cap) / 32 * 32);
         return 1;
     }
-    return fail(JG_ERR_NOMEM, "%s: mesh mode: a triangle candidate queue overflowed even at 256 configurations per pass "
-                "(%d entries per link shape, the maximum): simplify the obstacle mesh", who, e->cap);
+    return fail(JG_ERR_NOMEM, "%s: mesh mode: a triangle candidate queue overflowed even at %d configurations per pass "
+                "(%d entries per link shape, the maximum): simplify the obstacle mesh", who, min_pass, e->cap);
 }
 static void mesh_first_pass(jg_engine* e) {
-    if (e->mesh && e->mesh_pass <= 0) e->mesh_pass = std::max(256, std::min(e->cap / 16, 65536) / 32 * 32);
+    if (e->mesh && e->mesh_pass <= 0) e->mesh_pass = std::max(256, std::min(e->cap / 2, e->mesh_cfg_cap) / 32 * 32);
+    if (e->mesh) e->mesh_pass = std::min(e->mesh_pass, e->mesh_cfg_cap / 32 * 32);
+}
+
+constexpr int MESH_GROUP = 8;   // lanes that walk the LBVH together for one (configuration, shape) query
+// the triangle candidates of a mesh-mode pass (the broad phase has put the shape transforms down): one group of lanes per
+// query.  use_shapes == NULL: every shape of the robot (k_broadphase), else the gripper's shape list (k_broadphase_poses).
+// Boolean fast path: verdict only, zero margins, every queried shape is exactly its box -> exact box-vs-triangle tests
+// in the traversal itself, nothing queued.  Returns 1 when the pass must be redone (queue overflow), < 0 on error.
+static int mesh_candidates(jg_engine* e, PassArgs& a, int n_cfg, int n_use, const int* d_use, const std::vector<int>& use_host,
+                           uint32_t flags, cudaStream_t st, const char* who, int min_pass = 256) {
+    if (!(flags & JG_SCENE)) return 0;
+    bool boolean = (flags & JG_NO_EPA) && a.qd <= 1e-5f && e->mesh_margin == 0.f;
+    for (int k = 0; boolean && k < n_use; ++k) {
+        const ShapeRec& Sh = e->h_robot.shapes[use_host.empty() ? k : use_host[k]];
+        boolean = Sh.is_box && Sh.margin == 0.f;
+    }
+    a.mesh_n_use = n_use;
+    const int n_q = n_cfg * n_use;
+    const int per_block = 256 / MESH_GROUP;
+    const size_t smem = sizeof(int) * per_block * 32 * MESH_GROUP;
+    if (n_q > 0) {
+        if (boolean) k_mesh_traverse<MESH_GROUP, true><<<(n_q + per_block - 1) / per_block, 256, smem, st>>>(a, n_q, d_use);
+        else k_mesh_traverse<MESH_GROUP, false><<<(n_q + per_block - 1) / per_block, 256, smem, st>>>(a, n_q, d_use);
+        e->stats.kernel_launches += 1;
+    }
+    int err = 0;
+    prof_end(e, st);
+    CUDA_TRY(cudaMemcpyAsync(&err, e->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (err & 2) {
+        cudaMemsetAsync(e->d_err, 0, sizeof(int), st);
+        return fail(JG_ERR_UNSUPPORTED, "%s: mesh mode: the LBVH traversal stack of a query overflowed (%d entries): the tree over this "
+                    "mesh is too deep / too wide for the shared-memory stack; no result was produced", who, 32 * MESH_GROUP);
+    }
+    if (err) {
+        const int rc = mesh_overflow_retry(e, st, who, min_pass);
+        return rc < 0 ? rc : 1;
+    }
+    prof_begin(e, 0, st);
+    return 0;
 }
 
 extern "C" int jg_check(jg_engine* e, const float* q, int64_t n, int dof, uint32_t flags, uint32_t* bits, float* min_dist,
@@ -939,17 +999,10 @@ extern "C" int jg_check(jg_engine* e, const float* q, int64_t n, int dof, uint32
         prof_begin(e, 0, st);
         launch_broadphase(e, a, (m + BP_BLOCK - 1) / BP_BLOCK, bp_smem(e, flags), st);
         e->stats.kernel_launches += 1;
-        if (e->mesh) {   // secondary path: check the queue-overflow flag synchronously before going on
-            int err = 0;
-            prof_end(e, st);
-            CUDA_TRY(cudaMemcpyAsync(&err, e->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaStreamSynchronize(st));
-            if (err) {
-                rc = mesh_overflow_retry(e, st, "jg_check");
-                if (rc < 0) return rc;
-                continue;   // redo this pass at the smaller size
-            }
-            prof_begin(e, 0, st);
+        if (e->mesh) {   // triangle candidates: group-cooperative LBVH traversal; a full queue means: redo the pass smaller
+            rc = mesh_candidates(e, a, m, e->S, nullptr, {}, flags, st, "jg_check");
+            if (rc < 0) return rc;
+            if (rc > 0) continue;
         }
         rc = run_narrow_and_finalize(e, a, m, flags, bits + off / 32, min_dist ? min_dist + off : nullptr,
                                      reason ? reason + off : nullptr, st);
@@ -964,17 +1017,21 @@ extern "C" int jg_check_edges(jg_engine* e, const float* qa, const float* qb, in
     if (!e) return fail(JG_ERR_INVALID, "jg_check_edges: engine is NULL");
     if (dof != e->dof) return fail(JG_ERR_INVALID, "jg_check_edges: dof %d does not match the robot's %d", dof, e->dof);
     if (substeps < 2 || substeps > e->cap_max / 32) return fail(JG_ERR_INVALID, "jg_check_edges: substeps %d out of range [2,%d]", substeps, e->cap_max / 32);
-    if (e->mesh) return fail(JG_ERR_INVALID, "jg_check_edges: not available in mesh mode");
     if (m < 0 || (m && (!qa || !qb || !bits))) return fail(JG_ERR_INVALID, "jg_check_edges: NULL qa/qb/bits");
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaSetDevice(e->device));
-    int rc = ensure_arena(e, std::max<int64_t>(m, 32) * substeps);
+    int rc = ensure_arena(e, std::max<int64_t>(m, 32) * substeps * (e->mesh ? 16 : 1));
     if (rc) return rc;
+    if (e->mesh && 32 * substeps > e->mesh_cfg_cap)
+        return fail(JG_ERR_INVALID, "jg_check_edges: mesh mode takes at most %d substeps per edge", e->mesh_cfg_cap / 32);
     rc = begin_call(e, st);
     if (rc) return rc;
     e->stats.configs = m * substeps;
-    const int edges_per_pass = (e->cap / substeps) / 32 * 32;   // keep packed words aligned across passes
-    for (int64_t off = 0; off < m; off += edges_per_pass) {
+    mesh_first_pass(e);
+    for (int64_t off = 0; off < m;) {
+        // packed words stay aligned across passes: a pass holds a multiple of 32 edges (mesh mode: adaptive pass size)
+        const int pass_cfgs = e->mesh ? std::max(e->mesh_pass, 32 * substeps) : e->cap;
+        const int edges_per_pass = (pass_cfgs / substeps) / 32 * 32;
         const int me = (int)std::min<int64_t>(edges_per_pass, m - off);
         PassArgs a;
         fill_args(e, a, flags, min_dist != nullptr);
@@ -985,8 +1042,14 @@ extern "C" int jg_check_edges(jg_engine* e, const float* qa, const float* qb, in
         k_init_scratch<<<(me + 255) / 256, 256, 0, st>>>(e->enc_scene, e->enc_self, e->champ_scene, e->champ_self, me);
         launch_broadphase(e, a, (a.n + BP_BLOCK - 1) / BP_BLOCK, bp_smem(e, flags), st);
         e->stats.kernel_launches += 2;
+        if (e->mesh) {
+            rc = mesh_candidates(e, a, a.n, e->S, nullptr, {}, flags, st, "jg_check_edges", 32 * substeps);
+            if (rc < 0) return rc;
+            if (rc > 0) continue;
+        }
         rc = run_narrow_and_finalize(e, a, me, flags, bits + off / 32, min_dist ? min_dist + off : nullptr, nullptr, st);
         if (rc) return rc;
+        off += me;
     }
     return JG_OK;
 }
@@ -1071,6 +1134,7 @@ extern "C" int jg_check_poses(jg_engine* e, const float* poses, int64_t n, int f
         PassArgs a;
         fill_args(e, a, flags, min_dist != nullptr);
         a.n = m;
+        a.mesh_n_use = (int)use.size();
         CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * JG_COUNTS_INTS(e->n_keys), st));
         const size_t smem = sizeof(RobotTab) + sizeof(PieceRec) * e->P;
         prof_begin(e, 0, st);
@@ -1082,16 +1146,9 @@ extern "C" int jg_check_poses(jg_engine* e, const float* poses, int64_t n, int f
                 a, poses + off * stride, fmt, e->d_rel, e->d_use_shapes, (int)use.size());
         e->stats.kernel_launches += 1;
         if (e->mesh) {
-            int err = 0;
-            prof_end(e, st);
-            CUDA_TRY(cudaMemcpyAsync(&err, e->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaStreamSynchronize(st));
-            if (err) {
-                rc = mesh_overflow_retry(e, st, "jg_check_poses");
-                if (rc < 0) return rc;
-                continue;
-            }
-            prof_begin(e, 0, st);
+            rc = mesh_candidates(e, a, m, (int)use.size(), e->d_use_shapes, use, flags, st, "jg_check_poses");
+            if (rc < 0) return rc;
+            if (rc > 0) continue;
         }
         rc = run_narrow_and_finalize(e, a, m, flags, bits + off / 32, min_dist ? min_dist + off : nullptr, nullptr, st);
         if (rc) return rc;
@@ -1144,7 +1201,12 @@ static int ensure_staging(jg_engine* e) {
         }
         e->staging_ready = true;
     }
-    if (e->staging_cap == e->cap) return JG_OK;
+    if (e->staging_cap >= e->cap) return JG_OK;
+    {
+        const int rc = drain_pending(e);      // a ticket in flight still uses the old buffers
+        if (rc) return rc;
+        CUDA_TRY(cudaDeviceSynchronize());
+    }
     staging_free(e);
     for (int i = 0; i < 2; ++i) {
         CUDA_TRY(cudaMalloc(&e->stage_q[i], sizeof(float) * e->cap * e->dof));
@@ -1224,26 +1286,29 @@ extern "C" int jg_check_host(jg_engine* e, const float* q, int64_t n, int dof, u
     rc = ensure_staging(e);
     if (rc) return rc;
     const bool pq = is_pinned(q), pb = is_pinned(bits), pd = dist && is_pinned(dist), pr = reason && is_pinned(reason);
-    if (e->mesh || n == 0) {   // secondary path: plain staged copy around the device entry point
-        float* dq = nullptr;
-        uint32_t* db = nullptr;
-        float* dd = nullptr;
-        uint8_t* dr = nullptr;
-        if (n == 0) return JG_OK;
-        CUDA_TRY(cudaMalloc(&dq, sizeof(float) * n * dof));
-        CUDA_TRY(cudaMalloc(&db, sizeof(uint32_t) * ((n + 31) / 32)));
-        if (dist) CUDA_TRY(cudaMalloc(&dd, sizeof(float) * n));
-        if (reason) CUDA_TRY(cudaMalloc(&dr, n));
-        CUDA_TRY(cudaMemcpyAsync(dq, q, sizeof(float) * n * dof, cudaMemcpyHostToDevice, e->s_run));
-        rc = jg_check(e, dq, n, dof, flags, db, dd, dr, e->s_run);
-        if (rc == JG_OK) {
-            CUDA_TRY(cudaMemcpyAsync(bits, db, sizeof(uint32_t) * ((n + 31) / 32), cudaMemcpyDeviceToHost, e->s_run));
-            if (dist) CUDA_TRY(cudaMemcpyAsync(dist, dd, sizeof(float) * n, cudaMemcpyDeviceToHost, e->s_run));
-            if (reason) CUDA_TRY(cudaMemcpyAsync(reason, dr, n, cudaMemcpyDeviceToHost, e->s_run));
+    if (n == 0) return JG_OK;
+    if (e->mesh) {
+        // mesh mode: the device entry point checks its queue-overflow flag per pass (a host round trip), so the host
+        // path is a staged copy around it: `cap` configurations at a time through the pinned staging buffers
+        const int chunk = e->staging_cap;      // (the arena may grow inside jg_check; the staging buffers do not)
+        for (int64_t off = 0; off < n; off += chunk) {
+            const int m = (int)std::min<int64_t>(chunk, n - off);
+            const float* src = q + off * dof;
+            if (!pq) { memcpy(e->pin_q[0], src, sizeof(float) * m * dof); src = e->pin_q[0]; }
+            CUDA_TRY(cudaMemcpyAsync(e->stage_q[0], src, sizeof(float) * m * dof, cudaMemcpyHostToDevice, e->s_run));
+            rc = jg_check(e, e->stage_q[0], m, dof, flags, e->stage_bits[0], dist ? e->stage_dist[0] : nullptr,
+                          reason ? e->stage_reason[0] : nullptr, e->s_run);
+            if (rc) return rc;
+            CUDA_TRY(cudaMemcpyAsync(pb ? bits + off / 32 : e->pin_bits[0], e->stage_bits[0], sizeof(uint32_t) * ((m + 31) / 32),
+                                     cudaMemcpyDeviceToHost, e->s_run));
+            if (dist) CUDA_TRY(cudaMemcpyAsync(pd ? dist + off : e->pin_dist[0], e->stage_dist[0], sizeof(float) * m, cudaMemcpyDeviceToHost, e->s_run));
+            if (reason) CUDA_TRY(cudaMemcpyAsync(pr ? reason + off : e->pin_reason[0], e->stage_reason[0], m, cudaMemcpyDeviceToHost, e->s_run));
             CUDA_TRY(cudaStreamSynchronize(e->s_run));
+            if (!pb) memcpy(bits + off / 32, e->pin_bits[0], sizeof(uint32_t) * ((m + 31) / 32));
+            if (dist && !pd) memcpy(dist + off, e->pin_dist[0], sizeof(float) * m);
+            if (reason && !pr) memcpy(reason + off, e->pin_reason[0], m);
         }
-        cudaFree(dq); cudaFree(db); cudaFree(dd); cudaFree(dr);
-        return rc;
+        return JG_OK;
     }
     // One engine pass per `cap` configurations.  Within a pass the upload is cut into slices: the broad phase of slice
     // i runs while slice i+1 is still crossing PCIe (the broad phase is per-configuration, so it can be launched
@@ -1289,7 +1354,15 @@ extern "C" int jg_check_host_submit(jg_engine* e, const float* q, int64_t n, int
     if (!e || !ticket) return fail(JG_ERR_INVALID, "jg_check_host_submit: NULL engine / ticket");
     if (dof != e->dof) return fail(JG_ERR_INVALID, "jg_check_host_submit: dof %d does not match the robot's %d", dof, e->dof);
     if (n <= 0 || !q || !bits) return fail(JG_ERR_INVALID, "jg_check_host_submit: empty batch or NULL q/bits");
-    if (e->mesh) return fail(JG_ERR_UNSUPPORTED, "jg_check_host_submit: mesh-mode engines use jg_check_host");
+    if (e->mesh) {
+        // mesh-mode passes check their queue-overflow flag on the host, so there is nothing to overlap: the batch is done
+        // when this returns and its ticket is already complete (jg_check_host_wait returns at once)
+        if (e->pending[0].busy || e->pending[1].busy) return fail(JG_ERR_INVALID, "jg_check_host_submit: wait for the tickets in flight first");
+        const int rc0 = jg_check_host(e, q, n, dof, flags, bits, dist, reason);
+        if (rc0) return rc0;
+        *ticket = e->next_ticket++;
+        return JG_OK;
+    }
     if (n > e->cap_max) return fail(JG_ERR_INVALID, "jg_check_host_submit: %lld configurations exceed the pass capacity %d (use jg_check_host)",
                                     (long long)n, e->cap_max);
     CUDA_TRY(cudaSetDevice(e->device));

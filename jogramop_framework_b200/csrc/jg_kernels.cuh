@@ -65,7 +65,8 @@ struct ShapeRec {
     int voff, vn;      // core vertices
     int poff, pn;      // plane / EPA vertices
     int link;
-    int pad[3];
+    int is_box;        // the core vertices are exactly the 8 corners of the local box (c, h): exact box tests may be used
+    int pad[2];
 };
 
 struct RobotTab {
@@ -156,6 +157,8 @@ struct PassArgs {
     int bvh_n;
     float mesh_margin;
     int* q_tri;                // [n_keys*cap] triangle slot of a mesh queue entry (aliases epa_slot: no EPA on triangles)
+    float4* mesh_T;            // [mesh pass][shapes used][3] rows of every shape's transform: the queries of k_mesh_traverse
+    int mesh_n_use;            // shapes per configuration in mesh_T
     int* err_flag;             // set when a mesh queue overflowed
     // per-configuration scratch
     int* enc_scene;    // encoded min contact distance vs scene+plane
@@ -353,89 +356,16 @@ __device__ __forceinline__ bool plane_test(const PassArgs& a, const ShapeRec& Sh
 // MESH is a compile-time switch: the triangle path's candidate lists must not cost the hull path registers
 template <bool MESH>
 __device__ __forceinline__ void shape_vs_scene(const PassArgs& a, const ShapeRec& Sh, int s, const PieceRec* pieces,
-                                               const Tf& T, bool valid, int out_idx, Champ* local) {
+                                               const Tf& T, bool valid, int out_idx, Champ* local, int qslot) {
     if (MESH && (a.flags & 1u)) {
-        // world box of the shape, inflated by everything a reported distance may span; every triangle whose box
-        // overlaps it is a candidate (per-lane LBVH traversal; lanes that emit together share one atomicAdd)
-        const float infl = a.qd + Sh.margin + a.mesh_margin + 1e-5f;
-        const float cx = fmaf(T.r00, Sh.c[0], fmaf(T.r01, Sh.c[1], fmaf(T.r02, Sh.c[2], T.tx)));
-        const float cy = fmaf(T.r10, Sh.c[0], fmaf(T.r11, Sh.c[1], fmaf(T.r12, Sh.c[2], T.ty)));
-        const float cz = fmaf(T.r20, Sh.c[0], fmaf(T.r21, Sh.c[1], fmaf(T.r22, Sh.c[2], T.tz)));
-        const float hx = fmaf(fabsf(T.r00), Sh.h[0], fmaf(fabsf(T.r01), Sh.h[1], fabsf(T.r02) * Sh.h[2])) + infl;
-        const float hy = fmaf(fabsf(T.r10), Sh.h[0], fmaf(fabsf(T.r11), Sh.h[1], fabsf(T.r12) * Sh.h[2])) + infl;
-        const float hz = fmaf(fabsf(T.r20), Sh.h[0], fmaf(fabsf(T.r21), Sh.h[1], fabsf(T.r22) * Sh.h[2])) + infl;
-        const float qlo[3] = {cx - hx, cy - hy, cz - hz}, qhi[3] = {cx + hx, cy + hy, cz + hz};
-        const int key = s * (a.P + 1);
-        const int lane = threadIdx.x & 31;
-        // candidates are first collected per lane, then the warp reserves its slots with ONE atomicAdd (an atomic per
-        // emitted triangle inside the divergent traversal was most of this kernel's time)
-        constexpr int MAXC = 32;
-        unsigned short cand[MAXC];
-        float cov[MAXC];
-        int nc = 0;
-        unsigned long long best = 0ull;
-        auto write_out = [&](int base) {   // entries cand[0..nc) -> queue slots [base, base+nc)
-            if (base + nc > a.cap) { *a.err_flag = 1; nc = max(0, min(nc, a.cap - base)); }
-            for (int i = 0; i < nc; ++i) {
-                const int idx = base + i;
-                const size_t slot = (size_t)key * a.cap + idx;
-                a.q_r0[slot] = make_float4(T.r00, T.r01, T.r02, T.tx);
-                a.q_r1[slot] = make_float4(T.r10, T.r11, T.r12, T.ty);
-                a.q_r2[slot] = make_float4(T.r20, T.r21, T.r22, T.tz);
-                a.q_cfg[slot] = out_idx;
-                a.q_tri[slot] = (int)cand[i];
-                // bound for the champion-first staging: a triangle pair never reports less than -(margins), so the
-                // bound only ranks the candidates (largest box overlap first); the overlap includes the inflation
-                const float prio = prio_of(cov[i] - infl, Sh.margin + a.mesh_margin);
-                a.q_prio[slot] = prio;
-                const unsigned long long code = ((unsigned long long)__float_as_uint(prio) << 32) | (unsigned)((key << 20) | idx);
-                if (code > best) best = code;
-            }
-            nc = 0;
-        };
-        if (valid)
-            lbvh_traverse(a.bvh_nodes, a.bvh_tri, a.bvh_n, qlo, qhi, [&](int tri, float ov_infl, V3 p0, V3 p1, V3 p2) {
-                // separating axes beyond the world boxes (conservative: a culled triangle is provably further than the
-                // inflation from the shape's box): the triangle's plane, then the three axes of the shape's own box.
-                // One third of the candidates goes away here (13.9 instead of 20.9 per configuration in scenario 011).
-                const V3 cw = mk(cx, cy, cz);
-                const V3 a0 = mk(T.r00, T.r10, T.r20), a1 = mk(T.r01, T.r11, T.r21), a2 = mk(T.r02, T.r12, T.r22);
-                const V3 nt = cross(p1 - p0, p2 - p0);
-                const float l2 = norm2(nt);
-                if (l2 > 1e-24f) {
-                    const float r = fabsf(dot(nt, a0)) * Sh.h[0] + fabsf(dot(nt, a1)) * Sh.h[1] + fabsf(dot(nt, a2)) * Sh.h[2];
-                    const float dc = fabsf(dot(nt, cw - p0));
-                    if (dc > r + infl * sqrtf(l2)) return;
-                }
-                const V3 d0 = p0 - cw, d1 = p1 - cw, d2 = p2 - cw;
-                {
-                    const float t0 = dot(a0, d0), t1 = dot(a0, d1), t2 = dot(a0, d2), lim = Sh.h[0] + infl;
-                    if (fminf(t0, fminf(t1, t2)) > lim || fmaxf(t0, fmaxf(t1, t2)) < -lim) return;
-                }
-                {
-                    const float t0 = dot(a1, d0), t1 = dot(a1, d1), t2 = dot(a1, d2), lim = Sh.h[1] + infl;
-                    if (fminf(t0, fminf(t1, t2)) > lim || fmaxf(t0, fmaxf(t1, t2)) < -lim) return;
-                }
-                {
-                    const float t0 = dot(a2, d0), t1 = dot(a2, d1), t2 = dot(a2, d2), lim = Sh.h[2] + infl;
-                    if (fminf(t0, fminf(t1, t2)) > lim || fmaxf(t0, fmaxf(t1, t2)) < -lim) return;
-                }
-                if (nc == MAXC) write_out(atomicAdd(a.counts + key, nc));   // rare: the lane's list is full, flush it alone
-                cand[nc] = (unsigned short)tri;
-                cov[nc] = ov_infl;
-                ++nc;
-            });
-        int incl = nc;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if (lane >= o) incl += up;
+        // mesh mode: the triangle candidates of this shape are found by k_mesh_traverse (a group of lanes per query walks
+        // the LBVH together); here the query -- the shape's transform -- is only put down
+        if (valid) {
+            float4* q = a.mesh_T + (size_t)qslot * 3;
+            q[0] = make_float4(T.r00, T.r01, T.r02, T.tx);
+            q[1] = make_float4(T.r10, T.r11, T.r12, T.ty);
+            q[2] = make_float4(T.r20, T.r21, T.r22, T.tz);
         }
-        int base = 0;
-        if (lane == 31 && incl > 0) base = atomicAdd(a.counts + key, incl);
-        base = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - nc;
-        write_out(base);
-        if (best) atomicMax(a.champ_scene + out_idx, best);
     }
     // Hull pieces + plane.  The slot reservation is an atomic with return (~1 us round trip under load); issued per
     // (shape, piece) it was a third of this kernel's time.  So: first test ALL keys of the shape (bit k of `hm` = this
@@ -592,7 +522,7 @@ __global__ void __launch_bounds__(BLOCK, JG_BP_OCC) k_broadphase(const PassArgs 
     Tf cur = tf_identity(), saved = tf_identity();
     if (want_scene)
         for (int s = R->base_shape_first; s < R->base_shape_first + R->base_shape_count; ++s)
-            shape_vs_scene<MESH>(a, R->shapes[s], s, pieces, cur, valid, out_idx, lc);
+            shape_vs_scene<MESH>(a, R->shapes[s], s, pieces, cur, valid, out_idx, lc, (cfg - a.cfg_base) * a.mesh_n_use + s);
 
     for (int i = 0; i < R->L; ++i) {
         const JointRec& J = R->joints[i];
@@ -629,11 +559,184 @@ __global__ void __launch_bounds__(BLOCK, JG_BP_OCC) k_broadphase(const PassArgs 
         }
         if (want_scene)
             for (int s = J.shape_first; s < J.shape_first + J.shape_count; ++s)
-                shape_vs_scene<MESH>(a, R->shapes[s], s, pieces, cur, valid, out_idx, lc);
+                shape_vs_scene<MESH>(a, R->shapes[s], s, pieces, cur, valid, out_idx, lc, (cfg - a.cfg_base) * a.mesh_n_use + s);
     }
     if (lc) {
         if (want_scene) champ_publish(a, champ.scene, a.champ_scene, out_idx, valid);
         if (want_self) champ_publish(a, champ.self, a.champ_self, out_idx, valid);
+    }
+}
+
+// ------------------------------------------------------------------------------------------- mesh mode: candidates
+// One GROUP of G lanes per query (configuration, link shape): the group walks the LBVH together.  Its frontier lives in
+// a shared-memory stack; every step the group pops up to G nodes (one per lane: coalesced 32-byte node reads), each lane
+// tests its node's box against the query's oriented box and the survivors' children go back on the stack (ballot +
+// prefix inside the group) or, if they are leaves, through the triangle tests.  All groups of a warp step in lockstep
+// (no per-lane divergent walk, no local-memory stack; a full stack raises the error flag instead of dropping a child).
+//   BOOLEAN = false: triangles that survive the separating-axis culls are queued for the hull-vs-triangle GJK stage
+//                    (slots reserved once per step and key by the lanes that emit together);
+//   BOOLEAN = true : the shape IS its box (ShapeRec::is_box) and only "does it touch a surface" is asked (zero margins,
+//                    verdict only): exact box-vs-triangle test at the leaves, first hit ends the query, nothing queued.
+template <int G, bool BOOLEAN>
+__global__ void __launch_bounds__(256) k_mesh_traverse(const PassArgs a, int n_q, const int* __restrict__ use_shapes) {
+    constexpr int STK = 32 * G;
+    extern __shared__ int stack_all[];
+    const int lane = threadIdx.x & 31, gl = lane & (G - 1), shift = lane & ~(G - 1);
+    const unsigned gfull = G == 32 ? 0xFFFFFFFFu : ((1u << G) - 1u);
+    const unsigned lower = (1u << gl) - 1u, lane_lt = (1u << lane) - 1u;
+    int* stack = stack_all + (threadIdx.x / G) * STK;
+    const int q = blockIdx.x * (256 / G) + threadIdx.x / G;
+    bool active = q < n_q;
+    const int n_use = a.mesh_n_use;
+    const int cfg_l = active ? q / n_use : 0, k = active ? q - cfg_l * n_use : 0;
+    const int s = use_shapes ? use_shapes[k] : k;
+    const int out_idx = a.substeps <= 1 ? cfg_l : cfg_l / a.substeps;
+    const ShapeRec Sh = a.robot->shapes[s];
+    const int key = s * (a.P + 1);
+    const float msum = Sh.margin + a.mesh_margin;
+    if (active && a.substeps <= 1 && cfg_l >= a.n) active = false;
+    if (active && a.substeps > 1 && cfg_l >= a.n) active = false;
+    // this configuration is already known to touch (another shape of it, or an earlier query): nothing left to learn
+    if (BOOLEAN && active && dec_float(a.enc_scene[out_idx]) <= -msum) active = false;
+    Tf T = tf_identity();
+    if (active) {
+        const float4 r0 = a.mesh_T[(size_t)q * 3], r1 = a.mesh_T[(size_t)q * 3 + 1], r2 = a.mesh_T[(size_t)q * 3 + 2];
+        T.r00 = r0.x; T.r01 = r0.y; T.r02 = r0.z; T.tx = r0.w;
+        T.r10 = r1.x; T.r11 = r1.y; T.r12 = r1.z; T.ty = r1.w;
+        T.r20 = r2.x; T.r21 = r2.y; T.r22 = r2.z; T.tz = r2.w;
+    }
+    const float infl = a.qd + msum + (BOOLEAN ? 0.f : 1e-5f);
+    ObbQuery Q;
+    Q.c = tf_apply(T, mk(Sh.c[0], Sh.c[1], Sh.c[2]));
+    Q.a0 = mk(T.r00, T.r10, T.r20); Q.a1 = mk(T.r01, T.r11, T.r21); Q.a2 = mk(T.r02, T.r12, T.r22);
+    Q.h = mk(Sh.h[0] + infl, Sh.h[1] + infl, Sh.h[2] + infl);
+    Q.e = mk(fmaf(fabsf(T.r00), Sh.h[0], fmaf(fabsf(T.r01), Sh.h[1], fabsf(T.r02) * Sh.h[2])) + infl,
+             fmaf(fabsf(T.r10), Sh.h[0], fmaf(fabsf(T.r11), Sh.h[1], fabsf(T.r12) * Sh.h[2])) + infl,
+             fmaf(fabsf(T.r20), Sh.h[0], fmaf(fabsf(T.r21), Sh.h[1], fabsf(T.r22) * Sh.h[2])) + infl);
+    int sp = 0;
+    int single = -1;      // a one-triangle mesh has no internal node
+    if (active) {
+        if (a.bvh_n == 1) single = 0;
+        else if (a.bvh_n > 1) { if (gl == 0) stack[0] = 0; sp = 1; }
+    }
+    bool hit = false;
+    unsigned long long best = 0ull;
+    bool first = true;
+    while (__any_sync(0xFFFFFFFFu, sp > 0 || (first && single >= 0))) {
+        // ---- pop up to G nodes, test them, put their internal children back
+        const int take = min(sp, G);
+        __syncwarp();
+        int node = -1;
+        if (gl < take) node = stack[sp - 1 - gl];
+        sp -= take;
+        __syncwarp();
+        int chL = 0, chR = 0;
+        bool pass = false;
+        if (node >= 0) {
+            const float4* np = reinterpret_cast<const float4*>(a.bvh_nodes + node);
+            const float4 n0 = np[0], n1 = np[1];     // lo.xyz hi.x | hi.yz left right
+            const float lo[3] = {n0.x, n0.y, n0.z}, hi[3] = {n0.w, n1.x, n1.y};
+            pass = obb_vs_aabb(Q, lo, hi);
+            chL = __float_as_int(n1.z);
+            chR = __float_as_int(n1.w);
+        }
+        const bool pL = pass && chL >= 0, pR = pass && chR >= 0;
+        const unsigned bL = (__ballot_sync(0xFFFFFFFFu, pL) >> shift) & gfull, bR = (__ballot_sync(0xFFFFFFFFu, pR) >> shift) & gfull;
+        const int nL = __popc(bL), nR = __popc(bR);
+        if (sp + nL + nR > STK) {        // group-uniform: never drop a child silently
+            if (gl == 0) atomicOr(a.err_flag, 2);
+            sp = 0;
+            active = false;
+        } else {
+            if (pL) stack[sp + __popc(bL & lower)] = chL;
+            if (pR) stack[sp + nL + __popc(bR & lower)] = chR;
+            sp += nL + nR;
+        }
+        // ---- leaf children: up to two triangles per lane
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            int slot = -1;
+            if (c == 0) { if (pass && chL < 0) slot = ~chL; else if (first && single >= 0 && gl == 0) slot = single; }
+            else if (pass && chR < 0) slot = ~chR;
+            if (!active) slot = -1;
+            bool cand = false;
+            float cov = 0.f;
+            if (slot >= 0) {
+                const float4 v0 = a.bvh_tri[3 * slot], v1 = a.bvh_tri[3 * slot + 1], v2 = a.bvh_tri[3 * slot + 2];
+                const V3 p0 = mk(v0.x, v0.y, v0.z), p1 = mk(v1.x, v1.y, v1.z), p2 = mk(v2.x, v2.y, v2.z);
+                if (BOOLEAN) {
+                    JG_WORK(JG_WORK_TRI_TESTS, 1u);
+                    cand = box_tri_overlap(Q, p0, p1, p2);
+                } else {
+                    // the triangle's own box against the query's world box (also the bound that ranks the candidate),
+                    // then the triangle's plane and the three axes of the shape's box
+                    const float tlo[3] = {fminf(p0.x, fminf(p1.x, p2.x)), fminf(p0.y, fminf(p1.y, p2.y)), fminf(p0.z, fminf(p1.z, p2.z))};
+                    const float thi[3] = {fmaxf(p0.x, fmaxf(p1.x, p2.x)), fmaxf(p0.y, fmaxf(p1.y, p2.y)), fmaxf(p0.z, fmaxf(p1.z, p2.z))};
+                    cov = fminf(fminf(fminf(Q.c.x + Q.e.x, thi[0]) - fmaxf(Q.c.x - Q.e.x, tlo[0]),
+                                      fminf(Q.c.y + Q.e.y, thi[1]) - fmaxf(Q.c.y - Q.e.y, tlo[1])),
+                                fminf(Q.c.z + Q.e.z, thi[2]) - fmaxf(Q.c.z - Q.e.z, tlo[2]));
+                    cand = cov >= 0.f;
+                    if (cand) {
+                        const V3 nt = cross(p1 - p0, p2 - p0);
+                        const float l2 = norm2(nt);
+                        if (l2 > 1e-24f) {
+                            const float r = fabsf(dot(nt, Q.a0)) * Sh.h[0] + fabsf(dot(nt, Q.a1)) * Sh.h[1] + fabsf(dot(nt, Q.a2)) * Sh.h[2];
+                            if (fabsf(dot(nt, Q.c - p0)) > r + infl * sqrtf(l2)) cand = false;
+                        }
+                    }
+                    if (cand) {
+                        const V3 d0 = p0 - Q.c, d1 = p1 - Q.c, d2 = p2 - Q.c;
+                        const float t0 = dot(Q.a0, d0), t1 = dot(Q.a0, d1), t2 = dot(Q.a0, d2);
+                        if (fminf(t0, fminf(t1, t2)) > Q.h.x || fmaxf(t0, fmaxf(t1, t2)) < -Q.h.x) cand = false;
+                        const float u0 = dot(Q.a1, d0), u1 = dot(Q.a1, d1), u2 = dot(Q.a1, d2);
+                        if (fminf(u0, fminf(u1, u2)) > Q.h.y || fmaxf(u0, fmaxf(u1, u2)) < -Q.h.y) cand = false;
+                        const float w0 = dot(Q.a2, d0), w1 = dot(Q.a2, d1), w2 = dot(Q.a2, d2);
+                        if (fminf(w0, fminf(w1, w2)) > Q.h.z || fmaxf(w0, fmaxf(w1, w2)) < -Q.h.z) cand = false;
+                    }
+                }
+            }
+            if (BOOLEAN) {
+                const unsigned hb = (__ballot_sync(0xFFFFFFFFu, cand) >> shift) & gfull;
+                if (hb) { hit = true; sp = 0; active = false; }       // first hit ends the query (group-uniform)
+            } else {
+                const unsigned cm = __ballot_sync(0xFFFFFFFFu, cand);
+                if (cand) {     // lanes of one key reserve their slots together
+                    const unsigned peers = __match_any_sync(cm, key);
+                    const int leader = __ffs(peers) - 1;
+                    int base = 0;
+                    if (lane == leader) base = atomicAdd(a.counts + key, __popc(peers));
+                    base = __shfl_sync(peers, base, leader);
+                    const int idx = base + __popc(peers & lane_lt);
+                    if (idx < a.cap) {
+                        const size_t qs = (size_t)key * a.cap + idx;
+                        a.q_r0[qs] = make_float4(T.r00, T.r01, T.r02, T.tx);
+                        a.q_r1[qs] = make_float4(T.r10, T.r11, T.r12, T.ty);
+                        a.q_r2[qs] = make_float4(T.r20, T.r21, T.r22, T.tz);
+                        a.q_cfg[qs] = out_idx;
+                        a.q_tri[qs] = slot;
+                        // a triangle pair never reports less than -(margins): the bound only ranks the candidates
+                        const float prio = prio_of(cov - infl, msum);
+                        a.q_prio[qs] = prio;
+                        const unsigned long long code = ((unsigned long long)__float_as_uint(prio) << 32) | (unsigned)((key << 20) | idx);
+                        if (code > best) best = code;
+                    } else {
+                        atomicOr(a.err_flag, 1);     // queue full: the host redoes the pass with fewer configurations
+                    }
+                }
+            }
+        }
+        first = false;
+    }
+    if (BOOLEAN) {
+        if (hit && gl == 0) atomicMin(a.enc_scene + out_idx, enc_float(-msum));
+    } else {
+        // the group's best candidate becomes (a candidate for) the configuration's champion
+#pragma unroll
+        for (int o = G / 2; o; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+            if (other > best) best = other;
+        }
+        if (gl == 0 && best) atomicMax(a.champ_scene + out_idx, best);
     }
 }
 
@@ -1445,7 +1548,7 @@ __global__ void __launch_bounds__(BLOCK) k_broadphase_poses(const PassArgs a, co
     for (int k = 0; k < n_use; ++k) {
         const int s = use_shapes[k];
         const Tf T = tf_mul(Pz, rel[k]);
-        shape_vs_scene<MESH>(a, R->shapes[s], s, pieces, T, valid, cfg, lc);
+        shape_vs_scene<MESH>(a, R->shapes[s], s, pieces, T, valid, cfg, lc, cfg * n_use + k);
     }
     if (lc) champ_publish(a, champ.scene, a.champ_scene, cfg, valid);
 }

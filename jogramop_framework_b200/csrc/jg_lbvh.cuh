@@ -157,4 +157,57 @@ __device__ __forceinline__ void lbvh_traverse(const BvhNode* __restrict__ nodes,
     }
 }
 
+// ------------------------------------------------------------------------------------ group-cooperative traversal
+// The query of one (configuration, link shape): the shape's own (oriented) box, inflated by everything a reported
+// distance may span.  Nodes are culled with the 6 face axes of the two boxes (3 world axes, 3 axes of the shape's
+// box): conservative (the 9 edge-edge axes are left out) and much tighter than world box vs world box for a rotated link.
+struct ObbQuery {
+    V3 c;            // centre (robot frame)
+    V3 a0, a1, a2;   // unit axes of the shape's box (columns of the shape's rotation)
+    V3 h;            // half extents along a0, a1, a2 INCLUDING the inflation
+    V3 e;            // half extents of its axis-aligned bounding box INCLUDING the inflation
+};
+
+__device__ __forceinline__ bool obb_vs_aabb(const ObbQuery& Q, const float* lo, const float* hi) {
+    const V3 nh = mk(0.5f * (hi[0] - lo[0]), 0.5f * (hi[1] - lo[1]), 0.5f * (hi[2] - lo[2]));
+    const V3 d = mk(0.5f * (hi[0] + lo[0]) - Q.c.x, 0.5f * (hi[1] + lo[1]) - Q.c.y, 0.5f * (hi[2] + lo[2]) - Q.c.z);
+    if (fabsf(d.x) > Q.e.x + nh.x || fabsf(d.y) > Q.e.y + nh.y || fabsf(d.z) > Q.e.z + nh.z) return false;
+    if (fabsf(dot(Q.a0, d)) > Q.h.x + fmaf(fabsf(Q.a0.x), nh.x, fmaf(fabsf(Q.a0.y), nh.y, fabsf(Q.a0.z) * nh.z))) return false;
+    if (fabsf(dot(Q.a1, d)) > Q.h.y + fmaf(fabsf(Q.a1.x), nh.x, fmaf(fabsf(Q.a1.y), nh.y, fabsf(Q.a1.z) * nh.z))) return false;
+    if (fabsf(dot(Q.a2, d)) > Q.h.z + fmaf(fabsf(Q.a2.x), nh.x, fmaf(fabsf(Q.a2.y), nh.y, fabsf(Q.a2.z) * nh.z))) return false;
+    return true;
+}
+
+// Exact box-vs-triangle overlap (separating axes: 3 box faces, the triangle's plane, 9 edge cross products); the box is
+// Q's (centre, axes, half extents h).  Closed sets: touching counts as overlapping.
+__device__ __forceinline__ bool box_tri_overlap(const ObbQuery& Q, V3 p0, V3 p1, V3 p2) {
+    const V3 d0 = p0 - Q.c, d1 = p1 - Q.c, d2 = p2 - Q.c;
+    const V3 v0 = mk(dot(Q.a0, d0), dot(Q.a1, d0), dot(Q.a2, d0));
+    const V3 v1 = mk(dot(Q.a0, d1), dot(Q.a1, d1), dot(Q.a2, d1));
+    const V3 v2 = mk(dot(Q.a0, d2), dot(Q.a1, d2), dot(Q.a2, d2));
+    const V3 h = Q.h;
+    if (fminf(v0.x, fminf(v1.x, v2.x)) > h.x || fmaxf(v0.x, fmaxf(v1.x, v2.x)) < -h.x) return false;
+    if (fminf(v0.y, fminf(v1.y, v2.y)) > h.y || fmaxf(v0.y, fmaxf(v1.y, v2.y)) < -h.y) return false;
+    if (fminf(v0.z, fminf(v1.z, v2.z)) > h.z || fmaxf(v0.z, fmaxf(v1.z, v2.z)) < -h.z) return false;
+    const V3 e0 = v1 - v0, e1 = v2 - v1, e2 = v0 - v2;
+    const V3 n = cross(e0, e1);
+    if (fabsf(dot(n, v0)) > fmaf(h.x, fabsf(n.x), fmaf(h.y, fabsf(n.y), h.z * fabsf(n.z)))) return false;
+    // axis = (box axis u_j) x (edge e): projections of the three vertices (two of them coincide) against the box radius
+#define JG_AXIS(ex, ey, ez, va, vb)                                                                              \
+    {                                                                                                            \
+        const float fx = fabsf(ex), fy = fabsf(ey), fz = fabsf(ez);                                               \
+        { const float pa = ey * va.z - ez * va.y, pb = ey * vb.z - ez * vb.y;   /* u = x */                       \
+          if (fminf(pa, pb) > h.y * fz + h.z * fy || fmaxf(pa, pb) < -(h.y * fz + h.z * fy)) return false; }     \
+        { const float pa = ez * va.x - ex * va.z, pb = ez * vb.x - ex * vb.z;   /* u = y */                       \
+          if (fminf(pa, pb) > h.x * fz + h.z * fx || fmaxf(pa, pb) < -(h.x * fz + h.z * fx)) return false; }     \
+        { const float pa = ex * va.y - ey * va.x, pb = ex * vb.y - ey * vb.x;   /* u = z */                       \
+          if (fminf(pa, pb) > h.x * fy + h.y * fx || fmaxf(pa, pb) < -(h.x * fy + h.y * fx)) return false; }     \
+    }
+    JG_AXIS(e0.x, e0.y, e0.z, v0, v2)   // along e0 the vertices v0 and v1 project alike
+    JG_AXIS(e1.x, e1.y, e1.z, v1, v0)
+    JG_AXIS(e2.x, e2.y, e2.z, v2, v1)
+#undef JG_AXIS
+    return true;
+}
+
 }  // namespace jg

@@ -99,6 +99,66 @@ def test_overflow_kernel_parity(robot, scene_loader, engines):
     assert 65536 // 4 < es.stats()['overflow_run'] < 65536
 
 
+def _tri_scene(sc, margin=0.001):
+    import copy
+    t = copy.copy(sc)
+    t.piece_verts = sc.tri_verts[sc.tris].reshape(-1, 3)
+    t.piece_vert_offset = (np.arange(len(sc.tris) + 1) * 3).astype(np.int32)
+    t.piece_body = sc.tri_body
+    t.piece_margin = np.full(len(sc.tris), margin)
+    return t
+
+
+def test_mesh_mode_edges_host_path_and_deep_trees(robot, scene_loader):
+    """Mesh mode beyond single configurations: edge validation (substeps share the LBVH queries), the host-buffer entry
+    points (blocking and ticket form), scenario 045, and a degenerate mesh whose LBVH is a long chain (many coincident
+    centroids -> Morton ties) plus one far larger than a lane's old 64-entry stack could hold a frontier of."""
+    import copy
+    from jogramop_framework_b200.engine import CollisionEngine
+    sc = scene_loader(45)
+    o = Oracle(robot, _tri_scene(sc))
+    e = CollisionEngine(robot, sc, mesh_mode=True)
+    fl = oracle.SCENE | oracle.PLANE | oracle.NO_EPA
+    lim = robot.joint_limits[robot.arm_joint_ids]
+    qa = uniform_configs(robot, 1500, 451)
+    qb = np.clip(qa + np.random.default_rng(452).uniform(-0.25, 0.25, qa.shape), lim[:, 0], lim[:, 1]).astype(np.float32)
+    rb, rd = o.check_edges(qa.astype(np.float64), qb.astype(np.float64), substeps=16, flags=fl)
+    b, d = e.check_edges(qa, qb, substeps=16, flags=fl)
+    compare(b, d, rb, rd)
+    q = uniform_configs(robot, 30000, 453)
+    rb, rd = o.check(q.astype(np.float64), flags=fl)
+    b, d, _ = e.check(q, flags=fl)
+    compare(b, d, rb, rd)
+    hb, hd, _ = e.check_host(q, flags=fl)
+    assert np.array_equal(np.unpackbits(hb.numpy().view(np.uint8), bitorder='little')[:len(q)].astype(bool), b.cpu().numpy())
+    assert np.array_equal(hd.numpy(), d.cpu().numpy())
+    tk = e.check_host_submit(q, flags=fl)
+    tb, td, _ = e.check_host_wait(tk)
+    assert np.array_equal(tb.numpy(), hb.numpy()) and np.array_equal(td.numpy(), hd.numpy())
+    e.close()
+    # degenerate mesh: 3000 copies of a few triangles at one place (identical Morton codes: the hierarchy is decided by
+    # the index tie-break) + a dense fan of slivers around the robot's workspace
+    rng = np.random.default_rng(7)
+    base = np.array([[0.5, -0.2, 0.3], [0.7, -0.2, 0.3], [0.6, 0.0, 0.45]])
+    tv = [base + 1e-7 * rng.normal(size=(3, 3)) for _ in range(3000)]
+    ang = np.linspace(0, 2 * np.pi, 2000, endpoint=False)
+    tv += [np.array([[0.6, 0.3, 0.2], [0.6 + 0.5 * np.cos(a), 0.3 + 0.5 * np.sin(a), 0.6], [0.6 + 0.5 * np.cos(a + 0.004), 0.3 + 0.5 * np.sin(a + 0.004), 0.6]]) for a in ang]
+    deg = copy.copy(sc)
+    deg.tri_verts = np.concatenate(tv)
+    deg.tris = np.arange(len(deg.tri_verts)).reshape(-1, 3).astype(np.int32)
+    deg.tri_body = np.zeros(len(deg.tris), np.int32)
+    od = Oracle(robot, _tri_scene(deg))
+    ed = CollisionEngine(robot, deg, mesh_mode=True)
+    q = uniform_configs(robot, 4000, 454)
+    q[:, 0] = np.random.default_rng(455).uniform(-0.3, 0.3, len(q))     # base near the slivers / the stack of copies
+    q[:, 1] = np.random.default_rng(456).uniform(-0.2, 0.6, len(q))
+    rb, rd = od.check(q.astype(np.float64), flags=fl)
+    b, d, _ = ed.check(q, flags=fl)
+    compare(b, d, rb, rd)
+    assert 0.05 < rb.mean() < 0.95
+    ed.close()
+
+
 @pytest.mark.parametrize('sid', [11, 34])
 def test_mesh_mode_lbvh_parity(sid, robot, scene_loader):
     """Mesh mode: link hulls vs the merged triangle mesh (export/obstacles.obj) through the GPU-built LBVH ==
