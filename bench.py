@@ -313,6 +313,26 @@ def bench_other_configs(robot, dev, budget_s=1.0):
     except Exception as exc:
         c5['burg_gripper_visual_meshes'] = {'unavailable': repr(exc)[:300]}
     out['config5_gripper_poses'] = c5
+
+    # ---- the headline workload on the simplified geometry profile (mobile_panda_fingersSmallMesh.urdf: boxes around the
+    #      links, what the sister planners load; not the pyBullet model of the reference)
+    try:
+        from jogramop_framework_b200.ingest import RobotModel
+        small = RobotModel.load(os.path.join(data, 'robot_mobile_panda_simplified.npz'))
+        scene = SceneModel.load(os.path.join(data, 'scene_011.npz'))
+        eng = CollisionEngine(small, scene, device=dev.index)
+        qh = make_configs(small, 1_000_000, 11)
+        q = torch.from_numpy(qh).to(dev)
+        ms_s = timed(lambda: eng.check(q, flags=SCENE | PLANE, packed=True), reps=5, warm=3)
+        rb, rd = oracle.Oracle(small, scene).check(qh[:20000].astype(np.float64), flags=3)
+        gb, gd, _ = eng.check(q[:20000], flags=SCENE | PLANE)
+        out['simplified_geometry_profile'] = {
+            'workload': 'scenario 011, 1 000 000 uniform configurations, bit + signed min distance, robot = mobile_panda_fingersSmallMesh.urdf '
+                        '(13 shapes, 204 hull vertices instead of 1 370)',
+            'ms': ms_s, 'checks_per_s': 1e6 / ms_s * 1e3, 'parity': parity(gb, gd, rb, rd)}
+        eng.close()
+    except Exception as exc:
+        out['simplified_geometry_profile'] = {'unavailable': repr(exc)[:300]}
     return out
 
 

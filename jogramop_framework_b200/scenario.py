@@ -119,13 +119,14 @@ class Scenario:
         rng = np.random.default_rng(seed)
         self.select_indices = rng.choice(len(self.gs), n, replace=False)
 
-    def get_robot_and_sim(self, with_gui=False):
-        """Get the robot and simulator handles (scenario.py:59-67)."""
+    def get_robot_and_sim(self, with_gui=False, geometry='full'):
+        """Get the robot and simulator handles (scenario.py:59-67).  ``geometry='simplified'`` loads the sister planners'
+        box profile of the robot instead of the full collision meshes (see simulation.load_robot_model)."""
         sim = GraspingSimulator(verbose=with_gui, device=self.device)
         sim.add_scene(self._scene_model)
         sim.scene = self.scene
         sim._visual_model_fn = self.visual_scene_model
-        robot = FrankaRobot(sim, self.robot_pose, with_platform=self.with_platform)
+        robot = FrankaRobot(sim, self.robot_pose, with_platform=self.with_platform, geometry=geometry)
         return robot, sim
 
     @staticmethod

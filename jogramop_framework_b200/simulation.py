@@ -34,13 +34,21 @@ def reference_root():
     return None
 
 
-def load_robot_model(with_platform):
+def load_robot_model(with_platform, geometry='full'):
+    """``geometry='full'``: the URDFs the reference's Python uses (mobile_panda.urdf / panda.urdf, meshes/collision/*.obj,
+    simulation.py:137-139).  ``'simplified'``: mobile_panda_fingersSmallMesh.urdf -- boxes around the links
+    (meshes/collisionSmall/*BBox.obj), the profile the sister C++ planners load; not what pyBullet checks in the reference,
+    so its verdicts are more conservative (bigger shapes), and several times cheaper to check."""
+    if geometry not in ('full', 'simplified'):
+        raise ValueError("geometry must be 'full' or 'simplified'")
+    if geometry == 'simplified' and not with_platform:
+        raise NotImplementedError('the reference ships the simplified profile only for the mobile robot')
     root = reference_root()
     name = 'mobile_panda' if with_platform else 'panda'
+    urdf = f'{name}.urdf' if geometry == 'full' else 'mobile_panda_fingersSmallMesh.urdf'
     if root is not None:
-        return ingest.load_robot_urdf(os.path.join(root, 'robots', 'franka_panda', f'{name}.urdf'),
-                                      with_platform=with_platform)
-    return ingest.RobotModel.load(os.path.join(_DATA, f'robot_{name}.npz'))
+        return ingest.load_robot_urdf(os.path.join(root, 'robots', 'franka_panda', urdf), with_platform=with_platform)
+    return ingest.RobotModel.load(os.path.join(_DATA, f'robot_{name}.npz' if geometry == 'full' else 'robot_mobile_panda_simplified.npz'))
 
 
 class GraspingSimulator:
@@ -286,11 +294,12 @@ class FrankaRobot:
         0, 0, 0, 1
     ]).reshape(4, 4)
 
-    def __init__(self, simulator, pose, with_platform=False):
+    def __init__(self, simulator, pose, with_platform=False, geometry='full'):
         self._simulator = simulator
         self._bullet_client = None
         self.pose = np.asarray(pose, dtype=np.float64)
-        self.model = load_robot_model(with_platform)
+        self.geometry = geometry
+        self.model = load_robot_model(with_platform, geometry)
         pos, _ = util.position_and_quaternion_from_tf(self.pose)
         if pos[2] < 0.05:   # simulation.py:146-148
             print('WARNING: consider a larger z-value for your robot, to avoid false positives during collision '

@@ -168,3 +168,34 @@ def test_calls_on_different_streams_share_the_arena_safely(robot, scene_loader):
         hb_bits = np.unpackbits(hb.numpy().view(np.uint8), bitorder='little')[:len(q2)].astype(bool)
         assert np.array_equal(hb_bits, r2b.cpu().numpy()) and np.array_equal(hd.numpy(), r2d.cpu().numpy())
     e.close()
+
+
+def test_simplified_geometry_profile(scene_loader):
+    """mobile_panda_fingersSmallMesh.urdf (boxes around the links: the sister planners' profile; 13 shapes, panda_link7
+    carries TWO of them, so its self pairs cover several shape combinations): all flags vs the oracle, and the drop-in
+    classes with ``geometry='simplified'``."""
+    from jogramop_framework_b200.engine import CollisionEngine
+    from jogramop_framework_b200.ingest import RobotModel
+    from jogramop_framework_b200.scenario import Scenario
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    small = RobotModel.load(os.path.join(ROOT, 'jogramop_framework_b200', 'data', 'robot_mobile_panda_simplified.npz'))
+    assert small.n_shapes == 13 and (small.shape_link == 9).sum() == 2
+    for sid in (11, 34):
+        scene = scene_loader(sid)
+        e, o = CollisionEngine(small, scene), Oracle(small, scene)
+        q = uniform_configs(small, N, 9100 + sid)
+        rb, rd = o.check(q.astype(np.float64), flags=ALL)
+        b, d, _ = e.check(q, flags=ALL)
+        _cmp(f'{sid:03d} simplified geometry, all flags {N}', b, d, rb, rd)
+        e.close()
+    s = Scenario(11)
+    rob, sim = s.get_robot_and_sim(geometry='simplified')
+    full, sim2 = s.get_robot_and_sim()
+    q = uniform_configs(small, 20000, 9200)
+    bs, _ = rob.in_collision_batch(q)
+    bf, _ = full.in_collision_batch(q)
+    # the boxes contain the links: whatever collides with the full meshes (well inside) collides with the boxes
+    assert bs.float().mean() > bf.float().mean()
+    assert (bs | ~bf).float().mean() > 0.995
+    sim.dismiss()
+    sim2.dismiss()

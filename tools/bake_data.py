@@ -11,6 +11,7 @@ recipe that generated them:
 
 Outputs
   jogramop_framework_b200/data/robot_{mobile_panda,panda}.npz   RobotModel
+  jogramop_framework_b200/data/robot_mobile_panda_simplified.npz  RobotModel of mobile_panda_fingersSmallMesh.urdf
   jogramop_framework_b200/data/scene_<id>.npz                   SceneModel (+ grasps_world)
   jogramop_framework_b200/data/scene_045_singlehull.npz         045 with the stale one-piece gate (quirk Q1)
   jogramop_framework_b200/data/gate_0_54_pieces.npz             recovered 2-piece gate decomposition
@@ -56,7 +57,10 @@ def main():
     os.makedirs(data, exist_ok=True)
     os.makedirs(gold, exist_ok=True)
 
-    for urdf, out in (('mobile_panda.urdf', 'robot_mobile_panda.npz'), ('panda.urdf', 'robot_panda.npz')):
+    # mobile_panda_fingersSmallMesh.urdf: the simplified geometry profile of the sister planners (boxes around the links,
+    # meshes/collisionSmall/*BBox.obj); pyBullet's checks in the reference use the full meshes, this one is optional
+    for urdf, out in (('mobile_panda.urdf', 'robot_mobile_panda.npz'), ('panda.urdf', 'robot_panda.npz'),
+                      ('mobile_panda_fingersSmallMesh.urdf', 'robot_mobile_panda_simplified.npz')):
         r = I.load_robot_urdf(os.path.join(ref, 'robots/franka_panda', urdf))
         r.save(os.path.join(data, out))
         print(out, 'links', r.n_links, 'shapes', r.n_shapes, 'hull verts', len(r.core_verts))
