@@ -357,7 +357,9 @@ def run_b200(args):
         dist.init_process_group('nccl', device_id=dev)
     robot, scene = load_models(args.scenario)
     flags = SCENE | PLANE | (NO_EPA if args.no_epa else 0)
-    n = args.n
+    # --strong: the SAME total batch (args.n configurations) cut into 32-aligned shards, one per GPU (builder-run record of
+    # where the fixed per-pass costs start to show; the driver's scaling run is the weak form)
+    n = args.n if not args.strong else ((args.n + world - 1) // world + 31) // 32 * 32
     ROT = 4                                    # rotating input batches: 4 x 36 MB > L2
     q_hosts = [make_configs(robot, n, 11 + 1000 * rank + 7919 * r) for r in range(ROT)]
     q_host = q_hosts[0]
@@ -491,7 +493,7 @@ def run_b200(args):
         line = {
             'metric': 'configuration collision checks/sec', 'value': value, 'unit': 'checks/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_total / args.steps,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'higher_is_better': True, 'scaling': 'strong' if args.strong else 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': f'scenario {args.scenario:03d}: {n} uniformly sampled mobile-Panda configurations per GPU, '
                                    'collision bit + signed min distance (SCENE+PLANE)',
                        'configs_per_gpu': n, 'seed': '11 + 1000*rank (+ 7919*r for the rotating batches r = 1..3)', 'flags': int(flags),
@@ -646,6 +648,7 @@ def main():
     ap.add_argument('--no-count', action='store_true', help='skip the counted-work audit (instrumented library)')
     ap.add_argument('--no-extras', action='store_true', help='skip the CUDA-graph line, the soak and the configs 3/4/5 block')
     ap.add_argument('--soak', type=float, default=2.0, help='seconds of the soak loop (sustained clocks)')
+    ap.add_argument('--strong', action='store_true', help='strong scaling: --n is the TOTAL batch, split over the GPUs')
     ap.add_argument('--cpu-budget', type=float, default=10.0, help='seconds of CPU work for the cpu_baseline sample')
     ap.add_argument('--ref-sample', type=int, default=200_000, help='configurations per step of the reference arm')
     args = ap.parse_args()

@@ -23,7 +23,7 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from jogramop_framework_b200.dist import gather_bits, shard_bounds  # noqa: E402
+from jogramop_framework_b200.dist import GatherBuffer, gather_bits, shard_bounds  # noqa: E402
 from jogramop_framework_b200.engine import PLANE, SCENE, CollisionEngine  # noqa: E402
 from jogramop_framework_b200.ingest import RobotModel, SceneModel  # noqa: E402
 
@@ -81,16 +81,14 @@ def main():
         g = torch.Generator(device=dev)
         g.manual_seed(sid * 1000 + rank)
         q = lo_q + (hi_q - lo_q) * torch.rand((hi - lo, 9), generator=g, device=dev)
-        words = torch.empty(((hi - lo) + 31) // 32, dtype=torch.int32, device=dev)
+        buf = GatherBuffer(n_cfg, dev)        # the kernels write into this rank's slot: in-place all-gather
         dmin = torch.empty(hi - lo, dtype=torch.float32, device=dev)
 
         def run():
             for c0 in range(0, hi - lo, CHUNK):
                 c1 = min(c0 + CHUNK, hi - lo)
-                b, d, _ = eng.check(q[c0:c1], flags=SCENE | PLANE, packed=True)
-                words[c0 // 32:c0 // 32 + b.numel()] = b
-                dmin[c0:c1] = d
-            return gather_bits(words, n_cfg)
+                eng.check(q[c0:c1], flags=SCENE | PLANE, packed=True, bits_out=buf.slot[c0 // 32:], dist_out=dmin[c0:c1])
+            return buf.gather()
 
         ms, allw = timed(run)
         total_ms += ms
@@ -162,7 +160,30 @@ def main():
 
     ms, allw = timed(run_poses)
     hit = torch.bitwise_and(allw.view(-1, 1) >> torch.arange(32, device=dev, dtype=torch.int32), 1).sum().item() / n_cfg
-    emit(config=5, scenario=11, n=n_cfg, n_gpus=world, ms=ms, checks_per_s=n_cfg / ms * 1e3, collision_rate=hit)
+    emit(config=5, scenario=11, n=n_cfg, n_gpus=world, ms=ms, checks_per_s=n_cfg / ms * 1e3, collision_rate=hit,
+         model='panda_hand + finger hulls (Bullet margins) vs the convex pieces, bit + signed distance')
+    del eng
+    # the reference's own filter: burg two-finger gripper vs the visual meshes, boolean (create_graspset.py:53-59)
+    import contextlib
+    import io
+    from jogramop_framework_b200.graspset import burg_gripper_model
+    from jogramop_framework_b200.scenario import Scenario
+    with contextlib.redirect_stdout(io.StringIO()):
+        vis = Scenario(11, device=local).visual_scene_model()
+    geng = CollisionEngine(burg_gripper_model(), vis, device=local, threshold=1e-6, finger_open=0.0, mesh_mode=True, mesh_margin=0.0)
+
+    def run_burg():
+        words = torch.empty(((hi - lo) + 31) // 32, dtype=torch.int32, device=dev)
+        for c0 in range(0, hi - lo, CHUNK):
+            c1 = min(c0 + CHUNK, hi - lo)
+            b, _ = geng.check_poses(pq[c0:c1], links=[0], ee_link=0, want_dist=False, packed=True)
+            words[c0 // 32:c0 // 32 + b.numel()] = b
+        return gather_bits(words, n_cfg)
+
+    ms, allw = timed(run_burg)
+    hit = torch.bitwise_and(allw.view(-1, 1) >> torch.arange(32, device=dev, dtype=torch.int32), 1).sum().item() / n_cfg
+    emit(config=5, scenario=11, n=n_cfg, n_gpus=world, ms=ms, checks_per_s=n_cfg / ms * 1e3, collision_rate=hit,
+         model=f'burg two-finger gripper vs the visual meshes ({len(vis.tris)} triangles, LBVH) + plane, boolean: the reference filter')
     if world > 1:
         dist.destroy_process_group()
 
