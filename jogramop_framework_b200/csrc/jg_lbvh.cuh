@@ -1,5 +1,6 @@
 // jg_lbvh.cuh -- linear BVH over the triangles of the merged obstacle mesh, built on the GPU at scene load
-// (Morton codes -> radix sort -> Karras 2012 hierarchy -> bottom-up box refit), and its per-thread traversal.
+// (Morton codes -> radix sort -> Karras 2012 hierarchy -> bottom-up box refit), and the tests of its traversal (the
+// traversal kernel itself, k_mesh_traverse, is in jg_kernels.cuh: a group of lanes per query walks the tree together).
 //
 // The reference exports every scenario's obstacles as ONE triangle mesh (create_cpp_export.py:40-69,
 // scenarios/<id>/export/obstacles.obj) for the sister planners; "mesh mode" answers the same query against that mesh
@@ -121,39 +122,6 @@ __global__ void k_lbvh_refit(const float4* __restrict__ tri_v, int n, BvhNode* _
         for (int a = 0; a < 3; ++a) { N.lo[a] = lo[a]; N.hi[a] = hi[a]; }
         __threadfence();
         node = parent[node];
-    }
-}
-
-// Calls f(slot, overlap, p0, p1, p2) for every triangle whose box overlaps [qlo, qhi] (the vertices come along so that the
-// caller can apply further separating-axis tests).  Per-thread stack; depth of a 30-bit Morton tree with index
-// tie-break is bounded by 64.
-template <class F>
-__device__ __forceinline__ void lbvh_traverse(const BvhNode* __restrict__ nodes, const float4* __restrict__ tri_v, int n,
-                                              const float* qlo, const float* qhi, F f) {
-    if (n <= 0) return;
-    // leaf test; on a hit f(slot, ov) gets the smallest signed axis overlap of the query box and the triangle's box
-    auto leaf = [&](int slot) {
-        const float4 p0 = tri_v[3 * slot], p1 = tri_v[3 * slot + 1], p2 = tri_v[3 * slot + 2];
-        const float lo[3] = {fminf(p0.x, fminf(p1.x, p2.x)), fminf(p0.y, fminf(p1.y, p2.y)), fminf(p0.z, fminf(p1.z, p2.z))};
-        const float hi[3] = {fmaxf(p0.x, fmaxf(p1.x, p2.x)), fmaxf(p0.y, fmaxf(p1.y, p2.y)), fmaxf(p0.z, fmaxf(p1.z, p2.z))};
-        const float ov = fminf(fminf(fminf(qhi[0], hi[0]) - fmaxf(qlo[0], lo[0]), fminf(qhi[1], hi[1]) - fmaxf(qlo[1], lo[1])),
-                               fminf(qhi[2], hi[2]) - fmaxf(qlo[2], lo[2]));
-        if (ov >= 0.f) f(slot, ov, mk(p0.x, p0.y, p0.z), mk(p1.x, p1.y, p1.z), mk(p2.x, p2.y, p2.z));
-    };
-    if (n == 1) {
-        leaf(0);
-        return;
-    }
-    int stack[64];
-    int sp = 0;
-    stack[sp++] = 0;
-    while (sp > 0) {
-        const BvhNode N = nodes[stack[--sp]];
-        if (!(N.lo[0] <= qhi[0] && N.hi[0] >= qlo[0] && N.lo[1] <= qhi[1] && N.hi[1] >= qlo[1] && N.lo[2] <= qhi[2] &&
-              N.hi[2] >= qlo[2]))
-            continue;
-        if (N.left < 0) leaf(~N.left); else if (sp < 64) stack[sp++] = N.left;
-        if (N.right < 0) leaf(~N.right); else if (sp < 64) stack[sp++] = N.right;
     }
 }
 
