@@ -196,6 +196,22 @@ def test_readers_on_awkward_files(tmp_path):
     assert same_point_sets(d['verts'][d['off'][1]:], np.array([[0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1], [0.5, 0.5, 3.0]], float))
     assert len(d['verts'][:d['off'][1]]) == 6
     L.jg_scene_free(s)
+    # an OBJ without groups holding two separate boxes: ONE hull for pyBullet's reading, two with connected components
+    def box(o, n0):
+        v = ''.join(f'v {o + x} {y} {z}\n' for x in (0, 1) for y in (0, 1) for z in (0, 1))
+        f = [(1, 2, 4, 3), (5, 7, 8, 6), (1, 5, 6, 2), (3, 4, 8, 7), (1, 3, 7, 5), (2, 6, 8, 4)]
+        return v + ''.join('f ' + ' '.join(str(i + n0) for i in q) + '\n' for q in f)
+    (lib / 'vhacd' / 'two.obj').write_text(box(0.0, 0) + box(5.0, 8))
+    (lib / 'object_library.yaml').write_text((lib / 'object_library.yaml').read_text() +
+                                             '- identifier: two\n  scale: 1.0\n  vhacd_fn: vhacd/two.obj\n')
+    s1 = L.jg_scene_load_ex(scene(['two']), (C.c_double * 16)(*np.eye(4).reshape(-1)), 0)
+    s2 = L.jg_scene_load_ex(scene(['two']), (C.c_double * 16)(*np.eye(4).reshape(-1)), 1)
+    d1, d2 = describe_scene(L, s1), describe_scene(L, s2)
+    assert d1['n_pieces'] == 1 and len(d1['verts']) == 8 and d1['verts'][:, 0].max() == 6.0        # hull of both boxes
+    assert d2['n_pieces'] == 2 and d2['off'].tolist() == [0, 8, 16] and d2['body'].tolist() == [0, 0]
+    assert not L.jg_scene_load_ex(scene(['two']), None, 7) and b'policy' in L.jg_last_error()
+    L.jg_scene_free(s1)
+    L.jg_scene_free(s2)
     assert not L.jg_scene_load(scene(['scaled']), None) and b'scale' in L.jg_last_error()
     assert not L.jg_scene_load(scene(['ghost']), None) and b'none.obj' in L.jg_last_error()
     assert not L.jg_scene_load(scene(['unknown']), None) and b'unknown' in L.jg_last_error()
