@@ -448,8 +448,15 @@ class FrankaRobot:
         return bool(bits[0])
 
     def in_collision(self):
-        """``simulation.py:466-472``: robot against the scene (plane, obstacles, target object); no self collisions."""
-        return self._simulator.body_in_collision(self.body_id)
+        """``simulation.py:466-472``: robot against the scene (plane, obstacles, target object); no self collisions.
+        The reference walks the bodies one by one (``body_in_collision``) and returns at the first hit; the verdict is
+        "any body", so ONE engine call against all registered bodies gives it.  With DEBUG logging on, the per-body walk
+        (and its log lines, simulation.py:103-120) is kept."""
+        if _log.isEnabledFor(logging.DEBUG):
+            return self._simulator.body_in_collision(self.body_id)
+        bits, _, _ = self._simulator._engine('full').check(np.asarray(self._q, dtype=np.float32)[None],
+                                                           flags=_engine.SCENE | _engine.PLANE, want_dist=False)
+        return bool(bits[0])
 
     # ------------------------------------------------------------------ batched, pure
     def forward_kinematics_batch(self, q, all_links=False, as_matrix=False):

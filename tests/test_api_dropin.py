@@ -205,6 +205,7 @@ def test_single_shot_queries_match_oracle(robot, scene_loader, golden):
         rob.reset_arm_joints(q[i])
         if abs(rd[i] + 0.001) > 1e-3:
             assert rob.in_collision() == bool(rb[i])
+            assert sim.body_in_collision(rob.body_id) == bool(rb[i])       # the reference's per-body walk: same verdict
         if abs(sd[i] + 0.001) > 1e-3:
             assert rob.in_self_collision() == bool(sb[i])
     # one link pair (links_in_collision, simulation.py:82-95)
