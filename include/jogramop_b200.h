@@ -179,7 +179,9 @@ int jg_fk(jg_engine*, const float* q, int64_t n, int dof, const int32_t* link_id
  * q [n,dof] device fp32.  bits: ceil(n/32) uint32 words, bit i%32 of word i/32 = configuration i collides
  * (or violates limits if JG_LIMITS).  min_dist [n] (may be NULL): min contactDistance over everything
  * checked, clamped to query_distance.  With min_dist == NULL only verdicts are computed: the engine then prunes
- * everything that cannot flip a bit (same bits, several times faster).  reason [n] uint8 (may be NULL): 0 ok, 1 limits, 2 self, 3 scene. */
+ * everything that cannot flip a bit (same bits, several times faster).  reason [n] uint8 (may be NULL): 0 ok, 1 limits, 2 self, 3 scene.
+ * A configuration (edge end point, pose) with a NaN or infinite component has no geometry: its bit is set and its reason
+ * is 1 whatever `flags` says; its distance is the query distance. */
 int jg_check(jg_engine*, const float* q, int64_t n, int dof, uint32_t flags, uint32_t* bits, float* min_dist,
              uint8_t* reason, void* stream);
 

@@ -995,7 +995,7 @@ extern "C" int jg_check(jg_engine* e, const float* q, int64_t n, int dof, uint32
         fill_args(e, a, flags, min_dist != nullptr);
         a.q = q + off * dof; a.n = m;
         CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * JG_COUNTS_INTS(e->n_keys), st));
-        if (flags & JG_LIMITS) CUDA_TRY(cudaMemsetAsync(e->viol, 0, sizeof(uint32_t) * (e->cap / 32 + 1), st));
+        CUDA_TRY(cudaMemsetAsync(e->viol, 0, sizeof(uint32_t) * (e->cap / 32 + 1), st));
         prof_begin(e, 0, st);
         launch_broadphase(e, a, (m + BP_BLOCK - 1) / BP_BLOCK, bp_smem(e, flags), st);
         e->stats.kernel_launches += 1;
@@ -1037,7 +1037,7 @@ extern "C" int jg_check_edges(jg_engine* e, const float* qa, const float* qb, in
         fill_args(e, a, flags, min_dist != nullptr);
         a.q = qa + off * dof; a.qb = qb + off * dof; a.n = me * substeps; a.substeps = substeps;
         CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * JG_COUNTS_INTS(e->n_keys), st));
-        if (flags & JG_LIMITS) CUDA_TRY(cudaMemsetAsync(e->viol, 0, sizeof(uint32_t) * (e->cap / 32 + 1), st));
+        CUDA_TRY(cudaMemsetAsync(e->viol, 0, sizeof(uint32_t) * (e->cap / 32 + 1), st));
         prof_begin(e, 0, st);
         k_init_scratch<<<(me + 255) / 256, 256, 0, st>>>(e->enc_scene, e->enc_self, e->champ_scene, e->champ_self, me);
         launch_broadphase(e, a, (a.n + BP_BLOCK - 1) / BP_BLOCK, bp_smem(e, flags), st);
@@ -1136,6 +1136,7 @@ extern "C" int jg_check_poses(jg_engine* e, const float* poses, int64_t n, int f
         a.n = m;
         a.mesh_n_use = (int)use.size();
         CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * JG_COUNTS_INTS(e->n_keys), st));
+        CUDA_TRY(cudaMemsetAsync(e->viol, 0, sizeof(uint32_t) * (e->cap / 32 + 1), st));
         const size_t smem = sizeof(RobotTab) + sizeof(PieceRec) * e->P;
         prof_begin(e, 0, st);
         if (e->mesh)
@@ -1241,7 +1242,7 @@ static int host_pass(jg_engine* e, int b, const float* q, int64_t off, int m, in
     fill_args(e, a, fl, dist != nullptr);
     a.q = e->stage_q[b]; a.n = m;
     CUDA_TRY(cudaMemsetAsync(e->counts, 0, sizeof(int) * JG_COUNTS_INTS(e->n_keys), st));
-    if (fl & JG_LIMITS) CUDA_TRY(cudaMemsetAsync(e->viol, 0, sizeof(uint32_t) * (e->cap / 32 + 1), st));
+    CUDA_TRY(cudaMemsetAsync(e->viol, 0, sizeof(uint32_t) * (e->cap / 32 + 1), st));
     const int slice = std::max(1024, ((m + SLICES - 1) / SLICES + 1023) / 1024 * 1024);
     prof_begin(e, 0, st);
     for (int c0 = 0; c0 < m; c0 += slice) {

@@ -502,11 +502,12 @@ __global__ void __launch_bounds__(BLOCK, JG_BP_OCC) k_broadphase(const PassArgs 
             a.champ_scene[out_idx] = 0ull;
             a.champ_self[out_idx] = 0ull;
         }
-        if (a.flags & 8u) {
+        {   // joint limits (JG_LIMITS); a NaN / infinite joint value is rejected whatever the flags say: it has no pose
+            const bool limits = (a.flags & 8u) != 0;
             bool bad = false;
             for (int j = 0; j < dof; ++j) {
                 const float v = qs[j * BLOCK + tid];
-                bad |= !(R->qlo[j] <= v && v <= R->qhi[j]);
+                bad |= !(fabsf(v) <= FLT_MAX) || (limits && !(R->qlo[j] <= v && v <= R->qhi[j]));
             }
             if (bad) atomicOr(a.viol + (out_idx >> 5), 1u << (out_idx & 31));
         }
@@ -1475,7 +1476,7 @@ __global__ void k_finalize(const int* __restrict__ enc_scene, const int* __restr
     if (valid) {
         ds = dec_float(enc_scene[i]);
         dself = dec_float(enc_self[i]);
-        lim = (flags & 8u) && ((viol[i >> 5] >> (i & 31)) & 1u);
+        lim = (viol[i >> 5] >> (i & 31)) & 1u;    // outside the joint limits (JG_LIMITS) or not a finite configuration / pose
     }
     const bool cself = dself < threshold, cscene = ds < threshold;
     const bool bit = valid && (lim || cself || cscene);
@@ -1541,6 +1542,9 @@ __global__ void __launch_bounds__(BLOCK) k_broadphase_poses(const PassArgs a, co
             Pz.r20 = 2.f * (x * z - y * w);       Pz.r21 = 2.f * (y * z + x * w);       Pz.r22 = 1.f - 2.f * (x * x + y * y);
             Pz.tx = p[0]; Pz.ty = p[1]; Pz.tz = p[2];
         }
+        const float chk = fabsf(Pz.r00) + fabsf(Pz.r01) + fabsf(Pz.r02) + fabsf(Pz.r10) + fabsf(Pz.r11) + fabsf(Pz.r12) + fabsf(Pz.r20) +
+                          fabsf(Pz.r21) + fabsf(Pz.r22) + fabsf(Pz.tx) + fabsf(Pz.ty) + fabsf(Pz.tz);
+        if (!(chk <= FLT_MAX)) atomicOr(a.viol + (cfg >> 5), 1u << (cfg & 31));   // NaN / infinite pose: rejected
     }
     Champ champ;
     champ.scene = champ.self = 0ull;

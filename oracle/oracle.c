@@ -647,6 +647,13 @@ static void check_one(const orc_robot* r, const orc_scene* sc, const double* q, 
     fk_links(r, q, finger_open, links);
     shape_transforms(r, links, shapeT);
     int lim = 0;
+    for (int j = 0; j < r->dof; ++j)
+        if (!isfinite(q[j])) {   /* a NaN / infinite joint value has no pose: rejected whatever the flags say */
+            if (bit) *bit = 1;
+            if (dist) *dist = qd;
+            if (reason) *reason = 1;
+            return;
+        }
     if (flags & ORC_LIMITS)
         for (int j = 0; j < r->dof; ++j)
             if (!(r->q_limits[2 * j] <= q[j] && q[j] <= r->q_limits[2 * j + 1])) lim = 1;
@@ -707,6 +714,13 @@ static void poses_range(int64_t b, int64_t e, void* p) {
     for (int64_t i = b; i < e; ++i) {
         tf shapeT[MAX_LINKS];
         const tf* P = (const tf*)(c->poses + 12 * i);
+        int finite = 1;
+        for (int k = 0; k < 12; ++k) finite &= isfinite(c->poses[12 * i + k]) ? 1 : 0;
+        if (!finite) {   /* no geometry: rejected */
+            if (c->bits) c->bits[i] = 1;
+            if (c->dist) c->dist[i] = c->qd;
+            continue;
+        }
         for (int k = 0; k < c->ns; ++k) shapeT[c->shapes[k]] = tf_mul(P, &c->rel[c->shapes[k]]);
         double d = scene_min_distance(c->r, c->sc, shapeT, c->shapes, c->ns, c->qd, c->flags, NULL);
         if (c->bits) c->bits[i] = (uint8_t)(d < c->threshold);

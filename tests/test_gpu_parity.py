@@ -469,6 +469,35 @@ def test_async_host_path_two_batches_in_flight(robot, scene_loader, engines):
     assert torch.equal(unpack_bits(wb.cuda(), len(batches[0])), ref[0][0])
 
 
+def test_non_finite_inputs_are_rejected_on_the_gpu(robot, scene_loader, engines):
+    """NaN / inf joint values and poses: bit set, reason 1, distance = query distance, with or without JG_LIMITS -- as the
+    oracle does (tests/test_oracle_properties.py); the neighbours of such a row are untouched."""
+    e = engines(11)
+    o = Oracle(robot, scene_loader(11))
+    q = uniform_configs(robot, 4096, 606)
+    bad = [5, 64, 1000, 4095]
+    q[5, 2] = np.nan
+    q[64, 0] = np.inf
+    q[1000, 8] = -np.inf
+    q[4095, 4] = np.nan
+    for fl in (oracle.SCENE | oracle.PLANE, oracle.SCENE | oracle.PLANE | oracle.SELF | oracle.LIMITS):
+        rb, rd, rr = o.check(q.astype(np.float64), flags=fl, want_reason=True)
+        b, d, r = e.check(q, flags=fl, want_reason=True)
+        b, d, r = b.cpu().numpy(), d.cpu().numpy(), r.cpu().numpy()
+        assert b[bad].all() and (r[bad] == 1).all() and np.allclose(d[bad], 0.01) and rb[bad].all()
+        compare(torch.from_numpy(b), torch.from_numpy(d), rb, rd)
+    bv, _, _ = e.check(q, flags=3, want_dist=False)
+    assert bv.cpu().numpy()[bad].all()
+    eb, ed = e.check_edges(q[:64], q[64:128], substeps=8)
+    assert bool(eb[5]) and bool(eb[0] == o.check_edges(q[:1].astype(np.float64), q[64:65].astype(np.float64), substeps=8)[0][0])
+    links = [robot.end_effector_id - 3, *robot.finger_joint_ids]
+    T = np.tile(np.eye(4, dtype=np.float32)[:3], (64, 1, 1))
+    T[:, :, 3] = [2.0, 0.0, 1.0]
+    T[7, 1, 1] = np.nan
+    pb, pd = e.check_poses(T, links=links)
+    assert bool(pb[7]) and not bool(pb[6]) and abs(float(pd[7]) - 0.01) < 1e-7
+
+
 def test_error_conventions(robot, scene_loader, engines):
     from jogramop_framework_b200._lib import JogramopError
     e = engines(34)

@@ -70,3 +70,23 @@ def test_finger_symmetry(robot):
     rel_l = hand[:, :3].T @ (lf[:, 3] - hand[:, 3])
     rel_r = hand[:, :3].T @ (rf[:, 3] - hand[:, 3])
     assert np.allclose(rel_l * np.array([1, -1, 1]), rel_r, atol=1e-12) and abs(rel_l[1] - 0.04) < 1e-12
+
+
+def test_non_finite_inputs_are_rejected(robot, scene_loader):
+    """A NaN / infinite joint value (or pose entry) has no geometry: bit set, reason 1, distance = query distance, whatever
+    the flags say -- the convention the CUDA path follows too (include/jogramop_b200.h, jg_check)."""
+    import oracle
+    o = oracle.Oracle(robot, scene_loader(11))
+    q = np.tile(np.array([0.0, 0.0, -0.0178, -0.76, 0.0198, -2.342, 0.0298, 1.541, 0.753]), (4, 1))
+    q[1, 3] = np.nan
+    q[2, 0] = np.inf
+    b, d, r = o.check(q, flags=oracle.SCENE | oracle.PLANE, want_reason=True)
+    assert b.tolist() == [False, True, True, False] and r.tolist() == [0, 1, 1, 0]
+    assert d[1] == d[2] == 0.01 and d[0] == d[3]
+    T = np.tile(np.eye(4), (3, 1, 1))
+    T[:, :3, 3] = [2.0, 0.0, 1.0]
+    T[1, 0, 3] = np.nan
+    pb, pd = o.check_poses(T, links=[11, 12, 13])
+    assert pb.tolist() == [False, True, False] and pd[1] == 0.01
+    eb, ed = o.check_edges(q[[0, 1]], q[[3, 3]], substeps=8)
+    assert eb.tolist() == [False, True]
