@@ -605,6 +605,11 @@ __global__ void __launch_bounds__(256) k_mesh_traverse(const PassArgs a, int n_q
         T.r00 = r0.x; T.r01 = r0.y; T.r02 = r0.z; T.tx = r0.w;
         T.r10 = r1.x; T.r11 = r1.y; T.r12 = r1.z; T.ty = r1.w;
         T.r20 = r2.x; T.r21 = r2.y; T.r22 = r2.z; T.tz = r2.w;
+        // a NaN / infinite configuration has no geometry (its verdict bit is set by the broad phase): it must not walk
+        // the tree -- every box test is "not separated" for NaN
+        const float chk = fabsf(T.r00) + fabsf(T.r01) + fabsf(T.r02) + fabsf(T.r10) + fabsf(T.r11) + fabsf(T.r12) + fabsf(T.r20) +
+                          fabsf(T.r21) + fabsf(T.r22) + fabsf(T.tx) + fabsf(T.ty) + fabsf(T.tz);
+        if (!(chk <= FLT_MAX)) active = false;
     }
     const float infl = a.qd + msum + (BOOLEAN ? 0.f : 1e-5f);
     ObbQuery Q;

@@ -496,6 +496,14 @@ def test_non_finite_inputs_are_rejected_on_the_gpu(robot, scene_loader, engines)
     T[7, 1, 1] = np.nan
     pb, pd = e.check_poses(T, links=links)
     assert bool(pb[7]) and not bool(pb[6]) and abs(float(pd[7]) - 0.01) < 1e-7
+    # mesh mode: a NaN query must not walk the LBVH (every box test is "not separated" for NaN)
+    from jogramop_framework_b200.engine import CollisionEngine
+    em = CollisionEngine(robot, scene_loader(11), mesh_mode=True)
+    mb, md, _ = em.check(q[:256], flags=oracle.SCENE | oracle.PLANE | oracle.NO_EPA)
+    assert bool(mb[5]) and bool(mb[64]) and abs(float(md[5]) - 0.01) < 1e-7
+    pm, _ = em.check_poses(T, links=links, flags=oracle.SCENE | oracle.PLANE | oracle.NO_EPA)
+    assert bool(pm[7]) and not bool(pm[6])
+    em.close()
 
 
 def test_error_conventions(robot, scene_loader, engines):
