@@ -520,8 +520,8 @@ static int build_tables(jg_engine* e, const jg_robot* r, const jg_scene* sc) {
         const int la = r->self_pairs[2 * k], lb = r->self_pairs[2 * k + 1];
         if (la < 0 || lb < 0 || la >= r->L || lb >= r->L || la >= lb)
             return fail(JG_ERR_INVALID, "self pair %d: link ids (%d,%d) must satisfy 0 <= first < second < %d", k, la, lb, r->L);
-        if (e->link_first_shape[la + 1] < 0 || e->link_first_shape[lb + 1] < 0)
-            return fail(JG_ERR_INVALID, "self pair %d: link without collision shape", k);
+        // a link without a collision shape yields no closest points in pyBullet: the pair can never collide
+        if (e->link_first_shape[la + 1] < 0 || e->link_first_shape[lb + 1] < 0) continue;
         if (R.joints[la].stash_slot < 0) R.joints[la].stash_slot = R.n_stash++;
         // getClosestPoints(linkA, linkB) covers every collision shape of both links: one key per shape combination
         for (int sa = 0; sa < r->S; ++sa) {

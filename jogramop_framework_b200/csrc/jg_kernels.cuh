@@ -360,7 +360,7 @@ __device__ __forceinline__ void shape_vs_scene(const PassArgs& a, const ShapeRec
     if (MESH && (a.flags & 1u)) {
         // mesh mode: the triangle candidates of this shape are found by k_mesh_traverse (a group of lanes per query walks
         // the LBVH together); here the query -- the shape's transform -- is only put down
-        if (valid) {
+        if (qslot >= 0) {   // every in-range query is written (a NaN transform included: the traversal skips it)
             float4* q = a.mesh_T + (size_t)qslot * 3;
             q[0] = make_float4(T.r00, T.r01, T.r02, T.tx);
             q[1] = make_float4(T.r10, T.r11, T.r12, T.ty);
@@ -494,6 +494,7 @@ __global__ void __launch_bounds__(BLOCK, JG_BP_OCC) k_broadphase(const PassArgs 
     }
     __syncthreads();
     const int out_idx = a.substeps <= 1 ? cfg : cfg / a.substeps;
+    bool finite = true;
 
     if (valid) {
         if (a.substeps <= 1) {
@@ -507,11 +508,15 @@ __global__ void __launch_bounds__(BLOCK, JG_BP_OCC) k_broadphase(const PassArgs 
             bool bad = false;
             for (int j = 0; j < dof; ++j) {
                 const float v = qs[j * BLOCK + tid];
-                bad |= !(fabsf(v) <= FLT_MAX) || (limits && !(R->qlo[j] <= v && v <= R->qhi[j]));
+                const bool fin = fabsf(v) <= FLT_MAX;
+                finite = finite && fin;
+                bad |= !fin || (limits && !(R->qlo[j] <= v && v <= R->qhi[j]));
             }
             if (bad) atomicOr(a.viol + (out_idx >> 5), 1u << (out_idx & 31));
         }
     }
+    // ... and takes no part in the geometry (no pairs, distance stays at the query distance)
+    const bool geo = valid && finite;
     const bool want_self = (a.flags & 4u) != 0;
     const bool want_scene = (a.flags & 3u) != 0;
     // one thread owns all pairs of its configuration: champion in registers (not for edge substeps / mesh queues)
@@ -523,7 +528,7 @@ __global__ void __launch_bounds__(BLOCK, JG_BP_OCC) k_broadphase(const PassArgs 
     Tf cur = tf_identity(), saved = tf_identity();
     if (want_scene)
         for (int s = R->base_shape_first; s < R->base_shape_first + R->base_shape_count; ++s)
-            shape_vs_scene<MESH>(a, R->shapes[s], s, pieces, cur, valid, out_idx, lc, (cfg - a.cfg_base) * a.mesh_n_use + s);
+            shape_vs_scene<MESH>(a, R->shapes[s], s, pieces, cur, geo, out_idx, lc, valid ? (cfg - a.cfg_base) * a.mesh_n_use + s : -1);
 
     for (int i = 0; i < R->L; ++i) {
         const JointRec& J = R->joints[i];
@@ -548,7 +553,7 @@ __global__ void __launch_bounds__(BLOCK, JG_BP_OCC) k_broadphase(const PassArgs 
                 const ShapeRec& Sb = R->shapes[sr.sb];
                 const float msum = Sa.margin + Sb.margin;
                 const float ov = aabb_overlap(rel, Sb.c, Sb.h, Sa.c, Sa.h);
-                const bool hit = valid && ov + a.qd + msum >= 0.f;
+                const bool hit = geo && ov + a.qd + msum >= 0.f;
                 queue_push(a, hit, a.n_scene_keys + k, rel, out_idx, prio_of(ov, msum), a.champ_self, lc ? &lc->self : nullptr, false);
             }
             if (J.stash_slot >= 0) {
@@ -560,7 +565,7 @@ __global__ void __launch_bounds__(BLOCK, JG_BP_OCC) k_broadphase(const PassArgs 
         }
         if (want_scene)
             for (int s = J.shape_first; s < J.shape_first + J.shape_count; ++s)
-                shape_vs_scene<MESH>(a, R->shapes[s], s, pieces, cur, valid, out_idx, lc, (cfg - a.cfg_base) * a.mesh_n_use + s);
+                shape_vs_scene<MESH>(a, R->shapes[s], s, pieces, cur, geo, out_idx, lc, valid ? (cfg - a.cfg_base) * a.mesh_n_use + s : -1);
     }
     if (lc) {
         if (want_scene) champ_publish(a, champ.scene, a.champ_scene, out_idx, valid);
@@ -1525,6 +1530,7 @@ __global__ void __launch_bounds__(BLOCK) k_broadphase_poses(const PassArgs a, co
     __syncthreads();
     const int cfg = blockIdx.x * BLOCK + tid;
     const bool valid = cfg < a.n;
+    bool geo = valid;
     Tf Pz = tf_identity();
     if (valid) {
         a.enc_scene[cfg] = JG_ENC_INF;
@@ -1549,7 +1555,10 @@ __global__ void __launch_bounds__(BLOCK) k_broadphase_poses(const PassArgs a, co
         }
         const float chk = fabsf(Pz.r00) + fabsf(Pz.r01) + fabsf(Pz.r02) + fabsf(Pz.r10) + fabsf(Pz.r11) + fabsf(Pz.r12) + fabsf(Pz.r20) +
                           fabsf(Pz.r21) + fabsf(Pz.r22) + fabsf(Pz.tx) + fabsf(Pz.ty) + fabsf(Pz.tz);
-        if (!(chk <= FLT_MAX)) atomicOr(a.viol + (cfg >> 5), 1u << (cfg & 31));   // NaN / infinite pose: rejected
+        if (!(chk <= FLT_MAX)) {   // NaN / infinite pose: rejected, no geometry
+            atomicOr(a.viol + (cfg >> 5), 1u << (cfg & 31));
+            geo = false;
+        }
     }
     Champ champ;
     champ.scene = champ.self = 0ull;
@@ -1557,7 +1566,7 @@ __global__ void __launch_bounds__(BLOCK) k_broadphase_poses(const PassArgs a, co
     for (int k = 0; k < n_use; ++k) {
         const int s = use_shapes[k];
         const Tf T = tf_mul(Pz, rel[k]);
-        shape_vs_scene<MESH>(a, R->shapes[s], s, pieces, T, valid, cfg, lc, cfg * n_use + k);
+        shape_vs_scene<MESH>(a, R->shapes[s], s, pieces, T, geo, cfg, lc, valid ? cfg * n_use + k : -1);
     }
     if (lc) champ_publish(a, champ.scene, a.champ_scene, cfg, valid);
 }

@@ -62,3 +62,20 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert 'import oracle' not in txt and 'from oracle' not in txt and 'liboracle' not in txt, f
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): one JSON line with the same metric /
+    unit as the GPU arm, impl = reference, a cpu_baseline block of kind "port" and a zero-copy e2e block."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '1',
+                          '--ref-sample', '2000'], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['metric'] == 'configuration collision checks/sec' and line['unit'] == 'checks/s'
+    assert line['higher_is_better'] is True and line['value'] > 0 and line['steps'] == 1
+    assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1 and line['cpu_baseline']['value'] == line['value']
+    assert line['e2e'] == {'value': line['value'], 'unit': 'checks/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
