@@ -30,6 +30,11 @@ enum { JG_GJK_SEPARATED = 0, JG_GJK_FAR = 1, JG_GJK_PENETRATING = 2 };
 // step are reduced with a max tree and only the group index is tracked: 5.5 issue slots per vertex instead of 7 and a
 // loop-carried dependency once per 4 vertices.  The winner inside the winning group is located afterwards by
 // repeating the same arithmetic (bitwise identical values); ties resolve to the lowest index, like a sequential scan.
+#ifndef JG_SCAN_UNROLL
+#define JG_SCAN_UNROLL 2
+#endif
+#define JG_STR_(x) #x
+#define JG_UNROLL(n) _Pragma(JG_STR_(unroll n))
 __device__ __forceinline__ float dot4(const float4 p, V3 d) { return fmaf(p.x, d.x, fmaf(p.y, d.y, p.z * d.z)); }
 
 __device__ __forceinline__ int support_scan(const float4* __restrict__ verts, int n, V3 d) {
@@ -37,7 +42,7 @@ __device__ __forceinline__ int support_scan(const float4* __restrict__ verts, in
     JG_WORK(JG_WORK_DOTS, (unsigned)(4 * ng + 3));
     float best = -FLT_MAX;
     int bg = 0;
-#pragma unroll 2
+    JG_UNROLL(JG_SCAN_UNROLL)
     for (int g = 0; g < ng; ++g) {
         const float s0 = dot4(verts[4 * g], d), s1 = dot4(verts[4 * g + 1], d);
         const float s2 = dot4(verts[4 * g + 2], d), s3 = dot4(verts[4 * g + 3], d);

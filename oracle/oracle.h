@@ -23,8 +23,14 @@
  * PARITY PIN: pybullet cannot be installed in this image, so the oracle is pinned by the golden
  * artefacts the reference ships (tests/golden/export_golden.npz: 89 accepted IK rows = FK known
  * answers + collision known-negatives, grasps.csv frames, obstacles.obj merge) and by independent
- * numerical cross-checks (scipy NNLS / qhull on the Minkowski difference).  There are no golden
- * positives and no golden distances: distance parity is "oracle-pinned", see DESIGN.md.
+ * numerical cross-checks (scipy NNLS / qhull on the Minkowski difference).  Round 2 added two pins
+ * from data the reference ships: the 20 x 200 grasps of scenarios/<id>/grasps.npy, which all passed
+ * the reference's gripper filter (create_graspset.py:53-60) -- the restated filter (zero-margin
+ * gripper boxes vs the triangles of the mesh_fn meshes, orc_check_poses on triangle pieces) accepts
+ * 4 000 of 4 000 and every change of the recovered gripper geometry starts rejecting them
+ * (tests/test_graspset.py) -- and the row counts of export/grasp_IK_solutions.csv (IK outcomes,
+ * tests/test_export_and_ik.py).  There are still no golden positives and no golden distances for the
+ * robot path: its distance parity is "oracle-pinned", see DESIGN.md section 3.
  */
 #ifndef JG_ORACLE_H
 #define JG_ORACLE_H
