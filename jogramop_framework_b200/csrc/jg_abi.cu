@@ -816,6 +816,25 @@ static void fill_args(const jg_engine* e, PassArgs& a, uint32_t& flags, bool wan
     a.enc_scene = e->enc_scene; a.enc_self = e->enc_self; a.viol = e->viol;
 }
 
+// Launch a kernel of a pass so that it may start while its predecessor in the stream is still draining (programmatic
+// dependent launch: the kernel waits for the predecessor's results at its JG_WAIT_FOR_PREDECESSOR()).  Off while the
+// per-section profiling events sit between the kernels, or with JG_NO_PDL=1 in the environment.
+template <class... KArgs, class... Args>
+static void launch_dep(const jg_engine* e, void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+    static const bool disabled = getenv("JG_NO_PDL") != nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (disabled || e->profiling) ? 0 : 1;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // narrow phase + finalize of the pass described by `a` (queues already filled)
 static int run_narrow_and_finalize(jg_engine* e, const PassArgs& a, int n_out, uint32_t flags, uint32_t* bits, float* dist,
                                    uint8_t* reason, cudaStream_t st) {
@@ -827,14 +846,14 @@ static int run_narrow_and_finalize(jg_engine* e, const PassArgs& a, int n_out, u
     const size_t sel_smem = sizeof(int) * (2 * e->n_keys + 2);
     auto launch_penetration = [&](const PassArgs& a) {
         switch (e->epa_threads) {
-            case 416: k_penetration<416><<<e->epa_blocks, 416, e->smem_epa, st>>>(a); break;
-            case 384: k_penetration<384><<<e->epa_blocks, 384, e->smem_epa, st>>>(a); break;
-            case 352: k_penetration<352><<<e->epa_blocks, 352, e->smem_epa, st>>>(a); break;
-            case 320: k_penetration<320><<<e->epa_blocks, 320, e->smem_epa, st>>>(a); break;
-            case 256: k_penetration<256><<<e->epa_blocks, 256, e->smem_epa, st>>>(a); break;
-            case 192: k_penetration<192><<<e->epa_blocks, 192, e->smem_epa, st>>>(a); break;
-            case 128: k_penetration<128><<<e->epa_blocks, 128, e->smem_epa, st>>>(a); break;
-            default: k_penetration<64><<<e->epa_blocks, 64, e->smem_epa, st>>>(a); break;
+            case 416: launch_dep(e, k_penetration<416>, e->epa_blocks, 416, e->smem_epa, st, a); break;
+            case 384: launch_dep(e, k_penetration<384>, e->epa_blocks, 384, e->smem_epa, st, a); break;
+            case 352: launch_dep(e, k_penetration<352>, e->epa_blocks, 352, e->smem_epa, st, a); break;
+            case 320: launch_dep(e, k_penetration<320>, e->epa_blocks, 320, e->smem_epa, st, a); break;
+            case 256: launch_dep(e, k_penetration<256>, e->epa_blocks, 256, e->smem_epa, st, a); break;
+            case 192: launch_dep(e, k_penetration<192>, e->epa_blocks, 192, e->smem_epa, st, a); break;
+            case 128: launch_dep(e, k_penetration<128>, e->epa_blocks, 128, e->smem_epa, st, a); break;
+            default: launch_dep(e, k_penetration<64>, e->epa_blocks, 64, e->smem_epa, st, a); break;
         }
     };
     // The stage lists live in two sets: every k_select builds the next stage's lists in one set and clears the set of
@@ -850,12 +869,12 @@ static int run_narrow_and_finalize(jg_engine* e, const PassArgs& a, int n_out, u
             if (!listed) {
                 if (prev_slot >= 0) set ^= 1;
                 as.stage_set = set;
-                k_select<256><<<e->sm_count * 4, 256, sel_smem, st>>>(as, round == 0 ? SEL_GJK_CHAMP : SEL_GJK_REST, n_sel++,
-                                                                     prev_slot, round == 1 && epa ? 1 : 0);
+                launch_dep(e, k_select<256>, e->sm_count * 4, 256, sel_smem, st, as, (int)(round == 0 ? SEL_GJK_CHAMP : SEL_GJK_REST), n_sel++,
+                           prev_slot, (int)(round == 1 && epa ? 1 : 0));
                 e->stats.kernel_launches += 1;
             }
             as.stage_set = set;
-            k_narrowphase<NP_BLOCK><<<e->np_blocks, NP_BLOCK, e->smem_narrow, st>>>(as);
+            launch_dep(e, k_narrowphase<NP_BLOCK>, e->np_blocks, NP_BLOCK, e->smem_narrow, st, as);
             prev_slot = 4;
             prof_end(e, st);
             e->stats.kernel_launches += 1;
@@ -863,7 +882,7 @@ static int run_narrow_and_finalize(jg_engine* e, const PassArgs& a, int n_out, u
                 prof_begin(e, 2, st);
                 set ^= 1;
                 as.stage_set = set;
-                k_select<256><<<e->sm_count * 4, 256, sel_smem, st>>>(as, SEL_EPA_NEW, n_sel++, prev_slot, 0);
+                launch_dep(e, k_select<256>, e->sm_count * 4, 256, sel_smem, st, as, (int)SEL_EPA_NEW, n_sel++, prev_slot, 0);
                 launch_penetration(as);
                 prev_slot = 5;
                 prof_end(e, st);
@@ -872,7 +891,7 @@ static int run_narrow_and_finalize(jg_engine* e, const PassArgs& a, int n_out, u
         }
         if (epa) {
             prof_begin(e, 2, st);
-            k_penetration_big<EPA_BIG_BLOCK><<<e->sm_count * 2, EPA_BIG_BLOCK, e->smem_epa_big, st>>>(a);
+            launch_dep(e, k_penetration_big<EPA_BIG_BLOCK>, e->sm_count * 2, EPA_BIG_BLOCK, e->smem_epa_big, st, a);
             prof_end(e, st);
             e->stats.kernel_launches += 1;
         }
@@ -882,8 +901,8 @@ static int run_narrow_and_finalize(jg_engine* e, const PassArgs& a, int n_out, u
     // stage, which no k_select followed)
     StatArgs sa = {nullptr, 0, 0, 0, nullptr, 0, -1};
     if (e->n_keys > 0) sa = StatArgs{e->counts, e->n_scene_keys, e->n_keys, e->P, e->d_stats, set, prev_slot};
-    k_finalize<<<(n_out + 255) / 256 + 1, 256, 0, st>>>(e->enc_scene, e->enc_self, e->viol, n_out, a.qd, a.threshold, flags, bits,
-                                                        dist, reason, sa);
+    launch_dep(e, k_finalize, (n_out + 255) / 256 + 1, 256, 0, st, (const int*)e->enc_scene, (const int*)e->enc_self, (const uint32_t*)e->viol,
+               n_out, a.qd, a.threshold, flags, bits, dist, reason, sa);
     e->stats.kernel_launches += 1;
     prof_end(e, st);
     CUDA_TRY(cudaGetLastError());

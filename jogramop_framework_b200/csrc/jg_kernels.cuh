@@ -37,6 +37,20 @@
 #define JG_BOUNDS(cond, what) ((void)0)
 #endif
 
+// Programmatic dependent launch (sm_90+): the kernels of a pass are launched with the programmatic-stream-serialization
+// attribute (jg_abi.cu launch_dep), so a kernel may START while its predecessor is still draining; it loads what does not
+// depend on the predecessor (vertex table, key table -> shared memory), then waits here for the predecessor's results.
+// Persistent kernels (one resident wave) also announce early that their successor may be scheduled: its blocks then take
+// over each SM as soon as this kernel's block on it has exited -- the successor's prologue hides under this kernel's tail.
+// Without the launch attribute both calls are no-ops.
+#if defined(__CUDA_ARCH__) && !defined(JG_HOST_EMU)
+#define JG_WAIT_FOR_PREDECESSOR() cudaGridDependencySynchronize()
+#define JG_SUCCESSOR_MAY_START() cudaTriggerProgrammaticLaunchCompletion()
+#else
+#define JG_WAIT_FOR_PREDECESSOR() ((void)0)
+#define JG_SUCCESSOR_MAY_START() ((void)0)
+#endif
+
 namespace jg {
 
 #ifndef JG_BP_OCC
@@ -916,12 +930,14 @@ __global__ void __launch_bounds__(BLOCK) k_narrowphase(const PassArgs a) {
     KeyRec* keys = reinterpret_cast<KeyRec*>(smem_raw + sizeof(float4) * a.n_verts);
     int* prefix = reinterpret_cast<int*>(keys + a.n_keys);   // [n_keys+1], then G
     const int tid = threadIdx.x, lane = tid & 31;
+    JG_SUCCESSOR_MAY_START();
     for (int i = tid; i < a.n_verts; i += BLOCK) verts[i] = a.verts[i];
     {
         const int* ks = reinterpret_cast<const int*>(a.keys);
         int* kd = reinterpret_cast<int*>(keys);
         for (int i = tid; i < (int)(sizeof(KeyRec) / 4) * a.n_keys; i += BLOCK) kd[i] = ks[i];
     }
+    JG_WAIT_FOR_PREDECESSOR();         // the tables above do not depend on it; the stage lists and queues do
     const int* acounts = cnt_act(a);   // entries selected for this stage (k_select)
     if (tid < 32) sched_prefix(acounts, a.n_keys, prefix, lane);
     __syncthreads();
@@ -1096,6 +1112,8 @@ __global__ void __launch_bounds__(BLOCK) k_select(const PassArgs a, int mode, in
     int* prefix = reinterpret_cast<int*>(smem_raw);   // [n_keys + 2]
     int* span = prefix + a.n_keys + 2;                // [n_keys] entries to look at per key
     const int tid = threadIdx.x, lane = tid & 31;
+    JG_SUCCESSOR_MAY_START();
+    JG_WAIT_FOR_PREDECESSOR();
     const bool epa = mode == SEL_EPA_NEW;
     const int* qcount = epa ? cnt_epa(a) : cnt_pair(a);
     const int* qstart = cnt_done(a);
@@ -1218,7 +1236,9 @@ __global__ void __launch_bounds__(BLOCK) k_penetration(const PassArgs a) {
     uint32_t* poly_words = reinterpret_cast<uint32_t*>(prefix + ((a.n_keys + 2 + 3) & ~3));
     const int tid = threadIdx.x, lane = tid & 31;
     const int* ecounts = cnt_act(a);   // entries selected for this stage (k_select)
+    JG_SUCCESSOR_MAY_START();
     for (int i = tid; i < a.n_verts; i += BLOCK) verts[i] = a.verts[i];
+    JG_WAIT_FOR_PREDECESSOR();
     if (tid < 32) sched_prefix(ecounts, a.n_keys, prefix, lane);
     __syncthreads();
     const int total = prefix[a.n_keys];
@@ -1354,6 +1374,8 @@ __global__ void __launch_bounds__(BLOCK) k_penetration_big(const PassArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* verts = reinterpret_cast<float4*>(smem_raw);
     uint32_t* poly_words = reinterpret_cast<uint32_t*>(smem_raw + sizeof(float4) * a.n_verts);
+    JG_SUCCESSOR_MAY_START();
+    JG_WAIT_FOR_PREDECESSOR();
     const int n = min(cnt_misc(a)[CTR_OVF], a.ovf_cap);
     if (n == 0) return;
     for (int i = threadIdx.x; i < a.n_verts; i += BLOCK) verts[i] = a.verts[i];
@@ -1475,6 +1497,7 @@ __device__ __forceinline__ void accumulate_stats(const StatArgs& t, int lane) {
 __global__ void k_finalize(const int* __restrict__ enc_scene, const int* __restrict__ enc_self,
                            const uint32_t* __restrict__ viol, int n, float qd, float threshold, uint32_t flags,
                            uint32_t* __restrict__ bits, float* __restrict__ dist, uint8_t* __restrict__ reason, const StatArgs st) {
+    JG_WAIT_FOR_PREDECESSOR();
     if (blockIdx.x == gridDim.x - 1) {
         if (st.counts != nullptr && threadIdx.x < 32) accumulate_stats(st, threadIdx.x);
         return;
