@@ -339,7 +339,7 @@ def bench_other_configs(robot, dev, budget_s=1.0):
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from jogramop_framework_b200.engine import CollisionEngine, SCENE, PLANE, NO_EPA, measure_fp32_peak
+    from jogramop_framework_b200.engine import EnginePool, SCENE, PLANE, NO_EPA, measure_fp32_peak
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -363,36 +363,44 @@ def run_b200(args):
     ROT = 4                                    # rotating input batches: 4 x 36 MB > L2
     q_hosts = [make_configs(robot, n, 11 + 1000 * rank + 7919 * r) for r in range(ROT)]
     q_host = q_hosts[0]
-    eng = CollisionEngine(robot, scene, device=local, chunk=args.chunk)
+    # args.lanes whole batches in flight: one engine (scratch arena) + stream per lane, steps handed out round-robin
+    # (EnginePool); the kernels of one batch fill the tails and idle issue slots of the others
+    lanes = max(1, args.lanes)
+    pool = EnginePool(robot, scene, device=local, lanes=lanes, chunk=args.chunk)
+    eng = pool.engines[0]
     q_devs = [torch.from_numpy(q).to(dev) for q in q_hosts]
     q_dev = q_devs[0]
     words = (n + 31) // 32
-    # the receive buffers of the all-gather, double-buffered; the kernels write into this rank's slot of one of them
-    gathered = [torch.zeros((world * words,), dtype=torch.int32, device=dev) for _ in range(2)]
+    # the receive buffers of the all-gather, one more than batches in flight; the kernels write into this rank's slot
+    NB = lanes + 1
+    gathered = [torch.zeros((world * words,), dtype=torch.int32, device=dev) for _ in range(NB)]
     slots = [g[rank * words:(rank + 1) * words] for g in gathered]
-    dist_out = torch.empty((n,), dtype=torch.float32, device=dev)
+    dist_outs = [torch.empty((n,), dtype=torch.float32, device=dev) for _ in range(lanes)]
+    dist_out = dist_outs[0]
     side = torch.cuda.Stream(device=dev)
-    ev_check = [torch.cuda.Event() for _ in range(2)]
-    ev_gather = [torch.cuda.Event() for _ in range(2)]
-    gather_pending = [False, False]
+    ev_gather = [torch.cuda.Event() for _ in range(NB)]
+    gather_pending = [False] * NB
 
     fp32_peak = measure_fp32_peak(local) if rank == 0 else None
 
     def step(i):
-        b = i & 1
+        b = i % NB
         main = torch.cuda.current_stream(dev)
         if gather_pending[b]:
-            main.wait_event(ev_gather[b])      # the gather of step i-2 read this slot: long finished
-        eng.check(q_devs[i % ROT], flags=flags, packed=True, bits_out=slots[b], dist_out=dist_out)
+            main.wait_event(ev_gather[b])      # the gather of step i-NB read this slot: long finished
+        tk = pool.submit(q_devs[i % ROT], flags=flags, packed=True, bits_out=slots[b], dist_out=dist_outs[pool.next_lane])
         if world > 1:
-            ev_check[b].record(main)
-            side.wait_event(ev_check[b])
-            with torch.cuda.stream(side):      # the all-gather of step i runs under the kernels of step i+1
+            side.wait_event(tk.event)
+            with torch.cuda.stream(side):      # the all-gather of step i runs under the kernels of the following steps
                 dist.all_gather_into_tensor(gathered[b], slots[b])
                 ev_gather[b].record(side)
             gather_pending[b] = True
 
+    def serial_step(i):                         # one batch at a time on the current stream (kernel split, single-lane figure)
+        eng.check(q_devs[i % ROT], flags=flags, packed=True, bits_out=slots[0], dist_out=dist_out)
+
     def drain():
+        pool.drain()
         torch.cuda.current_stream(dev).wait_stream(side)
 
     def barrier():
@@ -400,7 +408,8 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
+    n_warm = max(args.warmup, 3, lanes)        # every lane's arena has grown to its working size before the timed region
+    for i in range(n_warm):
         step(i)
     drain()
     barrier()
@@ -418,13 +427,21 @@ def run_b200(args):
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
     stats = eng.stats()
-    # kernel split / roofline durations: the SAME K steps again, directly after the timed region, with the library's
-    # per-section CUDA events on the launching stream.  (The events are not free -- 8 records per pass cost 2.5 % of the
-    # step -- so the timed region itself carries none.)
+    # single-lane figure: the same K steps, one batch at a time on one stream (no collective: per-GPU kernel time)
+    torch.cuda.synchronize()
+    sv0, sv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sv0.record()
+    for s in range(args.steps):
+        serial_step(s)
+    sv1.record()
+    torch.cuda.synchronize()
+    serial_ms = sv0.elapsed_time(sv1) / args.steps
+    # kernel split / roofline durations: the SAME K steps again, one batch at a time, with the library's per-section
+    # CUDA events on the launching stream.  (The events are not free -- 8 records per pass cost 2.5 % of the step --
+    # and sections of overlapping batches would time each other, so the timed region itself carries none.)
     eng.profile(True)
     for s in range(args.steps):
-        step(s)
-    drain()
+        serial_step(s)
     barrier()
     prof = eng.get_profile()
     eng.profile(False)
@@ -452,20 +469,26 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * n * args.steps / float(te.item())
-    # the same steps with two batches in flight (jg_check_host_submit / _wait): what a caller streaming batches gets --
-    # every step still uploads its inputs from pinned host memory and downloads its results inside the timed region
-    out2 = {'bits': torch.empty((words,), dtype=torch.int32, pin_memory=True),
-            'dist': torch.empty((n,), dtype=torch.float32, pin_memory=True), 'reason': None}
-    outs = [out, out2]
-    eng.check_host_wait(eng.check_host_submit(q_pin, flags=flags, out=outs[0]))
+    # the same steps with several batches in flight (jg_check_host_submit / _wait on every lane's engine): what a caller
+    # streaming batches gets -- every step still uploads its inputs from pinned host memory and downloads its results
+    # inside the timed region
+    depth = max(2, lanes * args.e2e_per_lane)
+    outs = [out] + [{'bits': torch.empty((words,), dtype=torch.int32, pin_memory=True),
+                     'dist': torch.empty((n,), dtype=torch.float32, pin_memory=True), 'reason': None} for _ in range(depth - 1)]
+    from collections import deque
+
+    def e2e_loop(k_steps):
+        tks = deque()
+        for s_i in range(k_steps):
+            if len(tks) == depth:
+                pool.wait_host(tks.popleft())
+            tks.append(pool.submit_host(q_pins[s_i % ROT], flags=flags, out=outs[s_i % depth]))
+        while tks:
+            pool.wait_host(tks.popleft())
+    e2e_loop(2 * depth)
     barrier()
     t0 = time.perf_counter()
-    tk = eng.check_host_submit(q_pins[0], flags=flags, out=outs[0])
-    for s_i in range(1, args.steps):
-        nxt = eng.check_host_submit(q_pins[s_i % ROT], flags=flags, out=outs[s_i & 1])
-        eng.check_host_wait(tk)
-        tk = nxt
-    eng.check_host_wait(tk)
+    e2e_loop(args.steps)
     e2e_pipe_s = time.perf_counter() - t0
     tp = torch.tensor([e2e_pipe_s], dtype=torch.float64, device=dev)
     if world > 1:
@@ -499,7 +522,7 @@ def run_b200(args):
         step_tf = value / world * FLOPS_PER_CHECK / 1e12
         line = {
             'metric': 'configuration collision checks/sec', 'value': value, 'unit': 'checks/s', 'n_gpus': world,
-            'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_total / args.steps,
+            'steps': args.steps, 'warmup': n_warm, 'ms_per_step': ms_total / args.steps,
             'higher_is_better': True, 'scaling': 'strong' if args.strong else 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': f'scenario {args.scenario:03d}: {n} uniformly sampled mobile-Panda configurations per GPU, '
                                    'collision bit + signed min distance (SCENE+PLANE)',
@@ -510,12 +533,17 @@ def run_b200(args):
                        'collective': ('ncclAllGather of the packed verdict bits, in place (the kernels write into the rank\'s slot), '
                                       'on a side stream under the next step\'s kernels; the timed region ends after the last gather')
                        if world > 1 else 'none (1 GPU)',
+                       'in_flight': f'{lanes} batches in flight: EnginePool, one engine (scratch arena) and CUDA stream per lane, steps '
+                                    'handed out round-robin; every step is a full pass over its own batch, all K inside the timed region',
                        'pass_size': args.chunk or 'auto (<= 2^20 configurations per pass)',
                        'cpu_affinity': f'process bound to the {bound} CPUs local to its GPU (NVML)' if bound else 'not set'},
             'clocks': clocks,
+            'single_lane': {'value': n / serial_ms * 1e3, 'unit': 'checks/s per GPU', 'ms_per_step': serial_ms,
+                            'note': 'one batch at a time on one stream (no overlap between batches, no collective); '
+                                    'kernel_ms_per_step and roofline durations are taken in this form'},
             'e2e': {'value': e2e_pipe_value, 'unit': 'checks/s', 'h2d_bytes_per_step': int(n * 36),
                     'd2h_bytes_per_step': int(n * 4 + words * 4),
-                    'api': 'jg_check_host_submit / jg_check_host_wait, two 1 M batches in flight (pinned host buffers)',
+                    'api': f'jg_check_host_submit / jg_check_host_wait on {lanes} engines, {depth} batches in flight (pinned host buffers)',
                     'synchronous_call_value': e2e_value,
                     'synchronous_api': 'jg_check_host: one blocking call per step (copies overlap only within the batch)'},
             'gpu_launches': int(launches_per_step * args.steps),
@@ -630,7 +658,7 @@ def run_b200(args):
                               'max_abs_distance_error_m': float(np.abs(gd - rd).max()),
                               'collision_rate': float(rb.mean())}
         if world == 1 and not args.no_extras:
-            eng.close()
+            pool.close()
             del q_devs, q_pins
             torch.cuda.empty_cache()
             try:
@@ -638,7 +666,7 @@ def run_b200(args):
             except Exception as exc:
                 line['configs'] = {'unavailable': repr(exc)[:300]}
         print(json.dumps(line), flush=True)
-    eng.close()
+    pool.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -652,6 +680,8 @@ def main():
     ap.add_argument('--scenario', type=int, default=11)
     ap.add_argument('--n', type=int, default=1_000_000)
     ap.add_argument('--chunk', type=int, default=0)
+    ap.add_argument('--lanes', type=int, default=4, help='batches in flight (engines / streams of the EnginePool)')
+    ap.add_argument('--e2e-per-lane', type=int, default=1, help='host-path batches in flight per lane (1 or 2)')
     ap.add_argument('--no-epa', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-count', action='store_true', help='skip the counted-work audit (instrumented library)')

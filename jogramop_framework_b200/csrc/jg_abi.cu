@@ -845,6 +845,13 @@ static int run_narrow_and_finalize(jg_engine* e, const PassArgs& a, int n_out, u
     const bool epa = !(flags & JG_NO_EPA);
     const size_t sel_smem = sizeof(int) * (2 * e->n_keys + 2);
     auto launch_penetration = [&](const PassArgs& a) {
+#ifdef JG_TRACE
+        {
+            static int trace_slot = 0;
+            const int slot = trace_slot++ & 1;
+            cudaMemcpyToSymbolAsync(g_jg_trace_slot, &slot, sizeof(int), 0, cudaMemcpyHostToDevice, st);
+        }
+#endif
         switch (e->epa_threads) {
             case 416: launch_dep(e, k_penetration<416>, e->epa_blocks, 416, e->smem_epa, st, a); break;
             case 384: launch_dep(e, k_penetration<384>, e->epa_blocks, 384, e->smem_epa, st, a); break;
@@ -1492,6 +1499,18 @@ extern "C" int jg_work_counters(int device, uint64_t out[4]) {
 #else
     (void)device; (void)out;
     return fail(JG_ERR_UNSUPPORTED, "jg_work_counters: this library was built without -DJG_COUNT_WORK");
+#endif
+}
+
+// JG_TRACE build only: the per-warp timeline of the last two penetration-kernel launches: out[2][4096][4]
+extern "C" int jg_trace_read(unsigned long long* out) {
+#ifdef JG_TRACE
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpyFromSymbol(out, g_jg_trace, sizeof(unsigned long long) * 2 * 4096 * 8));
+    return JG_OK;
+#else
+    (void)out;
+    return fail(JG_ERR_UNSUPPORTED, "jg_trace_read: this library was built without -DJG_TRACE");
 #endif
 }
 

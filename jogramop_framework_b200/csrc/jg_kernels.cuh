@@ -53,6 +53,14 @@
 
 namespace jg {
 
+// JG_TRACE build (experiments only, never shipped): per-warp timeline of the penetration kernel -- when each warp started and
+// ended, how many keys it visited and how many polytopes it started -- to see where the SMs idle at the end of a stage.
+#ifdef JG_TRACE
+__device__ unsigned long long g_jg_trace[2][4096][8];
+__device__ int g_jg_trace_slot;
+__device__ __forceinline__ unsigned long long jg_now() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#endif
+
 #ifndef JG_BP_OCC
 #define JG_BP_OCC 7   /* resident blocks per SM the broad phase is compiled for (register budget) */
 #endif
@@ -1252,10 +1260,19 @@ __global__ void __launch_bounds__(BLOCK) k_penetration(const PassArgs a) {
     X.poly.nv = X.poly.nf = 0;
     X.lb = 0.f; X.ub = FLT_MAX; X.it = 0;
 
+#ifdef JG_TRACE
+    const unsigned long long tr_t0 = jg_now();
+    int tr_keys = 0, tr_started = 0, tr_steps = 0, tr_steps_at_last = 0, tr_key0 = -1;
+    unsigned long long tr_last = 0;
+#endif
     int key = sched_find_key(prefix, a.n_keys, (int)((long long)gw * total / n_warps));
     for (;;) {
         key = sched_next_key(ecounts, cur, a.n_keys, key, lane);
         if (key < 0) break;
+#ifdef JG_TRACE
+        ++tr_keys;
+        if (tr_key0 < 0) tr_key0 = key;
+#endif
         const KeyRec K = a.keys[key];
         const size_t kbase = (size_t)key * a.cap;
         int* enc = K.kind == KEY_SELF ? a.enc_self : a.enc_scene;
@@ -1272,6 +1289,11 @@ __global__ void __launch_bounds__(BLOCK) k_penetration(const PassArgs a) {
             [&](int jj, int slot, int c) {
                 myj = jj;
                 cfg = c;
+#ifdef JG_TRACE
+                ++tr_started;
+                tr_last = jg_now();
+                tr_steps_at_last = tr_steps;
+#endif
                 JG_BOUNDS(jj >= 0 && jj < a.cap && slot >= 0 && slot < a.cap && c >= 0 && c < a.cap, "stage list entry (penetration refill)");
                 const size_t j = kbase + myj;
                 const int e0 = enc[cfg];
@@ -1290,6 +1312,9 @@ __global__ void __launch_bounds__(BLOCK) k_penetration(const PassArgs a) {
                 }
             },
             [&]() {
+#ifdef JG_TRACE
+                ++tr_steps;
+#endif
                 if (phase == 1) {
                     const int st = gjk_step(S, A, K.ea_n, SetSupport{B, K.eb_n}, T, 1e30f);
                     if (st == JG_GJK_PENETRATING) {
@@ -1332,6 +1357,23 @@ __global__ void __launch_bounds__(BLOCK) k_penetration(const PassArgs a) {
                 }
             });
     }
+#ifdef JG_TRACE
+    {
+        int started = tr_started, sal = tr_steps_at_last;
+        unsigned long long last = tr_last;
+        for (int o = 16; o; o >>= 1) {
+            started += __shfl_xor_sync(0xFFFFFFFFu, started, o);
+            sal = max(sal, __shfl_xor_sync(0xFFFFFFFFu, sal, o));
+            const unsigned long long ol = __shfl_xor_sync(0xFFFFFFFFu, last, o);
+            last = ol > last ? ol : last;
+        }
+        if (lane == 0 && gw < 4096) {
+            unsigned long long* r = g_jg_trace[g_jg_trace_slot & 1][gw];
+            r[0] = tr_t0; r[1] = jg_now(); r[2] = (unsigned long long)tr_keys; r[3] = (unsigned long long)started;
+            r[4] = last; r[5] = (unsigned long long)tr_key0; r[6] = (unsigned long long)tr_steps; r[7] = (unsigned long long)(tr_steps - sal);
+        }
+    }
+#endif
 }
 
 // Overflow pass: the few pairs whose polytope outgrew the fast storage class.  ONE PAIR PER WARP: the lanes split

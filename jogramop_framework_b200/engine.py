@@ -310,6 +310,102 @@ class CollisionEngine:
         return {k: (ms[i], n[i]) for i, k in enumerate(('broadphase', 'narrowphase', 'penetration', 'finalize'))}
 
 
+class PoolTicket:
+    """One batch in flight in an ``EnginePool``: ``event`` fires on the lane's stream when its kernels are done."""
+    __slots__ = ('lane', 'event', 'result', 'keep')
+
+    def __init__(self, lane, event, result, keep):
+        self.lane, self.event, self.result, self.keep = lane, event, result, keep
+
+
+class EnginePool:
+    """``lanes`` engines (one scratch arena each) on ``lanes`` CUDA streams, handed whole batches round-robin.
+
+    One pass is a chain of dependent kernels whose persistent narrow-phase stages end in tails (a polytope is a serial
+    chain of ~10 expansions; the last ones of a stage run on mostly idle SMs) and which run at 13 warps per SM by
+    shared-memory budget.  Nothing orders the passes of DIFFERENT batches, so with a second arena the next batch's
+    kernels fill those tails and idle issue slots: measured 5.65e8 -> 6.3e8 (2 lanes) -> 6.7e8 checks/s (4 lanes) on
+    scenario 011.  A lane's arena is sized by its largest batch (~16 KB per configuration for the Panda +
+    scenario 011 tables), so four lanes of 1 M configurations hold ~62 GB of the 180 GB.
+
+    ``submit`` returns at once; ``wait`` makes the CURRENT stream wait for that batch (no host synchronisation) and hands
+    out its result tensors.  A C caller gets the same by creating one ``jg_engine`` per stream."""
+
+    def __init__(self, robot, scene=None, device=0, lanes=4, **engine_kw):
+        assert lanes >= 1
+        self.engines = [CollisionEngine(robot, scene, device=device, **engine_kw) for _ in range(lanes)]
+        self.device = self.engines[0].device
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(lanes)]
+        self.lanes = lanes
+        self._next = 0
+        self._host_inflight = [0] * lanes
+
+    def close(self):
+        for e in self.engines:
+            e.close()
+        self.engines = []
+
+    @property
+    def next_lane(self):
+        """Index of the lane the next ``submit`` / ``submit_host`` will use."""
+        return self._next
+
+    def _lane(self):
+        i = self._next
+        self._next = (i + 1) % self.lanes
+        return i
+
+    def submit(self, q, **check_kw):
+        """Queue ``CollisionEngine.check(q, **check_kw)`` on the next lane, ordered after everything the current stream
+        holds so far (so a ``q`` produced there is ready) and after that lane's previous batch -> PoolTicket."""
+        i = self._lane()
+        cur, st = torch.cuda.current_stream(self.device), self.streams[i]
+        st.wait_stream(cur)
+        with torch.cuda.stream(st):
+            res = self.engines[i].check(q, **check_kw)
+            ev = torch.cuda.Event()
+            ev.record(st)
+        if isinstance(q, torch.Tensor) and q.is_cuda:
+            q.record_stream(st)
+        return PoolTicket(i, ev, res, q)
+
+    def wait(self, ticket):
+        """The current stream waits for the batch -> (collides, min_dist, reason) as ``check`` returns them."""
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ticket.event)
+        for t in ticket.result:
+            if t is not None:
+                t.record_stream(cur)
+        return ticket.result
+
+    def drain(self):
+        """The current stream waits for every lane."""
+        cur = torch.cuda.current_stream(self.device)
+        for st in self.streams:
+            cur.wait_stream(st)
+
+    def check_many(self, batches, **check_kw):
+        """All ``batches`` (a sequence of [n_i, dof] arrays / tensors) with up to ``lanes`` of them in flight -> list of
+        ``check`` results in order."""
+        tickets = [self.submit(q, **check_kw) for q in batches]
+        return [self.wait(t) for t in tickets]
+
+    # host-buffer form: lane i's engine pipelines upload / kernels / download itself (two tickets per engine)
+    def submit_host(self, q, **kw):
+        if self._host_inflight[self._next] >= 2:
+            raise _lib.JogramopError('EnginePool.submit_host: more than 2 * lanes batches in flight; wait for the oldest first')
+        i = self._lane()
+        self._host_inflight[i] += 1
+        return {'lane': i, 'inner': self.engines[i].check_host_submit(q, **kw), 'collected': False}
+
+    def wait_host(self, ticket):
+        res = self.engines[ticket['lane']].check_host_wait(ticket['inner'])
+        if not ticket['collected']:
+            ticket['collected'] = True
+            self._host_inflight[ticket['lane']] -= 1
+        return res
+
+
 def measure_fp32_peak(device=0, reps=5):
     """FP32 FMA micro-benchmark on `device` -> TFLOP/s (roofline denominator of the narrow phase)."""
     out = C.c_double(0)

@@ -469,6 +469,63 @@ def test_async_host_path_two_batches_in_flight(robot, scene_loader, engines):
     assert torch.equal(unpack_bits(wb.cuda(), len(batches[0])), ref[0][0])
 
 
+def test_engine_pool_batches_in_flight(robot, scene_loader):
+    """EnginePool: whole batches side by side on several arenas / streams give exactly what one engine gives batch by
+    batch -- inputs produced on the caller's stream just before the submit, preallocated outputs, ragged sizes, more
+    batches than lanes, the host-buffer form, and the oracle on one of them."""
+    from jogramop_framework_b200._lib import JogramopError
+    from jogramop_framework_b200.engine import CollisionEngine, EnginePool, unpack_bits
+    scene = scene_loader(11)
+    single = CollisionEngine(robot, scene, chunk=8192)
+    pool = EnginePool(robot, scene, lanes=3, chunk=8192)
+    sizes = [8192, 20000, 33, 5000, 8192 * 2 + 1, 1, 7000, 12345, 64, 30000]
+    host = [uniform_configs(robot, n, 700 + i) for i, n in enumerate(sizes)]
+    ref = [single.check(q, flags=15, want_reason=True) for q in host]
+    tickets = []
+    for q in host:
+        qd = torch.from_numpy(q).cuda() * 2.0
+        qd = qd * 0.5                                   # produced on the current stream right before the submit
+        tickets.append(pool.submit(qd, flags=15, want_reason=True))
+        del qd
+    for tk, (b1, d1, r1) in zip(tickets, ref):
+        b, d, r = pool.wait(tk)
+        assert torch.equal(b, b1) and torch.equal(d, d1) and torch.equal(r, r1)
+    # check_many + preallocated outputs
+    outs = pool.check_many(host[:4], flags=3, packed=True)
+    for (w, d, _), q in zip(outs, host[:4]):
+        b1, d1, _ = single.check(q, flags=3)
+        assert torch.equal(unpack_bits(w, len(q)), b1) and torch.equal(d, d1)
+    words = torch.zeros((4, 1024), dtype=torch.int32, device='cuda')
+    dists = torch.zeros((4, 20000), dtype=torch.float32, device='cuda')
+    tks = [pool.submit(host[i], flags=3, packed=True, bits_out=words[i], dist_out=dists[i]) for i in range(4)]
+    pool.drain()
+    for i, q in enumerate(host[:4]):
+        b1, d1, _ = single.check(q, flags=3)
+        assert torch.equal(unpack_bits(words[i, :(len(q) + 31) // 32], len(q)), b1) and torch.equal(dists[i, :len(q)], d1)
+    # host buffers: 2 tickets per lane, then refused
+    small = [torch.from_numpy(q).pin_memory() for q in host if len(q) <= 8192]
+    ht = [pool.submit_host(small[i % len(small)], flags=15, want_reason=True) for i in range(6)]
+    with pytest.raises(JogramopError):
+        pool.submit_host(small[0], flags=15)
+    for i, t in enumerate(ht):
+        wb, wd, wr = pool.wait_host(t)
+        q = small[i % len(small)]
+        b1, d1, r1 = single.check(q.numpy(), flags=15, want_reason=True)
+        assert torch.equal(unpack_bits(wb.cuda(), len(q)), b1) and torch.equal(wd.cuda(), d1) and torch.equal(wr.cuda(), r1)
+    pool.wait_host(ht[0])                               # waiting twice is harmless
+    t = pool.submit_host(small[0], flags=15)
+    pool.wait_host(t)
+    # against the oracle
+    o = Oracle(robot, scene)
+    rb, rd = o.check(host[3].astype(np.float64), flags=15)[:2]
+    b, d, _ = pool.wait(pool.submit(host[3], flags=15))
+    b, d = b.cpu().numpy().astype(bool), d.cpu().numpy()
+    outside = np.abs(rd + 0.001) > 1e-3
+    assert (b[outside] == rb[outside]).all() and np.abs(d - rd).max() < 1e-4
+    pool.close()
+    single.close()
+
+
 def test_non_finite_inputs_are_rejected_on_the_gpu(robot, scene_loader, engines):
     """NaN / inf joint values and poses: bit set, reason 1, distance = query distance, with or without JG_LIMITS -- as the
     oracle does (tests/test_oracle_properties.py); the neighbours of such a row are untouched."""
