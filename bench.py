@@ -180,9 +180,10 @@ def bench_other_configs(robot, dev, budget_s=1.0):
     repetitions after warm-up, plus a parity sample against the CPU oracle for each (the checker, never the timed path)."""
     import torch
     import oracle
-    from jogramop_framework_b200.engine import CollisionEngine, SCENE, PLANE
+    from jogramop_framework_b200.engine import CollisionEngine, EnginePool, SCENE, PLANE
     from jogramop_framework_b200.ingest import SceneModel
     data = os.path.join(ROOT, 'jogramop_framework_b200', 'data')
+    LANES = 4
     lim = robot.joint_limits[robot.arm_joint_ids]
     out = {}
 
@@ -240,7 +241,18 @@ def bench_other_configs(robot, dev, budget_s=1.0):
     rb, rd = o.check_edges(qa[:k].astype(np.float64), qb[:k].astype(np.float64), substeps=64)
     gb, gd = eng.check_edges(qa_d[:k], qb_d[:k], substeps=64)
     gbv, _ = eng.check_edges(qa_d[:k], qb_d[:k], substeps=64, want_dist=False)
-    bits_all, _ = eng.check_edges(qa_d, qb_d, substeps=64)
+    bits_all, dist_all = eng.check_edges(qa_d, qb_d, substeps=64)
+    eng.close()
+    # the same call with its 62 passes side by side on four arenas / streams (EnginePool.check_edges)
+    pool = EnginePool(robot, scene, device=dev.index, lanes=LANES)
+    ms_dp = timed(lambda: pool.check_edges(qa_d, qb_d, substeps=64, packed=True))
+    ms_vp = timed(lambda: pool.check_edges(qa_d, qb_d, substeps=64, packed=True, want_dist=False))
+    pb, pd = pool.check_edges(qa_d, qb_d, substeps=64)
+    pooled4 = {'lanes': LANES, 'verdict_and_distance_ms': ms_dp, 'verdict_and_distance_substep_checks_per_s': m * 64 / ms_dp * 1e3,
+               'verdict_only_ms': ms_vp, 'verdict_only_substep_checks_per_s': m * 64 / ms_vp * 1e3,
+               'identical_to_one_engine': bool(torch.equal(pb, bits_all) and torch.equal(pd, dist_all))}
+    pool.close()
+    del pb, pd, dist_all
     out['config4_edges'] = {
         'workload': 'scenario 034: 1 000 000 edges x 64 interpolated substeps (qa seed 34, qb = clip(qa + U(-0.25, 0.25)) seed 3400); '
                     'checks counted = edges x 64, no early-exit credit',
@@ -248,8 +260,8 @@ def bench_other_configs(robot, dev, budget_s=1.0):
                                  'parity': parity(gb, gd, rb, rd)},
         'verdict_only': {'ms': ms_v, 'substep_checks_per_s': m * 64 / ms_v * 1e3, 'edges_per_s': m / ms_v * 1e3,
                          'parity': parity(gbv, None, rb, rd)},
+        'passes_side_by_side': pooled4,
         'edge_collision_rate': float(bits_all.float().mean().item())}
-    eng.close()
     del qa_d, qb_d
 
     # ---- config 5: scenario 011, 10 M free-floating gripper poses
@@ -267,13 +279,20 @@ def bench_other_configs(robot, dev, budget_s=1.0):
     o = oracle.Oracle(robot, scene)
     rb, rd = o.check_poses(T, links=links, flags=3)
     gb, gd = eng.check_poses(pq_d[:k], links=links)
-    bits_all, _ = eng.check_poses(pq_d, links=links)
+    bits_all, dist_all = eng.check_poses(pq_d, links=links)
+    eng.close()
+    pool = EnginePool(robot, scene, device=dev.index, lanes=LANES)
+    ms_pp = timed(lambda: pool.check_poses(pq_d, links=links, packed=True))
+    pb, pd = pool.check_poses(pq_d, links=links)
+    pooled5 = {'lanes': LANES, 'ms': ms_pp, 'poses_per_s': m / ms_pp * 1e3,
+               'identical_to_one_engine': bool(torch.equal(pb, bits_all) and torch.equal(pd, dist_all))}
+    pool.close()
+    del pb, pd, dist_all
     c5 = {'workload': 'scenario 011: 10 000 000 free-floating gripper poses (position uniform in the target box + 0.25 m, '
                       'uniform rotations, seed 5011) vs target + obstacles + plane',
           'panda_hand_hulls': {'model': 'panda_hand + two finger hulls at 0.04, Bullet margins, convex pieces, bit + signed distance',
                                'ms': ms_p, 'poses_per_s': m / ms_p * 1e3, 'collision_rate': float(bits_all.float().mean().item()),
-                               'parity': parity(gb, gd, rb, rd)}}
-    eng.close()
+                               'parity': parity(gb, gd, rb, rd), 'passes_side_by_side': pooled5}}
     # the reference's own filter (create_graspset.py:53-59): burg two-finger gripper vs the visual meshes, boolean
     try:
         from jogramop_framework_b200.scenario import Scenario
@@ -354,7 +373,13 @@ def run_b200(args):
         bound = bind_to_gpu_cpus(local)    # pinned staging buffers of the host path end up on the GPU's NUMA node
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=dev)
+        # the collective's kernels get a high-priority stream: with several batches in flight the SMs are never idle, and a
+        # pending all-gather block must be the first thing scheduled when a persistent block retires
+        pg_opts = None
+        if not os.environ.get('JG_BENCH_NO_PRIO'):
+            pg_opts = dist.ProcessGroupNCCL.Options()
+            pg_opts.is_high_priority_stream = True
+        dist.init_process_group('nccl', device_id=dev, pg_options=pg_opts)
     robot, scene = load_models(args.scenario)
     flags = SCENE | PLANE | (NO_EPA if args.no_epa else 0)
     # --strong: the SAME total batch (args.n configurations) cut into 32-aligned shards, one per GPU (builder-run record of
@@ -377,7 +402,7 @@ def run_b200(args):
     slots = [g[rank * words:(rank + 1) * words] for g in gathered]
     dist_outs = [torch.empty((n,), dtype=torch.float32, device=dev) for _ in range(lanes)]
     dist_out = dist_outs[0]
-    side = torch.cuda.Stream(device=dev)
+    side = torch.cuda.Stream(device=dev, priority=0 if os.environ.get('JG_BENCH_NO_PRIO') else -1)
     ev_gather = [torch.cuda.Event() for _ in range(NB)]
     gather_pending = [False] * NB
 

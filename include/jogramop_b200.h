@@ -167,6 +167,10 @@ jg_engine* jg_engine_create(const jg_robot*, const jg_scene* /* may be NULL: FK 
                             int device, const jg_params* /* NULL = defaults */);
 void jg_engine_free(jg_engine*);
 int jg_engine_device(const jg_engine*);
+/* Configurations one pass of this engine holds at most (jg_params.chunk, or what the memory budget allowed; <= 2^20).
+ * Larger calls are processed pass after pass on the engine's one scratch arena; a caller that wants the passes of a large
+ * call side by side cuts it at multiples of this size (and of 32) over several engines on several streams. */
+int64_t jg_engine_pass_size(const jg_engine*);
 
 /* ---- forward kinematics: replaces reset_arm_joints + getLinkState (simulation.py:206-212, 223-249) ----
  * q [n,dof] device fp32; link_ids [L_out] HOST ints; out [n,L_out,12] device fp32: link frames (URDF link

@@ -12,6 +12,8 @@ LIB_COUNT = os.path.join(HERE, 'libjogramop_b200_count.so')
 # same sources with -DJG_DEBUG_BOUNDS: device-side index checks that trap (the stand-in for compute-sanitizer, which the
 # GPU pool does not offer); run the GPU suite against it with JG_B200_LIB_PATH=<this file>
 LIB_BOUNDS = os.path.join(HERE, 'libjogramop_b200_bounds.so')
+# same sources with -DJG_TRACE: per-warp timeline of the penetration kernel (tools/trace_penetration.py); built on demand only
+LIB_TRACE = os.path.join(HERE, 'libjogramop_b200_trace.so')
 SOURCES = ['jg_abi.cu', 'jg_ingest.cpp']
 HEADERS = ['jg_handles.h', 'jg_math.cuh', 'jg_gjk.cuh', 'jg_epa.cuh', 'jg_lbvh.cuh', 'jg_kernels.cuh', os.path.join('..', '..', 'include', 'jogramop_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
@@ -42,6 +44,12 @@ def build(force=False, verbose=False, counting=False):
            ['-o', lib] + SOURCES)
     subprocess.check_call(cmd, cwd=CSRC)
     return lib
+
+
+def build_trace(force=False):
+    if force or is_stale(LIB_TRACE):
+        subprocess.check_call([_nvcc()] + NVCC_FLAGS + ['-DJG_TRACE', '-o', LIB_TRACE] + SOURCES, cwd=CSRC)
+    return LIB_TRACE
 
 
 # PyTorch operator shim (TORCH_LIBRARY(jogramop, ...), csrc/jg_torch.cpp): a host-only translation unit over the C-ABI,

@@ -792,6 +792,7 @@ extern "C" jg_engine* jg_engine_create(const jg_robot* r, const jg_scene* sc, in
 }
 extern "C" void jg_engine_free(jg_engine* e) { engine_release(e); }
 extern "C" int jg_engine_device(const jg_engine* e) { return e ? e->device : JG_ERR_INVALID; }
+extern "C" int64_t jg_engine_pass_size(const jg_engine* e) { return e ? (int64_t)e->cap_max : (int64_t)JG_ERR_INVALID; }
 
 // ----------------------------------------------------------------------------------------------- passes
 // want_dist = false: the caller only wants verdict bits.  The verdict is "some contact distance < threshold", so the

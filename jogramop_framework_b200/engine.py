@@ -90,6 +90,11 @@ class CollisionEngine:
         """The ``jg_engine*`` as an integer: what ``torch.ops.jogramop.*`` (torch_ops.py) and C callers take."""
         return int(self._e)
 
+    @property
+    def pass_size(self):
+        """Configurations one pass holds at most (larger calls run pass after pass on the engine's one arena)."""
+        return int(self._L.jg_engine_pass_size(self._e))
+
     def close(self):
         L = self._L
         if getattr(self, '_e', None):
@@ -120,6 +125,22 @@ class CollisionEngine:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def _outputs(self, n, want_dist, bits_out, dist_out):
+        words = (n + 31) // 32
+        if bits_out is not None:
+            assert bits_out.dtype == torch.int32 and bits_out.is_contiguous() and bits_out.numel() >= words and \
+                bits_out.device == self.device, 'bits_out must be a contiguous int32 device tensor of >= ceil(n/32) words'
+            bits = bits_out[:words]
+        else:
+            bits = torch.empty((words,), device=self.device, dtype=torch.int32)
+        if dist_out is not None:
+            assert dist_out.dtype == torch.float32 and dist_out.is_contiguous() and dist_out.numel() >= n and \
+                dist_out.device == self.device, 'dist_out must be a contiguous fp32 device tensor of >= n elements'
+            dist, want_dist = dist_out[:n], True
+        else:
+            dist = torch.empty((n,), device=self.device, dtype=torch.float32) if want_dist else None
+        return bits, dist
+
     # ------------------------------------------------------------------ queries
     def fk(self, q, link_ids=None, base_pose=None):
         """Link frames [n, len(link_ids), 3, 4] (fp32, device).  base_pose: 4x4 or 3x4 pre-multiplied pose."""
@@ -132,27 +153,22 @@ class CollisionEngine:
                                      out.data_ptr(), self._stream()), 'jg_fk')
         return out
 
-    def check(self, q, flags=SCENE | PLANE, want_dist=True, want_reason=False, packed=False, bits_out=None, dist_out=None):
+    def check(self, q, flags=SCENE | PLANE, want_dist=True, want_reason=False, packed=False, bits_out=None, dist_out=None,
+              reason_out=None):
         """-> (collides bool[n] (or packed int32 words), min_dist fp32[n] | None, reason uint8[n] | None).
         ``bits_out`` / ``dist_out``: preallocated device tensors the kernels write into directly (int32 words, at least
         ceil(n/32); fp32 [n]) -- e.g. this rank's slot of an all-gather buffer (``dist.GatherBuffer``), so that no copy
         sits between the finalize kernel and the collective."""
         q = self._dev_f32(q, self.dof)
         n = q.shape[0]
-        words = (n + 31) // 32
-        if bits_out is not None:
-            assert bits_out.dtype == torch.int32 and bits_out.is_contiguous() and bits_out.numel() >= words and \
-                bits_out.device == self.device, 'bits_out must be a contiguous int32 device tensor of >= ceil(n/32) words'
-            bits = bits_out[:words]
+        bits, dist = self._outputs(n, want_dist, bits_out, dist_out)
+        want_dist = dist is not None
+        if reason_out is not None:
+            assert reason_out.dtype == torch.uint8 and reason_out.is_contiguous() and reason_out.numel() >= n and \
+                reason_out.device == self.device
+            reason, want_reason = reason_out[:n], True
         else:
-            bits = torch.empty((words,), device=self.device, dtype=torch.int32)
-        if dist_out is not None:
-            assert dist_out.dtype == torch.float32 and dist_out.is_contiguous() and dist_out.numel() >= n and \
-                dist_out.device == self.device
-            dist, want_dist = dist_out[:n], True
-        else:
-            dist = torch.empty((n,), device=self.device, dtype=torch.float32) if want_dist else None
-        reason = torch.empty((n,), device=self.device, dtype=torch.uint8) if want_reason else None
+            reason = torch.empty((n,), device=self.device, dtype=torch.uint8) if want_reason else None
         with torch.cuda.device(self.device):
             _lib.check(self._L.jg_check(self._e, q.data_ptr(), n, self.dof, flags, bits.data_ptr(),
                                         dist.data_ptr() if want_dist else None,
@@ -183,19 +199,20 @@ class CollisionEngine:
                 run()
         return g.replay, bits, dist, reason
 
-    def check_edges(self, qa, qb, substeps=64, flags=SCENE | PLANE, want_dist=True, packed=False):
+    def check_edges(self, qa, qb, substeps=64, flags=SCENE | PLANE, want_dist=True, packed=False, bits_out=None, dist_out=None):
         qa, qb = self._dev_f32(qa, self.dof), self._dev_f32(qb, self.dof)
         m = qa.shape[0]
         assert qb.shape[0] == m, 'qa and qb must hold the same number of edges'
-        bits = torch.empty(((m + 31) // 32,), device=self.device, dtype=torch.int32)
-        dist = torch.empty((m,), device=self.device, dtype=torch.float32) if want_dist else None
+        bits, dist = self._outputs(m, want_dist, bits_out, dist_out)
+        want_dist = dist is not None
         with torch.cuda.device(self.device):
             _lib.check(self._L.jg_check_edges(self._e, qa.data_ptr(), qb.data_ptr(), m, self.dof, substeps, flags,
                                               bits.data_ptr(), dist.data_ptr() if want_dist else None,
                                               self._stream()), 'jg_check_edges')
         return (bits if packed else unpack_bits(bits, m)), dist
 
-    def check_poses(self, poses, links, ee_link=None, flags=SCENE | PLANE, want_dist=True, packed=False):
+    def check_poses(self, poses, links, ee_link=None, flags=SCENE | PLANE, want_dist=True, packed=False, bits_out=None,
+                    dist_out=None):
         """poses: [n,4,4] / [n,3,4] matrices or [n,7] (pos, quat xyzw) of link `ee_link` in the robot frame."""
         if isinstance(poses, torch.Tensor):
             shp = tuple(poses.shape)
@@ -215,8 +232,8 @@ class CollisionEngine:
         n = p.shape[0]
         links = _i32(links)
         ee = self.robot.end_effector_id if ee_link is None else ee_link
-        bits = torch.empty(((n + 31) // 32,), device=self.device, dtype=torch.int32)
-        dist = torch.empty((n,), device=self.device, dtype=torch.float32) if want_dist else None
+        bits, dist = self._outputs(n, want_dist, bits_out, dist_out)
+        want_dist = dist is not None
         with torch.cuda.device(self.device):
             _lib.check(self._L.jg_check_poses(self._e, p.data_ptr(), n, fmt, ee, _p(links), len(links), flags,
                                               bits.data_ptr(), dist.data_ptr() if want_dist else None,
@@ -355,19 +372,23 @@ class EnginePool:
         self._next = (i + 1) % self.lanes
         return i
 
-    def submit(self, q, **check_kw):
-        """Queue ``CollisionEngine.check(q, **check_kw)`` on the next lane, ordered after everything the current stream
-        holds so far (so a ``q`` produced there is ready) and after that lane's previous batch -> PoolTicket."""
+    def _submit_call(self, method, args, kw):
         i = self._lane()
         cur, st = torch.cuda.current_stream(self.device), self.streams[i]
         st.wait_stream(cur)
         with torch.cuda.stream(st):
-            res = self.engines[i].check(q, **check_kw)
+            res = getattr(self.engines[i], method)(*args, **kw)
             ev = torch.cuda.Event()
             ev.record(st)
-        if isinstance(q, torch.Tensor) and q.is_cuda:
-            q.record_stream(st)
-        return PoolTicket(i, ev, res, q)
+        for t in args:
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                t.record_stream(st)
+        return PoolTicket(i, ev, res, args)
+
+    def submit(self, q, **check_kw):
+        """Queue ``CollisionEngine.check(q, **check_kw)`` on the next lane, ordered after everything the current stream
+        holds so far (so a ``q`` produced there is ready) and after that lane's previous batch -> PoolTicket."""
+        return self._submit_call('check', (q,), check_kw)
 
     def wait(self, ticket):
         """The current stream waits for the batch -> (collides, min_dist, reason) as ``check`` returns them."""
@@ -389,6 +410,54 @@ class EnginePool:
         ``check`` results in order."""
         tickets = [self.submit(q, **check_kw) for q in batches]
         return [self.wait(t) for t in tickets]
+
+    # ---- ONE large call cut into pass-sized pieces that run side by side on the lanes, results in one set of tensors
+    def _pieces(self, n, unit):
+        unit = max(32, unit // 32 * 32)               # packed words stay aligned
+        return [(off, min(unit, n - off)) for off in range(0, n, unit)]
+
+    def check(self, q, flags=SCENE | PLANE, want_dist=True, want_reason=False, packed=False):
+        """``CollisionEngine.check`` for any n: the passes of a call larger than one pass run on different lanes."""
+        e0 = self.engines[0]
+        q = e0._dev_f32(q, e0.dof)
+        n = q.shape[0]
+        bits = torch.empty(((n + 31) // 32,), device=self.device, dtype=torch.int32)
+        dist = torch.empty((n,), device=self.device, dtype=torch.float32) if want_dist else None
+        reason = torch.empty((n,), device=self.device, dtype=torch.uint8) if want_reason else None
+        tks = [self._submit_call('check', (q[off:off + m],), dict(
+            flags=flags, want_dist=want_dist, packed=True, bits_out=bits[off // 32:],
+            dist_out=dist[off:] if want_dist else None, reason_out=reason[off:] if want_reason else None))
+            for off, m in self._pieces(n, e0.pass_size)]
+        for t in tks:
+            self.wait(t)
+        return (bits if packed else unpack_bits(bits, n)), dist, reason
+
+    def check_edges(self, qa, qb, substeps=64, flags=SCENE | PLANE, want_dist=True, packed=False):
+        """``CollisionEngine.check_edges`` with the passes (pass_size / substeps edges each) side by side on the lanes."""
+        e0 = self.engines[0]
+        qa, qb = e0._dev_f32(qa, e0.dof), e0._dev_f32(qb, e0.dof)
+        m = qa.shape[0]
+        assert qb.shape[0] == m, 'qa and qb must hold the same number of edges'
+        bits = torch.empty(((m + 31) // 32,), device=self.device, dtype=torch.int32)
+        dist = torch.empty((m,), device=self.device, dtype=torch.float32) if want_dist else None
+        tks = [self._submit_call('check_edges', (qa[off:off + k], qb[off:off + k]), dict(
+            substeps=substeps, flags=flags, want_dist=want_dist, packed=True, bits_out=bits[off // 32:],
+            dist_out=dist[off:] if want_dist else None)) for off, k in self._pieces(m, e0.pass_size // max(substeps, 1))]
+        for t in tks:
+            self.wait(t)
+        return (bits if packed else unpack_bits(bits, m)), dist
+
+    def check_poses(self, poses, links, ee_link=None, flags=SCENE | PLANE, want_dist=True, packed=False):
+        """``CollisionEngine.check_poses`` with the passes side by side on the lanes."""
+        n = int(poses.shape[0])
+        bits = torch.empty(((n + 31) // 32,), device=self.device, dtype=torch.int32)
+        dist = torch.empty((n,), device=self.device, dtype=torch.float32) if want_dist else None
+        tks = [self._submit_call('check_poses', (poses[off:off + k], links), dict(
+            ee_link=ee_link, flags=flags, want_dist=want_dist, packed=True, bits_out=bits[off // 32:],
+            dist_out=dist[off:] if want_dist else None)) for off, k in self._pieces(n, self.engines[0].pass_size)]
+        for t in tks:
+            self.wait(t)
+        return (bits if packed else unpack_bits(bits, n)), dist
 
     # host-buffer form: lane i's engine pipelines upload / kernels / download itself (two tickets per engine)
     def submit_host(self, q, **kw):

@@ -502,6 +502,27 @@ def test_engine_pool_batches_in_flight(robot, scene_loader):
     for i, q in enumerate(host[:4]):
         b1, d1, _ = single.check(q, flags=3)
         assert torch.equal(unpack_bits(words[i, :(len(q) + 31) // 32], len(q)), b1) and torch.equal(dists[i, :len(q)], d1)
+    # ONE large call cut into passes that run side by side: configurations, edges, gripper poses
+    assert pool.engines[0].pass_size == 8192
+    big = uniform_configs(robot, 8192 * 5 + 77, 811)
+    b1, d1, r1 = single.check(big, flags=15, want_reason=True)
+    b, d, r = pool.check(big, flags=15, want_reason=True)
+    assert torch.equal(b, b1) and torch.equal(d, d1) and torch.equal(r, r1)
+    assert torch.equal(pool.check(big, flags=3, want_dist=False)[0], single.check(big, flags=3, want_dist=False)[0])
+    assert pool.check(big[:0], flags=3)[0].numel() == 0
+    qa = uniform_configs(robot, 3001, 812)
+    qb = (qa + np.random.default_rng(813).uniform(-0.2, 0.2, qa.shape)).astype(np.float32)
+    eb1, ed1 = single.check_edges(qa, qb, substeps=10)
+    eb, ed = pool.check_edges(qa, qb, substeps=10)
+    assert torch.equal(eb, eb1) and torch.equal(ed, ed1)
+    rng = np.random.default_rng(814)
+    pq = np.concatenate([rng.uniform(-0.6, 0.6, (20001, 3)) + [0, 0, 0.6], rng.normal(size=(20001, 4))], 1)
+    pq[:, 3:] /= np.linalg.norm(pq[:, 3:], axis=1, keepdims=True)
+    pq = pq.astype(np.float32)
+    links = [robot.end_effector_id - 3, *robot.finger_joint_ids]
+    pb1, pd1 = single.check_poses(pq, links=links)
+    pb, pd = pool.check_poses(pq, links=links)
+    assert torch.equal(pb, pb1) and torch.equal(pd, pd1) and 0.02 < pb1.float().mean().item() < 0.98
     # host buffers: 2 tickets per lane, then refused
     small = [torch.from_numpy(q).pin_memory() for q in host if len(q) <= 8192]
     ht = [pool.submit_host(small[i % len(small)], flags=15, want_reason=True) for i in range(6)]

@@ -1,6 +1,11 @@
+"""Per-warp timeline of the two penetration-depth stages of one 1 M-configuration pass (scenario 011), from the -DJG_TRACE
+build of the library (build it here first: python -c "from jogramop_framework_b200 import build; build.build_trace()").
+Never a timed or shipped path.  Output of the round-2 run: profiles/r02_penetration_timeline.txt."""
 import sys, os, ctypes as C, numpy as np, torch
-sys.path.insert(0,'/root/repo')
-os.environ.setdefault('JG_B200_LIB_PATH', 'exp/lib_trace.so')
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.chdir(ROOT)
+os.environ.setdefault('JG_B200_LIB_PATH', os.path.join(ROOT, 'jogramop_framework_b200', 'libjogramop_b200_trace.so'))
 from jogramop_framework_b200 import _lib
 from jogramop_framework_b200.engine import CollisionEngine
 from jogramop_framework_b200.ingest import RobotModel, SceneModel
