@@ -413,16 +413,21 @@ class EnginePool:
 
     # ---- ONE large call cut into pass-sized pieces that run side by side on the lanes, results in one set of tensors
     def _pieces(self, n, unit):
-        unit = max(32, unit // 32 * 32)               # packed words stay aligned
-        return [(off, min(unit, n - off)) for off in range(0, n, unit)]
+        """(offset, size) of the fewest equal pieces of at most ``unit`` (a multiple of 32: packed words stay aligned);
+        a call that fits one pass is NOT cut (every pass pays ~0.5 ms of fixed cost: DESIGN.md 8)."""
+        unit = max(32, unit // 32 * 32)
+        k = max(1, -(-n // unit))
+        piece = max(32, min(unit, (-(-n // k) + 31) // 32 * 32))
+        return [(off, min(piece, n - off)) for off in range(0, n, piece)]
 
-    def check(self, q, flags=SCENE | PLANE, want_dist=True, want_reason=False, packed=False):
-        """``CollisionEngine.check`` for any n: the passes of a call larger than one pass run on different lanes."""
+    def check(self, q, flags=SCENE | PLANE, want_dist=True, want_reason=False, packed=False, bits_out=None, dist_out=None):
+        """``CollisionEngine.check`` for any n: the passes of a call larger than one pass run on different lanes (so an
+        ``EnginePool`` can stand wherever an engine's ``check`` is called, e.g. ``dist.check_sharded``)."""
         e0 = self.engines[0]
         q = e0._dev_f32(q, e0.dof)
         n = q.shape[0]
-        bits = torch.empty(((n + 31) // 32,), device=self.device, dtype=torch.int32)
-        dist = torch.empty((n,), device=self.device, dtype=torch.float32) if want_dist else None
+        bits, dist = e0._outputs(n, want_dist, bits_out, dist_out)
+        want_dist = dist is not None
         reason = torch.empty((n,), device=self.device, dtype=torch.uint8) if want_reason else None
         tks = [self._submit_call('check', (q[off:off + m],), dict(
             flags=flags, want_dist=want_dist, packed=True, bits_out=bits[off // 32:],

@@ -510,6 +510,10 @@ def test_engine_pool_batches_in_flight(robot, scene_loader):
     assert torch.equal(b, b1) and torch.equal(d, d1) and torch.equal(r, r1)
     assert torch.equal(pool.check(big, flags=3, want_dist=False)[0], single.check(big, flags=3, want_dist=False)[0])
     assert pool.check(big[:0], flags=3)[0].numel() == 0
+    from jogramop_framework_b200.dist import check_sharded
+    from jogramop_framework_b200.engine import unpack_bits as ub
+    w, dd = check_sharded(pool, torch.from_numpy(big).cuda(), 15, want_dist=True)       # world size 1: the pool in an engine's place
+    assert torch.equal(ub(w, len(big)), b1) and torch.equal(dd, d1)
     qa = uniform_configs(robot, 3001, 812)
     qb = (qa + np.random.default_rng(813).uniform(-0.2, 0.2, qa.shape)).astype(np.float32)
     eb1, ed1 = single.check_edges(qa, qb, substeps=10)
