@@ -180,7 +180,7 @@ def bench_other_configs(robot, dev, budget_s=1.0):
     repetitions after warm-up, plus a parity sample against the CPU oracle for each (the checker, never the timed path)."""
     import torch
     import oracle
-    from jogramop_framework_b200.engine import CollisionEngine, EnginePool, SCENE, PLANE
+    from jogramop_framework_b200.engine import CollisionEngine, SCENE, PLANE
     from jogramop_framework_b200.ingest import SceneModel
     data = os.path.join(ROOT, 'jogramop_framework_b200', 'data')
     LANES = 4
@@ -243,12 +243,12 @@ def bench_other_configs(robot, dev, budget_s=1.0):
     gbv, _ = eng.check_edges(qa_d[:k], qb_d[:k], substeps=64, want_dist=False)
     bits_all, dist_all = eng.check_edges(qa_d, qb_d, substeps=64)
     eng.close()
-    # the same call with its 62 passes side by side on four arenas / streams (EnginePool.check_edges)
-    pool = EnginePool(robot, scene, device=dev.index, lanes=LANES)
+    # the same call with its 62 passes side by side on four arenas / internal streams (jg_engine_set_lanes)
+    pool = CollisionEngine(robot, scene, device=dev.index, lanes=LANES)
     ms_dp = timed(lambda: pool.check_edges(qa_d, qb_d, substeps=64, packed=True))
     ms_vp = timed(lambda: pool.check_edges(qa_d, qb_d, substeps=64, packed=True, want_dist=False))
     pb, pd = pool.check_edges(qa_d, qb_d, substeps=64)
-    pooled4 = {'lanes': LANES, 'verdict_and_distance_ms': ms_dp, 'verdict_and_distance_substep_checks_per_s': m * 64 / ms_dp * 1e3,
+    pooled4 = {'lanes': LANES, 'api': 'jg_engine_set_lanes(4) + one jg_check_edges call', 'verdict_and_distance_ms': ms_dp, 'verdict_and_distance_substep_checks_per_s': m * 64 / ms_dp * 1e3,
                'verdict_only_ms': ms_vp, 'verdict_only_substep_checks_per_s': m * 64 / ms_vp * 1e3,
                'identical_to_one_engine': bool(torch.equal(pb, bits_all) and torch.equal(pd, dist_all))}
     pool.close()
@@ -281,10 +281,10 @@ def bench_other_configs(robot, dev, budget_s=1.0):
     gb, gd = eng.check_poses(pq_d[:k], links=links)
     bits_all, dist_all = eng.check_poses(pq_d, links=links)
     eng.close()
-    pool = EnginePool(robot, scene, device=dev.index, lanes=LANES)
+    pool = CollisionEngine(robot, scene, device=dev.index, lanes=LANES)
     ms_pp = timed(lambda: pool.check_poses(pq_d, links=links, packed=True))
     pb, pd = pool.check_poses(pq_d, links=links)
-    pooled5 = {'lanes': LANES, 'ms': ms_pp, 'poses_per_s': m / ms_pp * 1e3,
+    pooled5 = {'lanes': LANES, 'api': 'jg_engine_set_lanes(4) + one jg_check_poses call', 'ms': ms_pp, 'poses_per_s': m / ms_pp * 1e3,
                'identical_to_one_engine': bool(torch.equal(pb, bits_all) and torch.equal(pd, dist_all))}
     pool.close()
     del pb, pd, dist_all
@@ -396,35 +396,54 @@ def run_b200(args):
     q_devs = [torch.from_numpy(q).to(dev) for q in q_hosts]
     q_dev = q_devs[0]
     words = (n + 31) // 32
-    # the receive buffers of the all-gather, one more than batches in flight; the kernels write into this rank's slot
-    NB = lanes + 1
-    gathered = [torch.zeros((world * words,), dtype=torch.int32, device=dev) for _ in range(NB)]
-    slots = [g[rank * words:(rank + 1) * words] for g in gathered]
+    # the receive buffers of the all-gather: a buffer takes the words of G consecutive steps (--gather-every, default 1: one
+    # collective per step) and enough buffers rotate that none is rewritten while its gather or a batch in flight uses it;
+    # the kernels write straight into this rank's part
+    G = max(1, args.gather_every)
+    NB = (lanes + G - 1) // G + 1
+    gathered = [torch.zeros((world * G * words,), dtype=torch.int32, device=dev) for _ in range(NB)]
+    mine = [g[rank * G * words:(rank + 1) * G * words] for g in gathered]
+    slots = [m[:words] for m in mine]
     dist_outs = [torch.empty((n,), dtype=torch.float32, device=dev) for _ in range(lanes)]
     dist_out = dist_outs[0]
     side = torch.cuda.Stream(device=dev, priority=0 if os.environ.get('JG_BENCH_NO_PRIO') else -1)
     ev_gather = [torch.cuda.Event() for _ in range(NB)]
     gather_pending = [False] * NB
+    group = {'events': [], 'buf': 0}
 
     fp32_peak = measure_fp32_peak(local) if rank == 0 else None
 
-    def step(i):
-        b = i % NB
-        main = torch.cuda.current_stream(dev)
-        if gather_pending[b]:
-            main.wait_event(ev_gather[b])      # the gather of step i-NB read this slot: long finished
-        tk = pool.submit(q_devs[i % ROT], flags=flags, packed=True, bits_out=slots[b], dist_out=dist_outs[pool.next_lane])
-        if world > 1:
-            side.wait_event(tk.event)
-            with torch.cuda.stream(side):      # the all-gather of step i runs under the kernels of the following steps
-                dist.all_gather_into_tensor(gathered[b], slots[b])
+    def flush():
+        b = group['buf']
+        if world > 1 and group['events'] and not os.environ.get('JG_BENCH_NO_GATHER'):
+            for ev in group['events']:
+                side.wait_event(ev)
+            with torch.cuda.stream(side):      # the all-gather runs under the kernels of the following steps
+                dist.all_gather_into_tensor(gathered[b], mine[b])
                 ev_gather[b].record(side)
             gather_pending[b] = True
+        group['events'] = []
+
+    def step(i):
+        b, j = (i // G) % NB, i % G
+        main = torch.cuda.current_stream(dev)
+        if j == 0:
+            if group['events']:
+                flush()                        # (a partial group left by the warm-up)
+            group['buf'] = b
+            if gather_pending[b]:
+                main.wait_event(ev_gather[b])  # the gather that last read this buffer: long finished
+        tk = pool.submit(q_devs[i % ROT], flags=flags, packed=True, bits_out=mine[b][j * words:(j + 1) * words],
+                         dist_out=dist_outs[pool.next_lane])
+        group['events'].append(tk.event)
+        if j == G - 1:
+            flush()
 
     def serial_step(i):                         # one batch at a time on the current stream (kernel split, single-lane figure)
         eng.check(q_devs[i % ROT], flags=flags, packed=True, bits_out=slots[0], dist_out=dist_out)
 
     def drain():
+        flush()
         pool.drain()
         torch.cuda.current_stream(dev).wait_stream(side)
 
@@ -556,7 +575,8 @@ def run_b200(args):
                        'l2': f'inputs larger than L2: the steps rotate over {ROT} different {n}-configuration batches '
                              f'({ROT * n * 36 / 1e6:.0f} MB > 126 MB L2); one CUDA-event pair around all timed steps',
                        'collective': ('ncclAllGather of the packed verdict bits, in place (the kernels write into the rank\'s slot), '
-                                      'on a side stream under the next step\'s kernels; the timed region ends after the last gather')
+                                      f'one per {G} step(s), on a high-priority side stream under the following steps\' kernels; '
+                                      'the timed region ends after the last gather')
                        if world > 1 else 'none (1 GPU)',
                        'in_flight': f'{lanes} batches in flight: EnginePool, one engine (scratch arena) and CUDA stream per lane, steps '
                                     'handed out round-robin; every step is a full pass over its own batch, all K inside the timed region',
@@ -706,6 +726,7 @@ def main():
     ap.add_argument('--n', type=int, default=1_000_000)
     ap.add_argument('--chunk', type=int, default=0)
     ap.add_argument('--lanes', type=int, default=4, help='batches in flight (engines / streams of the EnginePool)')
+    ap.add_argument('--gather-every', type=int, default=1, help='steps whose verdict words share one all-gather (N > 1)')
     ap.add_argument('--e2e-per-lane', type=int, default=1, help='host-path batches in flight per lane (1 or 2)')
     ap.add_argument('--no-epa', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')

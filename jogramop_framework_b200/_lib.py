@@ -56,6 +56,8 @@ def load():
     L.jg_engine_free.argtypes = [vp]
     L.jg_engine_device.argtypes = [vp]
     L.jg_engine_pass_size.argtypes = [vp]
+    L.jg_engine_set_lanes.argtypes = [vp, C.c_int]
+    L.jg_engine_lanes.argtypes = [vp]
     L.jg_engine_pass_size.restype = C.c_int64
     L.jg_fk.argtypes = [vp, vp, i64, i32, vp, i32, vp, vp, vp]
     L.jg_check.argtypes = [vp, vp, i64, i32, u32, vp, vp, vp, vp]
@@ -111,6 +113,6 @@ def check(rc, what=''):
 EXPORTED_SYMBOLS = [
     'jg_default_params', 'jg_last_error', 'jg_abi_version', 'jg_device_count', 'jg_robot_create', 'jg_robot_free',
     'jg_scene_create', 'jg_scene_create_mesh', 'jg_scene_free', 'jg_robot_load', 'jg_scene_load', 'jg_scene_load_ex', 'jg_scene_load_mesh',
-    'jg_robot_describe', 'jg_robot_link_index', 'jg_scene_describe', 'jg_engine_create', 'jg_engine_free', 'jg_engine_device', 'jg_engine_pass_size', 'jg_fk', 'jg_check',
+    'jg_robot_describe', 'jg_robot_link_index', 'jg_scene_describe', 'jg_engine_create', 'jg_engine_free', 'jg_engine_device', 'jg_engine_pass_size', 'jg_engine_set_lanes', 'jg_engine_lanes', 'jg_fk', 'jg_check',
     'jg_check_edges', 'jg_check_poses', 'jg_check_host', 'jg_check_host_submit', 'jg_check_host_wait', 'jg_ik', 'jg_get_stats', 'jg_profile_enable', 'jg_get_profile',
     'jg_measure_fp32_peak', 'jg_work_counters', 'jg_work_counters_reset']

@@ -238,6 +238,19 @@ struct jg_engine {
     unsigned long long* d_stats = nullptr;       // [8]
     cudaStream_t last_stream = nullptr;
     bool have_last_stream = false;
+    // lanes (jg_engine_set_lanes): a call of more than one pass hands its passes round-robin to this engine and to
+    // lanes - 1 sibling engines (own tables, own arena, created on first use), each on its own stream, so that one pass's
+    // kernels run under the tails of the others
+    int lanes = 1;
+    std::vector<jg_engine*> sib;
+    std::vector<cudaStream_t> lane_stream;
+    std::vector<cudaEvent_t> lane_ev;
+    cudaEvent_t ev_fork = nullptr;
+    jg_robot robot_copy;
+    jg_scene scene_copy;
+    bool has_scene = false;
+    bool accumulate_stats = false;       // a lane's second, third ... piece of one call: keep counting
+    int last_call_lanes = 0;             // lanes the last call used (jg_get_stats adds the siblings' counters)
     int sm_count = 148;
     int np_blocks = 0, epa_blocks = 0, epa_threads = 0;
     size_t smem_narrow = 0, smem_epa = 0, smem_epa_big = 0;
@@ -315,7 +328,12 @@ static void staging_free(jg_engine* e) {
 
 static void engine_release(jg_engine* e) {
     if (!e) return;
+    for (jg_engine* sb : e->sib) engine_release(sb);
+    e->sib.clear();
     cudaSetDevice(e->device);
+    for (cudaStream_t ls : e->lane_stream) cudaStreamDestroy(ls);
+    for (cudaEvent_t ev : e->lane_ev) cudaEventDestroy(ev);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     cudaFree(e->d_robot); cudaFree(e->d_pieces); cudaFree(e->d_selfs); cudaFree(e->d_keys); cudaFree(e->d_verts);
     arena_free(e);
     cudaFree(e->bvh.nodes); cudaFree(e->bvh.tri_v); cudaFree(e->bvh.tri_id); cudaFree(e->d_err); cudaFree(e->d_qrest); cudaFree(e->counts);
@@ -697,6 +715,8 @@ extern "C" jg_engine* jg_engine_create(const jg_robot* r, const jg_scene* sc, in
     e->device = device;
     if (prm) e->prm = *prm; else jg_default_params(&e->prm);
     e->L = r->L; e->S = r->S; e->dof = r->dof;
+    e->robot_copy = *r;                   // (a few hundred KB: what sibling engines are built from)
+    if (sc) { e->scene_copy = *sc; e->has_scene = true; }
     if (build_tables(e, r, sc) != JG_OK) { engine_release(e); return nullptr; }
     if (e->mesh && build_lbvh(e, sc) != JG_OK) { engine_release(e); return nullptr; }
     cudaDeviceProp prop;
@@ -935,9 +955,80 @@ static int begin_call(jg_engine* e, cudaStream_t st) {
         e->have_last_stream = true;
         e->last_stream = st;
     }
-    e->stats = jg_stats{};
-    CUDA_TRY(cudaMemsetAsync(e->d_stats, 0, sizeof(unsigned long long) * 8, st));
+    e->last_call_lanes = 0;
+    if (!e->accumulate_stats) {
+        e->stats = jg_stats{};
+        CUDA_TRY(cudaMemsetAsync(e->d_stats, 0, sizeof(unsigned long long) * 8, st));
+    }
     return JG_OK;
+}
+
+// ---- lanes
+extern "C" int jg_engine_set_lanes(jg_engine* e, int lanes) {
+    if (!e) return fail(JG_ERR_INVALID, "jg_engine_set_lanes: engine is NULL");
+    if (lanes < 1 || lanes > 8) return fail(JG_ERR_INVALID, "jg_engine_set_lanes: %d lanes out of range [1,8]", lanes);
+    CUDA_TRY(cudaSetDevice(e->device));
+    while ((int)e->sib.size() > lanes - 1) {   // fewer lanes: give the siblings' arenas back
+        CUDA_TRY(cudaDeviceSynchronize());
+        engine_release(e->sib.back());
+        e->sib.pop_back();
+    }
+    e->lanes = lanes;
+    return JG_OK;
+}
+extern "C" int jg_engine_lanes(const jg_engine* e) { return e ? e->lanes : JG_ERR_INVALID; }
+
+static int ensure_lanes(jg_engine* e) {
+    while ((int)e->sib.size() < e->lanes - 1) {
+        jg_engine* sb = jg_engine_create(&e->robot_copy, e->has_scene ? &e->scene_copy : nullptr, e->device, &e->prm);
+        if (!sb) return JG_ERR_CUDA;   // jg_last_error() holds the reason
+        e->sib.push_back(sb);
+    }
+    while ((int)e->lane_stream.size() < e->lanes) {
+        cudaStream_t ls;
+        cudaEvent_t ev;
+        CUDA_TRY(cudaStreamCreateWithFlags(&ls, cudaStreamNonBlocking));
+        e->lane_stream.push_back(ls);
+        CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        e->lane_ev.push_back(ev);
+    }
+    if (!e->ev_fork) CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    return JG_OK;
+}
+
+// may this call be cut over the lanes?  (not while profiling: sections of overlapping passes would time each other; not
+// while its stream is being captured; not from a sibling)
+static bool use_lanes(const jg_engine* e, int64_t n, int64_t unit, cudaStream_t st) {
+    if (e->lanes < 2 || n <= unit || e->profiling) return false;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    return !(cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive);
+}
+
+// n units in the fewest equal pieces of at most `unit` (multiples of 32: the packed words of the pieces stay aligned),
+// piece i on lane i % lanes: fork from the caller's stream, join back into it.  piece(engine, offset, count, stream).
+template <class F>
+static int run_lanes(jg_engine* e, int64_t n, int64_t unit, cudaStream_t st, F piece) {
+    int rc = ensure_lanes(e);
+    if (rc) return rc;
+    unit = std::max<int64_t>(32, unit / 32 * 32);
+    const int64_t k = (n + unit - 1) / unit;
+    const int64_t p = std::max<int64_t>(32, std::min<int64_t>(unit, ((n + k - 1) / k + 31) / 32 * 32));
+    const int L = (int)std::min<int64_t>(e->lanes, (n + p - 1) / p);
+    CUDA_TRY(cudaEventRecord(e->ev_fork, st));
+    for (int l = 0; l < L; ++l) CUDA_TRY(cudaStreamWaitEvent(e->lane_stream[l], e->ev_fork, 0));
+    int64_t i = 0;
+    for (int64_t off = 0; off < n && rc == JG_OK; off += p, ++i) {
+        const int l = (int)(i % L);
+        jg_engine* le = l == 0 ? e : e->sib[l - 1];
+        le->accumulate_stats = i >= L;
+        rc = piece(le, off, std::min<int64_t>(p, n - off), e->lane_stream[l]);
+        le->accumulate_stats = false;
+    }
+    for (int l = 0; l < L; ++l) {   // join (also after an error: nothing may still run on the lanes when the caller reads `st`)
+        if (cudaEventRecord(e->lane_ev[l], e->lane_stream[l]) == cudaSuccess) cudaStreamWaitEvent(st, e->lane_ev[l], 0);
+    }
+    e->last_call_lanes = L;
+    return rc;
 }
 
 // Mesh mode: a (pose, link shape) may queue many triangle candidates, so a pass takes fewer configurations than the
@@ -1009,11 +1100,16 @@ extern "C" int jg_check(jg_engine* e, const float* q, int64_t n, int dof, uint32
     if (n < 0 || (n && (!q || !bits))) return fail(JG_ERR_INVALID, "jg_check: NULL q/bits");
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaSetDevice(e->device));
+    if (use_lanes(e, n, e->cap_max, st))
+        return run_lanes(e, n, e->cap_max, st, [&](jg_engine* le, int64_t off, int64_t m, cudaStream_t ls) {
+            return jg_check(le, q + off * dof, m, dof, flags, bits + off / 32, min_dist ? min_dist + off : nullptr,
+                            reason ? reason + off : nullptr, ls);
+        });
     int rc = ensure_arena(e, e->mesh ? n * 16 : n);
     if (rc) return rc;
     rc = begin_call(e, st);
     if (rc) return rc;
-    e->stats.configs = n;
+    e->stats.configs += n;
     mesh_first_pass(e);
     for (int64_t off = 0; off < n;) {
         const int64_t pass = e->mesh ? e->mesh_pass : e->cap;
@@ -1047,13 +1143,18 @@ extern "C" int jg_check_edges(jg_engine* e, const float* qa, const float* qb, in
     if (m < 0 || (m && (!qa || !qb || !bits))) return fail(JG_ERR_INVALID, "jg_check_edges: NULL qa/qb/bits");
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaSetDevice(e->device));
+    if (use_lanes(e, m, (e->cap_max / substeps) / 32 * 32, st))
+        return run_lanes(e, m, (e->cap_max / substeps) / 32 * 32, st, [&](jg_engine* le, int64_t off, int64_t k, cudaStream_t ls) {
+            return jg_check_edges(le, qa + off * dof, qb + off * dof, k, dof, substeps, flags, bits + off / 32,
+                                  min_dist ? min_dist + off : nullptr, ls);
+        });
     int rc = ensure_arena(e, std::max<int64_t>(m, 32) * substeps * (e->mesh ? 16 : 1));
     if (rc) return rc;
     if (e->mesh && 32 * substeps > e->mesh_cfg_cap)
         return fail(JG_ERR_INVALID, "jg_check_edges: mesh mode takes at most %d substeps per edge", e->mesh_cfg_cap / 32);
     rc = begin_call(e, st);
     if (rc) return rc;
-    e->stats.configs = m * substeps;
+    e->stats.configs += m * substeps;
     mesh_first_pass(e);
     for (int64_t off = 0; off < m;) {
         // packed words stay aligned across passes: a pass holds a multiple of 32 edges (mesh mode: adaptive pass size)
@@ -1120,11 +1221,18 @@ extern "C" int jg_check_poses(jg_engine* e, const float* poses, int64_t n, int f
     flags &= (JG_SCENE | JG_PLANE | JG_NO_EPA);
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaSetDevice(e->device));
+    if (use_lanes(e, n, e->cap_max, st)) {
+        const int stride = fmt == JG_POSE_MAT34 ? 12 : 7;
+        return run_lanes(e, n, e->cap_max, st, [&](jg_engine* le, int64_t off, int64_t k, cudaStream_t ls) {
+            return jg_check_poses(le, poses + off * stride, k, fmt, ee_link, links, n_links, flags, bits + off / 32,
+                                  min_dist ? min_dist + off : nullptr, ls);
+        });
+    }
     int rc = ensure_arena(e, e->mesh ? n * 16 : n);
     if (rc) return rc;
     rc = begin_call(e, st);
     if (rc) return rc;
-    e->stats.configs = n;
+    e->stats.configs += n;
     // rigid offsets rel_s = inv(T_ee) * T_link(s)
     double fk[MAX_LINKS][12];
     host_fk(e->h_robot, e->prm.finger_open, fk);
@@ -1452,6 +1560,15 @@ extern "C" int jg_get_stats(jg_engine* e, jg_stats* out) {
     out->gjk_run = (int64_t)h[4];
     out->epa_run = (int64_t)h[5];
     out->overflow_run = (int64_t)h[6];
+    for (int l = 1; l < e->last_call_lanes; ++l) {   // a call that was cut over the lanes: add the siblings' share
+        jg_stats sb;
+        e->sib[l - 1]->last_call_lanes = 0;
+        const int rc = jg_get_stats(e->sib[l - 1], &sb);
+        if (rc) return rc;
+        out->configs += sb.configs; out->pairs += sb.pairs; out->plane_pairs += sb.plane_pairs; out->self_pairs += sb.self_pairs;
+        out->epa_pairs += sb.epa_pairs; out->gjk_run += sb.gjk_run; out->epa_run += sb.epa_run;
+        out->kernel_launches += sb.kernel_launches; out->overflow_run += sb.overflow_run;
+    }
     return JG_OK;
 }
 

@@ -45,9 +45,10 @@ def unpack_bits(words, n):
 
 class CollisionEngine:
     def __init__(self, robot, scene=None, device=0, threshold=-0.001, query_distance=0.01, finger_open=0.04,
-                 chunk=0, mesh_mode=False, mesh_margin=0.001):
+                 chunk=0, mesh_mode=False, mesh_margin=0.001, lanes=1):
         """mesh_mode: check against the scene's merged triangle mesh (``scene.tri_verts`` / ``scene.tris`` = the
-        reference's export/obstacles.obj) through a GPU-built LBVH instead of against the convex pieces."""
+        reference's export/obstacles.obj) through a GPU-built LBVH instead of against the convex pieces.
+        lanes: scratch arenas a call of more than one pass may use side by side (``jg_engine_set_lanes``)."""
         L = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.JogramopError('no CUDA device: the jogramop_framework_b200 engine has no CPU fallback')
@@ -84,6 +85,11 @@ class CollisionEngine:
         if not self._e:
             raise _lib.JogramopError('jg_engine_create: ' + L.jg_last_error().decode())
         self.threshold, self.query_distance, self.finger_open = threshold, query_distance, finger_open
+        if lanes != 1:
+            self.set_lanes(lanes)
+
+    def set_lanes(self, lanes):
+        _lib.check(self._L.jg_engine_set_lanes(self._e, int(lanes)), 'jg_engine_set_lanes')
 
     @property
     def handle(self):

@@ -551,6 +551,64 @@ def test_engine_pool_batches_in_flight(robot, scene_loader):
     single.close()
 
 
+def test_engine_lanes_cut_large_calls(robot, scene_loader):
+    """jg_engine_set_lanes: a call of several passes runs them on several arenas / internal streams -- same bits, distances
+    and reasons as the one-arena engine, counters of the whole call, stream semantics kept (results consumed on the caller's
+    stream right after the call), one-pass calls untouched, lanes can be taken away again."""
+    from jogramop_framework_b200._lib import JogramopError
+    from jogramop_framework_b200.engine import CollisionEngine
+    scene = scene_loader(11)
+    single = CollisionEngine(robot, scene, chunk=8192)
+    laned = CollisionEngine(robot, scene, chunk=8192, lanes=3)
+    assert laned._L.jg_engine_lanes(laned._e) == 3 and laned.pass_size == 8192
+    big = torch.from_numpy(uniform_configs(robot, 8192 * 7 + 1234, 901)).cuda()
+    for fl, wd in ((15, True), (3, True), (3, False)):
+        b1, d1, r1 = single.check(big, flags=fl, want_dist=wd, want_reason=True)
+        s1 = single.stats()
+        b, d, r = laned.check(big, flags=fl, want_dist=wd, want_reason=True)
+        nb = int(b.sum().item())                       # consumed on the caller's stream straight away
+        assert nb == int(b1.sum().item())
+        assert torch.equal(b, b1) and torch.equal(r, r1) and (not wd or torch.equal(d, d1))
+        s = laned.stats()
+        assert s['configs'] == len(big) == s1['configs'] and s['pairs'] == s1['pairs'] and s['gjk_run'] == s1['gjk_run']
+    small = big[:5000]
+    assert torch.equal(laned.check(small, flags=15)[0], single.check(small, flags=15)[0])       # one pass: not cut
+    assert laned.stats()['configs'] == 5000
+    qa = uniform_configs(robot, 5003, 902)
+    qb = (qa + np.random.default_rng(903).uniform(-0.2, 0.2, qa.shape)).astype(np.float32)
+    eb1, ed1 = single.check_edges(qa, qb, substeps=16)
+    eb, ed = laned.check_edges(qa, qb, substeps=16)
+    assert torch.equal(eb, eb1) and torch.equal(ed, ed1)
+    rng = np.random.default_rng(904)
+    pq = np.concatenate([rng.uniform(-0.6, 0.6, (30001, 3)) + [0, 0, 0.6], rng.normal(size=(30001, 4))], 1)
+    pq[:, 3:] /= np.linalg.norm(pq[:, 3:], axis=1, keepdims=True)
+    pq = pq.astype(np.float32)
+    links = [robot.end_effector_id - 3, *robot.finger_joint_ids]
+    pb1, pd1 = single.check_poses(pq, links=links)
+    pb, pd = laned.check_poses(pq, links=links)
+    assert torch.equal(pb, pb1) and torch.equal(pd, pd1)
+    x, y, z, w = (pq[:, 3 + k].astype(np.float64) for k in range(4))          # the matrix form has another stride
+    T = np.zeros((len(pq), 3, 4), np.float32)
+    T[:, 0, :3] = np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], 1)
+    T[:, 1, :3] = np.stack([2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)], 1)
+    T[:, 2, :3] = np.stack([2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], 1)
+    T[:, :, 3] = pq[:, :3]
+    pbm1, pdm1 = single.check_poses(T, links=links)
+    pbm, pdm = laned.check_poses(T, links=links)
+    assert torch.equal(pbm, pbm1) and torch.equal(pdm, pdm1) and torch.allclose(pdm, pd1, atol=1e-4)
+    # while profiling nothing is cut (sections of overlapping passes would time each other); results unchanged
+    laned.profile(True)
+    assert torch.equal(laned.check(big, flags=15)[0], single.check(big, flags=15)[0])
+    assert laned.get_profile()['broadphase'][1] == 8
+    laned.profile(False)
+    laned.set_lanes(1)
+    assert torch.equal(laned.check(big, flags=15)[0], single.check(big, flags=15)[0])
+    with pytest.raises(JogramopError):
+        laned.set_lanes(9)
+    laned.close()
+    single.close()
+
+
 def test_non_finite_inputs_are_rejected_on_the_gpu(robot, scene_loader, engines):
     """NaN / inf joint values and poses: bit set, reason 1, distance = query distance, with or without JG_LIMITS -- as the
     oracle does (tests/test_oracle_properties.py); the neighbours of such a row are untouched."""
