@@ -45,7 +45,7 @@ def test_library_is_loaded_and_no_cpu_fallback():
     L = _lib.load()
     assert L.jg_device_count() >= 1
     with open('/proc/self/maps') as fh:
-        assert 'libjogramop_b200.so' in fh.read()
+        assert 'libjogramop_b200' in fh.read()      # (.so, or the _bounds / _count twin a debug run selected)
 
 
 def test_fk_parity(robot, engines):

@@ -29,7 +29,7 @@ from jogramop_framework_b200.ingest import RobotModel, SceneModel  # noqa: E402
 
 DATA = os.path.join(ROOT, 'jogramop_framework_b200', 'data')
 IDS = [11, 12, 13, 14, 15, 21, 22, 23, 24, 25, 31, 32, 33, 34, 35, 41, 42, 43, 44, 45]
-CHUNK = 1 << 20   # configurations per engine call (= one pass)
+LANES = int(os.environ.get('JG_LANES', 4))   # scratch arenas a multi-pass call uses side by side (jg_engine_set_lanes)
 
 
 def main():
@@ -76,7 +76,7 @@ def main():
     total_ms = 0.0
     for sid in IDS:
         scene = SceneModel.load(os.path.join(DATA, f'scene_{sid:03d}.npz'))
-        eng = CollisionEngine(robot, scene, device=local)
+        eng = CollisionEngine(robot, scene, device=local, lanes=LANES)
         lo, hi = shard_bounds(n_cfg, world, rank)
         g = torch.Generator(device=dev)
         g.manual_seed(sid * 1000 + rank)
@@ -84,10 +84,8 @@ def main():
         buf = GatherBuffer(n_cfg, dev)        # the kernels write into this rank's slot: in-place all-gather
         dmin = torch.empty(hi - lo, dtype=torch.float32, device=dev)
 
-        def run():
-            for c0 in range(0, hi - lo, CHUNK):
-                c1 = min(c0 + CHUNK, hi - lo)
-                eng.check(q[c0:c1], flags=SCENE | PLANE, packed=True, bits_out=buf.slot[c0 // 32:], dist_out=dmin[c0:c1])
+        def run():   # one call: the library cuts it into passes and runs them side by side on its lanes
+            eng.check(q, flags=SCENE | PLANE, packed=True, bits_out=buf.slot, dist_out=dmin)
             return buf.gather()
 
         ms, allw = timed(run)
@@ -102,20 +100,15 @@ def main():
 
     # ---- config 4
     scene = SceneModel.load(os.path.join(DATA, 'scene_034.npz'))
-    eng = CollisionEngine(robot, scene, device=local)
+    eng = CollisionEngine(robot, scene, device=local, lanes=LANES)
     lo, hi = shard_bounds(n_edges, world, rank)
     g = torch.Generator(device=dev)
     g.manual_seed(34_000 + rank)
     qa = lo_q + (hi_q - lo_q) * torch.rand((hi - lo, 9), generator=g, device=dev)
     qb = torch.minimum(torch.maximum(qa + (torch.rand((hi - lo, 9), generator=g, device=dev) - 0.5) * 0.5, lo_q), hi_q)
-    ECH = 1 << 14   # edges per call: 2^14 x 64 substeps = one 2^20 pass
 
     def run_edges():
-        words = torch.empty(((hi - lo) + 31) // 32, dtype=torch.int32, device=dev)
-        for c0 in range(0, hi - lo, ECH):
-            c1 = min(c0 + ECH, hi - lo)
-            b, _ = eng.check_edges(qa[c0:c1], qb[c0:c1], substeps=64, packed=True)
-            words[c0 // 32:c0 // 32 + b.numel()] = b
+        words, _ = eng.check_edges(qa, qb, substeps=64, packed=True)
         return gather_bits(words, n_edges)
 
     ms, allw = timed(run_edges)
@@ -124,11 +117,7 @@ def main():
          edges_per_s=n_edges / ms * 1e3, edge_collision_rate=hit, outputs='verdict bit + min distance over the substeps')
 
     def run_edges_bits():
-        words = torch.empty(((hi - lo) + 31) // 32, dtype=torch.int32, device=dev)
-        for c0 in range(0, hi - lo, ECH):
-            c1 = min(c0 + ECH, hi - lo)
-            b, _ = eng.check_edges(qa[c0:c1], qb[c0:c1], substeps=64, packed=True, want_dist=False)
-            words[c0 // 32:c0 // 32 + b.numel()] = b
+        words, _ = eng.check_edges(qa, qb, substeps=64, packed=True, want_dist=False)
         return gather_bits(words, n_edges)
 
     ms, allw2 = timed(run_edges_bits)
@@ -139,7 +128,7 @@ def main():
 
     # ---- config 5
     scene = SceneModel.load(os.path.join(DATA, 'scene_011.npz'))
-    eng = CollisionEngine(robot, scene, device=local)
+    eng = CollisionEngine(robot, scene, device=local, lanes=LANES)
     lo, hi = shard_bounds(n_cfg, world, rank)
     tgt = scene.piece(0)
     blo = torch.tensor(tgt.min(0) - 0.25, dtype=torch.float32, device=dev)
@@ -151,11 +140,7 @@ def main():
     pq = torch.cat([pos, quat], 1).contiguous()
 
     def run_poses():
-        words = torch.empty(((hi - lo) + 31) // 32, dtype=torch.int32, device=dev)
-        for c0 in range(0, hi - lo, CHUNK):
-            c1 = min(c0 + CHUNK, hi - lo)
-            b, _ = eng.check_poses(pq[c0:c1], links=[11, 12, 13], packed=True)
-            words[c0 // 32:c0 // 32 + b.numel()] = b
+        words, _ = eng.check_poses(pq, links=[11, 12, 13], packed=True)
         return gather_bits(words, n_cfg)
 
     ms, allw = timed(run_poses)
@@ -170,14 +155,10 @@ def main():
     from jogramop_framework_b200.scenario import Scenario
     with contextlib.redirect_stdout(io.StringIO()):
         vis = Scenario(11, device=local).visual_scene_model()
-    geng = CollisionEngine(burg_gripper_model(), vis, device=local, threshold=1e-6, finger_open=0.0, mesh_mode=True, mesh_margin=0.0)
+    geng = CollisionEngine(burg_gripper_model(), vis, device=local, threshold=1e-6, finger_open=0.0, mesh_mode=True, mesh_margin=0.0)   # (lanes: no gain on the traversal path, measured)
 
     def run_burg():
-        words = torch.empty(((hi - lo) + 31) // 32, dtype=torch.int32, device=dev)
-        for c0 in range(0, hi - lo, CHUNK):
-            c1 = min(c0 + CHUNK, hi - lo)
-            b, _ = geng.check_poses(pq[c0:c1], links=[0], ee_link=0, want_dist=False, packed=True)
-            words[c0 // 32:c0 // 32 + b.numel()] = b
+        words, _ = geng.check_poses(pq, links=[0], ee_link=0, want_dist=False, packed=True)
         return gather_bits(words, n_cfg)
 
     ms, allw = timed(run_burg)
