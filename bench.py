@@ -375,6 +375,10 @@ def run_b200(args):
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         # the collective's kernels get a high-priority stream: with several batches in flight the SMs are never idle, and a
         # pending all-gather block must be the first thing scheduled when a persistent block retires
+        # ... and it is a 1 MB collective: two channels move it as fast as NCCL's default channel count, and its spinning
+        # CTAs then hold two SMs instead of a dozen while the ranks meet (profiles/r02_scale_probe_8gpu.txt: the gather
+        # costs 1.5 % of the 8-GPU step with the default channels, 0.4 % with two)
+        os.environ.setdefault('NCCL_MAX_NCHANNELS', '2')
         pg_opts = None
         if not os.environ.get('JG_BENCH_NO_PRIO'):
             pg_opts = dist.ProcessGroupNCCL.Options()
@@ -575,7 +579,7 @@ def run_b200(args):
                        'l2': f'inputs larger than L2: the steps rotate over {ROT} different {n}-configuration batches '
                              f'({ROT * n * 36 / 1e6:.0f} MB > 126 MB L2); one CUDA-event pair around all timed steps',
                        'collective': ('ncclAllGather of the packed verdict bits, in place (the kernels write into the rank\'s slot), '
-                                      f'one per {G} step(s), on a high-priority side stream under the following steps\' kernels; '
+                                      f'one per {G} step(s), NCCL_MAX_NCHANNELS={os.environ.get("NCCL_MAX_NCHANNELS")}, on a high-priority side stream under the following steps\' kernels; '
                                       'the timed region ends after the last gather')
                        if world > 1 else 'none (1 GPU)',
                        'in_flight': f'{lanes} batches in flight: EnginePool, one engine (scratch arena) and CUDA stream per lane, steps '
