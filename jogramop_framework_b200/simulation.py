@@ -56,9 +56,12 @@ class GraspingSimulator:
 
     PLANE_ID = 0
 
-    def __init__(self, verbose=False, device=0):
+    def __init__(self, verbose=False, device=0, lanes=4):
+        """``lanes``: scratch arenas a batched query of several passes (more than ~1 M configurations, or edges x substeps)
+        may use side by side on the GPU (``jg_engine_set_lanes``; arenas are only allocated when such a call is made)."""
         self.verbose = verbose
         self.device = device
+        self.lanes = int(lanes)
         self.bullet_client = None     # no Bullet client behind this simulator
         self._p = None
         self._env_bodies = {'plane': self.PLANE_ID}      # burg SimulatorBase._reset(plane_and_gravity=True)
@@ -146,7 +149,8 @@ class GraspingSimulator:
             scene = self._scene_for(bodies, with_plane)
             self._engines[full_key] = _engine.CollisionEngine(
                 model, scene, device=self.device, finger_open=full_key[1], chunk=4096 if small else 0,
-                mesh_mode=mesh_margin is not None, mesh_margin=0.001 if mesh_margin is None else mesh_margin)
+                mesh_mode=mesh_margin is not None, mesh_margin=0.001 if mesh_margin is None else mesh_margin,
+                lanes=1 if (small or mesh_margin is not None) else self.lanes)   # (no gain on the LBVH path: measured)
         return self._engines[full_key]
 
     # ------------------------------------------------------------------ reference API

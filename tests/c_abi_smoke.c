@@ -27,6 +27,9 @@ int main(int argc, char** argv) {
     jg_scene_describe(scene, &sd);
     jg_engine* eng = jg_engine_create(robot, scene, 0, NULL);
     if (!eng) { fprintf(stderr, "jg_engine_create: %s\n", jg_last_error()); return 4; }
+    /* lanes: arenas a device-pointer call of several passes may use side by side (not used by the host-buffer call below) */
+    if (jg_engine_set_lanes(eng, 2) != JG_OK || jg_engine_lanes(eng) != 2 || jg_engine_set_lanes(eng, 9) == JG_OK ||
+        jg_engine_pass_size(eng) < 32) { fprintf(stderr, "lanes / pass size: %s\n", jg_last_error()); return 4; }
     FILE* f = fopen(argv[3], "r");
     int n = 0;
     if (!f || fscanf(f, "%d", &n) != 1 || n <= 0) { fprintf(stderr, "cannot read %s\n", argv[3]); return 2; }

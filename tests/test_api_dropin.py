@@ -254,6 +254,9 @@ def test_batched_variants_and_filter(robot, scene_loader, golden):
         assert abs(float(gd[i]) - min(pd[9:12].min(), 0.01)) < 1e-4
     be, de = rob.edges_in_collision_batch(q[:100], q[100:200], substeps=8)
     assert be.shape == (100,) and de.dtype == torch.float32
+    # the batched queries' engine may spread a call of several passes over 4 arenas; per-body / per-pair helpers keep one
+    full = sim._engine('full')
+    assert sim.lanes == 4 and full._L.jg_engine_lanes(full._e) == 4
     # swept validation of a point-to-point trajectory (simulation.py:480-535 waypoints) with one batched check
     from jogramop_framework_b200.simulation import TrajectoryPlanner
     tr = TrajectoryPlanner.ptp(np.asarray(rob.home_conf), golden['ik_034'][0])
