@@ -5,12 +5,16 @@
 
 Workload (SURVEY.md §8d config 2 = BASELINE.json configs[1]): scenario 011, 1 000 000 uniformly sampled mobile-Panda
 configurations per GPU (np.random.default_rng(11 + 1000*rank), float32), flags SCENE+PLANE, outputs collision bit +
-signed min distance.  One "step" = one pass of the hot path over that batch.  Weak scaling: every rank checks its own
-1 M shard against a replicated scene; the packed verdict bitmasks are gathered with one NCCL all-gather inside the
-timed region.
+signed min distance.  One "step" = one pass of the hot path over that batch.  `--lanes` (4) steps are in flight at a
+time: the engine pool (engine.EnginePool) hands the steps round-robin to 4 engines (scratch arenas) on 4 streams, so one
+batch's kernels run under the tails of the others'; every step is still a full pass over its own 1 M batch, and all K
+finish inside the timed region.  `single_lane` reports the same K steps one batch at a time on one stream.  Weak scaling:
+every rank checks its own 1 M shards against a replicated scene; the packed verdict bitmasks of every step are gathered
+with one NCCL all-gather inside the timed region.
 
 `value`   : device-resident throughput (inputs already in HBM), CUDA events on the launching stream, max over ranks.
-`e2e`     : same metric through the host-buffer entry point (jg_check_host): pinned host q -> H2D -> kernels -> D2H.
+`e2e`     : same metric through the host-buffer entry points (jg_check_host_submit / _wait on the pool's engines; the
+            blocking jg_check_host beside it): pinned host q -> H2D -> kernels -> D2H, every step.
 `roofline`: narrow-phase kernel (the dominant one) against the measured FP32 FMA peak (the binding roof, SURVEY §8d);
             `roofline_hbm` gives the HBM view of the whole pass.
 `cpu_baseline`: the double-precision CPU oracle ("port": pybullet is not installable in this image) on the host cores.
@@ -19,9 +23,11 @@ timed region.
 Timing (all on the device, max over ranks): ONE CUDA-event pair around the K timed steps on the launching stream, after a
 barrier + synchronize; the steps rotate over 4 different 1 M input batches (144 MB > the 126 MB L2; the pass's own queue
 traffic evicts the rest), so no step finds its inputs in L2.  With N > 1 the kernels write their packed verdict words
-straight into the rank's slot of the all-gather buffer and the all-gather of step k runs on a side stream under the
-kernels of step k+1; the timed region ends when the last gather has finished.
-`soak`    : the same step looped for 2 s with NVML clock samples every 5 ms (sustained SM clock of THIS workload).
+straight into the rank's slot of the all-gather buffer and the all-gather of step k runs on a high-priority side stream
+under the kernels of the following steps; the timed region ends when the last gather has finished.  The kernel split
+(`kernel_ms_per_step`) and the roofline durations come from the same K steps run one batch at a time right after the
+timed region, with the library's section events on.
+`soak`    : the one-batch-at-a-time step looped for 2 s with NVML clock samples every 5 ms (sustained SM clock of THIS workload).
 `configs` : BASELINE.json configs 3 / 4 / 5 measured after the timed region (N = 1), each with a parity sample.
 """
 import argparse
